@@ -1,0 +1,68 @@
+"""CPU, build container only: oracle/*.py against the reference's OWN source files imported live from
+/root/reference (MONAI symbols supplied by oracle/monai_shim.py).  Skipped where the reference tree is absent
+(e.g. the GPU box) -- tests/test_oracle_goldens.py covers the same ground there through committed fixtures."""
+from unittest import mock
+
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import nets as onets
+from oracle import ref_loader, synth
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")]
+
+CASES = [("baseunet", 64, 4, 1), ("ms_dsa_net", 64, 4, 1), ("segresnet", 32, 8, 1), ("segresnetvae_dsa", 32, 8, 2)]
+
+
+@pytest.mark.parametrize("mt,patch,fs,batch", CASES)
+def test_forward_bit_exact(mt, patch, fs, batch):
+    params = ref_loader.default_params()
+    params.update(model_type=mt, patch_size=(patch,) * 3, feature_size=fs)
+    model, params = ref_loader.build_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=2)
+    model.load_state_dict(sd)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+            m.p = 0.0
+    model.train()
+    x = synth.image(batch, 2, patch, seed=4)
+    noise = synth.tensor((batch, 256), "vae_noise", 9, 1.0, dist="normal")
+    with mock.patch.object(torch, "randn_like", lambda t, **k: noise.to(t)), torch.no_grad():
+        ref = model(x)
+    bn = {}
+    with torch.no_grad():
+        ora = onets.forward(mt, sd, x, True, bn, noise)
+    if isinstance(ref, tuple):
+        assert torch.equal(ref[0], ora[0])
+        assert abs(float(ref[1]) - float(ora[1])) <= 1e-6 * abs(float(ref[1]))
+    else:
+        assert torch.equal(ref, ora)
+    msd = model.state_dict()
+    for k, v in bn.items():
+        assert torch.allclose(msd[k].float(), v.float(), rtol=0, atol=0), k
+
+
+def test_default_init_param_counts():
+    """MS_DSA_NET 43,524,802 and BaseUNet 22,966,690 trainable parameters at the default config."""
+    params = ref_loader.default_params()
+    params.update(patch_size=(128,) * 3)
+    for mt, n in (("ms_dsa_net", 43524802), ("baseunet", 22966690)):
+        params["model_type"] = mt
+        model, _ = ref_loader.build_model(params, init_weights=False)
+        assert sum(p.numel() for p in model.parameters() if p.requires_grad) == n
+
+
+def test_combined_loss_matches_reference():
+    _, gl, _ = ref_loader.load()
+    base = ref_loader.default_params()
+    pred = synth.tensor((1, 2, 12, 14, 16), "lp", 1, 2.0, dist="normal")
+    tgt = synth.label(1, (12, 14, 16), seed=2)
+    for over in (dict(loss="DiceCELoss"), dict(loss="DiceFocalLoss", tv_loss_weight=0.1, tv_loss_norm="l2"),
+                 dict(loss="DiceLoss", tv_loss_weight=0.3, tvloss_exclude_borders=True)):
+        p = dict(base)
+        p.update(over)
+        ref = gl.CombinedLoss(p, torch.device("cpu"))(pred, tgt)
+        ora = olosses.combined_loss(p, pred, tgt)
+        assert abs(float(ref) - float(ora)) <= 1e-6 * max(1.0, abs(float(ref))), over
