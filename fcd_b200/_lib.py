@@ -1,0 +1,102 @@
+"""ctypes binding of the C-ABI CUDA library (include/fcd_b200.h -> fcd_b200/libfcd_b200.so).
+
+The prototypes are parsed from the header, so the header is the single source of truth for argument order;
+call sites pass arguments BY NAME (`call("fcd_igemm", A=..., lda=..., ...)`).  There is no CPU fallback: if the
+library is missing the import raises, and every non-zero return code raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "fcd_b200.h")
+LIBPATH = os.path.join(_HERE, "libfcd_b200.so")
+
+_CT = {
+    "int": ctypes.c_int,
+    "float": ctypes.c_float,
+    "long long": ctypes.c_longlong,
+    "cudaStream_t": ctypes.c_void_p,
+}
+
+
+def parse_header(path: str = HEADER):
+    """Return {name: [(param_name, ctype), ...]} for every FCD_API prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"FCD_API\s+int\s+(\w+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2).strip()
+        params = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                pname = re.search(r"(\w+)$", a).group(1)
+                ptype = a[: -len(pname)].strip()
+                if "*" in ptype:
+                    ct = ctypes.c_void_p
+                else:
+                    ct = _CT[ptype.replace("const ", "").strip()]
+                params.append((pname, ct))
+        protos[name] = params
+    return protos
+
+
+PROTOS = parse_header()
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise RuntimeError(
+                f"{LIBPATH} is missing: build it with `python -m fcd_b200.build` (nvcc, sm_100a). "
+                "fcd_b200 has no CPU or library fallback.")
+        _lib = ctypes.CDLL(LIBPATH)
+        for name, params in PROTOS.items():
+            fn = getattr(_lib, name)       # raises AttributeError if the .so lacks a declared symbol
+            fn.restype = ctypes.c_int
+            fn.argtypes = [ct for _, ct in params]
+    return _lib
+
+
+def _ptr(v):
+    if v is None:
+        return None
+    if isinstance(v, torch.Tensor):
+        if not v.is_cuda:
+            raise RuntimeError("fcd_b200 kernels take CUDA tensors only (no CPU fallback)")
+        return v.data_ptr()
+    return v
+
+
+def call(name: str, **kw):
+    params = PROTOS[name]
+    fn = getattr(lib(), name)
+    if "stream" in [p for p, _ in params] and "stream" not in kw:
+        kw["stream"] = torch.cuda.current_stream().cuda_stream
+    args = []
+    for pname, ct in params:
+        if pname not in kw:
+            raise TypeError(f"{name}: missing argument {pname}")
+        v = kw.pop(pname)
+        args.append(_ptr(v) if ct is ctypes.c_void_p else v)
+    if kw:
+        raise TypeError(f"{name}: unexpected arguments {sorted(kw)}")
+    rc = fn(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed with code {rc}" + (" (unsupported shape)" if rc == -1 else " (CUDA error)"))
+    return rc
+
+
+def query(name: str) -> int:
+    """For the argument-less sizing helpers (fcd_loss_blocks, ...): they return a count, not an error code."""
+    return getattr(lib(), name)()
+
+
+LAUNCHES = 0   # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches evidence)

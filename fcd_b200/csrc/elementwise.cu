@@ -1,0 +1,555 @@
+// Bandwidth-bound kernels: layout conversion, max-pool, normalisation family (Instance/Batch/Group norm fused
+// with LeakyReLU/ReLU and the residual add), LayerNorm(+pos_embed), pixel-shuffle blur, dropout, small utilities.
+// All activations are channels-last bf16 [B][D][H][W][C] (C % 8 == 0), moved with 128-bit loads/stores.
+#include "common.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------- layout
+// NCDHW fp32 -> NDHWC bf16 with zero-padded channels (train.py:367-370 hands the model fp32 NCDHW batches).
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, int Cp,
+                                      long long S, long long total_vox) {
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total_vox;
+         v += (long long)gridDim.x * blockDim.x) {
+        long long b = v / S, s = v - b * S;
+        for (int c0 = 0; c0 < Cp; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = (c0 + i < C) ? src[(b * C + c0 + i) * S + s] : 0.f;
+            st8(dst + v * Cp + c0, pack8(f));
+        }
+    }
+}
+
+// NDHWC bf16 (row stride ld) -> NCDHW fp32 (first C channels)
+__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int C, long long ld,
+                                      long long S, long long total_vox) {
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total_vox;
+         v += (long long)gridDim.x * blockDim.x) {
+        long long b = v / S, s = v - b * S;
+        for (int c = 0; c < C; ++c) dst[(b * C + c) * S + s] = __bfloat162float(src[v * ld + c]);
+    }
+}
+
+// NCDHW fp32 gradient -> NDHWC bf16 is the same kernel as the forward conversion.
+
+// ----------------------------------------------------------------------------------------------- max-pool
+// torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382).
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Do, int Ho, int Wo,
+                                    int C8) {
+    const long long total = (long long)B * Do * Ho * Wo * C8;
+    const int Hi = Ho * 2, Wi = Wo * 2;
+    const long long C = C8 * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c8 = (int)(i % C8);
+        long long r = i / C8;
+        int ox = (int)(r % Wo); r /= Wo;
+        int oy = (int)(r % Ho); r /= Ho;
+        int oz = (int)(r % Do);
+        long long b = r / Do;
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            long long vox = ((b * (Do * 2) + oz * 2 + (t >> 2)) * Hi + oy * 2 + ((t >> 1) & 1)) * Wi + ox * 2 + (t & 1);
+            float f[8];
+            unpack8(ld8(x + vox * C + c8 * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        }
+        st8(y + (((b * Do + oz) * Ho + oy) * Wo + ox) * C + c8 * 8, pack8(m));
+    }
+}
+
+// Gradient goes to the FIRST maximal element in (z,y,x) scan order, as ATen's max_pool3d backward does.
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                    const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int Do, int Ho, int Wo,
+                                    int C8, int accumulate) {
+    const long long total = (long long)B * Do * Ho * Wo * C8;
+    const int Hi = Ho * 2, Wi = Wo * 2;
+    const long long C = C8 * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c8 = (int)(i % C8);
+        long long r = i / C8;
+        int ox = (int)(r % Wo); r /= Wo;
+        int oy = (int)(r % Ho); r /= Ho;
+        int oz = (int)(r % Do);
+        long long b = r / Do;
+        long long ovox = ((b * Do + oz) * Ho + oy) * Wo + ox;
+        float m[8], g[8];
+        bool done[8];
+        unpack8(ld8(y + ovox * C + c8 * 8), m);
+        unpack8(ld8(dy + ovox * C + c8 * 8), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) done[k] = false;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            long long vox = ((b * (Do * 2) + oz * 2 + (t >> 2)) * Hi + oy * 2 + ((t >> 1) & 1)) * Wi + ox * 2 + (t & 1);
+            float f[8], o[8];
+            unpack8(ld8(x + vox * C + c8 * 8), f);
+            if (accumulate) unpack8(ld8(dx + vox * C + c8 * 8), o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                bool hit = (!done[k]) && (f[k] == m[k]);
+                float v = hit ? g[k] : 0.f;
+                done[k] = done[k] || hit;
+                o[k] = accumulate ? o[k] + v : v;
+            }
+            st8(dx + vox * C + c8 * 8, pack8(o));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- norm stats
+// Per-(b, c) partial sums over a slab of rows: part[b][chunk][0..C) = sum x, part[b][chunk][C..2C) = sum x^2.
+// blockDim = 256; thread t owns channel chunk t % C8 and rows t / C8 + k * (256 / C8).
+__global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ part, long long S,
+                                  int C8, int nchunk) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int c8 = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
+    const long long rows_per = (S + nchunk - 1) / nchunk;
+    const long long s0 = chunk * rows_per, s1 = min(S, s0 + rows_per);
+    float sum[8], sq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
+    const bf16* base = x + (long long)b * S * ld + c8 * 8;
+    for (long long s = s0 + r0; s < s1; s += rstep) {
+        float f[8];
+        unpack8(ld8(base + s * ld), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sum[k] += f[k]; sq[k] = fmaf(f[k], f[k], sq[k]); }
+    }
+    __shared__ float sh[256 * 16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sh[threadIdx.x * 16 + k] = sum[k]; sh[threadIdx.x * 16 + 8 + k] = sq[k]; }
+    __syncthreads();
+    // threads with r0 == 0 reduce their column of rows
+    if (r0 == 0) {
+        for (int r = 1; r < rstep; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sum[k] += sh[(r * C8 + c8) * 16 + k];
+                sq[k] += sh[(r * C8 + c8) * 16 + 8 + k];
+            }
+        }
+        const int C = C8 * 8;
+        float* o = part + ((long long)b * nchunk + chunk) * 2 * C;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o[c8 * 8 + k] = sum[k]; o[C + c8 * 8 + k] = sq[k]; }
+    }
+}
+
+// mode 0 instance (per b,c), 1 batch (per c over b), 2 group-of-2-channels (per b, c/2).
+// Writes mean[b][c], rstd[b][c]; for batch mode also updates running stats (momentum, unbiased var) if given.
+__global__ void norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
+                                     int B, int C, int nchunk, long long S, int mode, float eps,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var, int crun,
+                                     float momentum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C;
+    double s = 0.0, q = 0.0, n = 0.0;
+    auto add = [&](int bb, int cc) {
+        const float* o = part + (long long)bb * nchunk * 2 * C;
+        for (int k = 0; k < nchunk; ++k) { s += o[(long long)k * 2 * C + cc]; q += o[(long long)k * 2 * C + C + cc]; }
+        n += (double)S;
+    };
+    if (mode == 0) {
+        add(b, c);
+    } else if (mode == 1) {
+        for (int bb = 0; bb < B; ++bb) add(bb, c);
+    } else {
+        add(b, c & ~1);
+        add(b, c | 1);
+    }
+    const double m = s / n;
+    double var = q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+    if (mode == 1 && b == 0 && running_mean != nullptr && c < crun) {
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// y = act( g1*(x1-mean1)*rstd1 + b1  [+ g2*(x2-mean2)*rstd2 + b2]  [+ r] ),  act(v) = v > 0 ? v : slope*v
+// mean/rstd are per (b,c); gamma/beta per c (nullptr => 1/0).  grid.y = B.
+__global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, const float* __restrict__ mean1,
+                                  const float* __restrict__ rstd1, const float* __restrict__ gamma1,
+                                  const float* __restrict__ beta1, const bf16* __restrict__ x2, long long ld2,
+                                  const float* __restrict__ mean2, const float* __restrict__ rstd2,
+                                  const bf16* __restrict__ res, long long ldr, bf16* __restrict__ y, long long ldy,
+                                  long long S, int C8, float slope) {
+    const int b = blockIdx.y;
+    const int C = C8 * 8;
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;      // multiple of C8 (C8 | 256)
+    const int c8 = (int)(gtid % C8);
+    float a1[8], o1[8], a2[8], o2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c8 * 8 + k;
+        float g = gamma1 ? gamma1[c] : 1.f, be = beta1 ? beta1[c] : 0.f;
+        float r = rstd1[b * C + c];
+        a1[k] = g * r;
+        o1[k] = be - mean1[b * C + c] * g * r;
+        if (x2) {
+            float r2 = rstd2[b * C + c];
+            a2[k] = r2;
+            o2[k] = -mean2[b * C + c] * r2;
+        } else {
+            a2[k] = o2[k] = 0.f;
+        }
+    }
+    const long long total = S * C8;
+    for (long long i = gtid; i < total; i += gstride) {
+        const long long s = i / C8;
+        const long long row = (long long)b * S + s;
+        float f[8], v[8];
+        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(f[k], a1[k], o1[k]);
+        if (x2) {
+            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += fmaf(f[k], a2[k], o2[k]);
+        }
+        if (res) {
+            unpack8(ld8(res + row * ldr + c8 * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+        st8(y + row * ldy + c8 * 8, pack8(v));
+    }
+}
+
+// Backward statistics.  ds = dy * act'(y) (y = saved forward output; nullptr => no activation).
+// part[b][chunk][0..C) = sum ds, [C..2C) = sum ds*xhat1, [2C..3C) = sum ds*xhat2 (if x2).
+__global__ void norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
+                                      long long ldy, const bf16* __restrict__ x1, long long ld1,
+                                      const float* __restrict__ mean1, const float* __restrict__ rstd1,
+                                      const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
+                                      const float* __restrict__ rstd2, float* __restrict__ part, long long S, int C8,
+                                      int nchunk, float slope) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int C = C8 * 8;
+    const int c8 = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
+    const long long rows_per = (S + nchunk - 1) / nchunk;
+    const long long s0 = chunk * rows_per, s1 = min(S, s0 + rows_per);
+    float m1[8], i1[8], m2[8], i2[8], a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c8 * 8 + k;
+        m1[k] = mean1[b * C + c]; i1[k] = rstd1[b * C + c];
+        m2[k] = x2 ? mean2[b * C + c] : 0.f; i2[k] = x2 ? rstd2[b * C + c] : 0.f;
+        a0[k] = a1[k] = a2[k] = 0.f;
+    }
+    for (long long s = s0 + r0; s < s1; s += rstep) {
+        const long long row = (long long)b * S + s;
+        float g[8], f[8];
+        unpack8(ld8(dy + row * lddy + c8 * 8), g);
+        if (y) {
+            unpack8(ld8(y + row * ldy + c8 * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = f[k] > 0.f ? g[k] : g[k] * slope;
+        }
+        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], (f[k] - m1[k]) * i1[k], a1[k]); }
+        if (x2) {
+            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a2[k] = fmaf(g[k], (f[k] - m2[k]) * i2[k], a2[k]);
+        }
+    }
+    __shared__ float sh[256 * 24];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sh[threadIdx.x * 24 + k] = a0[k];
+        sh[threadIdx.x * 24 + 8 + k] = a1[k];
+        sh[threadIdx.x * 24 + 16 + k] = a2[k];
+    }
+    __syncthreads();
+    if (r0 == 0) {
+        for (int r = 1; r < rstep; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a0[k] += sh[(r * C8 + c8) * 24 + k];
+                a1[k] += sh[(r * C8 + c8) * 24 + 8 + k];
+                a2[k] += sh[(r * C8 + c8) * 24 + 16 + k];
+            }
+        }
+        float* o = part + ((long long)b * nchunk + chunk) * 3 * C;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            o[c8 * 8 + k] = a0[k];
+            o[C + c8 * 8 + k] = a1[k];
+            o[2 * C + c8 * 8 + k] = a2[k];
+        }
+    }
+}
+
+// Turn the backward partial sums into per-(b,c) coefficients:
+//   dx_j = k1_j * ds - k2_j - k3_j * xhat_j     (j = 1, 2)
+// with k1 = gamma*rstd, k2 = rstd*mean_grp(gamma*ds), k3 = rstd*mean_grp(gamma*ds*xhat); also dgamma/dbeta (+=).
+// coef[b][c][0..2] for input 1, coef[b][c][3..5] for input 2.
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ rstd1,
+                                         const float* __restrict__ rstd2, const float* __restrict__ gamma1,
+                                         float* __restrict__ coef, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, int B, int C, int nchunk, long long S, int mode,
+                                         int has2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C;
+    auto sum3 = [&](int bb, int cc, double& s0, double& s1, double& s2) {
+        const float* o = part + (long long)bb * nchunk * 3 * C;
+        s0 = s1 = s2 = 0.0;
+        for (int k = 0; k < nchunk; ++k) {
+            s0 += o[(long long)k * 3 * C + cc];
+            s1 += o[(long long)k * 3 * C + C + cc];
+            s2 += o[(long long)k * 3 * C + 2 * C + cc];
+        }
+    };
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, n = 0.0;   // group sums of gamma*ds, gamma*ds*xhat1, ds*xhat2
+    auto addgrp = [&](int bb, int cc) {
+        double s0, s1, s2;
+        sum3(bb, cc, s0, s1, s2);
+        const double g = gamma1 ? (double)gamma1[cc] : 1.0;
+        g0 += g * s0; g1 += g * s1; g2 += s2;
+        n += (double)S;
+    };
+    if (mode == 0) addgrp(b, c);
+    else if (mode == 1) { for (int bb = 0; bb < B; ++bb) addgrp(bb, c); }
+    else { addgrp(b, c & ~1); addgrp(b, c | 1); }
+    const double g = gamma1 ? (double)gamma1[c] : 1.0;
+    float* o = coef + (long long)i * 6;
+    o[0] = (float)(g * rstd1[i]);
+    o[1] = (float)(rstd1[i] * (g0 / n));
+    o[2] = (float)(rstd1[i] * (g1 / n));
+    if (has2) {
+        // second input never has affine parameters; its ds sum is the un-weighted one
+        double u0 = 0.0, u2 = 0.0, nn = 0.0;
+        auto add2 = [&](int bb, int cc) { double s0, s1, s2; sum3(bb, cc, s0, s1, s2); u0 += s0; u2 += s2; nn += (double)S; };
+        if (mode == 0) add2(b, c);
+        else if (mode == 1) { for (int bb = 0; bb < B; ++bb) add2(bb, c); }
+        else { add2(b, c & ~1); add2(b, c | 1); }
+        o[3] = rstd2[i];
+        o[4] = (float)(rstd2[i] * (u0 / nn));
+        o[5] = (float)(rstd2[i] * (u2 / nn));
+    } else {
+        o[3] = o[4] = o[5] = 0.f;
+    }
+    (void)g2;
+    if (dgamma != nullptr && b == 0) {
+        double dg = 0.0, db = 0.0;
+        for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
+        dgamma[c] += (float)dg;
+        dbeta[c] += (float)db;
+    }
+}
+
+// dx1 = k1*ds - k2 - k3*xhat1 ; dx2 likewise (optional) ; dres = ds (optional).  ds = dy*act'(y).
+__global__ void norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
+                                      long long ldy, const bf16* __restrict__ x1, long long ld1,
+                                      const float* __restrict__ mean1, const float* __restrict__ rstd1,
+                                      const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
+                                      const float* __restrict__ rstd2, const float* __restrict__ coef,
+                                      bf16* __restrict__ dx1, long long ldd1, bf16* __restrict__ dx2, long long ldd2,
+                                      bf16* __restrict__ dres, long long lddr, long long S, int C8, float slope,
+                                      int acc_res) {
+    const int b = blockIdx.y;
+    const int C = C8 * 8;
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    const int c8 = (int)(gtid % C8);
+    float m1[8], i1[8], m2[8], i2[8], k[8][6];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int c = c8 * 8 + q;
+        m1[q] = mean1[b * C + c]; i1[q] = rstd1[b * C + c];
+        m2[q] = x2 ? mean2[b * C + c] : 0.f; i2[q] = x2 ? rstd2[b * C + c] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) k[q][j] = coef[((long long)b * C + c) * 6 + j];
+    }
+    const long long total = S * C8;
+    for (long long i = gtid; i < total; i += gstride) {
+        const long long row = (long long)b * S + i / C8;
+        float g[8], f[8], o[8];
+        unpack8(ld8(dy + row * lddy + c8 * 8), g);
+        if (y) {
+            unpack8(ld8(y + row * ldy + c8 * 8), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = f[q] > 0.f ? g[q] : g[q] * slope;
+        }
+        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = k[q][0] * g[q] - k[q][1] - k[q][2] * ((f[q] - m1[q]) * i1[q]);
+        st8(dx1 + row * ldd1 + c8 * 8, pack8(o));
+        if (x2) {
+            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = k[q][3] * g[q] - k[q][4] - k[q][5] * ((f[q] - m2[q]) * i2[q]);
+            st8(dx2 + row * ldd2 + c8 * 8, pack8(o));
+        }
+        if (dres) {
+            if (acc_res) {
+                unpack8(ld8(dres + row * lddr + c8 * 8), f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] += f[q];
+            }
+            st8(dres + row * lddr + c8 * 8, pack8(g));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- misc
+// out = a + b   (bf16, rows of C8*8 channels with independent strides)
+__global__ void add_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b, long long ldb,
+                           bf16* __restrict__ o, long long ldo, long long rows, int C8) {
+    const long long total = rows * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / C8;
+        const int c = (int)(i % C8) * 8;
+        float x[8], y[8];
+        unpack8(ld8(a + r * lda + c), x);
+        unpack8(ld8(b + r * ldb + c), y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] += y[k];
+        st8(o + r * ldo + c, pack8(x));
+    }
+}
+
+__global__ void copy_rows_kernel(const bf16* __restrict__ a, long long lda, bf16* __restrict__ o, long long ldo,
+                                 long long rows, int C8) {
+    const long long total = rows * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / C8;
+        const int c = (int)(i % C8) * 8;
+        st8(o + r * ldo + c, ld8(a + r * lda + c));
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, float* __restrict__ out, int C, int nchunk) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int k = 0; k < nchunk; ++k) s += part[(long long)k * 2 * C + c];
+    out[c] = (float)s;
+}
+
+inline int grid_for(long long total, int block, int mult) {
+    long long g = (total + block - 1) / block;
+    long long cap = (long long)fcd_num_sms() * mult;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+FCD_API int fcd_ncdhw_to_ndhwc(const float* src, void* dst, int B, int C, int Cp, long long S, cudaStream_t st) {
+    long long tv = (long long)B * S;
+    ncdhw_to_ndhwc_kernel<<<grid_for(tv, 256, 8), 256, 0, st>>>(src, (bf16*)dst, C, Cp, S, tv);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_ndhwc_to_ncdhw(const void* src, float* dst, int B, int C, long long ld, long long S, cudaStream_t st) {
+    long long tv = (long long)B * S;
+    ndhwc_to_ncdhw_kernel<<<grid_for(tv, 256, 8), 256, 0, st>>>((const bf16*)src, dst, C, ld, S, tv);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int Wo, int C, cudaStream_t st) {
+    if (C % 8) return -1;
+    long long total = (long long)B * Do * Ho * Wo * (C / 8);
+    maxpool2_fwd_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>((const bf16*)x, (bf16*)y, B, Do, Ho, Wo, C / 8);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,
+                             int C, int accumulate, cudaStream_t st) {
+    if (C % 8) return -1;
+    long long total = (long long)B * Do * Ho * Wo * (C / 8);
+    maxpool2_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy,
+                                                                 (bf16*)dx, B, Do, Ho, Wo, C / 8, accumulate);
+    FCD_LAUNCH_CHECK();
+}
+
+// Statistics for InstanceNorm3d / BatchNorm3d / GroupNorm(2 ch per group) (conv_blocks.py:418-419,437,56;
+// ms_dsa_net.py:217).  part: B*nchunk*2*C floats.  C/8 must divide 256.
+FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean, float* rstd, int B, long long S,
+                           int C, int nchunk, int mode, float eps, float* running_mean, float* running_var,
+                           int crun, float momentum, cudaStream_t st) {
+    if (C % 8 || 256 % (C / 8)) return -1;
+    dim3 grid(nchunk, B);
+    norm_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk);
+    norm_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
+                                                             running_mean, running_var, crun, momentum);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_norm_apply(const void* x1, long long ld1, const float* mean1, const float* rstd1, const float* gamma1,
+                           const float* beta1, const void* x2, long long ld2, const float* mean2, const float* rstd2,
+                           const void* res, long long ldr, void* y, long long ldy, int B, long long S, int C,
+                           float slope, cudaStream_t st) {
+    if (C % 8 || 256 % (C / 8)) return -1;
+    dim3 grid(grid_for(S * (C / 8), 256, 8), B);
+    norm_apply_kernel<<<grid, 256, 0, st>>>((const bf16*)x1, ld1, mean1, rstd1, gamma1, beta1, (const bf16*)x2, ld2,
+                                            mean2, rstd2, (const bf16*)res, ldr, (bf16*)y, ldy, S, C / 8, slope);
+    FCD_LAUNCH_CHECK();
+}
+
+// Backward of y = act(norm1(x1) [+ norm2(x2)] [+ res]).  part: B*nchunk*3*C floats, coef: B*C*6 floats.
+FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long long ldy, const void* x1, long long ld1,
+                         const float* mean1, const float* rstd1, const float* gamma1, const void* x2, long long ld2,
+                         const float* mean2, const float* rstd2, float* part, float* coef, float* dgamma,
+                         float* dbeta, void* dx1, long long ldd1, void* dx2, long long ldd2, void* dres,
+                         long long lddr, int acc_res, int B, long long S, int C, int nchunk, int mode, float slope,
+                         cudaStream_t st) {
+    if (C % 8 || 256 % (C / 8)) return -1;
+    dim3 g1(nchunk, B);
+    norm_bwd_stats_kernel<<<g1, 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
+                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope);
+    norm_bwd_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, rstd1, rstd2, gamma1, coef, dgamma, dbeta, B,
+                                                                 C, nchunk, S, mode, x2 != nullptr);
+    dim3 g2(grid_for(S * (C / 8), 256, 8), B);
+    norm_bwd_apply_kernel<<<g2, 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
+                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, coef, (bf16*)dx1, ldd1,
+                                              (bf16*)dx2, ldd2, (bf16*)dres, lddr, S, C / 8, slope, acc_res);
+    FCD_LAUNCH_CHECK();
+}
+
+// out[c] = sum over rows of x[row][c]  (bias gradients).  part: nchunk*2*C floats.
+FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, long long rows, int C, int nchunk,
+                       cudaStream_t st) {
+    if (C % 8 || 256 % (C / 8)) return -1;
+    dim3 grid(nchunk, 1);
+    norm_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk);
+    colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, out, C, nchunk);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_add(const void* a, long long lda, const void* b, long long ldb, void* o, long long ldo, long long rows,
+                    int C, cudaStream_t st) {
+    if (C % 8) return -1;
+    add_kernel<<<grid_for(rows * (C / 8), 256, 8), 256, 0, st>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)o,
+                                                                 ldo, rows, C / 8);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_copy_rows(const void* a, long long lda, void* o, long long ldo, long long rows, int C,
+                          cudaStream_t st) {
+    if (C % 8) return -1;
+    copy_rows_kernel<<<grid_for(rows * (C / 8), 256, 8), 256, 0, st>>>((const bf16*)a, lda, (bf16*)o, ldo, rows,
+                                                                       C / 8);
+    FCD_LAUNCH_CHECK();
+}

@@ -1,0 +1,268 @@
+// Generic implicit-GEMM convolution family on the legacy tensor path (mma.sync bf16, fp32 accumulate).
+//
+// This is the shape-generic fallback of the conv family: every Conv3d / ConvTranspose3d / Linear of the hot path
+// (reference conv_blocks.py:393-437, 640-649; DSA qkvv conv_blocks.py:225) can run through it.  The tcgen05 kernel
+// in conv_tc.cu takes over the FLOP-heavy 3x3x3 stride-1 layers; this one keeps odd shapes (stride 2, k2s2
+// transposed conv scatter, 1x1, tiny deep levels) correct.
+//
+//   C[m, n] (+)= bias[n] + sum_t sum_k A[src(m, t), k] * W[t][n][k]
+//
+// m runs over the "M grid" (B, Dm, Hm, Wm); src(m,t) maps into the source grid (B, Ds, Hs, Ws):
+//   mode 0 (forward conv):       s = m*stride + tap - pad
+//   mode 1 (data gradient):      q = m + pad - tap, valid iff q % stride == 0, s = q / stride
+// out_mode 1 scatters N = 8*Cq columns to the 2x2x2 sub-lattice of a (2Dm,2Hm,2Wm) grid (ConvTranspose3d k2 s2).
+#include "common.cuh"
+
+struct IGemmParams {
+    const bf16* A;
+    long long lda;
+    const bf16* W;
+    bf16* C;
+    long long ldc;
+    const float* bias;
+    int Bn, Ds, Hs, Ws, Dm, Hm, Wm;
+    int K, N;
+    int kd, kh, kw, stride, pad, mode, out_mode, accumulate;
+    int M, Cq;
+};
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int STAGES = 3;
+
+template <int BK>
+__device__ __forceinline__ int swz_off(int row, int chunk) {
+    // byte offset of 16B chunk `chunk` of row `row` in a [rows][BK] bf16 tile, XOR-swizzled for ldmatrix
+    if (BK == 32) return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+    return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4);
+}
+
+template <int BN, int WN, int BK>
+__global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParams p) {
+    constexpr int WARPS_N = BN / WN;
+    constexpr int NT = 128 * WARPS_N;
+    constexpr int CPR = BK / 8;                 // 16B chunks per tile row
+    constexpr int A_CHUNKS = BM * CPR;
+    constexpr int A_PER_T = A_CHUNKS / NT;
+    constexpr int B_CHUNKS = BN * CPR;
+    constexpr int A_BYTES = BM * BK * 2;
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(A_CHUNKS % NT == 0, "A tile must divide evenly");
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % 4, wn = warp / 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    // ---- per-thread gather rows (fixed across the K loop)
+    int r_z[A_PER_T], r_y[A_PER_T], r_x[A_PER_T];
+    long long r_base[A_PER_T];
+    bool r_ok[A_PER_T];
+    int r_row[A_PER_T], r_ch[A_PER_T];
+#pragma unroll
+    for (int i = 0; i < A_PER_T; ++i) {
+        int idx = tid + i * NT;
+        int row = idx / CPR;
+        r_row[i] = row;
+        r_ch[i] = idx % CPR;
+        int m = m0 + row;
+        r_ok[i] = m < p.M;
+        int mm = r_ok[i] ? m : 0;
+        int x = mm % p.Wm; mm /= p.Wm;
+        int y = mm % p.Hm; mm /= p.Hm;
+        int z = mm % p.Dm; mm /= p.Dm;
+        r_x[i] = x; r_y[i] = y; r_z[i] = z;
+        r_base[i] = (long long)mm * p.Ds * p.Hs * p.Ws;
+    }
+
+    const int kchunks = p.K / BK;
+    const int T = p.kd * p.kh * p.kw;
+    const int nk = T * kchunks;
+
+    auto load_stage = [&](int it, int slot) {
+        const int t = it / kchunks, kc = it - t * kchunks;
+        const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
+        const uint32_t sa = smem_base + slot * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int i = 0; i < A_PER_T; ++i) {
+            int sz, sy, sx;
+            bool ok = r_ok[i];
+            if (p.mode == 0) {
+                sz = r_z[i] * p.stride + tz - p.pad;
+                sy = r_y[i] * p.stride + ty - p.pad;
+                sx = r_x[i] * p.stride + tx - p.pad;
+            } else {
+                int qz = r_z[i] + p.pad - tz, qy = r_y[i] + p.pad - ty, qx = r_x[i] + p.pad - tx;
+                ok = ok && qz >= 0 && qy >= 0 && qx >= 0;
+                if (p.stride > 1) {
+                    ok = ok && (qz % p.stride == 0) && (qy % p.stride == 0) && (qx % p.stride == 0);
+                    sz = qz / p.stride; sy = qy / p.stride; sx = qx / p.stride;
+                } else {
+                    sz = qz; sy = qy; sx = qx;
+                }
+            }
+            ok = ok && sz >= 0 && sz < p.Ds && sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
+            const bf16* src = p.A;
+            if (ok) src += (r_base[i] + ((long long)sz * p.Hs + sy) * p.Ws + sx) * p.lda + kc * BK + r_ch[i] * 8;
+            cp_async16(sa + swz_off<BK>(r_row[i], r_ch[i]), src, ok);
+        }
+        for (int idx = tid; idx < B_CHUNKS; idx += NT) {
+            int n = idx / CPR, ch = idx % CPR;
+            bool ok = (n0 + n) < p.N;
+            const bf16* src = p.W;
+            if (ok) src += ((long long)t * p.N + n0 + n) * p.K + kc * BK + ch * 8;
+            cp_async16(sb + swz_off<BK>(n, ch), src, ok);
+        }
+    };
+
+    float acc[2][WN / 8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < WN / 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = it + STAGES - 1;
+            if (nx < nk) load_stage(nx, nx % STAGES);
+            cp_async_commit();
+        }
+        const uint32_t sa = smem_base + (it % STAGES) * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+            uint32_t af[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                int row = wm * 32 + mi * 16 + (lane & 15);
+                int ch = kk * 2 + (lane >> 4);
+                ldmatrix_x4(af[mi][0], af[mi][1], af[mi][2], af[mi][3], sa + swz_off<BK>(row, ch));
+            }
+#pragma unroll
+            for (int nj = 0; nj < WN / 16; ++nj) {
+                uint32_t b0, b1, b2, b3;
+                int n = wn * WN + nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+                int ch = kk * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(b0, b1, b2, b3, sb + swz_off<BK>(n, ch));
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) {
+                    mma_bf16_16816(acc[mi][nj * 2], af[mi], b0, b1);
+                    mma_bf16_16816(acc[mi][nj * 2 + 1], af[mi], b2, b3);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- epilogue: (+bias) -> bf16 tile in smem -> 16B coalesced rows (plain / accumulate / k2s2 scatter)
+    constexpr int CLD = BN + 8;   // padded row (elements)
+    bf16* ctile = reinterpret_cast<bf16*>(smem);
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nj = 0; nj < WN / 8; ++nj) {
+        int col = wn * WN + nj * 8 + tq * 2;
+        float bv0 = 0.f, bv1 = 0.f;
+        if (p.bias != nullptr && (n0 + col) < p.N) {
+            int nb = n0 + col;
+            if (p.out_mode == 1) nb = nb % p.Cq;
+            bv0 = p.bias[nb];
+            bv1 = p.bias[nb + 1];
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            int row = wm * 32 + mi * 16 + g;
+            *reinterpret_cast<__nv_bfloat162*>(&ctile[row * CLD + col]) =
+                __floats2bfloat162_rn(acc[mi][nj][0] + bv0, acc[mi][nj][1] + bv1);
+            *reinterpret_cast<__nv_bfloat162*>(&ctile[(row + 8) * CLD + col]) =
+                __floats2bfloat162_rn(acc[mi][nj][2] + bv0, acc[mi][nj][3] + bv1);
+        }
+    }
+    __syncthreads();
+    constexpr int C_CHUNKS = BM * (BN / 8);
+    for (int idx = tid; idx < C_CHUNKS; idx += NT) {
+        int row = idx / (BN / 8), c8 = idx % (BN / 8);
+        int m = m0 + row, n = n0 + c8 * 8;
+        if (m >= p.M || n >= p.N) continue;
+        bf16x8 v = *reinterpret_cast<const bf16x8*>(&ctile[row * CLD + c8 * 8]);
+        bf16* dst;
+        if (p.out_mode == 0) {
+            dst = p.C + (long long)m * p.ldc + n;
+        } else {
+            int tap = n / p.Cq, co = n - tap * p.Cq;
+            int mm = m;
+            int x = mm % p.Wm; mm /= p.Wm;
+            int y = mm % p.Hm; mm /= p.Hm;
+            int z = mm % p.Dm; mm /= p.Dm;
+            int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
+            long long vox = (((long long)mm * (2 * p.Dm) + oz) * (2 * p.Hm) + oy) * (2 * p.Wm) + ox;
+            dst = p.C + vox * p.ldc + co;
+        }
+        if (p.accumulate) {
+            float a[8], b[8];
+            unpack8(v, a);
+            unpack8(ld8(dst), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += b[i];
+            v = pack8(a);
+        }
+        st8(dst, v);
+    }
+}
+
+template <int BN, int WN, int BK>
+int launch_igemm(const IGemmParams& p, cudaStream_t stream) {
+    constexpr int NT = 128 * (BN / WN);
+    constexpr int pipe = STAGES * (BM * BK * 2 + BN * BK * 2);
+    constexpr int epi = BM * (BN + 8) * 2;
+    constexpr int smem = pipe > epi ? pipe : epi;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(igemm_kernel<BN, WN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+    igemm_kernel<BN, WN, BK><<<grid, NT, smem, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// Replaces torch.nn.functional.conv3d / conv_transpose3d / linear as dispatched by the reference's nn.Conv3d,
+// nn.ConvTranspose3d and nn.Linear modules (conv_blocks.py:393-437, 640-649, 225; ms_dsa_net.py:216,362).
+// Returns a cudaError_t value (0 = ok), -1 for unsupported shapes.
+FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
+                      int Bn, int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh, int kw,
+                      int stride, int pad, int mode, int out_mode, int accumulate, int Cq, cudaStream_t stream) {
+    if (K % 16 != 0 || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0) return -1;
+    if (out_mode == 1 && (Cq % 8 != 0 || N != 8 * Cq)) return -1;
+    IGemmParams p;
+    p.A = (const bf16*)A; p.lda = lda; p.W = (const bf16*)W; p.C = (bf16*)C; p.ldc = ldc; p.bias = bias;
+    p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
+    p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+    p.mode = mode; p.out_mode = out_mode; p.accumulate = accumulate; p.Cq = Cq > 0 ? Cq : 1;
+    long long M = (long long)Bn * Dm * Hm * Wm;
+    if (M <= 0 || M > 0x7fffffffLL) return -1;
+    p.M = (int)M;
+    const bool k32 = (K % 32 == 0);
+    if (N <= 16) return k32 ? launch_igemm<16, 16, 32>(p, stream) : launch_igemm<16, 16, 16>(p, stream);
+    if (N <= 32) return k32 ? launch_igemm<32, 32, 32>(p, stream) : launch_igemm<32, 32, 16>(p, stream);
+    if (N <= 64 || (long long)((M + BM - 1) / BM) * ((N + 127) / 128) < 2 * fcd_num_sms())
+        return k32 ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
+    return k32 ? launch_igemm<128, 64, 32>(p, stream) : launch_igemm<128, 64, 16>(p, stream);
+}

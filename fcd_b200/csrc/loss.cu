@@ -1,0 +1,261 @@
+// Fused segmentation loss: Dice (+ CE | + sigmoid-focal) (+ total variation), forward and backward.
+//
+// Replaces, for a 2-class prediction, the ~15 ATen kernels of the reference's CombinedLoss.forward
+// (get_loss.py:24-39): MONAI DiceLoss / DiceCELoss / DiceFocalLoss built at get_loss.py:46-78
+// (include_background=False, to_onehot_y=True, softmax=True, batch=True, smooth 1e-5) and
+// compute_total_variation_loss / dilate_mask (get_loss.py:100-165).
+// pred: fp32 NCDHW [B,2,D,H,W] logits; target: fp32 [B,1,D,H,W] in {0,1}.  All reductions are fp32 per thread,
+// combined in double by a single finalize block; nothing is read back to the host.
+#include "common.cuh"
+
+struct LossCfg {
+    int kind;        // 0 Dice, 1 DiceCE, 2 DiceFocal
+    float lambda_dice, lambda_2, w_bg, w_fg, gamma;
+    int squared, jaccard;
+    float smooth_nr, smooth_dr;
+    float tv_w;
+    int tv_norm, tv_exclude;
+};
+
+namespace {
+
+constexpr int LOSS_BLOCKS = 592;   // 4 x 148
+constexpr int LOSS_THREADS = 256;
+
+__device__ __forceinline__ float softplusf(float x) { return x > 0.f ? x + log1pf(__expf(-x)) : log1pf(__expf(x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// border mask of get_loss.py:141-150: 1 where the clipped 5^3 window holds both a 0 and a 1 of gt.
+__global__ void tv_mask_kernel(const float* __restrict__ gt, unsigned char* __restrict__ keep, int B, int D, int H,
+                               int W) {
+    const long long total = (long long)B * D * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int x = (int)(r % W); r /= W;
+        int y = (int)(r % H); r /= H;
+        int z = (int)(r % D);
+        long long b = r / D;
+        bool any1 = false, any0 = false;
+        for (int dz = -2; dz <= 2; ++dz) {
+            int zz = z + dz; if (zz < 0 || zz >= D) continue;
+            for (int dy = -2; dy <= 2; ++dy) {
+                int yy = y + dy; if (yy < 0 || yy >= H) continue;
+                for (int dx = -2; dx <= 2; ++dx) {
+                    int xx = x + dx; if (xx < 0 || xx >= W) continue;
+                    float g = gt[((b * D + zz) * H + yy) * W + xx];
+                    any1 |= (g > 0.f);
+                    any0 |= (g < 1.f);
+                }
+            }
+        }
+        keep[i] = (any1 && any0) ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_fwd_kernel(const float* __restrict__ pred,
+                                                                const float* __restrict__ target, long long S, int B,
+                                                                LossCfg cfg, const unsigned char* __restrict__ keep,
+                                                                float* __restrict__ pbuf, float* __restrict__ part) {
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // I, P, G, CE numerator, CE denominator, focal sum
+    const long long total = (long long)B * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / S, s = i - b * S;
+        const float l0 = pred[(b * 2) * S + s], l1 = pred[(b * 2 + 1) * S + s];
+        const float y = target[i] == 1.f ? 1.f : 0.f;
+        const float d = l1 - l0;
+        const float p = sigmoidf_(d);
+        a[0] += p * y;
+        a[1] += cfg.squared ? p * p : p;
+        a[2] += y;
+        if (cfg.kind == 1) {
+            const float w = y > 0.f ? cfg.w_fg : cfg.w_bg;
+            a[3] += w * softplusf(y > 0.f ? -d : d);
+            a[4] += w;
+        } else if (cfg.kind == 2) {
+            const float sgn = 2.f * y - 1.f;
+            const float bce = l1 - l1 * y + softplusf(-l1);          // x - x t - logsigmoid(x)
+            const float invp = -softplusf(l1 * sgn);                 // logsigmoid(-x (2t-1))
+            a[5] += __expf(cfg.gamma * invp) * bce;
+        }
+        if (pbuf) pbuf[i] = keep ? (keep[i] ? p : 0.f) : p;
+    }
+    __shared__ float sh[(LOSS_THREADS / 32) * 6];
+    block_sum<6>(a, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) part[blockIdx.x * 8 + k] = a[k];
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) tv_fwd_kernel(const float* __restrict__ pbuf, int B, int D, int H,
+                                                              int W, int norm, float* __restrict__ part) {
+    float a[3] = {0.f, 0.f, 0.f};
+    const long long total = (long long)B * D * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int x = (int)(r % W); r /= W;
+        int y = (int)(r % H); r /= H;
+        int z = (int)(r % D);
+        const float p = pbuf[i];
+        if (z + 1 < D) { float dd = pbuf[i + (long long)H * W] - p; a[0] += norm == 1 ? fabsf(dd) : dd * dd; }
+        if (y + 1 < H) { float dd = pbuf[i + W] - p; a[1] += norm == 1 ? fabsf(dd) : dd * dd; }
+        if (x + 1 < W) { float dd = pbuf[i + 1] - p; a[2] += norm == 1 ? fabsf(dd) : dd * dd; }
+    }
+    __shared__ float sh[(LOSS_THREADS / 32) * 3];
+    block_sum<3>(a, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 4 + 0] = a[0];
+        part[blockIdx.x * 4 + 1] = a[1];
+        part[blockIdx.x * 4 + 2] = a[2];
+    }
+}
+
+// res[0]=total, [1]=dice N, [2]=dice Dn, [3]=CE weight sum, [4..6]=tv_z,tv_y,tv_x, [7]=dice, [8]=ce|focal, [9]=tv
+__global__ void loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ tvpart, int nblk,
+                                     LossCfg cfg, int B, int D, int H, int W, float* __restrict__ res) {
+    __shared__ double sh[9];
+    if (threadIdx.x < 9) {
+        double s = 0.0;
+        if (threadIdx.x < 6) {
+            for (int k = 0; k < nblk; ++k) s += part[k * 8 + threadIdx.x];
+        } else if (tvpart != nullptr) {
+            for (int k = 0; k < nblk; ++k) s += tvpart[k * 4 + (threadIdx.x - 6)];
+        }
+        sh[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double I = sh[0], P = sh[1], G = sh[2];
+        const double N = 2.0 * I + cfg.smooth_nr;
+        double base = G + P;
+        if (cfg.jaccard) base = 2.0 * (base - I);
+        const double Dn = base + cfg.smooth_dr;
+        const double dice = 1.0 - N / Dn;
+        double second = 0.0;
+        const double vox = (double)B * D * H * W;
+        if (cfg.kind == 1) second = sh[3] / sh[4];
+        else if (cfg.kind == 2) second = sh[5] / vox;
+        double tv[3] = {0.0, 0.0, 0.0}, tvsum = 0.0;
+        if (tvpart != nullptr) {
+            const double cnt[3] = {(double)B * (D - 1) * H * W, (double)B * D * (H - 1) * W, (double)B * D * H * (W - 1)};
+            for (int k = 0; k < 3; ++k) {
+                tv[k] = cfg.tv_norm == 1 ? sh[6 + k] / cnt[k] : sqrt(sh[6 + k] / cnt[k] + 1e-10);
+                tvsum += tv[k];
+            }
+        }
+        double total = (cfg.kind == 0 ? dice : cfg.lambda_dice * dice + cfg.lambda_2 * second) + cfg.tv_w * tvsum;
+        res[0] = (float)total; res[1] = (float)N; res[2] = (float)Dn; res[3] = (float)sh[4];
+        res[4] = (float)tv[0]; res[5] = (float)tv[1]; res[6] = (float)tv[2];
+        res[7] = (float)dice; res[8] = (float)second; res[9] = (float)tvsum;
+    }
+}
+
+// dpred (fp32 NCDHW) = gout * dLoss/dpred
+__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(const float* __restrict__ pred,
+                                                                const float* __restrict__ target, int B, int D, int H,
+                                                                int W, LossCfg cfg,
+                                                                const unsigned char* __restrict__ keep,
+                                                                const float* __restrict__ pbuf,
+                                                                const float* __restrict__ res,
+                                                                const float* __restrict__ gout,
+                                                                float* __restrict__ dpred) {
+    const long long S = (long long)D * H * W;
+    const long long total = (long long)B * S;
+    const float go = gout[0];
+    const float N = res[1], Dn = res[2], cew = res[3];
+    const float ldice = cfg.kind == 0 ? 1.f : cfg.lambda_dice;
+    const float cntz = (float)((double)B * (D - 1) * H * W), cnty = (float)((double)B * D * (H - 1) * W),
+                cntx = (float)((double)B * D * H * (W - 1));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / S, s = i - b * S;
+        const float l0 = pred[(b * 2) * S + s], l1 = pred[(b * 2 + 1) * S + s];
+        const float y = target[i] == 1.f ? 1.f : 0.f;
+        const float d = l1 - l0;
+        const float p = sigmoidf_(d);
+        // dice: f = 1 - N/Dn
+        const float dP = cfg.squared ? 2.f * p : 1.f;
+        const float dDn = cfg.jaccard ? 2.f * (dP - y) : dP;
+        float gp = ldice * (-(2.f * y * Dn - N * dDn) / (Dn * Dn));     // dL/dp
+        if (pbuf != nullptr) {                                           // total variation on p' = p * keep
+            long long r = s;
+            const int x = (int)(r % W); r /= W;
+            const int yy = (int)(r % H);
+            const int z = (int)(r / H);
+            const float pc = pbuf[i];
+            float gt = 0.f;
+            auto term = [&](float diff, float cnt, float tvv) -> float {
+                // d/d(diff) of mean|diff| or sqrt(mean diff^2 + eps)
+                if (cfg.tv_norm == 1) return (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) / cnt;
+                return diff / (cnt * tvv);
+            };
+            if (z > 0) gt += term(pc - pbuf[i - (long long)H * W], cntz, res[4]);
+            if (z + 1 < D) gt -= term(pbuf[i + (long long)H * W] - pc, cntz, res[4]);
+            if (yy > 0) gt += term(pc - pbuf[i - W], cnty, res[5]);
+            if (yy + 1 < H) gt -= term(pbuf[i + W] - pc, cnty, res[5]);
+            if (x > 0) gt += term(pc - pbuf[i - 1], cntx, res[6]);
+            if (x + 1 < W) gt -= term(pbuf[i + 1] - pc, cntx, res[6]);
+            if (keep != nullptr && !keep[i]) gt = 0.f;
+            gp += cfg.tv_w * gt;
+        }
+        float gd = gp * p * (1.f - p);                                   // through p = sigmoid(l1 - l0)
+        float g1_extra = 0.f;
+        if (cfg.kind == 1) {
+            const float w = y > 0.f ? cfg.w_fg : cfg.w_bg;
+            gd += cfg.lambda_2 * w * (p - y) / cew;
+        } else if (cfg.kind == 2) {
+            const float sgn = 2.f * y - 1.f;
+            const float u = -l1 * sgn;
+            const float bce = l1 - l1 * y + softplusf(-l1);
+            const float invp = -softplusf(-u);
+            const float e = __expf(cfg.gamma * invp);
+            const float dfl = e * (cfg.gamma * (-sgn) * sigmoidf_(-u) * bce + (sigmoidf_(l1) - y));
+            g1_extra = cfg.lambda_2 * dfl / (float)total;
+        }
+        dpred[(b * 2) * S + s] = -go * gd;
+        dpred[(b * 2 + 1) * S + s] = go * (gd + g1_extra);
+    }
+}
+
+}  // namespace
+
+FCD_API int fcd_loss_blocks() { return LOSS_BLOCKS; }
+
+// Workspace: part >= LOSS_BLOCKS*8 floats, tvpart >= LOSS_BLOCKS*4 floats (or null), pbuf B*S floats (or null
+// when tv_w == 0), keep B*S bytes (only when tv_exclude), res >= 16 floats.
+FCD_API int fcd_loss_fwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
+                         float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
+                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
+                         unsigned char* keep, float* pbuf, float* part, float* tvpart, float* res, cudaStream_t st) {
+    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, smooth_nr, smooth_dr, tv_w, tv_norm,
+                tv_exclude};
+    const long long S = (long long)D * H * W;
+    const bool tv = tv_w > 0.f;
+    if (tv && pbuf == nullptr) return -1;
+    if (tv && tv_exclude) {
+        if (keep == nullptr) return -1;
+        tv_mask_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(target, keep, B, D, H, W);
+    }
+    loss_fwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pred, target, S, B, cfg, (tv && tv_exclude) ? keep : nullptr,
+                                                          tv ? pbuf : nullptr, part);
+    if (tv) tv_fwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pbuf, B, D, H, W, tv_norm, tvpart);
+    loss_finalize_kernel<<<1, 32, 0, st>>>(part, tv ? tvpart : nullptr, LOSS_BLOCKS, cfg, B, D, H, W, res);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
+                         float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
+                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
+                         const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
+                         float* dpred, cudaStream_t st) {
+    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, smooth_nr, smooth_dr, tv_w, tv_norm,
+                tv_exclude};
+    const bool tv = tv_w > 0.f;
+    loss_bwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pred, target, B, D, H, W, cfg,
+                                                          (tv && tv_exclude) ? keep : nullptr, tv ? pbuf : nullptr, res,
+                                                          gout, dpred);
+    FCD_LAUNCH_CHECK();
+}

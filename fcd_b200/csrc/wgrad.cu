@@ -1,0 +1,254 @@
+// Weight-gradient kernels for the conv family (mma.sync bf16, fp32 accumulate, deterministic split-M reduction).
+//
+//   dWp[split][t][n][k] = sum_{m in split} Q[m][n] * P[src(m, t)][k]
+//
+// For a forward conv (reference conv_blocks.py:393-437 via autograd) Q = dY on the output grid, P = X on the input
+// grid with src = m*stride + tap - pad.  For ConvTranspose3d k2 s2 (conv_blocks.py:640-649) the roles swap:
+// Q = X on the coarse grid, P = dY on the fine grid, src = 2m + tap (i.e. the wgrad of a k2 s2 p0 conv).
+// One CTA owns a 16(n) x 16(k) output block for up to TP taps; its 8 warps split the voxel (contraction) axis and
+// are reduced through shared memory at the end, so no atomics are needed.  fcd_wgrad_reduce sums the splits and
+// writes the fp32 gradient in the parameter's own (PyTorch) layout.
+#include "common.cuh"
+
+struct WGradParams {
+    const bf16* Q; long long ldq;
+    const bf16* P; long long ldp;
+    float* out;              // [nsplit][T][Np][Kp]
+    int Bn, Ds, Hs, Ws, Dm, Hm, Wm;
+    int Np, Kp, kd, kh, kw, stride, pad;
+    int M, nsplit, tiles_per_split;
+};
+
+namespace {
+
+constexpr int WBM = 128;   // voxels per stage (8 warps x 16)
+
+__device__ __forceinline__ int wswz(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
+
+template <int TP>
+__global__ void __launch_bounds__(256) wgrad_kernel(const WGradParams p) {
+    constexpr int Q_BYTES = WBM * 32;
+    constexpr int STAGE_BYTES = Q_BYTES * (1 + TP);
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = p.kd * p.kh * p.kw;
+    const int npass = (T + TP - 1) / TP;
+    const int nb = p.Np / 16, kb = p.Kp / 16;
+    int unit = blockIdx.y;
+    const int pass = unit % npass; unit /= npass;
+    const int kblk = unit % kb;
+    const int nblk = unit / kb;
+    (void)nb;
+    const int t0 = pass * TP;
+    const int ntap = min(TP, T - t0);
+    const int split = blockIdx.x;
+    const int tile0 = split * p.tiles_per_split;
+    const int ntiles_total = (p.M + WBM - 1) / WBM;
+    const int tile1 = min(tile0 + p.tiles_per_split, ntiles_total);
+
+    // each thread loads one 16B chunk of Q and of every tap's P tile: row = tid/2, chunk = tid&1
+    const int lrow = tid >> 1, lch = tid & 1;
+
+    auto load_stage = [&](int tile, int slot) {
+        const int m = tile * WBM + lrow;
+        const bool ok = m < p.M;
+        const uint32_t sq = sbase + slot * STAGE_BYTES;
+        const bf16* qsrc = p.Q;
+        if (ok) qsrc += (long long)m * p.ldq + nblk * 16 + lch * 8;
+        cp_async16(sq + wswz(lrow, lch), qsrc, ok);
+        int mm = ok ? m : 0;
+        const int x = mm % p.Wm; mm /= p.Wm;
+        const int y = mm % p.Hm; mm /= p.Hm;
+        const int z = mm % p.Dm; mm /= p.Dm;
+        const long long base = (long long)mm * p.Ds * p.Hs * p.Ws;
+#pragma unroll
+        for (int j = 0; j < TP; ++j) {
+            if (j < ntap) {
+                const int t = t0 + j;
+                const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
+                const int sz = z * p.stride + tz - p.pad, sy = y * p.stride + ty - p.pad, sx = x * p.stride + tx - p.pad;
+                const bool v = ok && sz >= 0 && sz < p.Ds && sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
+                const bf16* src = p.P;
+                if (v) src += (base + ((long long)sz * p.Hs + sy) * p.Ws + sx) * p.ldp + kblk * 16 + lch * 8;
+                cp_async16(sq + Q_BYTES * (1 + j) + wswz(lrow, lch), src, v);
+            }
+        }
+    };
+
+    float acc[TP][2][4];
+#pragma unroll
+    for (int j = 0; j < TP; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j][i][k] = 0.f;
+
+    if (tile0 < tile1) load_stage(tile0, 0);
+    cp_async_commit();
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int slot = (tile - tile0) & 1;
+        if (tile + 1 < tile1) load_stage(tile + 1, slot ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint32_t sq = sbase + slot * STAGE_BYTES;
+        // A fragment: Q^T block (16 n x 16 voxels of this warp)
+        uint32_t a[4];
+        {
+            int v = warp * 16 + (lane & 7) + ((lane >> 4) << 3);
+            int ch = (lane >> 3) & 1;
+            ldmatrix_x4_trans(a[0], a[1], a[2], a[3], sq + wswz(v, ch));
+        }
+#pragma unroll
+        for (int j = 0; j < TP; ++j) {
+            if (j < ntap) {
+                uint32_t b0, b1, b2, b3;
+                int v = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                int ch = lane >> 4;
+                ldmatrix_x4_trans(b0, b1, b2, b3, sq + Q_BYTES * (1 + j) + wswz(v, ch));
+                mma_bf16_16816(acc[j][0], a, b0, b1);
+                mma_bf16_16816(acc[j][1], a, b2, b3);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- cross-warp reduction, one tap at a time: red[warp][16][16]
+    float* red = reinterpret_cast<float*>(smem);
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+        if (j < ntap) {
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                int col = ni * 8 + tq * 2;
+                red[warp * 256 + g * 16 + col] = acc[j][ni][0];
+                red[warp * 256 + g * 16 + col + 1] = acc[j][ni][1];
+                red[warp * 256 + (g + 8) * 16 + col] = acc[j][ni][2];
+                red[warp * 256 + (g + 8) * 16 + col + 1] = acc[j][ni][3];
+            }
+        }
+        __syncthreads();
+        if (j < ntap) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w * 256 + tid];
+            const int n = nblk * 16 + (tid >> 4), k = kblk * 16 + (tid & 15);
+            p.out[(((long long)split * T + (t0 + j)) * p.Np + n) * p.Kp + k] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <int TP>
+int launch_wgrad(const WGradParams& p, cudaStream_t stream) {
+    constexpr int pipe = 2 * WBM * 32 * (1 + TP);
+    constexpr int red = 8 * 256 * 4;
+    constexpr int smem = pipe > red ? pipe : red;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(wgrad_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    const int T = p.kd * p.kh * p.kw;
+    const int npass = (T + TP - 1) / TP;
+    dim3 grid(p.nsplit, (p.Np / 16) * (p.Kp / 16) * npass);
+    wgrad_kernel<TP><<<grid, 256, smem, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// out[n*sn + kmap(k)*sk + t*st] = sum_split part[split][t][n][k];  kmap undoes the concat-segment padding.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int T, int N,
+                                    int K, int Np, int Kp, long long sn, long long sk, long long st, int kseg,
+                                    int ksegpad, int accumulate) {
+    const long long total = (long long)T * N * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i % K);
+        long long r = i / K;
+        int n = (int)(r % N);
+        int t = (int)(r / N);
+        int kp = (k / kseg) * ksegpad + (k % kseg);
+        float s = 0.f;
+        const long long off = ((long long)t * Np + n) * Kp + kp;
+        const long long sstride = (long long)T * Np * Kp;
+        for (int sp = 0; sp < nsplit; ++sp) s += part[sp * sstride + off];
+        const long long o = n * sn + k * sk + t * st;
+        out[o] = accumulate ? out[o] + s : s;
+    }
+}
+
+// dst[t][n][kp] (bf16, zero padded) = src[n*sn + k*sk + t*st]
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int T, int N, int K, int Np,
+                                   int Kp, long long sn, long long sk, long long st, int kseg, int ksegpad, int nseg,
+                                   int nsegpad) {
+    const long long total = (long long)T * Np * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int kp = (int)(i % Kp);
+        long long r = i / Kp;
+        int np_ = (int)(r % Np);
+        int t = (int)(r / Np);
+        float v = 0.f;
+        int seg = kp / ksegpad, within = kp % ksegpad;
+        int k = seg * kseg + within;
+        int nsg = np_ / nsegpad, nwithin = np_ % nsegpad;
+        int n = nsg * nseg + nwithin;
+        if (nwithin < nseg && n < N && within < kseg && k < K) v = src[n * sn + k * sk + t * st];
+        dst[i] = __float2bfloat16(v);
+    }
+}
+
+}  // namespace
+
+// Weight gradient of Conv3d / ConvTranspose3d / Linear (autograd of the modules cited in igemm.cu).
+// `part` must hold nsplit*T*Np*Kp floats.  tiles_per_split = ceil(ceil(M/128)/nsplit).
+FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
+                      int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
+                      int nsplit, cudaStream_t stream) {
+    if (Np % 16 != 0 || Kp % 16 != 0 || ldq % 8 != 0 || ldp % 8 != 0 || nsplit < 1) return -1;
+    WGradParams p;
+    p.Q = (const bf16*)Q; p.ldq = ldq; p.P = (const bf16*)P; p.ldp = ldp; p.out = part;
+    p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
+    p.Np = Np; p.Kp = Kp; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+    long long M = (long long)Bn * Dm * Hm * Wm;
+    if (M <= 0 || M > 0x7fffffffLL) return -1;
+    p.M = (int)M;
+    int ntiles = (p.M + WBM - 1) / WBM;
+    if (nsplit > ntiles) return -1;
+    p.nsplit = nsplit;
+    p.tiles_per_split = (ntiles + nsplit - 1) / nsplit;
+    const int T = kd * kh * kw;
+    if (T == 1) return launch_wgrad<1>(p, stream);
+    if (T == 8) return launch_wgrad<8>(p, stream);
+    return launch_wgrad<9>(p, stream);
+}
+
+FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, int N, int K, int Np, int Kp,
+                             long long sn, long long sk, long long st, int kseg, int ksegpad, int accumulate,
+                             cudaStream_t stream) {
+    long long total = (long long)T * N * K;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < 1) blocks = 1;
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(part, out, nsplit, T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad,
+                                                    accumulate);
+    FCD_LAUNCH_CHECK();
+}
+
+// fp32 parameter (PyTorch layout, described by strides) -> bf16 packed [T][Np][Kp], K contiguous, zero padded.
+FCD_API int fcd_pack_weight(const float* src, void* dst, int T, int N, int K, int Np, int Kp, long long sn,
+                            long long sk, long long st, int kseg, int ksegpad, int nseg, int nsegpad,
+                            cudaStream_t stream) {
+    long long total = (long long)T * Np * Kp;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < 1) blocks = 1;
+    pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, (bf16*)dst, T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg,
+                                                   nsegpad);
+    FCD_LAUNCH_CHECK();
+}

@@ -1,0 +1,450 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (fcd_b200/_lib.py).
+
+Activations between ops are channels-last bf16 tensors [B, D, H, W, Cp] with Cp = channels padded to a multiple
+of 16 (pad channels are identically zero and stay zero through every op).  Parameters stay fp32 nn.Parameters in
+the reference's own shapes; they are re-packed to the kernels' bf16 [tap][Cout][Cin] layout on the fly and their
+gradients come back fp32 in the parameter's layout.  Nothing here falls back to torch math on the data path:
+torch is used for allocation (torch.empty) and for O(C) bookkeeping on parameter-sized vectors only.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib
+
+call = _lib.call
+BF16 = torch.bfloat16
+
+
+def pad16(c: int) -> int:
+    return (int(c) + 15) // 16 * 16
+
+
+def _regular(t: torch.Tensor) -> bool:
+    if t.dtype != BF16 or t.dim() != 5 or t.stride(4) != 1:
+        return False
+    B, D, H, W, C = t.shape
+    ld = t.stride(3)
+    if ld % 8 or ld < C or (t.data_ptr() % 16):
+        return False
+    exp = [D * H * W * ld, H * W * ld, W * ld, ld]
+    return all(t.shape[i] == 1 or t.stride(i) == exp[i] for i in range(4)) and W > 1
+
+
+def rows(t: torch.Tensor) -> torch.Tensor:
+    """Return `t` itself if it is a row-regular channels-last operand (possibly a channel slice), else a copy."""
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    if t.is_contiguous() or _regular(t):
+        return t
+    return t.contiguous()
+
+
+def ld(t: torch.Tensor) -> int:
+    return t.shape[4] if t.is_contiguous() else t.stride(3)
+
+
+def _empty(shape, like, dtype=BF16):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _vpad(v, n, value=0.0):
+    """Pad an O(C) fp32 parameter vector to n entries."""
+    if v is None:
+        return None
+    v = v.detach().float()
+    return v if v.numel() == n else F.pad(v, (0, n - v.numel()), value=value)
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def to_channels_last(x: torch.Tensor, cp: int | None = None) -> torch.Tensor:
+    """fp32 NCDHW -> bf16 NDHWC (zero-padded to cp channels).  Input images carry no gradient (train.py:367)."""
+    B, C, D, H, W = x.shape
+    cp = cp or pad16(C)
+    x = x.detach().float().contiguous()
+    y = _empty((B, D, H, W, cp), x)
+    call("fcd_ncdhw_to_ndhwc", src=x, dst=y, B=B, C=C, Cp=cp, S=D * H * W)
+    return y
+
+
+def to_ncdhw(x: torch.Tensor, C: int) -> torch.Tensor:
+    x = rows(x)
+    B, D, H, W, _ = x.shape
+    y = _empty((B, C, D, H, W), x, torch.float32)
+    call("fcd_ndhwc_to_ncdhw", src=x, dst=y, B=B, C=C, ld=ld(x), S=D * H * W)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ conv family
+def pack_weight(w, T, N, K, Np, Kp, sn, sk, st, kseg=None, ksegpad=None, nseg=None, nsegpad=None):
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    dst = torch.empty((T, Np, Kp), dtype=BF16, device=w.device)
+    call("fcd_pack_weight", src=w, dst=dst, T=T, N=N, K=K, Np=Np, Kp=Kp, sn=sn, sk=sk, st=st,
+         kseg=kseg or K, ksegpad=ksegpad or Kp, nseg=nseg or N, nsegpad=nsegpad or Np)
+    return dst
+
+
+def _nsplit(M, Np, Kp, T):
+    ntiles = (M + 127) // 128
+    tp = 1 if T == 1 else (8 if T == 8 else 9)
+    gy = (Np // 16) * (Kp // 16) * ((T + tp - 1) // tp)
+    n = max(1, min(ntiles, 592 // max(gy, 1)))
+    cap = max(1, (64 << 20) // (T * Np * Kp * 4))
+    return max(1, min(n, cap))
+
+
+def _wgrad(Q, P, src_dims, m_dims, Np, Kp, k, stride, pad):
+    """part[nsplit][T][Np][Kp] = sum_m Q[m][n] P[src(m,t)][k]."""
+    B = Q.shape[0]
+    T = k ** 3
+    M = B * m_dims[0] * m_dims[1] * m_dims[2]
+    ns = _nsplit(M, Np, Kp, T)
+    part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=Q.device)
+    call("fcd_wgrad", Q=Q, ldq=ld(Q), P=P, ldp=ld(P), part=part, Bn=B, Ds=src_dims[0], Hs=src_dims[1], Ws=src_dims[2],
+         Dm=m_dims[0], Hm=m_dims[1], Wm=m_dims[2], Np=Np, Kp=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, nsplit=ns)
+    return part, ns
+
+
+def _colsum(x, C):
+    x = rows(x)
+    nrows = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+    Cp = x.shape[4]
+    nchunk = int(max(1, min(592, nrows // 512)))
+    part = torch.empty((nchunk, 2, Cp), dtype=torch.float32, device=x.device)
+    out = torch.empty((Cp,), dtype=torch.float32, device=x.device)
+    call("fcd_colsum", x=x, ld=ld(x), part=part, out=out, rows=nrows, C=Cp, nchunk=nchunk)
+    return out[:C]
+
+
+class ConvFn(Function):
+    """nn.Conv3d (k in {1,3}, stride in {1,2}, pad = (k-1)//2 or given) and nn.Linear (k=1) on channels-last rows.
+
+    cin_seg = (seg, segpad): the Cin channels of `weight` are spread over concat segments of `seg` real channels
+    each padded to `segpad` in x (torch.cat elimination, conv_blocks.py:685)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, stride, pad, cin_seg):
+        x = rows(x)
+        B, D, H, W, Kp = x.shape
+        Co, Ci = weight.shape[0], weight.shape[1]
+        T = k ** 3
+        Np = pad16(Co)
+        seg, segpad = cin_seg if cin_seg is not None else (Ci, Kp)
+        wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
+        Do, Ho, Wo = [(s + 2 * pad - k) // stride + 1 for s in (D, H, W)]
+        y = _empty((B, Do, Ho, Wo, Np), x)
+        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, Ds=D, Hs=H, Ws=W,
+             Dm=Do, Hm=Ho, Wm=Wo, K=Kp, N=Np, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=0, out_mode=0,
+             accumulate=0, Cq=0)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (k, stride, pad, seg, segpad, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        k, stride, pad, seg, segpad, has_bias = ctx.cfg
+        dy = rows(dy)
+        B, D, H, W, Kp = x.shape
+        _, Do, Ho, Wo, Np = dy.shape
+        Co, Ci = weight.shape[0], weight.shape[1]
+        T = k ** 3
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
+            dx = _empty((B, D, H, W, Kp), x)
+            call("fcd_igemm", A=dy, lda=ld(dy), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=Do, Hs=Ho, Ws=Wo,
+                 Dm=D, Hm=H, Wm=W, K=Np, N=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=1, out_mode=0,
+                 accumulate=0, Cq=0)
+        if ctx.needs_input_grad[1]:
+            part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=T, N=Co, K=Ci, Np=Np, Kp=Kp, sn=Ci * T, sk=T,
+                 st=1, kseg=seg, ksegpad=segpad, accumulate=0)
+            dw = dw.to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(dy, Co)
+        return dx, dw, db, None, None, None, None
+
+
+def conv3d(x, weight, bias=None, k=3, stride=1, pad=None, cin_seg=None):
+    if pad is None:
+        pad = (k - 1) // 2
+    return ConvFn.apply(x, weight, bias, k, stride, pad, cin_seg)
+
+
+def linear(x, weight):
+    """nn.Linear without bias on the channel axis (DSA qkvv, conv_blocks.py:225)."""
+    return ConvFn.apply(x, weight.view(weight.shape[0], weight.shape[1], 1, 1, 1), None, 1, 1, 0, None)
+
+
+class UpConcatFn(Function):
+    """ConvTranspose3d(k2, s2, no bias) scattered straight into the left half of the concat buffer, skip copied
+    into the right half: replaces transp_conv + torch.cat (conv_blocks.py:683-685)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, weight):
+        x, skip = rows(x), rows(skip)
+        B, D, H, W, Kp = x.shape
+        Ci, Co = weight.shape[0], weight.shape[1]
+        Cq = pad16(Co)
+        Cs = skip.shape[4]
+        wp = pack_weight(weight, 8, Co, Ci, Cq, Kp, sn=8, sk=Co * 8, st=1)
+        buf = _empty((B, 2 * D, 2 * H, 2 * W, Cq + Cs), x)
+        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=None, Bn=B, Ds=D, Hs=H, Ws=W, Dm=D, Hm=H,
+             Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0, Cq=Cq)
+        right = buf[..., Cq:]
+        call("fcd_copy_rows", a=skip, lda=ld(skip), o=right, ldo=Cq + Cs, rows=B * 8 * D * H * W, C=Cs)
+        ctx.save_for_backward(x, weight)
+        ctx.cq = Cq
+        return buf
+
+    @staticmethod
+    def backward(ctx, dbuf):
+        x, weight = ctx.saved_tensors
+        Cq = ctx.cq
+        dbuf = rows(dbuf)
+        B, D, H, W, Kp = x.shape
+        Ci, Co = weight.shape[0], weight.shape[1]
+        dleft = dbuf[..., :Cq]
+        dx = dw = dskip = None
+        if ctx.needs_input_grad[0]:
+            wt = pack_weight(weight, 8, Ci, Co, Kp, Cq, sn=Co * 8, sk=8, st=1)
+            dx = _empty((B, D, H, W, Kp), x)
+            call("fcd_igemm", A=dleft, lda=ld(dbuf), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=2 * D, Hs=2 * H,
+                 Ws=2 * W, Dm=D, Hm=H, Wm=W, K=Cq, N=Kp, kd=2, kh=2, kw=2, stride=2, pad=0, mode=0, out_mode=0,
+                 accumulate=0, Cq=0)
+        if ctx.needs_input_grad[2]:
+            B_ = x.shape[0]
+            M = B_ * D * H * W
+            ns = _nsplit(M, Kp, Cq, 8)
+            part = torch.empty((ns, 8, Kp, Cq), dtype=torch.float32, device=x.device)
+            call("fcd_wgrad", Q=x, ldq=ld(x), P=dleft, ldp=ld(dbuf), part=part, Bn=B_, Ds=2 * D, Hs=2 * H, Ws=2 * W,
+                 Dm=D, Hm=H, Wm=W, Np=Kp, Kp=Cq, kd=2, kh=2, kw=2, stride=2, pad=0, nsplit=ns)
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=8, N=Ci, K=Co, Np=Kp, Kp=Cq, sn=Co * 8, sk=8,
+                 st=1, kseg=Co, ksegpad=Cq, accumulate=0)
+            dw = dw.to(weight.dtype)
+        if ctx.needs_input_grad[1]:
+            dskip = dbuf[..., Cq:]
+        return dx, dskip, dw
+
+
+def up_concat(x, skip, weight):
+    return UpConcatFn.apply(x, skip, weight)
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+class MaxPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = rows(x)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        B, D, H, W, C = x.shape
+        y = _empty((B, D // 2, H // 2, W // 2, C), x)
+        call("fcd_maxpool2_fwd", x=x, y=y, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2, C=C)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = rows(dy).contiguous()
+        B, D, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        call("fcd_maxpool2_bwd", x=x, y=y, dy=dy, dx=dx, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2, C=C, accumulate=0)
+        return dx
+
+
+def max_pool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------ normalisation
+MODE = {"instance": 0, "batch": 1, "group2": 2}
+
+
+def _nchunk(B, S):
+    return int(max(1, min(592 // max(B, 1), S // 512)))
+
+
+def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0.1):
+    B, D, H, W, C = x.shape
+    S = D * H * W
+    nchunk = _nchunk(B, S)
+    part = torch.empty((B, nchunk, 2, C), dtype=torch.float32, device=x.device)
+    mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    call("fcd_norm_stats", x=x, ld=ld(x), part=part, mean=mean, rstd=rstd, B=B, S=S, C=C, nchunk=nchunk, mode=mode,
+         eps=eps, running_mean=running_mean, running_var=running_var, crun=crun, momentum=momentum)
+    return mean, rstd
+
+
+class NormActFn(Function):
+    """y = act( norm(x1)*gamma + beta  [+ norm(x2)]  [+ res] ),  act = LeakyReLU(slope) (slope=1: identity, 0: ReLU).
+
+    Covers InstanceNorm3d+LeakyReLU, the residual tail of UnetResBlock (conv_blocks.py:439-452), train/eval
+    BatchNorm3d of TransformerBlock.conv51 (conv_blocks.py:56), GroupNorm of patch_embedding (ms_dsa_net.py:217)
+    and MONAI ResBlock's IN+ReLU."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, res, gamma, beta, mode, slope, eps, bn_buffers, training, momentum):
+        x1 = rows(x1)
+        B, D, H, W, C = x1.shape
+        S = D * H * W
+        x2 = rows(x2) if x2 is not None else None
+        res = rows(res) if res is not None else None
+        g = _vpad(gamma, C, 1.0)
+        b = _vpad(beta, C, 0.0)
+        if mode == 1 and not training:
+            rm, rv = bn_buffers
+            mean1 = _vpad(rm, C).unsqueeze(0).expand(B, C).contiguous()
+            rstd1 = torch.rsqrt(_vpad(rv, C, 1.0) + eps).unsqueeze(0).expand(B, C).contiguous()
+        elif mode == 1:
+            rm, rv = bn_buffers
+            mean1, rstd1 = _stats(x1, 1, eps, rm, rv, rm.numel(), momentum)
+        else:
+            mean1, rstd1 = _stats(x1, mode, eps)
+        mean2 = rstd2 = None
+        if x2 is not None:
+            mean2, rstd2 = _stats(x2, mode, eps)
+        y = _empty((B, D, H, W, C), x1)
+        call("fcd_norm_apply", x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1, gamma1=g, beta1=b, x2=x2,
+             ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2, res=res,
+             ldr=ld(res) if res is not None else 0, y=y, ldy=C, B=B, S=S, C=C, slope=slope)
+        ctx.save_for_backward(x1, x2, y if slope != 1.0 else None, mean1, rstd1, mean2, rstd2, g)
+        ctx.cfg = (mode, slope, res is not None, gamma is not None, None if gamma is None else gamma.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, y, mean1, rstd1, mean2, rstd2, g = ctx.saved_tensors
+        mode, slope, has_res, has_affine, ntrue = ctx.cfg
+        dy = rows(dy)
+        B, D, H, W, C = x1.shape
+        S = D * H * W
+        nchunk = _nchunk(B, S)
+        part = torch.empty((B, nchunk, 3, C), dtype=torch.float32, device=x1.device)
+        coef = torch.empty((B, C, 6), dtype=torch.float32, device=x1.device)
+        dx1 = torch.empty((B, D, H, W, C), dtype=BF16, device=x1.device)
+        dx2 = torch.empty_like(dx1) if x2 is not None else None
+        dres = torch.empty_like(dx1) if (has_res and ctx.needs_input_grad[2]) else None
+        dgamma = dbeta = None
+        if has_affine:
+            dgamma = torch.zeros((C,), dtype=torch.float32, device=x1.device)
+            dbeta = torch.zeros((C,), dtype=torch.float32, device=x1.device)
+        call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1,
+             gamma1=g if has_affine else None, x2=x2, ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2,
+             part=part, coef=coef, dgamma=dgamma, dbeta=dbeta, dx1=dx1, ldd1=C, dx2=dx2, ldd2=C, dres=dres, lddr=C,
+             acc_res=0, B=B, S=S, C=C, nchunk=nchunk, mode=mode, slope=slope)
+        if has_affine:
+            dgamma, dbeta = dgamma[:ntrue], dbeta[:ntrue]
+        return dx1, dx2, dres, dgamma, dbeta, None, None, None, None, None, None
+
+
+def norm_act(x1, x2=None, res=None, gamma=None, beta=None, mode="instance", slope=1.0, eps=1e-5, bn_buffers=None,
+             training=True, momentum=0.1):
+    return NormActFn.apply(x1, x2, res, gamma, beta, MODE[mode], float(slope), float(eps), bn_buffers, training,
+                           momentum)
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = rows(a), rows(b)
+        B, D, H, W, C = a.shape
+        o = _empty((B, D, H, W, C), a)
+        call("fcd_add", a=a, lda=ld(a), b=b, ldb=ld(b), o=o, ldo=C, rows=B * D * H * W, C=C)
+        return o
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+def add(a, b):
+    return AddFn.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ output head
+class OutConvFn(Function):
+    """1x1x1 conv + bias -> fp32 NCDHW logits (UnetOutBlock ms_dsa_net.py:362; final_conv ms_dsa_net.py:82)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = rows(x)
+        B, D, H, W, Cp = x.shape
+        Co, Ci = weight.shape[0], weight.shape[1]
+        w = F.pad(weight.detach().float().reshape(Co, Ci), (0, Cp - Ci)).contiguous()
+        out = torch.empty((B, Co, D, H, W), dtype=torch.float32, device=x.device)
+        call("fcd_outconv_fwd", x=x, ld=ld(x), w=w, bias=None if bias is None else bias.detach().float().contiguous(),
+             out=out, B=B, S=D * H * W, C=Cp, Co=Co)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (tuple(weight.shape), bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        wshape, has_bias = ctx.cfg
+        B, D, H, W, Cp = x.shape
+        Co, Ci = wshape[0], wshape[1]
+        dout = dout.float().contiguous()
+        nblk = _lib.query("fcd_outconv_blocks")
+        part = torch.empty((nblk, Co, Cp + 1), dtype=torch.float32, device=x.device)
+        dw = torch.empty((Co, Cp), dtype=torch.float32, device=x.device)
+        db = torch.empty((Co,), dtype=torch.float32, device=x.device)
+        dx = torch.empty((B, D, H, W, Cp), dtype=BF16, device=x.device)
+        call("fcd_outconv_bwd", x=x, ld=ld(x), w=w, dout=dout, dx=dx, lddx=Cp, part=part, dw=dw, db=db, B=B,
+             S=D * H * W, C=Cp, Co=Co)
+        return dx, dw[:, :Ci].reshape(wshape), (db if has_bias else None)
+
+
+def out_conv(x, weight, bias):
+    return OutConvFn.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------ loss
+LOSS_KIND = {"DiceLoss": 0, "DiceCELoss": 1, "DiceFocalLoss": 2}
+
+
+class LossFn(Function):
+    @staticmethod
+    def forward(ctx, pred, target, cfg):
+        pred = pred.float().contiguous()
+        target = target.detach().float().contiguous()
+        B, C, D, H, W = pred.shape
+        if C != 2:
+            raise ValueError("fcd_b200 fused loss supports chans_out == 2 (background + FCD), as the reference config")
+        dev = pred.device
+        nblk = _lib.query("fcd_loss_blocks")
+        tv = cfg["tv_w"] > 0
+        part = torch.empty((nblk, 8), dtype=torch.float32, device=dev)
+        tvpart = torch.empty((nblk, 4), dtype=torch.float32, device=dev) if tv else None
+        pbuf = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if tv else None
+        keep = torch.empty((B, D, H, W), dtype=torch.uint8, device=dev) if (tv and cfg["tv_exclude"]) else None
+        res = torch.zeros((16,), dtype=torch.float32, device=dev)
+        call("fcd_loss_fwd", pred=pred, target=target, B=B, D=D, H=H, W=W, keep=keep, pbuf=pbuf, part=part,
+             tvpart=tvpart, res=res, **cfg)
+        ctx.save_for_backward(pred, target, keep, pbuf, res)
+        ctx.cfg = cfg
+        return res[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred, target, keep, pbuf, res = ctx.saved_tensors
+        B, C, D, H, W = pred.shape
+        dpred = torch.empty_like(pred)
+        gout = gout.detach().float().reshape(1).contiguous()
+        call("fcd_loss_bwd", pred=pred, target=target, B=B, D=D, H=H, W=W, keep=keep, pbuf=pbuf, res=res, gout=gout,
+             dpred=dpred, **ctx.cfg)
+        return dpred, None, None
+
+
+def fused_loss(pred, target, cfg):
+    return LossFn.apply(pred, target, cfg)
