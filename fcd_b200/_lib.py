@@ -68,6 +68,8 @@ def lib():
 def _ptr(v):
     if v is None:
         return None
+    if isinstance(v, ctypes.Array):      # the few documented HOST-pointer arguments (e.g. fcd_sw_gather starts)
+        return ctypes.cast(v, ctypes.c_void_p)
     if isinstance(v, torch.Tensor):
         if not v.is_cuda:
             raise RuntimeError("fcd_b200 kernels take CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,901 @@
+// Dual self-attention (DSA, sa_type='parallel') and the token-wise ops around it, forward and backward.
+//
+// Reference: networks/ms_dsa_net/conv_blocks.py -- TransformerBlock.forward 69-90 (pos_embed add, LayerNorm,
+// x + gamma * DSA(LN(x))) and DSA.forward 328-355.  All of it is linear in the token count N: the spatial branch
+// projects K and V_SA from N to P tokens with the learned EF[N,P]; the channel branch is a c x c Gram matrix.
+// So the whole block is a pair of streaming passes over the tokens (a reduction pass and an apply pass), HBM-bound,
+// and the [N,P] attention map (8.4 M elements per block at level 3) is never materialised.
+//
+// Layouts: tokens are channels-last rows r = b*N + n (bf16, row stride ld, true channel count C = h*c, h heads);
+// qkvv rows hold [q | k | v_CA | v_SA], each C wide, head-major (conv_blocks.py:330-332).
+// The reference's line 353 reinterprets x_SA's [B,c,h,N] memory as [B,N,C] (a scramble); we store
+// x_SA directly in that flat [c][h][N] order (tsa) so that the "scramble" is a plain flat read.
+#include "common.cuh"
+
+namespace {
+
+// counter-based Bernoulli keep-mask for the spatial-attention dropout (attn_drop_2, conv_blocks.py:352):
+// the same (seed, element) always gives the same bit, so backward regenerates the forward's mask.
+__device__ __forceinline__ bool sa_keep(unsigned long long seed, unsigned long long elem, uint32_t thresh) {
+    unsigned long long z = seed + elem * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32) >= thresh;
+}
+
+__device__ __forceinline__ float group_sum(float v, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm (+pos)
+// t = x + pos ; ln = LayerNorm_C(t) * w + b.   One thread per (row, 8-channel chunk); LPT = Cp/8 lanes per row.
+__global__ void ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ pos,
+                              const float* __restrict__ w, const float* __restrict__ bvec, bf16* __restrict__ t,
+                              long long ldt, bf16* __restrict__ ln, long long ldl, float* __restrict__ mean,
+                              float* __restrict__ rstd, long long rows, int N, int C, int LPT, float eps) {
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long row = gid / LPT;
+    const int chunk = (int)(gid % LPT);
+    const bool live = row < rows;
+    if (!live) row = rows - 1;
+    const int n = (int)(row % N);
+    float v[8];
+    unpack8(ld8(x + row * ldx + chunk * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = chunk * 8 + k;
+        if (c < C) {
+            if (pos) v[k] += pos[(long long)n * C + c];
+            v[k] = __bfloat162float(__float2bfloat16(v[k]));
+        } else {
+            v[k] = 0.f;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    s = group_sum(s, LPT);
+    const float m = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = chunk * 8 + k;
+        if (c < C) q += (v[k] - m) * (v[k] - m);
+    }
+    q = group_sum(q, LPT);
+    const float r = rsqrtf(q / C + eps);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = chunk * 8 + k;
+        o[k] = c < C ? (v[k] - m) * r * w[c] + bvec[c] : 0.f;
+    }
+    if (live) {
+        st8(t + row * ldt + chunk * 8, pack8(v));
+        st8(ln + row * ldl + chunk * 8, pack8(o));
+        if (chunk == 0) { mean[row] = m; rstd[row] = r; }
+    }
+}
+
+// dx = dt_direct + LN-backward(dln);  dpos[n][c] = sum_b dx[b][n][c];  per-block partials of dw, db.
+// One thread per (n, chunk), looping over the batch.  part: [gridDim.x][2][Cp].
+__global__ void ln_bwd_kernel(const bf16* __restrict__ dln, long long lddl, const bf16* __restrict__ dtd,
+                              long long lddt, const bf16* __restrict__ t, long long ldt,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ w, bf16* __restrict__ dx, long long lddx,
+                              float* __restrict__ dpos, float* __restrict__ part, int B, int N, int C, int LPT) {
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = gid / LPT;
+    const int chunk = (int)(gid % LPT);
+    const bool live = n < N;
+    if (!live) n = N - 1;
+    float wv[8], accp[8], accw[8], accb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = chunk * 8 + k;
+        wv[k] = c < C ? w[c] : 0.f;
+        accp[k] = accw[k] = accb[k] = 0.f;
+    }
+    for (int b = 0; b < B; ++b) {
+        const long long row = (long long)b * N + n;
+        float g[8], tv[8], d[8], xh[8];
+        unpack8(ld8(dln + row * lddl + chunk * 8), g);
+        unpack8(ld8(t + row * ldt + chunk * 8), tv);
+        unpack8(ld8(dtd + row * lddt + chunk * 8), d);
+        const float m = mean[row], r = rstd[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = chunk * 8 + k;
+            xh[k] = c < C ? (tv[k] - m) * r : 0.f;
+            if (live) { accw[k] = fmaf(g[k], xh[k], accw[k]); accb[k] += (c < C ? g[k] : 0.f); }
+            g[k] *= wv[k];
+            s1 += g[k];
+            s2 = fmaf(g[k], xh[k], s2);
+        }
+        s1 = group_sum(s1, LPT) / C;
+        s2 = group_sum(s2, LPT) / C;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = chunk * 8 + k;
+            o[k] = c < C ? r * (g[k] - s1 - xh[k] * s2) + d[k] : 0.f;
+            accp[k] += o[k];
+        }
+        if (live) st8(dx + row * lddx + chunk * 8, pack8(o));
+    }
+    if (live && dpos) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = chunk * 8 + k;
+            if (c < C) dpos[n * C + c] = accp[k];
+        }
+    }
+    __shared__ float sh[256 * 16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sh[threadIdx.x * 16 + k] = accw[k]; sh[threadIdx.x * 16 + 8 + k] = accb[k]; }
+    __syncthreads();
+    if ((int)threadIdx.x < LPT) {          // thread `chunk` == threadIdx.x sums its column over the block's rows
+        float a[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = 0.f;
+        for (int r = threadIdx.x; r < (int)blockDim.x; r += LPT)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] += sh[r * 16 + k];
+        const int Cp = LPT * 8;
+        float* o = part + (long long)blockIdx.x * 2 * Cp;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o[threadIdx.x * 8 + k] = a[k]; o[Cp + threadIdx.x * 8 + k] = a[8 + k]; }
+    }
+}
+
+// out0[c] = sum_k part[k][0][c], out1[c] = sum_k part[k][1][c]   (c < C)
+__global__ void pair_colsum_kernel(const float* __restrict__ part, int nblk, int Cp, int C, float* __restrict__ out0,
+                                   float* __restrict__ out1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nblk; ++k) { a += part[(long long)k * 2 * Cp + c]; b += part[(long long)k * 2 * Cp + Cp + c]; }
+    if (out0) out0[c] = (float)a;
+    if (out1) out1[c] = (float)b;
+}
+
+// ------------------------------------------------------------------------------------------ DSA forward
+// Partial layout per (b, tile): [Sqq: C][Skk: C][G: h*c*c][KP|VP: 2C*P]
+__device__ __forceinline__ long long dsa_osize(int C, int c, int P) { return 2LL * C + (long long)C * c + 2LL * C * P; }
+
+__global__ void __launch_bounds__(256) dsa_reduce_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                         const float* __restrict__ EF, float* __restrict__ part,
+                                                         int N, int C, int c, int P, int TN) {
+    extern __shared__ float sm[];
+    const int W3 = 3 * C;                       // [q | k | v_SA] per token
+    float* sQ = sm;                             // [TN][3C]
+    float* sE = sm + (long long)TN * W3;        // [TN][P]
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int n0 = tile * TN;
+    for (int i = threadIdx.x; i < TN * W3; i += blockDim.x) {
+        const int n = i / W3, col = i % W3;
+        float v = 0.f;
+        if (n0 + n < N) {
+            const int src = col < 2 * C ? col : col + C;        // skip v_CA (third slot)
+            v = __bfloat162float(qkvv[((long long)b * N + n0 + n) * ldq + src]);
+        }
+        sQ[i] = v;
+    }
+    for (int i = threadIdx.x; i < TN * P; i += blockDim.x) {
+        const int n = i / P;
+        sE[i] = (n0 + n < N) ? EF[(long long)(n0 + n) * P + (i % P)] : 0.f;
+    }
+    __syncthreads();
+    const int ntiles = gridDim.x;
+    float* out = part + ((long long)b * ntiles + tile) * dsa_osize(C, c, P);
+    const int P4 = P / 4;
+    const int n_kv = 2 * C * P4, n_g = C * c, n_s = 2 * C;
+    for (int it = threadIdx.x; it < n_kv + n_g + n_s; it += blockDim.x) {
+        if (it < n_kv) {
+            const int r = it / P4, p = (it % P4) * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int n = 0; n < TN; ++n) {
+                const float kv = sQ[n * W3 + C + r];
+                const float4 e = *reinterpret_cast<const float4*>(&sE[n * P + p]);
+                a.x = fmaf(kv, e.x, a.x); a.y = fmaf(kv, e.y, a.y); a.z = fmaf(kv, e.z, a.z); a.w = fmaf(kv, e.w, a.w);
+            }
+            *reinterpret_cast<float4*>(&out[2 * C + (long long)C * c + (long long)r * P + p]) = a;
+        } else if (it < n_kv + n_g) {
+            const int g = it - n_kv;
+            const int j = g % c, i = (g / c) % c, hd = g / (c * c);
+            float a = 0.f;
+            for (int n = 0; n < TN; ++n) a = fmaf(sQ[n * W3 + hd * c + i], sQ[n * W3 + C + hd * c + j], a);
+            out[2 * C + g] = a;
+        } else {
+            const int r = it - n_kv - n_g;
+            float a = 0.f;
+            for (int n = 0; n < TN; ++n) a = fmaf(sQ[n * W3 + r], sQ[n * W3 + r], a);
+            out[r] = a;
+        }
+    }
+}
+
+// grid (h, B).  Sums the tile partials and produces: inv_nq/inv_nk [B][C], Ghat [B][h][c][c], A = softmax rows,
+// KP/VP [B][2][C][P] (k projection then v_SA projection).
+__global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restrict__ part, int ntiles,
+                                                           const float* __restrict__ temperature,
+                                                           const float* __restrict__ ca_scale,
+                                                           float* __restrict__ inv_n, float* __restrict__ Ghat,
+                                                           float* __restrict__ A, float* __restrict__ Ad,
+                                                           float* __restrict__ KV, int C, int c, int P) {
+    extern __shared__ float sm[];
+    float* sG = sm;               // [c][c]
+    float* sN = sm + c * c;       // [2][c]
+    const int hd = blockIdx.x, b = blockIdx.y;
+    const long long O = dsa_osize(C, c, P);
+    const float* base = part + (long long)b * ntiles * O;
+    auto tsum = [&](long long off) {
+        float s = 0.f;
+        for (int k = 0; k < ntiles; ++k) s += base[(long long)k * O + off];
+        return s;
+    };
+    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
+        const int which = i / c, j = i % c;
+        const float s = tsum((long long)which * C + hd * c + j);
+        const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);          // F.normalize eps (conv_blocks.py:342-343)
+        sN[i] = inv;
+        inv_n[((long long)b * 2 + which) * C + hd * c + j] = inv;
+    }
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) sG[i] = tsum(2LL * C + (long long)hd * c * c + i);
+    for (int i = threadIdx.x; i < 2 * c * P; i += blockDim.x) {
+        const int which = i / (c * P), rem = i % (c * P);
+        const int j = rem / P, p = rem % P;
+        const long long r = (long long)which * C + hd * c + j;
+        KV[((long long)b * 2 * C + r) * P + p] = tsum(2LL * C + (long long)C * c + r * P + p);
+    }
+    __syncthreads();
+    const float tau = temperature[hd];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float mx = -INFINITY;
+        for (int j = 0; j < c; ++j) {
+            const float g = sG[i * c + j] * sN[i] * sN[c + j];
+            sG[i * c + j] = g;
+            mx = fmaxf(mx, g * tau);
+        }
+        float den = 0.f;
+        for (int j = 0; j < c; ++j) den += __expf(sG[i * c + j] * tau - mx);
+        const long long o = (((long long)b * gridDim.x + hd) * c + i) * c;
+        for (int j = 0; j < c; ++j) {
+            Ghat[o + j] = sG[i * c + j];
+            const float a = __expf(sG[i * c + j] * tau - mx) / den;
+            A[o + j] = a;
+            Ad[o + j] = ca_scale ? a * ca_scale[o + j] : a;     // attn_drop (conv_blocks.py:347)
+        }
+    }
+}
+
+// thread per (token, head): spatial softmax over P in registers, channel attention apply.
+// xca [B*N][C] fp32 (head-merged), tsa [B][c][h][N] fp32 (the reference's scrambled memory order).
+template <int CH, int P>
+__global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                        const float* __restrict__ inv_n, const float* __restrict__ A,
+                                                        const float* __restrict__ KV,
+                                                        const float* __restrict__ temperature2,
+                                                        float* __restrict__ xca, float* __restrict__ tsa, int N, int C,
+                                                        float drop_scale, uint32_t drop_thresh,
+                                                        unsigned long long seed) {
+    extern __shared__ float sm[];
+    float* sKP = sm;                    // [CH][P]
+    float* sVP = sm + CH * P;           // [CH][P]
+    float* sA = sm + 2 * CH * P;        // [CH][CH]
+    float* sIq = sA + CH * CH;          // [CH]
+    const int hd = blockIdx.y, b = blockIdx.z, H = gridDim.y;
+    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
+        sKP[i] = KV[((long long)b * 2 * C + hd * CH) * P + i];
+        sVP[i] = KV[((long long)b * 2 * C + C + hd * CH) * P + i];
+    }
+    for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) sA[i] = A[((long long)b * H + hd) * CH * CH + i];
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) sIq[i] = inv_n[(long long)b * 2 * C + hd * CH + i];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const bf16* row = qkvv + ((long long)b * N + n) * ldq;
+    const float tau2 = temperature2[hd];
+    float lg[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) lg[p] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < CH; ++j) {
+        const float qh = __bfloat162float(row[hd * CH + j]) * sIq[j];
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] = fmaf(qh, sKP[j * P + p], lg[p]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < P; ++p) { lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
+    float den = 0.f;
+#pragma unroll
+    for (int p = 0; p < P; ++p) { lg[p] = __expf(lg[p] - mx); den += lg[p]; }
+    float inv = 1.f / den;
+    if (drop_thresh) {
+        const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P;
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] = sa_keep(seed, e0 + p, drop_thresh) ? lg[p] : 0.f;
+        inv *= drop_scale;
+    }
+    for (int j = 0; j < CH; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) a = fmaf(lg[p], sVP[j * P + p], a);
+        tsa[(((long long)b * CH + j) * H + hd) * N + n] = a * inv;
+    }
+    float v[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = __bfloat162float(row[2 * C + hd * CH + j]);
+    for (int i = 0; i < CH; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) a = fmaf(sA[i * CH + j], v[j], a);
+        xca[((long long)b * N + n) * C + hd * CH + i] = a;
+    }
+}
+
+// y = t + gamma * (xca + tsa_flat)   (conv_blocks.py:77).  thread per (row, chunk).
+__global__ void dsa_combine_kernel(const bf16* __restrict__ t, long long ldt, const float* __restrict__ gamma,
+                                   const float* __restrict__ xca, const float* __restrict__ tsa, bf16* __restrict__ y,
+                                   long long ldy, long long rows, int N, int C, int LPT) {
+    const long long total = rows * LPT;
+    for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        const long long row = gid / LPT;
+        const int chunk = (int)(gid % LPT);
+        const long long b = row / N, n = row % N;
+        float v[8];
+        unpack8(ld8(t + row * ldt + chunk * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ch = chunk * 8 + k;
+            if (ch < C) v[k] += gamma[ch] * (xca[row * C + ch] + tsa[b * N * C + n * C + ch]);
+            else v[k] = 0.f;
+        }
+        st8(y + row * ldy + chunk * 8, pack8(v));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ DSA backward
+// dgamma partials: part[blk][0][c] = sum_rows dy * (xca + tsa_flat).
+__global__ void dsa_dgamma_kernel(const bf16* __restrict__ dy, long long lddy, const float* __restrict__ xca,
+                                  const float* __restrict__ tsa, float* __restrict__ part, long long rows, int N,
+                                  int C, int LPT) {
+    const int chunk = threadIdx.x % LPT, r0 = threadIdx.x / LPT, rstep = blockDim.x / LPT;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (long long row = (long long)blockIdx.x * rstep + r0; row < rows; row += (long long)gridDim.x * rstep) {
+        const long long b = row / N, n = row % N;
+        float g[8];
+        unpack8(ld8(dy + row * lddy + chunk * 8), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ch = chunk * 8 + k;
+            if (ch < C) acc[k] = fmaf(g[k], xca[row * C + ch] + tsa[b * N * C + n * C + ch], acc[k]);
+        }
+    }
+    __shared__ float sh[256 * 8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sh[threadIdx.x * 8 + k] = acc[k];
+    __syncthreads();
+    if ((int)threadIdx.x < LPT) {
+        const int Cp = LPT * 8;
+        float* o = part + (long long)blockIdx.x * 2 * Cp;
+        for (int k = 0; k < 8; ++k) {
+            float s = 0.f;
+            for (int r = threadIdx.x; r < (int)blockDim.x; r += LPT) s += sh[r * 8 + k];
+            o[threadIdx.x * 8 + k] = s;
+            o[Cp + threadIdx.x * 8 + k] = 0.f;
+        }
+    }
+}
+
+// Backward partial layout per (b, hd, tile): [dVP: c*P][dKP: c*P][dA: c*c][R1: c][dT2: 1]
+__device__ __forceinline__ long long dsa_bsize(int c, int P) { return 2LL * c * P + (long long)c * c + c + 1; }
+
+// Phase 1: thread per token (recompute the spatial softmax, form dlogits, write dqhat_sa); phase 2: the block
+// reduces the outer products over its TN tokens.
+template <int CH, int P>
+__global__ void __launch_bounds__(64) dsa_bwd_reduce_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                            const bf16* __restrict__ dy, long long lddy,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ inv_n,
+                                                            const float* __restrict__ KV,
+                                                            const float* __restrict__ temperature2,
+                                                            float* __restrict__ dqh, float* __restrict__ part, int N,
+                                                            int C, float drop_scale, uint32_t drop_thresh,
+                                                            unsigned long long seed) {
+    constexpr int TN = 64;
+    constexpr int ROW = 2 * P + 5 * CH + 1;
+    extern __shared__ float sm[];
+    float* sKP = sm;                        // [CH][P]
+    float* sVP = sm + CH * P;               // [CH][P]
+    float* sT = sm + 2 * CH * P;            // [TN][ROW]: a[P] | dlog[P] | dxs[CH] | qh[CH] | dxca[CH] | vca[CH] | r1[CH] | dt2
+    const int tile = blockIdx.x, hd = blockIdx.y, b = blockIdx.z, H = gridDim.y, ntiles = gridDim.x;
+    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
+        sKP[i] = KV[((long long)b * 2 * C + hd * CH) * P + i];
+        sVP[i] = KV[((long long)b * 2 * C + C + hd * CH) * P + i];
+    }
+    __syncthreads();
+    const int n = tile * TN + threadIdx.x;
+    float* my = sT + threadIdx.x * ROW;
+    if (n < N) {
+        const bf16* row = qkvv + ((long long)b * N + n) * ldq;
+        const float tau2 = temperature2[hd];
+        float lg[P], raw[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] = 0.f;
+        for (int j = 0; j < CH; ++j) {
+            const float qh = __bfloat162float(row[hd * CH + j]) * inv_n[(long long)b * 2 * C + hd * CH + j];
+            my[2 * P + CH + j] = qh;
+#pragma unroll
+            for (int p = 0; p < P; ++p) lg[p] = fmaf(qh, sKP[j * P + p], lg[p]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { raw[p] = lg[p]; lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
+        float den = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { lg[p] = __expf(lg[p] - mx); den += lg[p]; }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] *= inv;                       // a[p]
+        float da[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) da[p] = 0.f;
+        for (int j = 0; j < CH; ++j) {
+            // gradient of the scrambled x_SA element: flat index f -> (n', ch')
+            const long long f = ((long long)j * H + hd) * N + n;
+            const long long n2 = f / C;
+            const int ch2 = (int)(f % C);
+            const float dxs = gamma[ch2] * __bfloat162float(dy[((long long)b * N + n2) * lddy + ch2]);
+            my[2 * P + j] = dxs;
+#pragma unroll
+            for (int p = 0; p < P; ++p) da[p] = fmaf(dxs, sVP[j * P + p], da[p]);
+            const int chc = hd * CH + j;
+            my[2 * P + 2 * CH + j] = gamma[chc] * __bfloat162float(dy[((long long)b * N + n) * lddy + chc]);
+            my[2 * P + 3 * CH + j] = __bfloat162float(row[2 * C + chc]);
+        }
+        float s = 0.f;
+        float keepf[P];
+        if (drop_thresh) {
+            const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P;
+#pragma unroll
+            for (int p = 0; p < P; ++p) keepf[p] = sa_keep(seed, e0 + p, drop_thresh) ? drop_scale : 0.f;
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) keepf[p] = 1.f;
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) { da[p] *= keepf[p]; s = fmaf(lg[p], da[p], s); }
+        float dt2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float dl = lg[p] * (da[p] - s);
+            my[p] = lg[p] * keepf[p];
+            my[P + p] = dl;
+            dt2 = fmaf(dl, raw[p], dt2);
+            da[p] = dl;                                                   // reuse as dlog
+        }
+        my[ROW - 1] = dt2;
+        for (int j = 0; j < CH; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) a = fmaf(da[p], sKP[j * P + p], a);
+            a *= tau2;
+            dqh[((long long)b * N + n) * C + hd * CH + j] = a;
+            my[2 * P + 4 * CH + j] = a * my[2 * P + CH + j];
+        }
+    } else {
+        for (int i = 0; i < ROW; ++i) my[i] = 0.f;
+    }
+    __syncthreads();
+    float* out = part + (((long long)b * H + hd) * ntiles + tile) * dsa_bsize(CH, P);
+    const float tau2 = temperature2[hd];
+    const int n_vp = CH * P, n_a = CH * CH;
+    for (int it = threadIdx.x; it < 2 * n_vp + n_a + CH + 1; it += blockDim.x) {
+        float a = 0.f;
+        if (it < n_vp) {                                   // dVP[j][p] = sum a[p] dxs[j]
+            const int j = it / P, p = it % P;
+            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + p], sT[q * ROW + 2 * P + j], a);
+        } else if (it < 2 * n_vp) {                        // dKP[j][p] = tau2 sum qh[j] dlog[p]
+            const int j = (it - n_vp) / P, p = (it - n_vp) % P;
+            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + CH + j], sT[q * ROW + P + p], a);
+            a *= tau2;
+        } else if (it < 2 * n_vp + n_a) {                  // dA[i][j] = sum dxca[i] vca[j]
+            const int i = (it - 2 * n_vp) / CH, j = (it - 2 * n_vp) % CH;
+            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + 2 * CH + i], sT[q * ROW + 2 * P + 3 * CH + j], a);
+        } else if (it < 2 * n_vp + n_a + CH) {             // R1[j]
+            const int j = it - 2 * n_vp - n_a;
+            for (int q = 0; q < TN; ++q) a += sT[q * ROW + 2 * P + 4 * CH + j];
+        } else {
+            for (int q = 0; q < TN; ++q) a += sT[q * ROW + ROW - 1];
+        }
+        out[it] = a;
+    }
+}
+
+// grid (h, B): sums tile partials; softmax backward of the channel attention; emits
+// dKV [B][2][C][P] (dKP then dVP), dGhat [B][h][c][c], rqk [B][2][C] and accumulates dtemperature / dtemperature2.
+__global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __restrict__ part, int ntiles,
+                                                               const float* __restrict__ temperature,
+                                                               const float* __restrict__ Ghat,
+                                                               const float* __restrict__ A,
+                                                               const float* __restrict__ ca_scale,
+                                                               float* __restrict__ dKV,
+                                                               float* __restrict__ dGhat, float* __restrict__ rqk,
+                                                               float* __restrict__ dtemp, float* __restrict__ dtemp2,
+                                                               int C, int c, int P) {
+    extern __shared__ float sm[];
+    float* sdA = sm;                 // [c][c] -> dGhat
+    float* sR1 = sm + c * c;         // [c]
+    __shared__ float sred[256];
+    const int hd = blockIdx.x, b = blockIdx.y, H = gridDim.x;
+    const long long O = dsa_bsize(c, P);
+    const float* base = part + ((long long)b * H + hd) * ntiles * O;
+    auto tsum = [&](long long off) {
+        float s = 0.f;
+        for (int k = 0; k < ntiles; ++k) s += base[(long long)k * O + off];
+        return s;
+    };
+    for (int i = threadIdx.x; i < 2 * c * P; i += blockDim.x) {
+        const int which = i / (c * P), rem = i % (c * P);          // partial: 0 dVP, 1 dKP
+        const int j = rem / P, p = rem % P;
+        const int dst_which = which == 0 ? 1 : 0;                   // dKV: 0 dKP, 1 dVP
+        dKV[(((long long)b * 2 + dst_which) * C + hd * c + j) * P + p] = tsum(i);
+    }
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) {
+        const float v = tsum(2LL * c * P + i);
+        sdA[i] = ca_scale ? v * ca_scale[((long long)b * H + hd) * c * c + i] : v;
+    }
+    for (int i = threadIdx.x; i < c; i += blockDim.x) sR1[i] = tsum(2LL * c * P + (long long)c * c + i);
+    float t2 = 0.f;
+    if (threadIdx.x == 0) t2 = tsum(O - 1);
+    __syncthreads();
+    const float tau = temperature[hd];
+    const long long o = ((long long)b * H + hd) * c * c;
+    float dtau = 0.f;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < c; ++j) s = fmaf(A[o + i * c + j], sdA[i * c + j], s);
+        float rq = sR1[i];
+        for (int j = 0; j < c; ++j) {
+            const float dS = A[o + i * c + j] * (sdA[i * c + j] - s);     // d(tau * Ghat)
+            const float gh = Ghat[o + i * c + j];
+            dtau = fmaf(dS, gh, dtau);
+            const float dg = tau * dS;
+            sdA[i * c + j] = dg;
+            dGhat[o + i * c + j] = dg;
+            rq = fmaf(dg, gh, rq);
+        }
+        rqk[((long long)b * 2) * C + hd * c + i] = rq;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        float rk = 0.f;
+        for (int i = 0; i < c; ++i) rk = fmaf(sdA[i * c + j], Ghat[o + i * c + j], rk);
+        rqk[((long long)b * 2 + 1) * C + hd * c + j] = rk;
+    }
+    sred[threadIdx.x] = dtau;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (int)blockDim.x; ++i) s += sred[i];
+        atomicAdd(&dtemp[hd], s);
+        atomicAdd(&dtemp2[hd], t2);
+    }
+}
+
+// thread per (token, head): gradients of q, k, v_CA, v_SA -> dqkvv rows (bf16).
+template <int CH, int P>
+__global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                            const bf16* __restrict__ dy, long long lddy,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ EF,
+                                                            const float* __restrict__ inv_n,
+                                                            const float* __restrict__ A,
+                                                            const float* __restrict__ dGhat,
+                                                            const float* __restrict__ rqk,
+                                                            const float* __restrict__ dKV,
+                                                            const float* __restrict__ dqh, bf16* __restrict__ dqkvv,
+                                                            long long lddq, int N, int C) {
+    extern __shared__ float sm[];
+    float* sdKP = sm;                     // [CH][P]
+    float* sdVP = sm + CH * P;            // [CH][P]
+    float* sA = sm + 2 * CH * P;          // [CH][CH]
+    float* sdG = sA + CH * CH;            // [CH][CH]
+    float* sV = sdG + CH * CH;            // inv_nq | inv_nk | rq | rk : [4][CH]
+    const int hd = blockIdx.y, b = blockIdx.z, H = gridDim.y;
+    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
+        sdKP[i] = dKV[((long long)b * 2 * C + hd * CH) * P + i];
+        sdVP[i] = dKV[((long long)b * 2 * C + C + hd * CH) * P + i];
+    }
+    for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) {
+        sA[i] = A[((long long)b * H + hd) * CH * CH + i];
+        sdG[i] = dGhat[((long long)b * H + hd) * CH * CH + i];
+    }
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) {
+        sV[i] = inv_n[(long long)b * 2 * C + hd * CH + i];
+        sV[CH + i] = inv_n[(long long)b * 2 * C + C + hd * CH + i];
+        sV[2 * CH + i] = rqk[(long long)b * 2 * C + hd * CH + i];
+        sV[3 * CH + i] = rqk[(long long)b * 2 * C + C + hd * CH + i];
+    }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const long long r = (long long)b * N + n;
+    const bf16* row = qkvv + r * ldq;
+    bf16* drow = dqkvv + r * lddq;
+    float qh[CH], kh[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        qh[j] = __bfloat162float(row[hd * CH + j]) * sV[j];
+        kh[j] = __bfloat162float(row[C + hd * CH + j]) * sV[CH + j];
+    }
+    float ef[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) ef[p] = EF[(long long)n * P + p];
+    for (int i = 0; i < CH; ++i) {
+        // dq
+        float a = dqh[r * C + hd * CH + i];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) a = fmaf(sdG[i * CH + j], kh[j], a);
+        a = (a - qh[i] * sV[2 * CH + i]) * sV[i];
+        drow[hd * CH + i] = __float2bfloat16(a);
+    }
+    for (int j = 0; j < CH; ++j) {
+        // dk
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) a = fmaf(sdG[i * CH + j], qh[i], a);
+        a = (a - kh[j] * sV[3 * CH + j]) * sV[CH + j];
+        float e = 0.f, f = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { e = fmaf(sdKP[j * P + p], ef[p], e); f = fmaf(sdVP[j * P + p], ef[p], f); }
+        drow[C + hd * CH + j] = __float2bfloat16(a + e);
+        drow[3 * C + hd * CH + j] = __float2bfloat16(f);
+    }
+    // dv_CA[j] = sum_i A[i][j] dxca[i]   (reuse qh as dxca)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) qh[i] = gamma[hd * CH + i] * __bfloat162float(dy[r * lddy + hd * CH + i]);
+    for (int j = 0; j < CH; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) a = fmaf(sA[i * CH + j], qh[i], a);
+        drow[2 * C + hd * CH + j] = __float2bfloat16(a);
+    }
+}
+
+// dEF[n][p] = sum_b sum_ch ( k[b,n,ch] dKP[b][ch][p] + v_SA[b,n,ch] dVP[b][ch][p] ).  thread per (n, 4 p's).
+__global__ void __launch_bounds__(256) dsa_bwd_ef_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                         const float* __restrict__ dKV, float* __restrict__ dEF,
+                                                         int B, int N, int C, int P) {
+    const int P4 = P / 4;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = gid / P4;
+    const int p = (int)(gid % P4) * 4;
+    if (n >= N) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+        const bf16* row = qkvv + ((long long)b * N + n) * ldq;
+        const float* dkp = dKV + (long long)b * 2 * C * P;
+        const float* dvp = dkp + (long long)C * P;
+        for (int ch = 0; ch < C; ++ch) {
+            const float k = __bfloat162float(row[C + ch]), v = __bfloat162float(row[3 * C + ch]);
+            const float4 x = *reinterpret_cast<const float4*>(&dkp[(long long)ch * P + p]);
+            const float4 y = *reinterpret_cast<const float4*>(&dvp[(long long)ch * P + p]);
+            a.x = fmaf(k, x.x, fmaf(v, y.x, a.x));
+            a.y = fmaf(k, x.y, fmaf(v, y.y, a.y));
+            a.z = fmaf(k, x.z, fmaf(v, y.z, a.z));
+            a.w = fmaf(k, x.w, fmaf(v, y.w, a.w));
+        }
+    }
+    *reinterpret_cast<float4*>(&dEF[n * P + p]) = a;
+}
+
+template <int CH, int P>
+int launch_apply(const bf16* qkvv, long long ldq, const float* inv_n, const float* A, const float* KV,
+                 const float* t2, float* xca, float* tsa, int B, int N, int C, int H, float ds, uint32_t dth,
+                 unsigned long long seed, cudaStream_t st) {
+    const int smem = (2 * CH * P + CH * CH + CH) * 4;
+    static bool conf = false;
+    if (!conf) { cudaFuncSetAttribute(dsa_apply_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
+    dim3 grid((N + 127) / 128, H, B);
+    dsa_apply_kernel<CH, P><<<grid, 128, smem, st>>>(qkvv, ldq, inv_n, A, KV, t2, xca, tsa, N, C, ds, dth, seed);
+    return (int)cudaGetLastError();
+}
+
+template <int CH, int P>
+int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long lddy, const float* gamma,
+                      const float* inv_n, const float* KV, const float* t2, float* dqh, float* part, int B, int N,
+                      int C, int H, float ds, uint32_t dth, unsigned long long seed, cudaStream_t st) {
+    const int smem = (2 * CH * P + 64 * (2 * P + 5 * CH + 1)) * 4;
+    static bool conf = false;
+    if (!conf) { cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
+    dim3 grid((N + 63) / 64, H, B);
+    dsa_bwd_reduce_kernel<CH, P><<<grid, 64, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N, C, ds,
+                                                         dth, seed);
+    return (int)cudaGetLastError();
+}
+
+template <int CH, int P>
+int launch_bwd_apply(const bf16* qkvv, long long ldq, const bf16* dy, long long lddy, const float* gamma,
+                     const float* EF, const float* inv_n, const float* A, const float* dGhat, const float* rqk,
+                     const float* dKV, const float* dqh, bf16* dqkvv, long long lddq, int B, int N, int C, int H,
+                     cudaStream_t st) {
+    const int smem = (2 * CH * P + 2 * CH * CH + 4 * CH) * 4;
+    static bool conf = false;
+    if (!conf) { cudaFuncSetAttribute(dsa_bwd_apply_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
+    dim3 grid((N + 127) / 128, H, B);
+    dsa_bwd_apply_kernel<CH, P><<<grid, 128, smem, st>>>(qkvv, ldq, dy, lddy, gamma, EF, inv_n, A, dGhat, rqk, dKV,
+                                                         dqh, dqkvv, lddq, N, C);
+    return (int)cudaGetLastError();
+}
+
+#define DSA_DISPATCH(FN, ...)                                                    \
+    do {                                                                         \
+        if (P == 64) {                                                           \
+            switch (c) {                                                         \
+                case 2: return FN<2, 64>(__VA_ARGS__);                           \
+                case 4: return FN<4, 64>(__VA_ARGS__);                           \
+                case 8: return FN<8, 64>(__VA_ARGS__);                           \
+                case 16: return FN<16, 64>(__VA_ARGS__);                         \
+                case 32: return FN<32, 64>(__VA_ARGS__);                         \
+                default: return -1;                                              \
+            }                                                                    \
+        } else if (P == 32) {                                                    \
+            switch (c) {                                                         \
+                case 2: return FN<2, 32>(__VA_ARGS__);                           \
+                case 4: return FN<4, 32>(__VA_ARGS__);                           \
+                case 8: return FN<8, 32>(__VA_ARGS__);                           \
+                case 16: return FN<16, 32>(__VA_ARGS__);                         \
+                case 32: return FN<32, 32>(__VA_ARGS__);                         \
+                case 64: return FN<64, 32>(__VA_ARGS__);                         \
+                default: return -1;                                              \
+            }                                                                    \
+        }                                                                        \
+        return -1;                                                               \
+    } while (0)
+
+int dsa_tile_tokens(int C, int P) {
+    int tn = 64;
+    while (tn > 8 && (long long)tn * (3 * C + P) * 4 > 60 * 1024) tn >>= 1;
+    return tn;
+}
+
+}  // namespace
+
+// ---- C ABI -----------------------------------------------------------------------------------------------------
+// TransformerBlock.forward lines 72-77 up to LayerNorm: t = x + pos_embed, ln = LayerNorm(t) (conv_blocks.py:75-77).
+FCD_API int fcd_ln_fwd(const void* x, long long ldx, const float* pos, const float* w, const float* b, void* t,
+                       long long ldt, void* ln, long long ldl, float* mean, float* rstd, long long rows, int N, int C,
+                       int Cp, float eps, cudaStream_t st) {
+    const int LPT = Cp / 8;
+    if (Cp % 8 || LPT > 32 || (LPT & (LPT - 1)) || C > Cp) return -1;
+    const long long total = rows * LPT;
+    const long long grid = (total + 255) / 256;
+    ln_fwd_kernel<<<(unsigned)grid, 256, 0, st>>>((const bf16*)x, ldx, pos, w, b, (bf16*)t, ldt, (bf16*)ln, ldl, mean,
+                                                  rstd, rows, N, C, LPT, eps);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_ln_bwd_blocks(int N, int Cp) { return (int)(((long long)N * (Cp / 8) + 255) / 256); }
+
+// part: fcd_ln_bwd_blocks(N,Cp)*2*Cp floats.  dpos fp32 [N][C] (or null), dw/db fp32 [C].
+FCD_API int fcd_ln_bwd(const void* dln, long long lddl, const void* dtd, long long lddt, const void* t, long long ldt,
+                       const float* mean, const float* rstd, const float* w, void* dx, long long lddx, float* dpos,
+                       float* part, float* dw, float* db, int B, int N, int C, int Cp, cudaStream_t st) {
+    const int LPT = Cp / 8;
+    if (Cp % 8 || LPT > 32 || (LPT & (LPT - 1)) || C > Cp) return -1;
+    const int nblk = fcd_ln_bwd_blocks(N, Cp);
+    ln_bwd_kernel<<<nblk, 256, 0, st>>>((const bf16*)dln, lddl, (const bf16*)dtd, lddt, (const bf16*)t, ldt, mean, rstd,
+                                        w, (bf16*)dx, lddx, dpos, part, B, N, C, LPT);
+    pair_colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nblk, Cp, C, dw, db);
+    FCD_LAUNCH_CHECK();
+}
+
+static int dsa_tiles(int N, int C, int P) { const int tn = dsa_tile_tokens(C, P); return (N + tn - 1) / tn; }
+FCD_API int fcd_dsa_fwd_part_floats(int B, int N, int C, int H, int P) {
+    return (int)((long long)B * dsa_tiles(N, C, P) * (2LL * C + (long long)C * (C / H) + 2LL * C * P));
+}
+FCD_API int fcd_dsa_bwd_part_floats(int B, int N, int C, int H, int P) {
+    const int c = C / H;
+    return (int)((long long)B * H * ((N + 63) / 64) * (2LL * c * P + (long long)c * c + c + 1));
+}
+
+static inline void drop_params(float p, float& scale, uint32_t& thresh) {
+    if (p <= 0.f) { scale = 1.f; thresh = 0; return; }
+    scale = 1.f / (1.f - p);
+    double t = (double)p * 4294967296.0;
+    thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    if (thresh == 0) thresh = 1;
+}
+
+// DSA.forward (conv_blocks.py:328-355) + `x + gamma * dsa` (conv_blocks.py:77).
+// qkvv: bf16 rows [B*N][ldq] = Linear(LN(t)); EF fp32 [N][P]; temperature/temperature2 fp32 [H]; gamma fp32 [C].
+// Saved for backward: inv_n [B][2][C], Ghat/A [B][H][c][c], KV [B][2][C][P], xca [B*N][C], tsa [B][c][H][N].
+FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const float* temperature,
+                        const float* temperature2, const float* gamma, const void* t, long long ldt, void* y,
+                        long long ldy, const float* ca_scale, float sa_drop, long long seed, float* part, float* inv_n,
+                        float* Ghat, float* A, float* Ad, float* KV, float* xca, float* tsa, int B, int N, int C,
+                        int Cp, int H, int P, cudaStream_t st) {
+    if (C % H || P % 4 || Cp % 8) return -1;
+    const int c = C / H;
+    const int LPT = Cp / 8;
+    if (LPT > 32 || (LPT & (LPT - 1))) return -1;
+    const int tn = dsa_tile_tokens(C, P);
+    const int ntiles = (N + tn - 1) / tn;
+    const int smem_r = tn * (3 * C + P) * 4;
+    static int conf_r = 0;
+    if (smem_r > conf_r) {
+        cudaFuncSetAttribute(dsa_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r > 48 * 1024 ? smem_r : 48 * 1024);
+        conf_r = smem_r;
+    }
+    dsa_reduce_kernel<<<dim3(ntiles, B), 256, smem_r, st>>>((const bf16*)qkvv, ldq, EF, part, N, C, c, P, tn);
+    float ds; uint32_t dth;
+    drop_params(sa_drop, ds, dth);
+    dsa_finalize_kernel<<<dim3(H, B), 256, (c * c + 2 * c) * 4, st>>>(part, ntiles, temperature, ca_scale, inv_n, Ghat, A,
+                                                                     Ad, KV, C, c, P);
+    {
+        auto run = [&]() -> int {
+            DSA_DISPATCH(launch_apply, (const bf16*)qkvv, ldq, inv_n, Ad, KV, temperature2, xca, tsa, B, N, C, H, ds, dth,
+                         (unsigned long long)seed, st);
+        };
+        int rc = run();
+        if (rc != 0) return rc;
+    }
+    const long long rows = (long long)B * N;
+    long long grid = (rows * LPT + 255) / 256;
+    if (grid > 8LL * fcd_num_sms()) grid = 8LL * fcd_num_sms();
+    dsa_combine_kernel<<<(unsigned)grid, 256, 0, st>>>((const bf16*)t, ldt, gamma, xca, tsa, (bf16*)y, ldy, rows, N, C, LPT);
+    FCD_LAUNCH_CHECK();
+}
+
+// Backward of fcd_dsa_fwd w.r.t. qkvv, EF, temperature(2), gamma.  (dt = dy passes straight to fcd_ln_bwd.)
+// dtemp / dtemp2 [H] are ACCUMULATED (zero them first); dgamma [C], dEF [N][P] are overwritten.
+// work: dqh [B*N][C] fp32, dKV [B][2][C][P], dGhat [B][H][c][c], rqk [B][2][C], gpart 2*148*2*Cp floats.
+FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long long lddy, const float* EF,
+                        const float* temperature, const float* temperature2, const float* gamma,
+                        const float* ca_scale, float sa_drop, long long seed, const float* inv_n, const float* Ghat,
+                        const float* A, const float* Ad, const float* KV, const float* xca, const float* tsa,
+                        float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
+                        long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
+                        int Cp, int H, int P, cudaStream_t st) {
+    if (C % H || P % 4 || Cp % 8) return -1;
+    const int c = C / H;
+    const int LPT = Cp / 8;
+    if (LPT > 32 || (LPT & (LPT - 1))) return -1;
+    const long long rows = (long long)B * N;
+    const int gblk = 2 * fcd_num_sms();
+    float ds; uint32_t dth;
+    drop_params(sa_drop, ds, dth);
+    dsa_dgamma_kernel<<<gblk, 256, 0, st>>>((const bf16*)dy, lddy, xca, tsa, gpart, rows, N, C, LPT);
+    pair_colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(gpart, gblk, Cp, C, dgamma, nullptr);
+    {
+        auto run = [&]() -> int {
+            DSA_DISPATCH(launch_bwd_reduce, (const bf16*)qkvv, ldq, (const bf16*)dy, lddy, gamma, inv_n, KV, temperature2,
+                         dqh, part, B, N, C, H, ds, dth, (unsigned long long)seed, st);
+        };
+        int rc = run();
+        if (rc != 0) return rc;
+    }
+    const int ntiles = (N + 63) / 64;
+    dsa_bwd_finalize_kernel<<<dim3(H, B), 256, (c * c + c) * 4, st>>>(part, ntiles, temperature, Ghat, A, ca_scale, dKV,
+                                                                     dGhat, rqk, dtemp, dtemp2, C, c, P);
+    {
+        auto run = [&]() -> int {
+            DSA_DISPATCH(launch_bwd_apply, (const bf16*)qkvv, ldq, (const bf16*)dy, lddy, gamma, EF, inv_n, Ad, dGhat, rqk,
+                         dKV, dqh, (bf16*)dqkvv, lddq, B, N, C, H, st);
+        };
+        int rc = run();
+        if (rc != 0) return rc;
+    }
+    const long long tot = (long long)N * (P / 4);
+    dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    FCD_LAUNCH_CHECK();
+}

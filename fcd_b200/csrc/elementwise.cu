@@ -489,9 +489,10 @@ FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void*
 FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean, float* rstd, int B, long long S,
                            int C, int nchunk, int mode, float eps, float* running_mean, float* running_var,
                            int crun, float momentum, cudaStream_t st) {
-    if (C % 8 || 256 % (C / 8)) return -1;
+    if (C % 8 || C / 8 > 256) return -1;
+    const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, B);
-    norm_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk);
+    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk);
     norm_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
                                                              running_mean, running_var, crun, momentum);
     FCD_LAUNCH_CHECK();
@@ -501,9 +502,10 @@ FCD_API int fcd_norm_apply(const void* x1, long long ld1, const float* mean1, co
                            const float* beta1, const void* x2, long long ld2, const float* mean2, const float* rstd2,
                            const void* res, long long ldr, void* y, long long ldy, int B, long long S, int C,
                            float slope, cudaStream_t st) {
-    if (C % 8 || 256 % (C / 8)) return -1;
-    dim3 grid(grid_for(S * (C / 8), 256, 8), B);
-    norm_apply_kernel<<<grid, 256, 0, st>>>((const bf16*)x1, ld1, mean1, rstd1, gamma1, beta1, (const bf16*)x2, ld2,
+    if (C % 8 || C / 8 > 256) return -1;
+    const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
+    dim3 grid(grid_for(S * (C / 8), nt, 8), B);
+    norm_apply_kernel<<<grid, nt, 0, st>>>((const bf16*)x1, ld1, mean1, rstd1, gamma1, beta1, (const bf16*)x2, ld2,
                                             mean2, rstd2, (const bf16*)res, ldr, (bf16*)y, ldy, S, C / 8, slope);
     FCD_LAUNCH_CHECK();
 }
@@ -515,14 +517,15 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
                          float* dbeta, void* dx1, long long ldd1, void* dx2, long long ldd2, void* dres,
                          long long lddr, int acc_res, int B, long long S, int C, int nchunk, int mode, float slope,
                          cudaStream_t st) {
-    if (C % 8 || 256 % (C / 8)) return -1;
+    if (C % 8 || C / 8 > 256) return -1;
+    const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 g1(nchunk, B);
-    norm_bwd_stats_kernel<<<g1, 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
+    norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope);
     norm_bwd_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, rstd1, rstd2, gamma1, coef, dgamma, dbeta, B,
                                                                  C, nchunk, S, mode, x2 != nullptr);
-    dim3 g2(grid_for(S * (C / 8), 256, 8), B);
-    norm_bwd_apply_kernel<<<g2, 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
+    dim3 g2(grid_for(S * (C / 8), nt, 8), B);
+    norm_bwd_apply_kernel<<<g2, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, coef, (bf16*)dx1, ldd1,
                                               (bf16*)dx2, ldd2, (bf16*)dres, lddr, S, C / 8, slope, acc_res);
     FCD_LAUNCH_CHECK();
@@ -531,9 +534,10 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
 // out[c] = sum over rows of x[row][c]  (bias gradients).  part: nchunk*2*C floats.
 FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, long long rows, int C, int nchunk,
                        cudaStream_t st) {
-    if (C % 8 || 256 % (C / 8)) return -1;
+    if (C % 8 || C / 8 > 256) return -1;
+    const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, 1);
-    norm_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk);
+    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk);
     colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, out, C, nchunk);
     FCD_LAUNCH_CHECK();
 }

@@ -220,7 +220,46 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(const float* __r
     }
 }
 
+// F.mse_loss(net_input, x_vae) of the VAE branch (segresnet_dsa.py:357)
+__global__ void __launch_bounds__(LOSS_THREADS) mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               long long n, float* __restrict__ part) {
+    float s[1] = {0.f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        s[0] = fmaf(d, d, s[0]);
+    }
+    __shared__ float sh[LOSS_THREADS / 32];
+    block_sum<1>(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+
+__global__ void mse_finalize_kernel(const float* __restrict__ part, int nblk, long long n, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nblk; ++k) s += part[k];
+        out[0] = (float)(s / (double)n);
+    }
+}
+
+__global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                               const float* __restrict__ gout, float* __restrict__ da) {
+    const float g = gout[0] * 2.f / (float)n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        da[i] = g * (a[i] - b[i]);
+}
+
 }  // namespace
+
+FCD_API int fcd_mse_fwd(const float* a, const float* b, long long n, float* part, float* out, cudaStream_t st) {
+    mse_fwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(a, b, n, part);
+    mse_finalize_kernel<<<1, 32, 0, st>>>(part, LOSS_BLOCKS, n, out);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_mse_bwd(const float* a, const float* b, long long n, const float* gout, float* da, cudaStream_t st) {
+    mse_bwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(a, b, n, gout, da);
+    FCD_LAUNCH_CHECK();
+}
 
 FCD_API int fcd_loss_blocks() { return LOSS_BLOCKS; }
 

@@ -1,0 +1,129 @@
+// Sliding-window whole-volume inference support (monai.inferers.sliding_window_inference as called at reference
+// train.py:148-165 / seg_fcd_test.py:37-54, mode='constant'):
+//   gather  : cut sw_batch_size windows out of the fp32 NCDHW volume straight into the model's channels-last bf16
+//             input batch (replaces the torch slicing + torch.cat + dtype casts);
+//   blend   : out[win] += pred, fp32, one launch per window so the summation order is the reference's window order;
+//   finalize: out /= count (count = product of per-axis coverage counts, importance map == 1), and optionally the
+//             label map of train.py:185,209-211 (softmax >= 0.5 per channel) / get_transforms.py:142-154 (argmax).
+#include "common.cuh"
+
+namespace {
+
+struct WinStarts {
+    int z[8], y[8], x[8];
+};
+
+__global__ void sw_gather_kernel(const float* __restrict__ vol, bf16* __restrict__ dst, int C, int Cp, int D, int H,
+                                 int W, int r0, int r1, int r2, int pz, int py, int px, WinStarts ws, int nwin) {
+    // vol: [C][D][H][W] of ONE image; window voxel (z,y,x) reads vol[.., ws.z+z-pz, ..] with zero padding (images
+    // smaller than the roi are padded symmetrically by MONAI; pz/py/px are the low-side pads)
+    const long long per = (long long)r0 * r1 * r2;
+    const long long total = per * nwin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i / per);
+        long long r = i - (long long)j * per;
+        const int x = (int)(r % r2); r /= r2;
+        const int y = (int)(r % r1);
+        const int z = (int)(r / r1);
+        const int sz = ws.z[j] + z - pz, sy = ws.y[j] + y - py, sx = ws.x[j] + x - px;
+        const bool in = sz >= 0 && sz < D && sy >= 0 && sy < H && sx >= 0 && sx < W;
+        const long long so = ((long long)sz * H + sy) * W + sx;
+        for (int c0 = 0; c0 < Cp; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = (in && c0 + k < C) ? vol[(long long)(c0 + k) * D * H * W + so] : 0.f;
+            st8(dst + i * Cp + c0, pack8(f));
+        }
+    }
+}
+
+// out[c][z0+z][y0+y][x0+x] += pred[c][z][y][x]   (out: padded volume [C][Dp][Hp][Wp], pred: one window)
+__global__ void sw_blend_kernel(const float* __restrict__ pred, float* __restrict__ out, int C, int r0, int r1, int r2,
+                                int Hp, int Wp, long long vol_stride, int z0, int y0, int x0) {
+    const long long per = (long long)r0 * r1 * r2;
+    const long long total = per * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per);
+        long long r = i - (long long)c * per;
+        const int x = (int)(r % r2); r /= r2;
+        const int y = (int)(r % r1);
+        const int z = (int)(r / r1);
+        const long long o = (long long)c * vol_stride + ((long long)(z0 + z) * Hp + (y0 + y)) * Wp + (x0 + x);
+        out[o] += pred[i];
+    }
+}
+
+// dst[c][z][y][x] = acc[c][z+pz][y+py][x+px] / (cz[z+pz] * cy[y+py] * cx[x+px]);  label (optional):
+//   mode 1: label[c][..] = softmax(dst)[c] >= 0.5 (float {0,1}, C channels);  mode 2: label[..] = argmax_c (uint8)
+__global__ void sw_finalize_kernel(const float* __restrict__ acc, const int* __restrict__ cz,
+                                   const int* __restrict__ cy, const int* __restrict__ cx, float* __restrict__ dst,
+                                   float* __restrict__ label_f, unsigned char* __restrict__ label_u8, int C, int D,
+                                   int H, int W, int Hp, int Wp, long long vol_stride, int pz, int py, int px,
+                                   int z_lo, int z_hi, int mode) {
+    const long long total = (long long)(z_hi - z_lo) * H * W;
+    const long long S = (long long)D * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const int z = (int)(r / H) + z_lo;
+        const float inv = 1.f / (float)(cz[z + pz] * cy[y + py] * cx[x + px]);
+        const long long so = ((long long)(z + pz) * Hp + (y + py)) * Wp + (x + px);
+        const long long o = ((long long)z * H + y) * W + x;
+        float v[8];
+        float mx = -INFINITY;
+        int am = 0;
+        for (int c = 0; c < C; ++c) {
+            v[c] = acc[(long long)c * vol_stride + so] * inv;
+            dst[(long long)c * S + o] = v[c];
+            if (v[c] > mx) { mx = v[c]; am = c; }
+        }
+        if (mode == 1) {
+            float den = 0.f;
+            for (int c = 0; c < C; ++c) den += expf(v[c] - mx);
+            for (int c = 0; c < C; ++c) label_f[(long long)c * S + o] = (expf(v[c] - mx) / den >= 0.5f) ? 1.f : 0.f;
+        } else if (mode == 2) {
+            label_u8[o] = (unsigned char)am;
+        }
+    }
+}
+
+inline int sw_grid(long long total) {
+    long long g = (total + 255) / 256;
+    const long long cap = 8LL * fcd_num_sms();
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+// starts: host arrays of nwin (<= 8) window origins in the PADDED volume frame.
+FCD_API int fcd_sw_gather(const float* vol, void* dst, int C, int Cp, int D, int H, int W, int r0, int r1, int r2,
+                          int pz, int py, int px, const int* starts_zyx, int nwin, cudaStream_t st) {
+    if (nwin < 1 || nwin > 8 || Cp % 8) return -1;
+    WinStarts ws;
+    for (int j = 0; j < nwin; ++j) { ws.z[j] = starts_zyx[3 * j]; ws.y[j] = starts_zyx[3 * j + 1]; ws.x[j] = starts_zyx[3 * j + 2]; }
+    const long long total = (long long)nwin * r0 * r1 * r2;
+    sw_gather_kernel<<<sw_grid(total), 256, 0, st>>>(vol, (bf16*)dst, C, Cp, D, H, W, r0, r1, r2, pz, py, px, ws, nwin);
+    FCD_LAUNCH_CHECK();
+}
+
+FCD_API int fcd_sw_blend(const float* pred, float* out, int C, int r0, int r1, int r2, int Dp, int Hp, int Wp, int z0,
+                         int y0, int x0, cudaStream_t st) {
+    const long long total = (long long)C * r0 * r1 * r2;
+    sw_blend_kernel<<<sw_grid(total), 256, 0, st>>>(pred, out, C, r0, r1, r2, Hp, Wp, (long long)Dp * Hp * Wp, z0, y0, x0);
+    FCD_LAUNCH_CHECK();
+}
+
+// cz/cy/cx: device int arrays (padded-frame per-axis window coverage counts).  Processes slab z in [z_lo, z_hi).
+FCD_API int fcd_sw_finalize(const float* acc, const int* cz, const int* cy, const int* cx, float* dst, float* label_f,
+                            void* label_u8, int C, int D, int H, int W, int Dp, int Hp, int Wp, int pz, int py, int px,
+                            int z_lo, int z_hi, int mode, cudaStream_t st) {
+    if (C > 8 || z_lo < 0 || z_hi > D || z_hi <= z_lo) return -1;
+    const long long total = (long long)(z_hi - z_lo) * H * W;
+    sw_finalize_kernel<<<sw_grid(total), 256, 0, st>>>(acc, cz, cy, cx, dst, label_f, (unsigned char*)label_u8, C, D, H,
+                                                      W, Hp, Wp, (long long)Dp * Hp * Wp, pz, py, px, z_lo, z_hi, mode);
+    FCD_LAUNCH_CHECK();
+}

@@ -8,12 +8,15 @@ called: the block forwards below run the hand-written CUDA kernels on channels-l
 """
 from __future__ import annotations
 
+import random
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 
 LRELU_SLOPE = 0.01
+_host_rng = random.Random(0x5eed)
 
 
 class Convolution(nn.Sequential):
@@ -139,4 +142,137 @@ class UnetrUpBlock(nn.Module):
 
     def forward(self, inp, skip):
         buf = ops.up_concat(inp, skip, self.transp_conv.conv.weight)
+        return self.conv_block(buf, cin_seg=(self.out_channels, ops.pad16(self.out_channels)))
+
+
+class DSA(nn.Module):
+    """conv_blocks.py:211-359, sa_type='parallel' (the reference default, config.py:7)."""
+
+    def __init__(self, input_size, hidden_size, proj_size, num_heads=4, qkv_bias=False, channel_attn_drop=0.1,
+                 spatial_attn_drop=0.1, sa_type="parallel"):
+        super().__init__()
+        if sa_type != "parallel":
+            raise NotImplementedError("fcd_b200 DSA implements sa_type='parallel' (SURVEY 8f rank 4 lists the others)")
+        if qkv_bias:
+            raise NotImplementedError("qkv_bias=True is never used by get_model")
+        self.num_heads = num_heads
+        self.head_dim = hidden_size // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.temperature2 = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.sa_type = sa_type
+        self.num = 4
+        self.qkvv = nn.Linear(hidden_size, hidden_size * self.num, bias=qkv_bias)
+        ef = torch.zeros(int(input_size), proj_size)
+        std = 1.0 / (proj_size ** 0.5)
+        self.EF = nn.Parameter(ef.uniform_(-std, std))          # init_ (conv_blocks.py:145-149)
+        self.input_size = int(input_size)
+        self.proj_size = proj_size
+        self.hidden_size = hidden_size
+        self.attn_drop = nn.Dropout(channel_attn_drop)
+        self.attn_drop_2 = nn.Dropout(spatial_attn_drop)
+
+    def forward(self, ln, t, gamma):
+        """ln = LayerNorm(t); returns t + gamma * DSA(ln) (the residual of TransformerBlock line 77 is fused)."""
+        qkvv = ops.linear(ln, self.qkvv.weight)
+        B = t.shape[0]
+        c, H = self.head_dim, self.num_heads
+        ca_scale, sa_p, seed = None, 0.0, 0
+        if self.training:
+            if self.attn_drop.p > 0:
+                pk = self.attn_drop.p
+                ca_scale = (torch.rand((B, H, c, c), device=t.device) >= pk).float() / (1.0 - pk)
+            if self.attn_drop_2.p > 0:
+                sa_p = float(self.attn_drop_2.p)
+                seed = _host_rng.getrandbits(62)     # host-side counter RNG: no device sync
+        return ops.dsa_attention(qkvv, t, self.EF, self.temperature, self.temperature2, gamma, self.hidden_size, H,
+                                 self.proj_size, ca_scale, sa_p, seed)
+
+
+class TransformerBlock(nn.Module):
+    """conv_blocks.py:18-90."""
+
+    def __init__(self, input_size, hidden_size, proj_size, num_heads, dropout_rate=0.0, pos_embed=False,
+                 sa_type="parallel", norm_name="batch"):
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden_size should be divisible by num_heads.")
+        self.sa_type = sa_type
+        self.hidden_size = hidden_size
+        self.norm = nn.LayerNorm(hidden_size)
+        self.gamma = nn.Parameter(1e-6 * torch.ones(hidden_size), requires_grad=True)
+        self.conv51 = UnetResBlock(3, hidden_size, hidden_size, kernel_size=3, stride=1, norm_name="batch")
+        self.conv8 = nn.Sequential(nn.Dropout3d(0.1, False), nn.Conv3d(hidden_size, hidden_size, 1))
+        self.pos_embed = None
+        if pos_embed:
+            self.pos_embed = nn.Parameter(torch.zeros(1, int(input_size), hidden_size))
+        self.dsa = DSA(input_size=input_size, hidden_size=hidden_size, proj_size=proj_size, num_heads=num_heads,
+                       channel_attn_drop=dropout_rate, spatial_attn_drop=dropout_rate, sa_type=sa_type)
+
+    def forward(self, x):
+        B, D, H, W, _ = x.shape
+        if self.pos_embed is not None and D * H * W != self.pos_embed.shape[1]:
+            raise ValueError("input spatial size does not match the patch size the model was built for")
+        t, ln = ops.ln_pos(x, self.pos_embed, self.norm.weight, self.norm.bias, self.hidden_size, self.norm.eps)
+        y = self.dsa(ln, t, self.gamma)
+        z = self.conv51(y)
+        z = ops.dropout3d(z, self.conv8[0].p, self.training)
+        z = ops.conv3d(z, self.conv8[1].weight, self.conv8[1].bias, k=1)
+        return ops.add(y, z)
+
+
+class SubpixelUpsample(nn.Module):
+    """Container for MONAI SubpixelUpsample's parameters: `conv_block` = Conv3d(cin, cout*8, 3, pad 1, bias) with
+    ICNR init; `pad_pool` has no parameters."""
+
+    def __init__(self, in_channels, out_channels, bias=True):
+        super().__init__()
+        self.out_channels = out_channels
+        self.conv_block = nn.Conv3d(in_channels, out_channels * 8, kernel_size=3, stride=1, padding=1, bias=bias)
+        with torch.no_grad():   # icnr_init: every group of 8 sub-pixel kernels starts identical
+            k = nn.init.kaiming_normal_(torch.zeros(out_channels, in_channels, 3, 3, 3))
+            k = k.transpose(0, 1).reshape(out_channels, in_channels, -1).repeat(1, 1, 8)
+            k = k.reshape(in_channels, out_channels * 8, 3, 3, 3).transpose(0, 1)
+            self.conv_block.weight.copy_(k)
+        self.pad_pool = nn.Sequential(nn.ConstantPad3d((1, 0, 1, 0, 1, 0), 0.0), nn.AvgPool3d(kernel_size=2, stride=1))
+
+    def forward(self, x, skip=None, mode="plain"):
+        return ops.subpixel_upsample(x, self.conv_block.weight, self.conv_block.bias, self.out_channels, skip, mode)
+
+
+class UpSample(nn.Sequential):
+    """MONAI UpSample(mode='pixelshuffle') container: single child `pixelshuffle` (conv_blocks.py:727-735)."""
+
+    def __init__(self, spatial_dims, in_channels, out_channels, scale_factor=2, mode="pixelshuffle",
+                 interp_mode="linear", align_corners=False, bias=True):
+        super().__init__()
+        if str(mode).lower().split(".")[-1] != "pixelshuffle" or int(scale_factor) != 2 or spatial_dims != 3:
+            raise NotImplementedError("fcd_b200 UpSample implements mode='pixelshuffle', scale 2 (config.py:57); "
+                                      "'deconv' / 'nontrainable' are listed as next in SURVEY 8f rank 4")
+        self.add_module("pixelshuffle", SubpixelUpsample(in_channels, out_channels or in_channels, bias))
+
+    def forward(self, x, skip=None, mode="plain"):
+        return self.pixelshuffle(x, skip, mode)
+
+
+class GeneralUnetrUpBlock(nn.Module):
+    """conv_blocks.py:692-775 with upsample_mode='pixelshuffle' (MS_DSA_NET_PS, get_model.py:32-49)."""
+
+    def __init__(self, spatial_dims, in_channels, out_channels, kernel_size, norm_name,
+                 act_name=("leakyrelu", {"inplace": True, "negative_slope": 0.01}), res_block=False, bias=False,
+                 fuse="cat", upsample_mode="nontrainable", interpolate_mode="linear", scale_factor=2.0):
+        super().__init__()
+        if fuse != "cat" or not res_block:
+            raise NotImplementedError("fcd_b200 GeneralUnetrUpBlock: fuse='cat', res_block=True (as get_model)")
+        self.upsample = UpSample(spatial_dims, in_channels, out_channels, scale_factor=scale_factor,
+                                 mode=upsample_mode, interp_mode=interpolate_mode, align_corners=False)
+        self.fuse = fuse
+        self.out_channels = out_channels
+        self.conv_block = UnetResBlock(spatial_dims, out_channels * 2, out_channels, kernel_size, 1, norm_name,
+                                       act_name, bias=bias)
+
+    def forward(self, inp, skip):
+        buf = self.upsample(inp, skip, "concat")
         return self.conv_block(buf, cin_seg=(self.out_channels, ops.pad16(self.out_channels)))

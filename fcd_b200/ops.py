@@ -448,3 +448,261 @@ class LossFn(Function):
 
 def fused_loss(pred, target, cfg):
     return LossFn.apply(pred, target, cfg)
+
+
+# ------------------------------------------------------------------------------------------------ transformer path
+class LNPosFn(Function):
+    """t = x + pos_embed ; ln = LayerNorm_C(t)  (conv_blocks.py:72-77).  Returns (t, ln)."""
+
+    @staticmethod
+    def forward(ctx, x, pos, w, b, C, eps):
+        x = rows(x)
+        B, D, H, W, Cp = x.shape
+        N = D * H * W
+        t = _empty((B, D, H, W, Cp), x)
+        ln = _empty((B, D, H, W, Cp), x)
+        mean = torch.empty((B * N,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((B * N,), dtype=torch.float32, device=x.device)
+        posc = None if pos is None else pos.detach().float().contiguous()
+        wc, bc = w.detach().float().contiguous(), b.detach().float().contiguous()
+        call("fcd_ln_fwd", x=x, ldx=ld(x), pos=posc, w=wc, b=bc, t=t, ldt=Cp, ln=ln, ldl=Cp, mean=mean, rstd=rstd,
+             rows=B * N, N=N, C=C, Cp=Cp, eps=eps)
+        ctx.save_for_backward(t, mean, rstd, wc)
+        ctx.cfg = (C, pos is not None, None if pos is None else tuple(pos.shape))
+        return t, ln
+
+    @staticmethod
+    def backward(ctx, dt, dln):
+        t, mean, rstd, wc = ctx.saved_tensors
+        C, has_pos, pshape = ctx.cfg
+        B, D, H, W, Cp = t.shape
+        N = D * H * W
+        dt = rows(dt) if dt is not None else torch.zeros_like(t)
+        dln = rows(dln) if dln is not None else torch.zeros_like(t)
+        dx = torch.empty_like(t)
+        dpos = torch.empty((N, C), dtype=torch.float32, device=t.device) if has_pos else None
+        nblk = _lib.lib().fcd_ln_bwd_blocks(N, Cp)
+        part = torch.empty((nblk, 2, Cp), dtype=torch.float32, device=t.device)
+        dw = torch.empty((C,), dtype=torch.float32, device=t.device)
+        db = torch.empty((C,), dtype=torch.float32, device=t.device)
+        call("fcd_ln_bwd", dln=dln, lddl=ld(dln), dtd=dt, lddt=ld(dt), t=t, ldt=Cp, mean=mean, rstd=rstd, w=wc, dx=dx,
+             lddx=Cp, dpos=dpos, part=part, dw=dw, db=db, B=B, N=N, C=C, Cp=Cp)
+        return dx, (dpos.view(pshape) if has_pos else None), dw, db, None, None
+
+
+def ln_pos(x, pos, w, b, C, eps=1e-5):
+    return LNPosFn.apply(x, pos, w, b, C, eps)
+
+
+class DSAFn(Function):
+    """y = t + gamma * DSA(qkvv)  (conv_blocks.py:328-355 + line 77), qkvv = Linear(LayerNorm(t))."""
+
+    @staticmethod
+    def forward(ctx, qkvv, t, EF, temperature, temperature2, gamma, C, H, P, ca_scale, sa_drop, seed):
+        qkvv, t = rows(qkvv), rows(t)
+        B, D, Hs, W, Cp = t.shape
+        N = D * Hs * W
+        c = C // H
+        dev = t.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        part = torch.empty((lib.fcd_dsa_fwd_part_floats(B, N, C, H, P),), **f32)
+        inv_n = torch.empty((B, 2, C), **f32)
+        Ghat = torch.empty((B, H, c, c), **f32)
+        A = torch.empty((B, H, c, c), **f32)
+        Ad = torch.empty((B, H, c, c), **f32)
+        KV = torch.empty((B, 2, C, P), **f32)
+        xca = torch.empty((B * N, C), **f32)
+        tsa = torch.empty((B, C * N), **f32)
+        y = _empty((B, D, Hs, W, Cp), t)
+        EFc = EF.detach().float().contiguous()
+        t1 = temperature.detach().float().contiguous()
+        t2 = temperature2.detach().float().contiguous()
+        g = gamma.detach().float().contiguous()
+        call("fcd_dsa_fwd", qkvv=qkvv, ldq=ld(qkvv), EF=EFc, temperature=t1, temperature2=t2, gamma=g, t=t, ldt=ld(t),
+             y=y, ldy=Cp, ca_scale=ca_scale, sa_drop=float(sa_drop), seed=int(seed), part=part, inv_n=inv_n, Ghat=Ghat,
+             A=A, Ad=Ad, KV=KV, xca=xca, tsa=tsa, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
+        ctx.save_for_backward(qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale)
+        ctx.cfg = (C, H, P, float(sa_drop), int(seed), Cp, (B, D, Hs, W), tuple(temperature.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale = ctx.saved_tensors
+        C, H, P, sa_drop, seed, Cp, (B, D, Hs, W), tshape = ctx.cfg
+        N = D * Hs * W
+        c = C // H
+        dy = rows(dy)
+        dev = dy.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        part = torch.empty((lib.fcd_dsa_bwd_part_floats(B, N, C, H, P),), **f32)
+        dqh = torch.empty((B * N, C), **f32)
+        dKV = torch.empty((B, 2, C, P), **f32)
+        dGhat = torch.empty((B, H, c, c), **f32)
+        rqk = torch.empty((B, 2, C), **f32)
+        gpart = torch.empty((512, 2, Cp), **f32)
+        dqkvv = torch.empty_like(qkvv, memory_format=torch.contiguous_format)
+        dEF = torch.empty((N, P), **f32)
+        dtemp = torch.zeros((H,), **f32)
+        dtemp2 = torch.zeros((H,), **f32)
+        dgamma = torch.empty((C,), **f32)
+        call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
+             gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
+             xca=xca, tsa=tsa, part=part, dqh=dqh, dKV=dKV, dGhat=dGhat, rqk=rqk, gpart=gpart, dqkvv=dqkvv,
+             lddq=dqkvv.shape[4], dEF=dEF, dtemp=dtemp, dtemp2=dtemp2, dgamma=dgamma, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
+        return (dqkvv, dy, dEF, dtemp.view(tshape), dtemp2.view(tshape), dgamma, None, None, None, None, None, None)
+
+
+def dsa_attention(qkvv, t, EF, temperature, temperature2, gamma, C, H, P, ca_scale=None, sa_drop=0.0, seed=0):
+    return DSAFn.apply(qkvv, t, EF, temperature, temperature2, gamma, C, H, P, ca_scale, sa_drop, seed)
+
+
+class ChannelScaleFn(Function):
+    """y[b,...,c] = x[b,...,c] * scale[b,c]: nn.Dropout3d (conv_blocks.py:57; segresnet_dsa.py:197-198) with a
+    host-drawn O(B*C) Bernoulli mask."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = rows(x)
+        B, D, H, W, C = x.shape
+        zero = torch.zeros_like(scale)
+        y = _empty((B, D, H, W, C), x)
+        call("fcd_norm_apply", x1=x, ld1=ld(x), mean1=zero, rstd1=scale, gamma1=None, beta1=None, x2=None, ld2=0,
+             mean2=None, rstd2=None, res=None, ldr=0, y=y, ldy=C, B=B, S=D * H * W, C=C, slope=1.0)
+        ctx.save_for_backward(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        return ChannelScaleFn.apply(dy, scale), None
+
+
+def dropout3d(x, p, training):
+    """Channel dropout on channels-last activations; identity when not training or p == 0."""
+    if not training or p <= 0.0:
+        return x
+    B, C = x.shape[0], x.shape[4]
+    keep = (torch.rand((B, C), device=x.device) >= p).float() / (1.0 - p)
+    return ChannelScaleFn.apply(x, keep)
+
+
+# ------------------------------------------------------------------------------------------------ sub-pixel upsample
+def _ps_permute(weight, bias, cout, cq):
+    """Re-order SubpixelUpsample's conv (weight [cout*8, Cin, 3,3,3], bias [cout*8]; channel = c*8 + tap)
+    to tap-major rows padded to cq per tap: row tap*cq + c.  Differentiable, parameter-sized bookkeeping."""
+    ci = weight.shape[1]
+    w = weight.view(cout, 8, ci, 3, 3, 3).permute(1, 0, 2, 3, 4, 5)
+    w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, 0, 0, cq - cout)).reshape(8 * cq, ci, 3, 3, 3)
+    b = None
+    if bias is not None:
+        b = F.pad(bias.view(cout, 8).t(), (0, cq - cout)).reshape(8 * cq)
+    return w, b
+
+
+class PSBlurFn(Function):
+    """pixelshuffle(x2) + pad + avgpool of a tap-major conv output; mode 'plain' | 'add' (+ skip) | 'concat'
+    (result in the left half of a [.., Cq + Cs] buffer, skip copied into the right half)."""
+
+    @staticmethod
+    def forward(ctx, src, skip, cq, mode):
+        src = rows(src)
+        B, D, H, W, _ = src.shape
+        skip = rows(skip) if skip is not None else None
+        if mode == "concat":
+            cs = skip.shape[4]
+            out = _empty((B, 2 * D, 2 * H, 2 * W, cq + cs), src)
+            call("fcd_ps_blur_fwd", src=src, lds=ld(src), skip=None, ldk=0, out=out, ldo=cq + cs, B=B, D=D, H=H, W=W,
+                 Cq=cq)
+            call("fcd_copy_rows", a=skip, lda=ld(skip), o=out[..., cq:], ldo=cq + cs, rows=B * 8 * D * H * W, C=cs)
+        else:
+            out = _empty((B, 2 * D, 2 * H, 2 * W, cq), src)
+            sk = skip if mode == "add" else None
+            call("fcd_ps_blur_fwd", src=src, lds=ld(src), skip=sk, ldk=ld(sk) if sk is not None else 0, out=out,
+                 ldo=cq, B=B, D=D, H=H, W=W, Cq=cq)
+        ctx.cfg = (cq, mode, (B, D, H, W), src.shape[4])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cq, mode, (B, D, H, W), csrc = ctx.cfg
+        dout = rows(dout)
+        dsrc = torch.empty((B, D, H, W, csrc), dtype=BF16, device=dout.device)
+        call("fcd_ps_blur_bwd", dout=dout, lddo=ld(dout), dsrc=dsrc, ldds=csrc, B=B, D=D, H=H, W=W, Cq=cq)
+        dskip = None
+        if mode == "add":
+            dskip = dout
+        elif mode == "concat":
+            dskip = dout[..., cq:]
+        return dsrc, dskip, None, None
+
+
+def subpixel_upsample(x, weight, bias, cout, skip=None, mode="plain"):
+    """MONAI SubpixelUpsample: conv3x3x3 (cin -> 8*cout, bias) -> pixelshuffle -> pad -> avgpool."""
+    cq = pad16(cout)
+    w, b = _ps_permute(weight, bias, cout, cq)
+    y = conv3d(x, w, b, k=3)
+    return PSBlurFn.apply(y, skip, cq, mode)
+
+
+# ------------------------------------------------------------------------------------------------ small helpers
+class ActFn(Function):
+    """y = LeakyReLU_slope(x) on channels-last rows (self.act_mod(x_vae), segresnet_dsa.py:350)."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = rows(x)
+        B, D, H, W, C = x.shape
+        zero = torch.zeros((B, C), dtype=torch.float32, device=x.device)
+        one = torch.ones((B, C), dtype=torch.float32, device=x.device)
+        y = _empty((B, D, H, W, C), x)
+        call("fcd_norm_apply", x1=x, ld1=ld(x), mean1=zero, rstd1=one, gamma1=None, beta1=None, x2=None, ld2=0,
+             mean2=None, rstd2=None, res=None, ldr=0, y=y, ldy=C, B=B, S=D * H * W, C=C, slope=slope)
+        ctx.save_for_backward(y, zero, one)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, zero, one = ctx.saved_tensors
+        dy = rows(dy)
+        B, D, H, W, C = y.shape
+        S = D * H * W
+        part = torch.empty((B, 1, 3, C), dtype=torch.float32, device=y.device)
+        coef = torch.empty((B, C, 6), dtype=torch.float32, device=y.device)
+        scratch = torch.empty_like(y)
+        dres = torch.empty_like(y)
+        call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=y, ld1=C, mean1=zero, rstd1=one, gamma1=None, x2=None,
+             ld2=0, mean2=None, rstd2=None, part=part, coef=coef, dgamma=None, dbeta=None, dx1=scratch, ldd1=C,
+             dx2=None, ldd2=0, dres=dres, lddr=C, acc_res=0, B=B, S=S, C=C, nchunk=1, mode=0, slope=ctx.slope)
+        return dres, None
+
+
+def relu_rows(x, slope=0.0):
+    return ActFn.apply(x, float(slope))
+
+
+class MSEFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a.float().contiguous()
+        b = b.detach().float().contiguous()
+        n = a.numel()
+        part = torch.empty((_lib.query("fcd_loss_blocks"),), dtype=torch.float32, device=a.device)
+        out = torch.empty((1,), dtype=torch.float32, device=a.device)
+        call("fcd_mse_fwd", a=a, b=b, n=n, part=part, out=out)
+        ctx.save_for_backward(a, b)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a)
+        call("fcd_mse_bwd", a=a, b=b, n=a.numel(), gout=g.detach().float().reshape(1).contiguous(), da=da)
+        return da, None
+
+
+def mse_loss(pred, target):
+    """F.mse_loss(target, pred) with gradient to `pred` only (segresnet_dsa.py:357)."""
+    return MSEFn.apply(pred, target)

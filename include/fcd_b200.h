@@ -93,4 +93,53 @@ FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, i
                          const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
                          float* dpred, cudaStream_t stream);
 
+/* ---- TransformerBlock token path: pos_embed add + LayerNorm (conv_blocks.py:72-77) ---- */
+FCD_API int fcd_ln_fwd(const void* x, long long ldx, const float* pos, const float* w, const float* b, void* t,
+                       long long ldt, void* ln, long long ldl, float* mean, float* rstd, long long rows, int N, int C,
+                       int Cp, float eps, cudaStream_t stream);
+FCD_API int fcd_ln_bwd_blocks(int N, int Cp);
+FCD_API int fcd_ln_bwd(const void* dln, long long lddl, const void* dtd, long long lddt, const void* t, long long ldt,
+                       const float* mean, const float* rstd, const float* w, void* dx, long long lddx, float* dpos,
+                       float* part, float* dw, float* db, int B, int N, int C, int Cp, cudaStream_t stream);
+
+/* ---- DSA.forward, sa_type='parallel' (conv_blocks.py:328-355) fused with `x + gamma * dsa` (line 77).
+ *      ca_scale: optional [B][H][c][c] dropout scale (0 or 1/(1-p)) for attn_drop; sa_drop/seed: in-kernel
+ *      counter-based dropout of the [N,P] spatial attention map (attn_drop_2). ---- */
+FCD_API int fcd_dsa_fwd_part_floats(int B, int N, int C, int H, int P);
+FCD_API int fcd_dsa_bwd_part_floats(int B, int N, int C, int H, int P);
+FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const float* temperature,
+                        const float* temperature2, const float* gamma, const void* t, long long ldt, void* y,
+                        long long ldy, const float* ca_scale, float sa_drop, long long seed, float* part, float* inv_n,
+                        float* Ghat, float* A, float* Ad, float* KV, float* xca, float* tsa, int B, int N, int C,
+                        int Cp, int H, int P, cudaStream_t stream);
+FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long long lddy, const float* EF,
+                        const float* temperature, const float* temperature2, const float* gamma,
+                        const float* ca_scale, float sa_drop, long long seed, const float* inv_n, const float* Ghat,
+                        const float* A, const float* Ad, const float* KV, const float* xca, const float* tsa,
+                        float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
+                        long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
+                        int Cp, int H, int P, cudaStream_t stream);
+
+/* ---- MONAI SubpixelUpsample tail: pixelshuffle x2 + pad(1,0)x3 + AvgPool3d(2,1) (+ skip add / concat write)
+ *      (conv_blocks.py:727-735, 771; segresnet_dsa.py:133-141, 217).  src channels are ordered tap*Cq + c. ---- */
+FCD_API int fcd_ps_blur_fwd(const void* src, long long lds, const void* skip, long long ldk, void* out, long long ldo,
+                            int B, int D, int H, int W, int Cq, cudaStream_t stream);
+FCD_API int fcd_ps_blur_bwd(const void* dout, long long lddo, void* dsrc, long long ldds, int B, int D, int H, int W,
+                            int Cq, cudaStream_t stream);
+
+/* ---- F.mse_loss of the VAE reconstruction (segresnet_dsa.py:357); part: fcd_loss_blocks() floats ---- */
+FCD_API int fcd_mse_fwd(const float* a, const float* b, long long n, float* part, float* out, cudaStream_t stream);
+FCD_API int fcd_mse_bwd(const float* a, const float* b, long long n, const float* gout, float* da,
+                        cudaStream_t stream);
+
+/* ---- sliding_window_inference(mode="constant") support (train.py:148-165; seg_fcd_test.py:37-54; label map of
+ *      train.py:185,209-211 / get_transforms.py:142-154).  starts_zyx is a HOST array of nwin*3 ints. ---- */
+FCD_API int fcd_sw_gather(const float* vol, void* dst, int C, int Cp, int D, int H, int W, int r0, int r1, int r2,
+                          int pz, int py, int px, const int* starts_zyx, int nwin, cudaStream_t stream);
+FCD_API int fcd_sw_blend(const float* pred, float* out, int C, int r0, int r1, int r2, int Dp, int Hp, int Wp, int z0,
+                         int y0, int x0, cudaStream_t stream);
+FCD_API int fcd_sw_finalize(const float* acc, const int* cz, const int* cy, const int* cx, float* dst, float* label_f,
+                            void* label_u8, int C, int D, int H, int W, int Dp, int Hp, int Wp, int pz, int py, int px,
+                            int z_lo, int z_hi, int mode, cudaStream_t stream);
+
 #endif /* FCD_B200_H */

@@ -32,7 +32,7 @@ def dice(pred, target, smooth_nr=1e-5, smooth_dr=1e-5, squared_pred=False, jacca
 
 def cross_entropy(pred, target, w_bg=0.5, w_fg=0.5):
     """nn.CrossEntropyLoss(weight=[w_bg,w_fg], reduction='mean') on logits (get_loss.py:59-69)."""
-    w = torch.tensor([w_bg, w_fg], dtype=torch.float32)
+    w = torch.tensor([w_bg, w_fg], dtype=torch.float32, device=pred.device)
     return F.cross_entropy(pred.float(), target.squeeze(1).long(), weight=w)
 
 
@@ -47,7 +47,7 @@ def focal(pred, target, gamma=2.0):
 
 def _dilate(mask, iterations=2):
     """dilate_mask (get_loss.py:100-113): 3^3 all-ones conv > 0, repeated."""
-    k = torch.ones((1, 1, 3, 3, 3))
+    k = torch.ones((1, 1, 3, 3, 3), device=mask.device)
     d = mask
     for _ in range(iterations):
         d = (F.conv3d(d.float(), k, padding=1) > 0).float()

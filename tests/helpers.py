@@ -41,25 +41,35 @@ def loss_params(meta):
     return p
 
 
-def oracle_run(meta, training=True):
-    """Oracle forward (+loss +grads when training).  Returns dict(logits, loss, total, grads, bn)."""
+def oracle_run(meta, training=True, device="cpu", autocast=None):
+    """Oracle forward (+loss +grads when training).  Returns dict(logits, loss, total, grads, bn).
+
+    device/autocast: the SAME functional oracle evaluated by stock PyTorch on the GPU under bf16/fp16 autocast is
+    what calibrates the bf16 tolerances of the GPU parity tests (see tools/calibrate_bf16.py)."""
+    import contextlib
     sd, x, y, noise = case_inputs(meta)
     float_keys = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
-    leaf = {k: (v.clone().requires_grad_(training) if k in float_keys else v) for k, v in sd.items()}
+    leaf = {k: (v.to(device).clone().requires_grad_(training) if k in float_keys else v.to(device))
+            for k, v in sd.items()}
+    x, y, noise = x.to(device), y.to(device), noise.to(device)
     bn = {}
-    out = onets.forward(meta["model_type"], leaf, x, training, bn, noise)
-    vae = None
-    if isinstance(out, tuple):
-        out, vae = out
-    res = dict(logits=out.detach(), bn=bn)
+    ctx = torch.autocast("cuda", dtype=autocast) if autocast is not None else contextlib.nullcontext()
+    with ctx:
+        out = onets.forward(meta["model_type"], leaf, x, training, bn, noise)
+        vae = None
+        if isinstance(out, tuple):
+            out, vae = out
+        res = dict(logits=out.detach().float().cpu(), bn={k: v.detach().cpu() for k, v in bn.items()})
+        if training:
+            p = loss_params(meta)
+            loss = olosses.combined_loss(p, out, y)
+            total = loss + (p["loss_vae_weight"] * vae if vae is not None else 0.0)
     if training:
-        p = loss_params(meta)
-        loss = olosses.combined_loss(p, out, y)
-        total = loss + (p["loss_vae_weight"] * vae if vae is not None else 0.0)
         total.backward()
         res.update(loss=float(loss.detach()), total=float(total.detach()),
                    vae_loss=None if vae is None else float(vae.detach()),
-                   grads={k: leaf[k].grad for k in float_keys})
+                   grads={k: (None if leaf[k].grad is None else leaf[k].grad.detach().float().cpu())
+                          for k in float_keys})
     return res
 
 

@@ -281,3 +281,153 @@ def test_fused_loss_vs_oracle(over):
     assert abs(float(lg) - float(lo)) <= 2e-5 * max(1.0, abs(float(lo))), (float(lg), float(lo))
     (lg * 1.5).backward()
     close(pg.grad.cpu() / 1.5, pr.grad, rel=2e-4, mx=1e-3, what=f"loss grad {over}")
+
+
+@pytest.mark.parametrize("C,dims,P", [(32, (4, 4, 4), 64), (8, (4, 6, 4), 64), (64, (2, 4, 4), 32), (128, (2, 2, 2), 32)])
+def test_transformer_block_vs_oracle(ops, C, dims, P):
+    """TransformerBlock (pos_embed + LayerNorm + DSA incl. the line-353 scramble + conv51/BN + conv8) fwd and bwd."""
+    from fcd_b200.networks.blocks import TransformerBlock
+    from oracle import nets as onets
+    from oracle import synth
+    N = dims[0] * dims[1] * dims[2]
+    blk = TransformerBlock(input_size=N, hidden_size=C, proj_size=P, num_heads=4, dropout_rate=0.0, pos_embed=True)
+    sd = synth.synthetic_state_dict(synth.spec_of(blk.state_dict()), seed=7)
+    blk.load_state_dict(sd)
+    blk.conv8[0].p = 0.0
+    blk = blk.to(_dev()).train()
+    B = 2
+    x = rnd(B, C, *dims)
+    # oracle on the GPU in fp32 (same functional code the CPU oracle runs)
+    sdg = {("b." + k): v.to(_dev()).clone().requires_grad_(v.is_floating_point() and "running" not in k)
+           for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    bn = {}
+    ref = onets.transformer_block(sdg, "b", xr, True, bn)
+    dy = rnd(*ref.shape, seed=3)
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    grads = torch.autograd.grad(ref, [xr] + [sdg[k] for k in names], dy, allow_unused=True)
+    # calibration: the same oracle block under stock bf16 autocast (conv51's BatchNorm backward over B*N <= 128
+    # samples amplifies 16-bit rounding; see tests/test_gpu_models.py for the rationale)
+    sdc = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in sdg.items()}
+    xb = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        refb = onets.transformer_block(sdc, "b", xb, True, {})
+    gradsb = torch.autograd.grad(refb, [xb] + [sdc[k] for k in names], dy.to(refb.dtype), allow_unused=True)
+
+    def rl(a, b):
+        return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+    xc = cl(ops, x, True)
+    y = blk(xc)
+    close(ops.to_ncdhw(y, C), ref, rel=1e-2, mx=4e-2, what="transformer fwd")
+    y.backward(ops.to_channels_last(dy, ops.pad16(C)))
+    e_o, e_c = rl(ops.to_ncdhw(xc.grad, C), grads[0]), rl(gradsb[0].float(), grads[0])
+    assert e_o <= 2.5 * e_c + 1e-2, f"transformer dx: ours {e_o:.3e} vs stock bf16 {e_c:.3e}"
+    mine = dict(blk.named_parameters())
+    for k, g, gb in zip(names, grads[1:], gradsb[1:]):
+        if g is None or float(g.norm()) < 1e-6:
+            continue
+        e_o, e_c = rl(mine[k[2:]].grad, g), rl(gb.float(), g)
+        assert e_o <= 3.0 * e_c + 5e-2, f"transformer grad {k}: ours {e_o:.3e} vs stock bf16 {e_c:.3e}"
+    msd = blk.state_dict()
+    for k, v in bn.items():
+        if not k.endswith("num_batches_tracked"):
+            close(msd[k[2:]], v, rel=1e-2, mx=2e-2, what=k)
+
+
+def test_dsa_token_path_tight(ops):
+    """pos_embed + LayerNorm + qkvv + DSA (incl. the scramble) + gamma residual, WITHOUT the BatchNorm conv block:
+    well conditioned, so forward and every gradient are held to <= 1e-2 against fp32."""
+    from fcd_b200.networks.blocks import TransformerBlock
+    from oracle import nets as onets
+    from oracle import synth
+    for C, dims, P in [(32, (4, 4, 4), 64), (8, (4, 6, 4), 64), (64, (2, 4, 4), 32), (256, (2, 2, 2), 32)]:
+        N = dims[0] * dims[1] * dims[2]
+        blk = TransformerBlock(input_size=N, hidden_size=C, proj_size=P, num_heads=4, dropout_rate=0.0, pos_embed=True)
+        sd = synth.synthetic_state_dict(synth.spec_of(blk.state_dict()), seed=7)
+        blk.load_state_dict(sd)
+        blk = blk.to(_dev()).train()
+        B = 2
+        x = rnd(B, C, *dims)
+        sdg = {("b." + k): v.to(_dev()).clone().requires_grad_(v.is_floating_point() and "running" not in k)
+               for k, v in sd.items()}
+        xr = x.clone().requires_grad_(True)
+        t = xr.reshape(B, C, N).permute(0, 2, 1) + sdg["b.pos_embed"]
+        ln = F.layer_norm(t, (C,), sdg["b.norm.weight"], sdg["b.norm.bias"], 1e-5)
+        ref = t + sdg["b.gamma"] * onets.dsa(sdg, "b.dsa", ln)
+        dy = rnd(B, N, C, seed=3)
+        names = ["b.pos_embed", "b.norm.weight", "b.norm.bias", "b.gamma", "b.dsa.qkvv.weight", "b.dsa.EF",
+                 "b.dsa.temperature", "b.dsa.temperature2"]
+        grads = torch.autograd.grad(ref, [xr] + [sdg[k] for k in names], dy)
+        xc = cl(ops, x, True)
+        tt, lnn = ops.ln_pos(xc, blk.pos_embed, blk.norm.weight, blk.norm.bias, C, 1e-5)
+        y = blk.dsa(lnn, tt, blk.gamma)
+        close(y[..., :C].reshape(B, N, C), ref, rel=5e-3, mx=2e-2, what=f"dsa fwd C={C}")
+        dyc = torch.zeros_like(y)
+        dyc[..., :C] = dy.reshape(B, *dims, C).to(torch.bfloat16)
+        y.backward(dyc)
+        close(xc.grad[..., :C].reshape(B, N, C), grads[0].reshape(B, C, N).permute(0, 2, 1), rel=1e-2, mx=4e-2,
+              what=f"dsa dx C={C}")
+        mine = dict(blk.named_parameters())
+        for k, g in zip(names, grads[1:]):
+            close(mine[k[2:]].grad, g, rel=1.5e-2, mx=6e-2, what=f"dsa grad {k} C={C}")
+
+
+def test_dsa_dropout_is_reproducible_and_unbiased(ops):
+    """attn_drop / attn_drop_2 (p=0.1 in train mode, get_model.py:29): backward regenerates the forward's
+    counter-based mask (finite-difference consistency through the same seed) and E[out] matches p=0."""
+    B, C, dims, P, H = 2, 32, (4, 4, 4), 64, 4
+    N = 64
+    qkvv = rnd(B, 4 * C, *dims, scale=0.5)
+    t = rnd(B, C, *dims, seed=2)
+    EF = rnd(N, P, scale=0.125, seed=3)
+    t1, t2 = rnd(H, 1, 1, scale=0.1, seed=4) + 1.0, rnd(H, 1, 1, scale=0.1, seed=5) + 1.0
+    gamma = rnd(C, scale=0.1, seed=6) + 0.5
+    q, tt = ops.to_channels_last(qkvv, 4 * C), ops.to_channels_last(t)
+    y0 = ops.dsa_attention(q, tt, EF, t1, t2, gamma, C, H, P)
+    acc = torch.zeros_like(y0, dtype=torch.float32)
+    n_rep = 200
+    for i in range(n_rep):
+        acc += ops.dsa_attention(q, tt, EF, t1, t2, gamma, C, H, P, None, 0.1, 1000 + i).float()
+    close(acc / n_rep, y0.float(), rel=3e-2, mx=2e-1, what="dropout mean")
+    ya = ops.dsa_attention(q, tt, EF, t1, t2, gamma, C, H, P, None, 0.1, 77)
+    yb = ops.dsa_attention(q, tt, EF, t1, t2, gamma, C, H, P, None, 0.1, 77)
+    assert torch.equal(ya, yb) and not torch.equal(ya, y0)
+    # backward uses the forward's mask: d/d(gamma) of sum(y) == sum(xca + tsa) of that same masked forward
+    g = gamma.clone().requires_grad_(True)
+    ops.dsa_attention(q, tt, EF, t1, t2, g, C, H, P, None, 0.1, 77).float().sum().backward()
+    fd = (ya.float() - tt.float())[..., :C].sum(dim=(0, 1, 2, 3)) / gamma
+    close(g.grad, fd, rel=2e-2, mx=5e-2, what="dropout bwd mask")
+
+
+@pytest.mark.parametrize("Ci,Co,mode", [(16, 16, "add"), (32, 16, "concat"), (8, 4, "concat"), (16, 8, "plain")])
+def test_subpixel_upsample(ops, Ci, Co, mode):
+    B, D, H, W = 2, 4, 5, 6
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co * 8, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    b = rnd(Co * 8, scale=0.2, seed=2).requires_grad_(True)
+    skip = rnd(B, Co, 2 * D, 2 * H, 2 * W, seed=5)
+    xr, sr = x.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    u = F.conv3d(xr, w, b, padding=1)
+    u = u.reshape(B, Co, 2, 2, 2, D, H, W).permute(0, 1, 5, 2, 6, 3, 7, 4).reshape(B, Co, 2 * D, 2 * H, 2 * W)
+    u = F.avg_pool3d(F.pad(u, (1, 0, 1, 0, 1, 0)), 2, 1)
+    ref = u + sr if mode == "add" else (torch.cat((u, sr), 1) if mode == "concat" else u)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gs, gw, gb = torch.autograd.grad(ref, [xr, sr, w, b], dy, allow_unused=True)
+    xc, sc = cl(ops, x, True), cl(ops, skip, True)
+    w2, b2 = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y = ops.subpixel_upsample(xc, w2, b2, Co, sc if mode != "plain" else None, mode)
+    cq = ops.pad16(Co)
+    if mode == "concat":
+        got = torch.cat((ops.to_ncdhw(y[..., :cq], Co), ops.to_ncdhw(y[..., cq:], Co)), 1)
+        dyc = torch.cat((ops.to_channels_last(dy[:, :Co], cq), ops.to_channels_last(dy[:, Co:], cq)), -1)
+    else:
+        got = ops.to_ncdhw(y, Co)
+        dyc = ops.to_channels_last(dy, cq)
+    close(got, ref, what="subpixel fwd")
+    y.backward(dyc)
+    close(ops.to_ncdhw(xc.grad, Ci), gx, rel=8e-3, what="subpixel dx")
+    close(w2.grad, gw, rel=8e-3, what="subpixel dw")
+    close(b2.grad, gb, rel=8e-3, what="subpixel db")
+    if mode != "plain":
+        close(ops.to_ncdhw(sc.grad, Co), gs, what="subpixel dskip")
