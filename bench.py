@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the fcd_b200 hot path.   python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): MS_DSA_NET (feature_size 16, project_size 64, 'parallel' DSA, reference dropout
+p=0.1 active), bf16 compute, synthetic 2-channel 128^3 patches, batch 2 per GPU, DiceCELoss, AdamW(1e-4, wd 1e-5);
+one "step" = forward + fused loss + backward + gradient all-reduce (N>1) + optimizer step.  Weak scaling.
+
+  value : patches/s with the inputs resident in HBM (whole job, all ranks), CUDA-event timed, max over ranks.
+  e2e   : the same metric through the public API with HOST (pinned) inputs: the H2D copy of the batch and the D2H
+          read of the loss are inside every timed step.
+  roofline     : the conv kernel family (fcd_igemm + fcd_wgrad) measured with CUDA events inside one eager step.
+  cpu_baseline : the CPU oracle (oracle/, kind "port": the reference's MONAI dependency is not installable here)
+                 timed on the host cores on a bounded sample (rank 0, N=1 only).
+  aux          : sliding-window inference vols/s on a synthetic 256x256x192 volume (configs[4]).
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port) on the host cores.
+L2 note: every step streams > 3 GB of activations, far above the 126 MB L2 (config.l2 = "inputs_exceed_l2").
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms_dsa_net_train_patches_per_s"
+UNIT = "patches/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=2, help="patches per GPU")
+    ap.add_argument("--patch", type=int, default=128)
+    ap.add_argument("--model", default="ms_dsa_net")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="patches timed for the CPU baseline")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(model_type, patch, n_patches, warm=1):
+    """The reference's CPU implementation of the path: the oracle port (reference network files cannot travel, and
+    their MONAI dependency is not installable here) -- fp32, all host threads, batch 1, fwd + DiceCE + bwd."""
+    from oracle import losses as olosses
+    from oracle import nets as onets
+    from oracle import synth
+    import fcd_b200
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = fcd_b200.get_default_params()
+    params.update(model_type=model_type, patch_size=(patch,) * 3, loss="DiceCELoss")
+    # parameter names / shapes come from the product's module tree (identical to the reference's); values synthetic
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    spec = synth.spec_of(model.state_dict())
+    del model
+    sd = synth.synthetic_state_dict(spec, seed=1)
+    fk = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    leaf = {k: (v.requires_grad_(True) if k in fk else v) for k, v in sd.items()}
+    x = synth.image(1, 2, patch, seed=3)
+    y = synth.label(1, patch, seed=5)
+    times = []
+    for i in range(warm + n_patches):
+        t0 = time.perf_counter()
+        out = onets.forward(model_type, leaf, x, True, {})
+        loss = olosses.combined_loss(params, out, y)
+        loss.backward()
+        for k in fk:
+            leaf[k].grad = None
+        times.append(time.perf_counter() - t0)
+    t = times[warm:]
+    return len(t) / sum(t), sum(t) / len(t)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    k = max(1, min(args.steps, 3))
+    pps, sec = cpu_reference(args.model, args.patch, k, warm=1 if args.warmup > 0 else 0)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+        "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} train step (fwd + DiceCE + bwd), 2ch {args.patch}^3, batch 1, CPU"},
+        "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{k} patches of batch 1 after 1 warm-up, torch {torch.__version__} CPU fp32"},
+        "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import fcd_b200
+    from fcd_b200 import _lib, parallel, synthetic
+    from fcd_b200.inferers import sliding_window_inference
+
+    rank, local, world = parallel.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pk = peaks()
+
+    params = fcd_b200.get_default_params()
+    params.update(model_type=args.model, patch_size=(args.patch,) * 3, loss="DiceCELoss")
+    torch.manual_seed(42)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    model.apply(synthetic.initialize_weights)
+    model = model.to(dev).train()
+    loss_fn = fcd_b200.CombinedLoss(params, dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=params["lr"], weight_decay=params["weight_decay"], fused=True)
+    reducer = parallel.GradAllReducer(model.parameters())
+    reducer.sync_params()
+    B = args.batch
+    n_pool = 4
+    host = [synthetic.make_batch(B, 2, args.patch, seed=100 * rank + i, pin=True) for i in range(n_pool)]
+    sx = torch.empty_like(host[0][0], device=dev)
+    sy = torch.empty_like(host[0][1], device=dev)
+    sx.copy_(host[0][0])
+    sy.copy_(host[0][1])
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    static = {}
+
+    def fwd_bwd():
+        out = model(sx)
+        vae = None
+        if isinstance(out, (tuple, list)):
+            out, vae = out
+        loss = loss_fn(out, sy)
+        if vae is not None:
+            loss = loss + params["loss_vae_weight"] * vae
+        loss.backward()
+        return loss.detach()
+
+    # ---- eager warm-up (also configures every kernel's shared-memory attribute) + launch count + roofline pass
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        fwd_bwd()
+        reducer.allreduce()
+        opt.step()
+    torch.cuda.synchronize()
+    prof = _lib.Profiler()
+    _lib.set_profiler(prof)
+    opt.zero_grad(set_to_none=True)
+    fwd_bwd()
+    _lib.set_profiler(None)
+    agg = prof.summary()
+    gpu_launches = prof.launches
+    opt.step()
+
+    # ---- CUDA graph of forward + loss + backward (static input buffers, static gradient tensors)
+    graph = None
+    if not args.no_graph:
+        try:
+            opt.zero_grad(set_to_none=True)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    opt.zero_grad(set_to_none=True)
+                    fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static["loss"] = fwd_bwd()
+            torch.cuda.synchronize()
+        except Exception as e:  # keep the bench alive; the JSON line records that the step ran eagerly
+            graph = None
+            static["graph_error"] = f"{type(e).__name__}: {e}"[:200]
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            loss = static["loss"]
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = fwd_bwd()
+        reducer.allreduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_warm, n_steps, e2e):
+        it = 0
+        for _ in range(n_warm):
+            if e2e:
+                sx.copy_(host[it % n_pool][0], non_blocking=True)
+                sy.copy_(host[it % n_pool][1], non_blocking=True)
+                loss_host.copy_(step(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            else:
+                step()
+            it += 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            if e2e:
+                sx.copy_(host[it % n_pool][0], non_blocking=True)      # H2D of this step's batch (pinned)
+                sy.copy_(host[it % n_pool][1], non_blocking=True)
+                loss_host.copy_(step(), non_blocking=True)             # D2H of the step's loss ...
+                torch.cuda.current_stream().synchronize()              # ... read by the host every step (train.py:382)
+                _ = float(loss_host)
+            else:
+                step()
+            it += 1
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    W = max(args.warmup, 3)
+    graph_ok, graph_err = graph is not None, static.get("graph_error")
+    with ClockSampler(local) as clk:
+        ms_dev = timed(W, args.steps, e2e=False)
+        ms_e2e = timed(W, args.steps, e2e=True)
+    clocks = clk.summary()
+    patches = B * world * args.steps
+    value = patches / (ms_dev / 1e3)
+    e2e_value = patches / (ms_e2e / 1e3)
+    final_loss = float(loss_host)
+
+    # ---- roofline of the conv family from the profiled eager step
+    conv = [v for k, v in agg.items() if k.split(":")[0] in ("fcd_igemm", "fcd_wgrad")]
+    conv_ms = sum(v["ms"] for v in conv)
+    conv_fl = sum(v["flops"] for v in conv)
+    step_ms_eager = sum(v["ms"] for v in agg.values())
+    top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]
+    roof = {"bound": "tensor", "kernel": "fcd_igemm+fcd_wgrad (conv fwd/dgrad/wgrad family)",
+            "achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None, "peak": pk["tf_sust"],
+            "unit": "TFLOP/s", "frac": (conv_fl / (conv_ms * 1e-3) / 1e12 / pk["tf_sust"]) if conv_ms > 0 else None,
+            "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+            "share_of_step": conv_ms / step_ms_eager if step_ms_eager > 0 else None,
+            "launches": sum(v["calls"] for v in conv),
+            "top_calls_ms": {k: round(v["ms"], 3) for k, v in top}}
+    hbm = [v for k, v in agg.items() if k.split(":")[0] in ("fcd_norm_apply", "fcd_norm_stats", "fcd_norm_bwd")]
+    hbm_ms = sum(v["ms"] for v in hbm)
+    hbm_b = sum(v["bytes"] for v in hbm)
+    roof["hbm_family"] = {"kernel": "fcd_norm_stats/apply/bwd", "achieved_gbs": hbm_b / (hbm_ms * 1e-3) / 1e9
+                          if hbm_ms > 0 else None, "peak_gbs": pk["hbm"],
+                          "frac": hbm_b / (hbm_ms * 1e-3) / 1e9 / pk["hbm"] if hbm_ms > 0 else None,
+                          "share_of_step": hbm_ms / step_ms_eager if step_ms_eager > 0 else None}
+
+    # ---- sliding-window inference (configs[4]) : 256x256x192, roi 128, overlap 0.5 -> 18 windows
+    aux = {}
+    if not args.no_infer and args.model in ("ms_dsa_net", "baseunet", "segresnet"):
+        try:
+            del graph
+            static.clear()
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            model.eval()
+            vol = torch.randn((1, 2, 256, 256, 192), generator=torch.Generator().manual_seed(7)).pin_memory()
+            vol_d = torch.empty_like(vol, device=dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    vol_d.copy_(vol, non_blocking=True)
+                    sliding_window_inference(vol_d, args.patch, 2, model, overlap=0.5, label_mode="argmax")
+                barrier()
+                n_vol = 3
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n_vol):
+                    vol_d.copy_(vol, non_blocking=True)
+                    _, lab = sliding_window_inference(vol_d, args.patch, 2, model, overlap=0.5, label_mode="argmax")
+                    lab_h = lab.to("cpu", non_blocking=False)
+                e1.record()
+                barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ms = float(t)
+            aux = {"metric": "ms_dsa_net_sliding_window_vols_per_s", "value": n_vol / (ms / 1e3), "unit": "vols/s",
+                   "workload": "2ch 256x256x192, roi 128^3, overlap 0.5, 18 windows sharded over ranks, "
+                               "H2D volume + D2H uint8 label map inside the timed region",
+                   "fg_fraction": float(lab_h.float().mean())}
+        except Exception as e:
+            aux = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        pps, sec = cpu_reference(args.model, args.patch, args.cpu_sample, warm=1)
+        cpu = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} patches of batch 1 (fwd + DiceCE + bwd) after 1 warm-up, fp32, "
+                         f"{cores} host threads; ~{sec:.1f} s per patch"}
+    nbytes_in = sx.numel() * 4 + sy.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} train step: fwd + DiceCELoss + bwd + AdamW, 2ch {args.patch}^3 patches, "
+                               f"batch {B}/GPU, dropout p=0.1 active", "global_batch": B * world,
+                   "parallelism": f"dp{world}", "cuda_graph": graph_ok, "l2": "inputs_exceed_l2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": gpu_launches * args.steps, "gpu_launches_per_step": gpu_launches,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "aux": aux, "final_loss": final_loss,
+    }
+    if graph_err:
+        line["config"]["graph_error"] = graph_err
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,12 @@ _CT = {
     "cudaStream_t": ctypes.c_void_p,
 }
 
+# CUDA kernels launched by one call of each entry point (for bench.py's gpu_launches count)
+KERNELS_PER_CALL = {
+    "fcd_norm_stats": 2, "fcd_colsum": 2, "fcd_norm_bwd": 3, "fcd_outconv_bwd": 2, "fcd_loss_fwd": 2,
+    "fcd_ln_bwd": 2, "fcd_dsa_fwd": 4, "fcd_dsa_bwd": 6, "fcd_mse_fwd": 2,
+}
+
 
 def parse_header(path: str = HEADER):
     """Return {name: [(param_name, ctype), ...]} for every FCD_API prototype in the header."""
@@ -77,20 +83,70 @@ def _ptr(v):
     return v
 
 
+class Profiler:
+    """Per-entry-point CUDA-event timing + algorithmic work accounting (used by bench.py for the roofline object).
+
+    Events are recorded on the launching stream around each C-ABI call; nothing synchronises until summary()."""
+
+    def __init__(self):
+        self.records = []          # (name, tag, start_event, end_event, flops, bytes)
+        self.launches = 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, e0, e1, flops, nbytes in self.records:
+            key = name if tag is None else f"{name}:{tag}"
+            a = agg.setdefault(key, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += nbytes
+        return agg
+
+
+_profiler: Profiler | None = None
+_pending_work = [None, 0.0, 0.0]     # (tag, flops, bytes) announced by ops.py for the NEXT call
+LAUNCHES = 0                         # kernels launched through this binding since import
+
+
+def set_profiler(p: Profiler | None):
+    global _profiler
+    _profiler = p
+
+
+def note_work(tag=None, flops=0.0, nbytes=0.0):
+    """ops.py announces the algorithmic FLOPs / bytes of the call it is about to make (only read when profiling)."""
+    if _profiler is not None:
+        _pending_work[0], _pending_work[1], _pending_work[2] = tag, float(flops), float(nbytes)
+
+
 def call(name: str, **kw):
+    global LAUNCHES
     params = PROTOS[name]
     fn = getattr(lib(), name)
-    if "stream" in [p for p, _ in params] and "stream" not in kw:
-        kw["stream"] = torch.cuda.current_stream().cuda_stream
     args = []
     for pname, ct in params:
+        if pname == "stream" and "stream" not in kw:
+            kw["stream"] = torch.cuda.current_stream().cuda_stream
         if pname not in kw:
             raise TypeError(f"{name}: missing argument {pname}")
         v = kw.pop(pname)
         args.append(_ptr(v) if ct is ctypes.c_void_p else v)
     if kw:
         raise TypeError(f"{name}: unexpected arguments {sorted(kw)}")
+    prof = _profiler
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(*args)
+    if prof is not None:
+        e1.record()
+        prof.records.append((name, _pending_work[0], e0, e1, _pending_work[1], _pending_work[2]))
+        prof.launches += KERNELS_PER_CALL.get(name, 1)
+        _pending_work[0], _pending_work[1], _pending_work[2] = None, 0.0, 0.0
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed with code {rc}" + (" (unsupported shape)" if rc == -1 else " (CUDA error)"))
     return rc
@@ -99,6 +155,3 @@ def call(name: str, **kw):
 def query(name: str) -> int:
     """For the argument-less sizing helpers (fcd_loss_blocks, ...): they return a count, not an error code."""
     return getattr(lib(), name)()
-
-
-LAUNCHES = 0   # number of C-ABI kernel-launching calls made (bench.py reports it as gpu_launches evidence)

@@ -137,6 +137,7 @@ class ConvFn(Function):
         wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
         Do, Ho, Wo = [(s + 2 * pad - k) // stride + 1 for s in (D, H, W)]
         y = _empty((B, Do, Ho, Wo, Np), x)
+        _lib.note_work("fwd", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
         call("fcd_igemm", A=x, lda=ld(x), W=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, Ds=D, Hs=H, Ws=W,
              Dm=Do, Hm=Ho, Wm=Wo, K=Kp, N=Np, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=0, out_mode=0,
              accumulate=0, Cq=0)
@@ -157,10 +158,12 @@ class ConvFn(Function):
         if ctx.needs_input_grad[0]:
             wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
             dx = _empty((B, D, H, W, Kp), x)
+            _lib.note_work("dgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
             call("fcd_igemm", A=dy, lda=ld(dy), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=Do, Hs=Ho, Ws=Wo,
                  Dm=D, Hm=H, Wm=W, K=Np, N=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=1, out_mode=0,
                  accumulate=0, Cq=0)
         if ctx.needs_input_grad[1]:
+            _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
             part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
             dw = torch.empty_like(weight, dtype=torch.float32)
             call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=T, N=Co, K=Ci, Np=Np, Kp=Kp, sn=Ci * T, sk=T,
@@ -195,6 +198,7 @@ class UpConcatFn(Function):
         Cs = skip.shape[4]
         wp = pack_weight(weight, 8, Co, Ci, Cq, Kp, sn=8, sk=Co * 8, st=1)
         buf = _empty((B, 2 * D, 2 * H, 2 * W, Cq + Cs), x)
+        _lib.note_work("deconv_fwd", 2.0 * B * D * H * W * 8 * Co * Ci, 2.0 * B * D * H * W * (Ci + 8 * Co))
         call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=None, Bn=B, Ds=D, Hs=H, Ws=W, Dm=D, Hm=H,
              Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0, Cq=Cq)
         right = buf[..., Cq:]
@@ -215,6 +219,7 @@ class UpConcatFn(Function):
         if ctx.needs_input_grad[0]:
             wt = pack_weight(weight, 8, Ci, Co, Kp, Cq, sn=Co * 8, sk=8, st=1)
             dx = _empty((B, D, H, W, Kp), x)
+            _lib.note_work("deconv_dgrad", 2.0 * B * D * H * W * 8 * Co * Ci, 2.0 * B * D * H * W * (Ci + 8 * Co))
             call("fcd_igemm", A=dleft, lda=ld(dbuf), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=2 * D, Hs=2 * H,
                  Ws=2 * W, Dm=D, Hm=H, Wm=W, K=Cq, N=Kp, kd=2, kh=2, kw=2, stride=2, pad=0, mode=0, out_mode=0,
                  accumulate=0, Cq=0)
@@ -223,6 +228,7 @@ class UpConcatFn(Function):
             M = B_ * D * H * W
             ns = _nsplit(M, Kp, Cq, 8)
             part = torch.empty((ns, 8, Kp, Cq), dtype=torch.float32, device=x.device)
+            _lib.note_work("deconv_wgrad", 2.0 * B_ * D * H * W * 8 * Co * Ci, 2.0 * B_ * D * H * W * (Ci + 8 * Co))
             call("fcd_wgrad", Q=x, ldq=ld(x), P=dleft, ldp=ld(dbuf), part=part, Bn=B_, Ds=2 * D, Hs=2 * H, Ws=2 * W,
                  Dm=D, Hm=H, Wm=W, Np=Kp, Kp=Cq, kd=2, kh=2, kw=2, stride=2, pad=0, nsplit=ns)
             dw = torch.empty_like(weight, dtype=torch.float32)
@@ -280,6 +286,7 @@ def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0
     part = torch.empty((B, nchunk, 2, C), dtype=torch.float32, device=x.device)
     mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
     rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    _lib.note_work(None, 0.0, 2.0 * B * S * C)
     call("fcd_norm_stats", x=x, ld=ld(x), part=part, mean=mean, rstd=rstd, B=B, S=S, C=C, nchunk=nchunk, mode=mode,
          eps=eps, running_mean=running_mean, running_var=running_var, crun=crun, momentum=momentum)
     return mean, rstd
@@ -314,6 +321,7 @@ class NormActFn(Function):
         if x2 is not None:
             mean2, rstd2 = _stats(x2, mode, eps)
         y = _empty((B, D, H, W, C), x1)
+        _lib.note_work(None, 0.0, 2.0 * B * S * C * (2 + (x2 is not None) + (res is not None)))
         call("fcd_norm_apply", x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1, gamma1=g, beta1=b, x2=x2,
              ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2, res=res,
              ldr=ld(res) if res is not None else 0, y=y, ldy=C, B=B, S=S, C=C, slope=slope)
@@ -338,6 +346,8 @@ class NormActFn(Function):
         if has_affine:
             dgamma = torch.zeros((C,), dtype=torch.float32, device=x1.device)
             dbeta = torch.zeros((C,), dtype=torch.float32, device=x1.device)
+        nin = 2 + (y is not None) + (x2 is not None)
+        _lib.note_work(None, 0.0, 2.0 * B * S * C * (2 * nin + 1 + (x2 is not None) + (dres is not None)))
         call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1,
              gamma1=g if has_affine else None, x2=x2, ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2,
              part=part, coef=coef, dgamma=dgamma, dbeta=dbeta, dx1=dx1, ldd1=C, dx2=dx2, ldd2=C, dres=dres, lddr=C,

@@ -1,0 +1,171 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the module trees mirror the
+reference's state-dict layout, window enumeration matches the oracle, the loss parameter mapping, the no-CPU-fallback
+guarantee, and the world_size-2 (gloo) data-parallel plumbing."""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+from tests import helpers as H
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from fcd_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    lib = _lib.lib()                       # ctypes.CDLL: works without a GPU
+    for name in protos:
+        assert hasattr(lib, name), f"libfcd_b200.so lacks {name} declared in include/fcd_b200.h"
+    # argument-less sizing helpers run without touching the device state
+    assert _lib.query("fcd_loss_blocks") > 0
+
+
+def test_call_rejects_cpu_tensors_and_bad_arguments():
+    from fcd_b200 import _lib
+    with pytest.raises(TypeError):
+        _lib.call("fcd_add", a=None)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        _lib._ptr(torch.zeros(4))
+
+
+@pytest.mark.parametrize("name", H.MODEL_CASES)
+def test_state_dict_layout_matches_reference(name):
+    import fcd_b200
+    meta, _ = H.load_case(name)
+    params = fcd_b200.get_default_params()
+    params.update(model_type=meta["model_type"], patch_size=(meta["patch"],) * 3, feature_size=meta["feature_size"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in meta["spec"]]
+    for k, s, d in meta["spec"]:
+        assert tuple(sd[k].shape) == tuple(s) and str(sd[k].dtype).endswith(d), k
+    assert params["model_returns_vaeloss"] == ("vae" in meta["model_type"])
+
+
+def test_default_config_parameter_counts():
+    """43,524,802 (MS_DSA_NET) and 22,966,690 (BaseUNet) trainable parameters."""
+    import fcd_b200
+    for mt, n in (("MS_DSA_NET", 43524802), ("BaseUNet", 22966690)):
+        params = fcd_b200.get_default_params()
+        params.update(model_type=mt, patch_size=(128,) * 3)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            model, _ = fcd_b200.get_model(params)
+        assert sum(p.numel() for p in model.parameters() if p.requires_grad) == n
+        assert f"Trainable parameters: {n}" in buf.getvalue()      # get_model.py:246-248 prints it
+
+
+def test_get_model_contract():
+    import fcd_b200
+    params = fcd_b200.get_default_params()
+    params["model_type"] = "segresnetvae_dsa"
+    model, p = fcd_b200.get_model(params, return_model=False)        # train.py:437
+    assert model is None and p["model_returns_vaeloss"] is True
+    params["model_type"] = "swinunetr"
+    with pytest.raises(NotImplementedError):
+        fcd_b200.get_model(params)
+
+
+def test_no_cpu_fallback():
+    import fcd_b200
+    params = fcd_b200.get_default_params()
+    params.update(model_type="baseunet", patch_size=(64,) * 3, feature_size=4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 2, 64, 64, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fcd_b200.CombinedLoss(params, "cpu")(torch.zeros(1, 2, 8, 8, 8), torch.zeros(1, 1, 8, 8, 8))
+    from fcd_b200.inferers import sliding_window_inference
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sliding_window_inference(torch.zeros(1, 2, 8, 8, 8), 8, 1, lambda x: x)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fcd_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def test_loss_config_mapping():
+    from fcd_b200.get_loss import CombinedLoss, loss_config
+    p = H.loss_params(dict(loss_params=dict(loss="DiceFocalLoss", gamma_focal=3.0, lambda_focal=2.0,
+                                            tv_loss_weight=0.1, tv_loss_norm="l2", tvloss_exclude_borders=True)))
+    c = loss_config(p)
+    assert c["kind"] == 2 and c["gamma"] == 3.0 and c["lambda_2"] == 2.0 and c["tv_norm"] == 2 and c["tv_exclude"] == 1
+    for bad in (dict(loss="GeneralizedDiceLoss"), dict(sigmoid=True), dict(chans_out=3)):
+        q = dict(p)
+        q.update(bad)
+        with pytest.raises(NotImplementedError):
+            loss_config(q)
+    q = dict(p)
+    q["boundaryloss_weight"] = 0.3
+    with pytest.raises(NotImplementedError):
+        CombinedLoss(q, "cpu")
+
+
+def test_window_enumeration_matches_oracle():
+    from fcd_b200.inferers import window_starts
+    from oracle import inferer as oinf
+    for size in [(256, 256, 192), (182, 218, 182), (80, 72, 48), (24, 40, 32), (128, 128, 128), (130, 129, 257)]:
+        for roi in (32, 128):
+            for ov in (0.0, 0.25, 0.5, 0.75):
+                r = (roi,) * 3
+                s = tuple(max(a, b) for a, b in zip(size, r))
+                assert window_starts(s, r, ov) == oinf.window_starts(s, r, ov)
+    assert window_starts((256, 256, 192), (128,) * 3, 0.5) == [[0, 64, 128], [0, 64, 128], [0, 64]]   # 18 windows
+
+
+def test_shard_range_partitions_work():
+    from fcd_b200.parallel import shard_range
+    for n in (1, 9, 18, 100):
+        for w in (1, 2, 4, 8):
+            got = sorted(i for r in range(w) for i in shard_range(n, r, w))
+            assert got == list(range(n))
+
+
+def _ddp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from fcd_b200.parallel import GradAllReducer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(rank)                                   # replicas start DIFFERENT on purpose
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+        red = GradAllReducer(net.parameters())
+        red.sync_params(src=0)
+        w0 = [p.detach().clone() for p in net.parameters()]
+        x = torch.full((4, 5), float(rank + 1))
+        net(x).sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        red.allreduce()
+        gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+        for g, lst in zip(local, gathered):
+            dist.all_gather(lst, g)
+        ok = all(torch.allclose(p.grad, sum(lst) / world, atol=1e-6) for p, lst in zip(net.parameters(), gathered))
+        ws = [[torch.zeros_like(w) for _ in range(world)] for w in w0]
+        for w, lst in zip(w0, ws):
+            dist.all_gather(lst, w)
+        same = all(torch.equal(lst[0], lst[1]) for lst in ws)
+        ret[rank] = bool(ok and same)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_allreduce_world2_gloo():
+    """N>1 data-parallel path on CPU: parameters broadcast from rank 0, gradients averaged over ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] is True and ret[1] is True
