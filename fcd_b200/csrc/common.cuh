@@ -30,8 +30,15 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
     return p;
 }
 
-__device__ __forceinline__ bf16x8 ld8(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
-__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+// one 128-bit access each (a plain struct copy is split into four 32-bit accesses by the member-wise bfloat162 copy)
+__device__ __forceinline__ bf16x8 ld8(const bf16* p) {
+    bf16x8 r;
+    *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
 
 // streaming (read-once) 128-bit load that does not allocate in L1
 __device__ __forceinline__ bf16x8 ld8_stream(const bf16* p) {

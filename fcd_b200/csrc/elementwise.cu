@@ -531,6 +531,16 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
     FCD_LAUNCH_CHECK();
 }
 
+// mean/rstd from partial (sum, sum of squares) rows part[B][nchunk][2][C] -- the second half of fcd_norm_stats, for
+// producers that emit the partials themselves (fcd_conv3_tc's fused epilogue).
+FCD_API int fcd_norm_finalize(const float* part, float* mean, float* rstd, int B, long long S, int C, int nchunk,
+                              int mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
+                              cudaStream_t st) {
+    norm_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
+                                                             running_mean, running_var, crun, momentum);
+    FCD_LAUNCH_CHECK();
+}
+
 // out[c] = sum over rows of x[row][c]  (bias gradients).  part: nchunk*2*C floats.
 FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, long long rows, int C, int nchunk,
                        cudaStream_t st) {

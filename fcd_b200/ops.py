@@ -8,6 +8,8 @@ torch is used for allocation (torch.empty) and for O(C) bookkeeping on parameter
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
@@ -120,6 +122,24 @@ def _colsum(x, C):
     return out[:C]
 
 
+USE_TC = os.environ.get("FCD_TC", "1") != "0"     # tcgen05 conv path (debug switch; the default is on)
+_LAST_PART = [None]                               # fused InstanceNorm partials of the most recent ConvFn.forward
+
+
+def _tc_nseg(B, D, H, W, K, N, k, stride, pad, bias):
+    """d-segment count if the tcgen05 kernel takes this conv, else 0."""
+    if not USE_TC or k != 3 or stride != 1 or pad != 1 or bias is not None:
+        return 0
+    return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, N)
+
+
+def _w32(weight):
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    return w
+
+
 class ConvFn(Function):
     """nn.Conv3d (k in {1,3}, stride in {1,2}, pad = (k-1)//2 or given) and nn.Linear (k=1) on channels-last rows.
 
@@ -134,13 +154,25 @@ class ConvFn(Function):
         T = k ** 3
         Np = pad16(Co)
         seg, segpad = cin_seg if cin_seg is not None else (Ci, Kp)
-        wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
         Do, Ho, Wo = [(s + 2 * pad - k) // stride + 1 for s in (D, H, W)]
         y = _empty((B, Do, Ho, Wo, Np), x)
         _lib.note_work("fwd", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
-        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, Ds=D, Hs=H, Ws=W,
-             Dm=Do, Hm=Ho, Wm=Wo, K=Kp, N=Np, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=0, out_mode=0,
-             accumulate=0, Cq=0)
+        nseg = _tc_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias)
+        _LAST_PART[0] = None
+        if nseg > 0:
+            part = None
+            if Np <= 32:
+                nchunk = (H // 16) * (W // 8) * nseg
+                part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
+                _LAST_PART[0] = (part, nchunk)
+            call("fcd_conv3_tc", A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
+                 ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
+                 nseg=nseg)
+        else:
+            wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
+            call("fcd_igemm", A=x, lda=ld(x), W=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, Ds=D, Hs=H, Ws=W,
+                 Dm=Do, Hm=Ho, Wm=Wo, K=Kp, N=Np, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=0, out_mode=0,
+                 accumulate=0, Cq=0)
         ctx.save_for_backward(x, weight)
         ctx.cfg = (k, stride, pad, seg, segpad, bias is not None)
         return y
@@ -156,12 +188,19 @@ class ConvFn(Function):
         T = k ** 3
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
             dx = _empty((B, D, H, W, Kp), x)
             _lib.note_work("dgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
-            call("fcd_igemm", A=dy, lda=ld(dy), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=Do, Hs=Ho, Ws=Wo,
-                 Dm=D, Hm=H, Wm=W, K=Np, N=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=1, out_mode=0,
-                 accumulate=0, Cq=0)
+            nseg = _tc_nseg(B, D, H, W, Np, Kp, k, stride, pad, None)
+            if nseg > 0:
+                # dX = correlation of dY with the mirrored kernel: output channels = Cin (in concat segments)
+                call("fcd_conv3_tc", A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
+                     ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
+                     flip=1, nseg=nseg)
+            else:
+                wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
+                call("fcd_igemm", A=dy, lda=ld(dy), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=Do, Hs=Ho, Ws=Wo,
+                     Dm=D, Hm=H, Wm=W, K=Np, N=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=1, out_mode=0,
+                     accumulate=0, Cq=0)
         if ctx.needs_input_grad[1]:
             _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
             part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
@@ -177,7 +216,11 @@ class ConvFn(Function):
 def conv3d(x, weight, bias=None, k=3, stride=1, pad=None, cin_seg=None):
     if pad is None:
         pad = (k - 1) // 2
-    return ConvFn.apply(x, weight, bias, k, stride, pad, cin_seg)
+    y = ConvFn.apply(x, weight, bias, k, stride, pad, cin_seg)
+    if _LAST_PART[0] is not None:      # statistics of y came out of the conv epilogue: the next norm skips its pass
+        y._fcd_part = _LAST_PART[0]
+        _LAST_PART[0] = None
+    return y
 
 
 def linear(x, weight):
@@ -282,6 +325,14 @@ def _nchunk(B, S):
 def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0.1):
     B, D, H, W, C = x.shape
     S = D * H * W
+    fused = getattr(x, "_fcd_part", None)
+    if fused is not None and fused[0].shape[0] == B and fused[0].shape[3] == C:
+        part, nchunk = fused
+        mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        call("fcd_norm_finalize", part=part, mean=mean, rstd=rstd, B=B, S=S, C=C, nchunk=nchunk, mode=mode, eps=eps,
+             running_mean=running_mean, running_var=running_var, crun=crun, momentum=momentum)
+        return mean, rstd
     nchunk = _nchunk(B, S)
     part = torch.empty((B, nchunk, 2, C), dtype=torch.float32, device=x.device)
     mean = torch.empty((B, C), dtype=torch.float32, device=x.device)

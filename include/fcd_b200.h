@@ -45,6 +45,18 @@ FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, i
                              long long sn, long long sk, long long st, int kseg, int ksegpad, int accumulate,
                              cudaStream_t stream);
 
+/* tcgen05/TMEM implicit-GEMM path of the 3x3x3 stride-1 pad-1 convs (conv_blocks.py:393-416 conv1/conv2 of
+ * UnetResBlock; MONAI ResBlock segresnet_dsa.py:102) and, with flip=1, their data gradients.  TMA halo planes in,
+ * NDHWC bf16 out, weights read straight from the fp32 parameter (no pack kernel), optional fused InstanceNorm partial statistics part[Bn][nchunk][2][N] (sum, sum of squares of the
+ * rounded outputs; nchunk = (H/16)*(W/8)*nseg) to be finished by fcd_norm_finalize.  fcd_conv3_tc_nseg returns the
+ * number of d-segments to use (0: shape unsupported -> use fcd_igemm).  fcd_tc_error: first timed-out pipeline wait
+ * since the last call (0 = none; test / debug aid, synchronises the device). */
+FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N);
+FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
+                         long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
+                         int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream);
+FCD_API int fcd_tc_error(void);
+
 /* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382) ---- */
 FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int Wo, int C, cudaStream_t stream);
 FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,
@@ -56,6 +68,9 @@ FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void*
 FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean, float* rstd, int B, long long S,
                            int C, int nchunk, int mode, float eps, float* running_mean, float* running_var,
                            int crun, float momentum, cudaStream_t stream);
+FCD_API int fcd_norm_finalize(const float* part, float* mean, float* rstd, int B, long long S, int C, int nchunk,
+                              int mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
+                              cudaStream_t stream);
 FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, long long rows, int C, int nchunk,
                        cudaStream_t stream);
 FCD_API int fcd_norm_apply(const void* x1, long long ld1, const float* mean1, const float* rstd1, const float* gamma1,

@@ -1,0 +1,114 @@
+"""GPU parity of the tcgen05/TMEM implicit-GEMM conv (fcd_conv3_tc) against a plain PyTorch fp32 reference of the same
+op on the same bf16-exact inputs: forward, fused InstanceNorm statistics, data gradient (flip path), and the
+concat-segment weight maps.  Tolerance as in test_gpu_ops.py: outputs are bf16 (2^-9 rounding), math is fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.test_gpu_ops import cl, close, rnd
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from fcd_b200 import ops as _ops
+    assert _ops.USE_TC
+    return _ops
+
+
+def tc_error():
+    from fcd_b200 import _lib
+    return _lib.lib().fcd_tc_error()
+
+
+TC_CASES = [
+    # B, Ci, Co, D, H, W
+    (1, 16, 16, 5, 16, 8),
+    (2, 16, 16, 9, 32, 16),
+    (1, 2, 16, 6, 16, 16),        # first layer: 2 real input channels in a 16-channel row
+    (2, 32, 32, 7, 16, 24),
+    (1, 32, 16, 4, 32, 8),
+    (1, 16, 32, 3, 16, 8),
+    (1, 64, 32, 5, 16, 16),
+    (1, 32, 64, 5, 16, 8),
+    (1, 24, 12, 1, 16, 8),        # single plane, ragged real channel counts
+    (1, 16, 16, 40, 16, 8),       # several d-segments per column
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", TC_CASES)
+def test_conv3_tc_fwd_bwd(ops, B, Ci, Co, D, H, W):
+    from fcd_b200 import _lib
+    Kp, Np = ops.pad16(Ci), ops.pad16(Co)
+    assert _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, Kp, Np) > 0, "case must be taken by the tcgen05 kernel"
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gw = torch.autograd.grad(ref, [xr, w], dy)
+
+    xc = cl(ops, x, True)
+    w2 = w.detach().clone().requires_grad_(True)
+    before = _lib.LAUNCHES
+    y = ops.conv3d(xc, w2, None, k=3)
+    assert _lib.LAUNCHES == before + 1, "tcgen05 conv is ONE launch (no weight-pack kernel)"
+    assert tc_error() == 0
+    close(ops.to_ncdhw(y, Co), ref, what="tc conv fwd")
+    if Np > Co:
+        assert float(y[..., Co:].abs().max()) == 0.0
+    # fused statistics == statistics of the stored (rounded) output
+    if Np <= 32:
+        part, nchunk = y._fcd_part
+        s = part.sum(1)                                   # [B, 2, Np]
+        yf = y.float().reshape(B, -1, Np)
+        close(s[:, 0], yf.sum(1), rel=1e-4, mx=1e-3, what="fused sum")
+        close(s[:, 1], (yf * yf).sum(1), rel=1e-4, mx=1e-3, what="fused sum of squares")
+    y.backward(ops.to_channels_last(dy, Np))
+    assert tc_error() == 0
+    close(ops.to_ncdhw(xc.grad, Ci), gx, what="tc conv dgrad")
+    if Kp > Ci:
+        assert float(xc.grad[..., Ci:].abs().max()) == 0.0
+    close(w2.grad, gw, rel=6e-3, what="conv wgrad")
+
+
+def test_conv3_tc_matches_legacy_bitwise_layout(ops):
+    """Same conv through the tcgen05 kernel and the mma.sync kernel: both accumulate bf16 products in fp32, so the
+    bf16 outputs agree to 1 ulp almost everywhere (summation order differs)."""
+    x = rnd(2, 32, 8, 32, 32)
+    w = rnd(16, 32, 3, 3, 3, scale=0.05, seed=1)
+    xc = ops.to_channels_last(x)
+    y_tc = ops.conv3d(xc, w, None, k=3)
+    ops.USE_TC = False
+    try:
+        y_old = ops.conv3d(xc, w, None, k=3)
+    finally:
+        ops.USE_TC = True
+    assert tc_error() == 0
+    close(y_tc, y_old, rel=3e-3, mx=1e-2, what="tc vs legacy")
+
+
+def test_conv3_tc_concat_segments(ops):
+    """Input rows made of two concat segments (conv_blocks.py:685): 2 x (12 real channels padded to 16)."""
+    B, D, H, W = 1, 4, 16, 8
+    a, b = rnd(B, 12, D, H, W), rnd(B, 12, D, H, W, seed=7)
+    w = rnd(16, 24, 3, 3, 3, scale=0.07, seed=1).requires_grad_(True)
+    xr = torch.cat([a, b], 1).requires_grad_(True)
+    ref = F.conv3d(xr, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gw = torch.autograd.grad(ref, [xr, w], dy)
+    buf = torch.cat([ops.to_channels_last(a), ops.to_channels_last(b)], -1).requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    y = ops.conv3d(buf, w2, None, k=3, cin_seg=(12, 16))
+    close(ops.to_ncdhw(y, 16), ref, what="segmented fwd")
+    y.backward(ops.to_channels_last(dy, 16))
+    assert tc_error() == 0
+    g = buf.grad
+    close(torch.cat([ops.to_ncdhw(g[..., :16].contiguous(), 12), ops.to_ncdhw(g[..., 16:].contiguous(), 12)], 1), gx,
+          what="segmented dgrad")
+    assert float(g[..., 12:16].abs().max()) == 0.0 and float(g[..., 28:].abs().max()) == 0.0
+    close(w2.grad, gw, rel=6e-3, what="segmented wgrad")

@@ -1,0 +1,37 @@
+"""Time the conv kernels on the layer shapes of MS_DSA_NET (batch 2, 128^3): tcgen05 vs legacy mma.sync, fwd and dgrad.
+python tools/time_conv.py"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from fcd_b200 import ops, _lib
+
+dev = torch.device("cuda:0")
+SHAPES = [(2, 16, 16, 128), (2, 32, 16, 128), (2, 16, 32, 64), (2, 32, 32, 64), (2, 64, 32, 64), (2, 32, 64, 32)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def bench(fn, n=5):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        torch.cuda._sleep(4_000_000)      # ~2 ms of GPU spin: the CPU enqueues fn() meanwhile (no launch gap in the timing)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+
+for B, Ci, Co, S in SHAPES:
+    x = torch.randn(B, S, S, S, Ci, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Co, Ci, 3, 3, 3, device=dev) * 0.05)
+    gf = 2.0 * B * S ** 3 * Ci * Co * 27 / 1e9
+    res = {}
+    for tc in (True, False):
+        ops.USE_TC = tc
+        with torch.no_grad():
+            t = bench(lambda: ops.conv3d(x, w, None, k=3))
+        res[tc] = t
+    print(f"conv {Ci:3d}->{Co:3d} @{S}^3 b{B}: {gf:6.1f} GF  tc {res[True]:.3f} ms ({gf / res[True]:.0f} TF/s)  "
+          f"legacy {res[False]:.3f} ms ({gf / res[False]:.0f} TF/s)  err {_lib.lib().fcd_tc_error()}")
