@@ -5,7 +5,7 @@
 //   out[b, z, y, x, n] = sum_{kd,kh,kw,k} in[b, z+kd-1, y+kh-1, x+kw-1, k] * Wp[tap][n][k]        (tap = (kd*3+kh)*3+kw)
 //
 // Decomposition.  A work item is a column of output planes: batch b, a 16(h) x 8(w) tile, planes [d0, d0+DL).
-// A persistent CTA (one per SM, 7 warps) marches down the column:
+// A persistent CTA (one per SM, 9 warps) marches down the column:
 //   warps 0-1 producers: one halo plane (18 x 10 voxels x CIN) per step into a ring of NST stages, stored as
 //           [CIN/8][18*10 voxels][8 ch] -- the UMMA no-swizzle K-major canonical layout (core matrix = 8 consecutive
 //           voxels x 16 B).  The channel de-interleave makes every element a 16 B piece, so the feed is 16 B
@@ -13,12 +13,13 @@
 //           multiplied), completion handed to the MMA warp through an mbarrier after a generic->async proxy fence.
 //           (Measured on B200: the same box through a 5-D TMA tensor map is request-rate bound -- one 16 B inner row
 //           per ~6.5 cycles, 3300 cycles per Cin=16 plane against an 860-cycle MMA budget -- see DESIGN.md.)
-//   warp 2  MMA issuer (one thread): per output plane 27 * CIN/16 tcgen05.mma of M=128 voxels x N=COUT x K=16.  A tap
+//   warps 2-4 MMA issuers (warp kd owns input plane z+kd-1): per output plane 27 * CIN/16 tcgen05.mma of M=128 voxels
+//           x N=COUT x K=16 into three TMEM accumulators.  A tap
 //           shift is nothing but a different start address of the A descriptor inside the halo plane
 //           ((kh*10 + kw) * 16 B), so each halo plane is read from HBM/L2 once and reused by all 27 taps (9 per
 //           plane x 3 output planes).  All 27 weight taps stay resident in shared memory.  Two TMEM accumulators
 //           ping-pong so the epilogue of plane z overlaps the MMAs of plane z+1.
-//   warps 3-6 epilogue: tcgen05.ld (one voxel row of COUT fp32 per thread) -> bf16 -> 16 B stores into the NDHWC
+//   warps 5-8 epilogue: tcgen05.ld (one voxel row of COUT fp32 per thread) -> bf16 -> 16 B stores into the NDHWC
 //           output (any row pitch: writes straight into concat buffers), plus the per-(b, channel) sum / sum of
 //           squares of the ROUNDED outputs for the InstanceNorm that follows every conv (conv_blocks.py:439-452),
 //           so the separate statistics pass over the tensor disappears.
@@ -31,6 +32,11 @@ using namespace tc;
 constexpr int TH = 16, TW = 8;            // output tile per plane (UMMA M = 128 voxels)
 constexpr int HH = TH + 2, HW = TW + 2;   // halo plane
 constexpr int HV = HH * HW;               // 180 voxels
+
+constexpr int NPROD = 2;                  // producer warps
+constexpr int NMMA = 3;                   // MMA-issuing warps: one per kd tap plane, each with its own accumulator
+constexpr int NTHREADS = 32 * (NPROD + NMMA + 4);
+constexpr int DEPTH = 3;                  // cp.async groups in flight per producer lane
 
 struct ConvTcParams {
     const bf16* A;
@@ -57,21 +63,17 @@ struct Cfg {
     static constexpr int LBO_B = COUT * 16, SBO_B = 128;
     static constexpr int BUDGET = 220 * 1024 - W_BYTES;
     static constexpr int NST = BUDGET / PLANE_BYTES >= 6 ? 6 : BUDGET / PLANE_BYTES;
-    // Back-to-back tcgen05.mma into ONE accumulator serialise on the accumulate latency (~120 cycles measured with
-    // N=16/32, against an 8-16 cycle issue floor), so the taps of a plane are dealt round-robin over G independent
-    // accumulators that the epilogue adds up.
-    static constexpr int G = 1;   // measured: G=8 changed nothing while the issue loop was the limiter
-    static constexpr int TCOLS = 2 * G * COUT;
+    // One UTCHMMA costs its issuing warp ~55 cycles (ptxas wraps it in an ELECT loop) against a 32-40 cycle
+    // shared-memory-bound execution for N = 16/32, so three warps issue -- warp kd owns the 9 taps of input plane
+    // z+kd-1 and its own TMEM accumulator; the epilogue adds the (valid) three.  Measured: splitting the taps of ONE
+    // issuing warp over 4 or 8 accumulators changes nothing (the accumulate chain is not the limiter).
+    static constexpr int TCOLS = 2 * NMMA * COUT;
     static constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
     static_assert(TCOLS <= 512, "TMEM columns");
     static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;   // + barriers, tmem slot, stats scratch
     static_assert(NST >= 4, "need >= 4 halo-plane stages");
     static_assert(PLANE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "alignment");
 };
-
-constexpr int NPROD = 2;                  // producer warps
-constexpr int NTHREADS = 32 * (NPROD + 1 + 4);
-constexpr int DEPTH = 3;                  // cp.async groups in flight per producer lane
 
 struct Item {
     int n, h0, w0, d0, d1, p_lo, p_hi, chunk;
@@ -114,11 +116,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
 
     if (tid == 0) {
         *dead = 0;
-        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), 4); }
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), NMMA); }
+        for (int b = 0; b < 2; ++b) { mbar_init(TFULL(b), NMMA); mbar_init(TEMPTY(b), 4); }
         fence_barrier_init();
     }
-    if (warp == NPROD) tmem_alloc<K::TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == NPROD) tmem_alloc<K::TMEM_COLS>(smem_u32(tmem_slot));   // (warp NPROD also deallocates)
     // weights: fp32 parameter (any strides) -> bf16 smem [tap][k/8][n][8]  (K-major no-swizzle core matrices:
     // 8 couts x 16 B); padded / out-of-segment channels are zero.  No separate pack kernel, no packed copy in HBM.
     {
@@ -195,78 +197,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
         cp_async_wait<0>();
         fence_proxy_async();
         flush_to(seq);
-    } else if (warp == NPROD) {
-        // ===================================================================== MMA issuer (warp-convergent loop,
-        // the tcgen05 instructions predicated on lane 0)
+    } else if (warp < NPROD + NMMA) {
+        // ===================================================================== MMA issuers: warp kd multiplies input
+        // plane z+kd-1 (9 taps x CIN/16 k-steps) into accumulator kd of the output plane's TMEM buffer.  Every
+        // warp walks ALL loaded planes of an item in order (waiting FULL, arriving EMPTY) so the barrier phases stay
+        // in step even for the planes it never reads, and arrives on TFULL once per output plane.
         {
+            const int kd = warp - NPROD;
             constexpr uint32_t idesc = umma_idesc(128, COUT, 0, 0);
             constexpr uint32_t A_HI = ((K::SBO_A >> 4) & 0x3fffu) | (1u << 14);
             constexpr uint32_t B_HI = ((K::SBO_B >> 4) & 0x3fffu) | (1u << 14);
             constexpr int TAP16 = K::TAP_BYTES >> 4;
-            const uint32_t leader = lane == 0 ? 1u : 0u;
             const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_A >> 4) << 16);
             const uint32_t b_lo0 = ((smem_u32(wsm) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_B >> 4) << 16);
+            const uint32_t b_kd = b_lo0 + (FLIP ? 26 - kd * 9 : kd * 9) * TAP16;
             uint32_t seq_base = 0, odc = 0;
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
                 const Item it = decode(p, item);
                 const int nload = it.p_hi - it.p_lo + 1;
-                int waited = 0, released = 0;
+                int done = 0;                                  // planes of this item waited for + released by this warp
+                auto pass_planes = [&](int upto) {             // walk (without reading) planes [done, upto)
+                    while (done < upto) {
+                        const uint32_t sq = seq_base + done;
+                        mbar_wait(FULL(sq % NST), (sq / NST) & 1u, dead, 2);
+                        if (lane == 0) mbar_arrive(EMPTY(sq % NST));
+                        ++done;
+                    }
+                };
                 for (int od = it.d0; od < it.d1; ++od, ++odc) {
                     const int buf = odc & 1;
                     const uint32_t uph = (odc >> 1) & 1u;
-                    const int need = min(od + 1, p.D - 1) - it.p_lo + 1;
-                    while (waited < need) {
-                        const uint32_t sq = seq_base + waited;
+                    const int pl = od + kd - 1;
+                    const bool valid = pl >= 0 && pl < p.D;
+                    if (valid) {
+                        pass_planes(pl - it.p_lo);             // planes before mine that I never read (item start)
+                        const uint32_t sq = seq_base + done;   // == plane pl
                         mbar_wait(FULL(sq % NST), (sq / NST) & 1u, dead, 2);
-                        ++waited;
-                    }
-                    mbar_wait(TEMPTY(buf), uph ^ 1u, dead, 3);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * (K::G * COUT);
-                    uint32_t nmma = 0;
-#pragma unroll 1
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const int pl = od + kd - 1;
-                        if (pl < 0 || pl >= p.D) continue;
-                        const uint32_t sq = seq_base + (pl - it.p_lo);
+                        mbar_wait(TEMPTY(buf), uph ^ 1u, dead, 3);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (buf * NMMA + kd) * COUT;
                         const uint32_t a_pl = a_lo0 + (sq % NST) * (K::PLANE_BYTES >> 4);
-                        const uint32_t b_kd = b_lo0 + (FLIP ? 26 - kd * 9 : kd * 9) * TAP16;
+                        if (lane == 0) {
 #pragma unroll
-                        for (int khw = 0; khw < 9; ++khw) {
-                            constexpr int dummy = 0; (void)dummy;
-                            const int kh = khw / 3, kw = khw % 3;
+                            for (int khw = 0; khw < 9; ++khw) {
+                                const int kh = khw / 3, kw = khw % 3;
 #pragma unroll
-                            for (int kc = 0; kc < CIN / 16; ++kc) {
-                                const uint32_t a_lo = a_pl + (((kh * HW + kw) * 16 + kc * 2 * K::LBO_A) >> 4);
-                                const uint32_t b_lo = b_kd + (FLIP ? -khw * TAP16 : khw * TAP16) +
-                                                      ((kc * 2 * K::LBO_B) >> 4);
-                                const uint64_t ad = ((uint64_t)A_HI << 32) | a_lo;
-                                const uint64_t bd = ((uint64_t)B_HI << 32) | b_lo;
-                                if (K::G == 1) {
-                                    umma_f16_pred(d_tmem, ad, bd, idesc, nmma, leader);
-                                    nmma = 1;
-                                } else {
-                                    umma_f16_pred(d_tmem + (nmma % K::G) * COUT, ad, bd, idesc, nmma >= K::G ? 1u : 0u,
-                                                  leader);
-                                    ++nmma;
+                                for (int kc = 0; kc < CIN / 16; ++kc) {
+                                    const uint32_t a_lo = a_pl + (((kh * HW + kw) * 16 + kc * 2 * K::LBO_A) >> 4);
+                                    const uint32_t b_lo = b_kd + (FLIP ? -khw * TAP16 : khw * TAP16) +
+                                                          ((kc * 2 * K::LBO_B) >> 4);
+                                    umma_f16(d_tmem, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo,
+                                             idesc, (khw | kc) ? 1u : 0u);
                                 }
                             }
+                            umma_commit(EMPTY(sq % NST));      // my reads of plane pl are done when these MMAs are
+                            umma_commit(TFULL(buf));
                         }
+                        __syncwarp();
+                        ++done;
+                    } else {
+                        // zero-padding plane: nothing to add, but the epilogue still counts NMMA arrivals.  Wait for
+                        // the buffer first: an early arrive would be counted into the previous phase of TFULL(buf).
+                        mbar_wait(TEMPTY(buf), uph ^ 1u, dead, 3);
+                        if (lane == 0) mbar_arrive(TFULL(buf));
                     }
-                    // plane od-1 is not needed by the next output plane; after the last plane release everything.
-                    // (EMPTY commits first: once the epilogue has seen TFULL no arrive is still in flight at exit)
-                    const int rel = (od == it.d1 - 1) ? nload : max(0, od - it.p_lo);
-                    while (released < rel) {
-                        umma_commit_pred(EMPTY((seq_base + released) % NST), leader);
-                        ++released;
-                    }
-                    umma_commit_pred(TFULL(buf), leader);
                 }
+                pass_planes(nload);                            // planes after my last read (item end)
                 seq_base += nload;
             }
         }
     } else {
-        // ===================================================================== epilogue (warps 3..6)
+        // ===================================================================== epilogue (4 warps)
         const int q = warp & 3;                   // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;              // accumulator row = voxel (hh, ww) of the tile
         const int hh = r >> 3, ww = r & 7;
@@ -283,32 +284,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
                 const uint32_t uph = (odc >> 1) & 1u;
                 mbar_wait(TFULL(buf), uph, dead, 4);
                 tc_fence_after();
-                // every plane issues >= 9 * CIN/16 >= G MMAs, so all G partial accumulators are written
+                // accumulator kd is valid iff input plane od+kd-1 exists (kd = 1 always)
                 float v[COUT];
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (K::G * COUT);
-                if constexpr (K::G == 1) {
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (NMMA * COUT);
+                {
                     uint32_t t[COUT];
 #pragma unroll
-                    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(trow + c0, t + c0);
+                    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(trow + COUT + c0, t + c0);
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < COUT; ++k) v[k] = __uint_as_float(t[k]);
-                } else {
+                    if (od > 0) {
 #pragma unroll
-                    for (int c0 = 0; c0 < COUT; c0 += 16) {
+                        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(trow + c0, t + c0);
+                        tmem_wait_ld();
 #pragma unroll
-                        for (int g0 = 0; g0 < K::G; g0 += 4) {
-                            uint32_t t[4][16];
+                        for (int k = 0; k < COUT; ++k) v[k] += __uint_as_float(t[k]);
+                    }
+                    if (od < p.D - 1) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) tmem_ld16(trow + (g0 + g) * COUT + c0, t[g]);
-                            tmem_wait_ld();
+                        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(trow + 2 * COUT + c0, t + c0);
+                        tmem_wait_ld();
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                const float sum = (__uint_as_float(t[0][k]) + __uint_as_float(t[1][k])) +
-                                                  (__uint_as_float(t[2][k]) + __uint_as_float(t[3][k]));
-                                v[c0 + k] = g0 == 0 ? sum : v[c0 + k] + sum;
-                            }
-                        }
+                        for (int k = 0; k < COUT; ++k) v[k] += __uint_as_float(t[k]);
                     }
                 }
                 tc_fence_before();
@@ -337,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
                     if (lane == 0) { red[(q * 2 + 0) * COUT + c] = a; red[(q * 2 + 1) * COUT + c] = b; }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int e = tid - 32 * (NPROD + 1);   // 0..127 over the epilogue threads
+                const int e = tid - 32 * (NPROD + NMMA);   // 0..127 over the epilogue threads
                 if (e < 2 * COUT) {
                     const float t = red[e] + red[2 * COUT + e] + red[4 * COUT + e] + red[6 * COUT + e];
                     const long long nchunk = (long long)p.nht * p.nwt * p.nseg;
