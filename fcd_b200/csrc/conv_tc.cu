@@ -36,7 +36,6 @@ constexpr int HV = HH * HW;               // 180 voxels
 constexpr int NPROD = 2;                  // producer warps
 constexpr int NMMA = 3;                   // MMA-issuing warps: one per kd tap plane, each with its own accumulator
 constexpr int NTHREADS = 32 * (NPROD + NMMA + 4);
-constexpr int DEPTH = 3;                  // cp.async groups in flight per producer lane
 
 struct ConvTcParams {
     const bf16* A;
@@ -95,6 +94,7 @@ template <int CIN, int COUT, bool STATS, bool FLIP>
 __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParams p) {
     using K = Cfg<CIN, COUT>;
     constexpr int NST = K::NST;
+    constexpr int DEPTH = NST >= 6 ? 3 : NST - 3;   // cp.async groups in flight per producer lane (>= 1)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* wsm = smem;
     unsigned char* ring = smem + K::W_BYTES;
@@ -163,27 +163,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
         };
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const Item it = decode(p, item);
+            // per-lane source offsets of my NJ pieces inside a plane (the same for every plane of the column):
+            // element offset from the plane base, or -1 for the zero-filled halo outside the volume
+            int off[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int v = v0 + j * VS;
+                const int hh = v / HW, ww = v - hh * HW;
+                const int h = it.h0 - 1 + hh, w = it.w0 - 1 + ww;
+                const bool ok = v < HV && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                off[j] = ok ? (int)(((long long)h * p.W + w) * p.lda) + c8 * 8 : -1;
+            }
+            const long long plane_elems = (long long)p.H * p.W * p.lda;
             for (int pl = it.p_lo; pl <= it.p_hi; ++pl, ++seq) {
                 const int s = seq % NST;
                 const uint32_t ph = (seq / NST) & 1u;
-                if (!mbar_try(EMPTY(s), ph ^ 1u)) {
-                    // ring full: hand over everything in flight first (the consumer may need it to free this slot)
-                    cp_async_wait<0>();
-                    fence_proxy_async();
-                    flush_to(seq);
-                    mbar_wait(EMPTY(s), ph ^ 1u, dead, 1);
-                }
-                const bf16* plane = p.A + ((long long)it.n * p.D + pl) * p.H * p.W * p.lda + c8 * 8;
-                const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A;
-#pragma unroll 4
+                // Slot s frees when the MMAs that read plane seq-NST are done; those need planes <= seq-NST+2, all
+                // handed over already because hand-over lags issue by DEPTH-1 <= NST-3 planes.  So a plain wait cannot
+                // deadlock, and (unlike draining first) it keeps DEPTH planes in flight in steady state.
+                mbar_wait(EMPTY(s), ph ^ 1u, dead, 1);
+                const bf16* plane = p.A + ((long long)it.n * p.D + pl) * plane_elems;
+                const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A + v0 * 16;
+#pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    const int v = v0 + j * VS;
-                    if (v < HV) {
-                        const int hh = v / HW, ww = v - hh * HW;
-                        const int h = it.h0 - 1 + hh, w = it.w0 - 1 + ww;
-                        const bool ok = h >= 0 && h < p.H && w >= 0 && w < p.W;
-                        const bf16* src = ok ? plane + ((long long)h * p.W + w) * p.lda : p.A;
-                        cp_async16(dst0 + v * 16, src, ok);
+                    if ((NJ - 1) * VS + 32 * NPROD / C8 <= HV || j < NJ - 1 || v0 + j * VS < HV) {
+                        const bool ok = off[j] >= 0;
+                        cp_async16(dst0 + j * VS * 16, ok ? plane + off[j] : p.A, ok);
                     }
                 }
                 cp_async_commit();
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParam
                     fence_proxy_async();
                     flush_to(seq + 2 - DEPTH);
                 }
+                static_assert(NST >= DEPTH + 1 + 2, "ring too shallow for the hand-over lag");
             }
         }
         cp_async_wait<0>();
