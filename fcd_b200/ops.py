@@ -203,7 +203,18 @@ class ConvFn(Function):
                      accumulate=0, Cq=0)
         if ctx.needs_input_grad[1]:
             _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
-            part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
+            ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (USE_TC and k == 3 and stride == 1 and pad == 1) else 0
+            if ns > 0:
+                # tcgen05 path: 32- (or 16-) channel slices of x (shifted operand) against slices of dy
+                cs = 32 if Kp % 32 == 0 else 16
+                cu = 32 if Np % 32 == 0 else 16
+                part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
+                for n_off in range(0, Np, cu):
+                    for k_off in range(0, Kp, cs):
+                        call("fcd_wgrad3_tc", S=x[..., k_off:], lds=ld(x), U=dy[..., n_off:], ldu=ld(dy), part=part,
+                             ldn=Np, ldk=Kp, n_off=n_off, k_off=k_off, Bn=B, D=D, H=H, W=W, CS=cs, CU=cu)
+            else:
+                part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
             dw = torch.empty_like(weight, dtype=torch.float32)
             call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=T, N=Co, K=Ci, Np=Np, Kp=Kp, sn=Ci * T, sk=T,
                  st=1, kseg=seg, ksegpad=segpad, accumulate=0)

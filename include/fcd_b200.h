@@ -57,6 +57,15 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream);
 FCD_API int fcd_tc_error(void);
 
+/* tcgen05/TMEM weight gradient of the same 3x3x3 stride-1 pad-1 convs (autograd of conv_blocks.py:393-416).  S: the
+ * operand read shifted (conv input, CS channels from channel k_off), U: the unshifted one (output gradient, CU
+ * channels from n_off); CS, CU in {16, 32}, wider layers are cut into slices by the caller.  Each of the
+ * fcd_wgrad3_tc_nsplit() CTAs writes one partial part[cta][27][ldn][ldk] block; fcd_wgrad_reduce sums them. */
+FCD_API int fcd_wgrad3_tc_nsplit(int Bn, int D, int H, int W);
+FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long ldu, float* part, int ldn, int ldk,
+                          int n_off, int k_off, int Bn, int D, int H, int W, int CS, int CU, cudaStream_t stream);
+FCD_API int fcd_wgrad_tc_error(void);
+
 /* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382) ---- */
 FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int Wo, int C, cudaStream_t stream);
 FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,

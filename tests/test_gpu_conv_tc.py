@@ -112,3 +112,34 @@ def test_conv3_tc_concat_segments(ops):
           what="segmented dgrad")
     assert float(g[..., 12:16].abs().max()) == 0.0 and float(g[..., 28:].abs().max()) == 0.0
     close(w2.grad, gw, rel=6e-3, what="segmented wgrad")
+
+
+WG_CASES = [
+    # B, Ci, Co, D, H, W
+    (1, 16, 16, 4, 16, 8),
+    (1, 32, 32, 8, 16, 16),
+    (2, 16, 32, 8, 32, 16),
+    (1, 64, 32, 4, 16, 8),        # two 32-channel slices of the shifted operand
+    (1, 32, 64, 8, 16, 8),        # two slices of the unshifted operand
+    (1, 2, 16, 8, 16, 16),
+    (1, 24, 12, 4, 16, 8),
+    (2, 32, 16, 16, 128, 128),    # enough columns for 8-plane items (DL = 8)
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", WG_CASES)
+def test_wgrad3_tc(ops, B, Ci, Co, D, H, W):
+    """Weight gradient through the tcgen05 kernel (kd taps folded into M, MN-major operands) vs torch autograd."""
+    from fcd_b200 import _lib
+    assert _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) > 0, "case must be taken by the tcgen05 wgrad kernel"
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    ref = F.conv3d(x, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    (gw,) = torch.autograd.grad(ref, [w], dy)
+    xc = ops.to_channels_last(x)
+    w2 = w.detach().clone().requires_grad_(True)
+    y = ops.conv3d(xc, w2, None, k=3)
+    y.backward(ops.to_channels_last(dy, ops.pad16(Co)))
+    assert _lib.lib().fcd_wgrad_tc_error() == 0 and tc_error() == 0
+    close(w2.grad, gw, rel=6e-3, what="tc wgrad")
