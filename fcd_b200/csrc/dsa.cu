@@ -218,9 +218,36 @@ __global__ void __launch_bounds__(256) dsa_reduce_kernel(const bf16* __restrict_
     }
 }
 
+// In-place first level of the tile sums: for each of `nsets` partial sets (rows of O floats, `ntiles` rows per set),
+// row g (g < G) becomes the sum of rows g, g+G, g+2G, ...  Column j of row g is read and written by one thread only,
+// so this is race-free, deterministic, coalesced, and leaves the finalize kernels a G-row loop instead of ntiles.
+constexpr int kTileGroups = 8;
+__global__ void __launch_bounds__(128) tile_group_sum_kernel(float* __restrict__ part, int ntiles, long long O) {
+    const long long j = blockIdx.x * 128LL + threadIdx.x;
+    const int g = blockIdx.y;
+    if (j >= O || g >= ntiles) return;
+    float* base = part + (long long)blockIdx.z * ntiles * O + j;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = g;
+    for (; k + 3 * kTileGroups < ntiles; k += 4 * kTileGroups) {
+        a0 += base[(long long)k * O];
+        a1 += base[(long long)(k + kTileGroups) * O];
+        a2 += base[(long long)(k + 2 * kTileGroups) * O];
+        a3 += base[(long long)(k + 3 * kTileGroups) * O];
+    }
+    for (; k < ntiles; k += kTileGroups) a0 += base[(long long)k * O];
+    base[(long long)g * O] = (a0 + a1) + (a2 + a3);
+}
+static inline void tile_group_sum(float* part, int nsets, int ntiles, long long O, cudaStream_t st) {
+    if (ntiles <= kTileGroups) return;
+    dim3 grid((unsigned)((O + 127) / 128), kTileGroups, nsets);
+    tile_group_sum_kernel<<<grid, 128, 0, st>>>(part, ntiles, O);
+}
+static inline int tile_rows_after_sum(int ntiles) { return ntiles <= kTileGroups ? ntiles : kTileGroups; }
+
 // grid (h, B).  Sums the tile partials and produces: inv_nq/inv_nk [B][C], Ghat [B][h][c][c], A = softmax rows,
 // KP/VP [B][2][C][P] (k projection then v_SA projection).
-__global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restrict__ part, int ntiles,
+__global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restrict__ part, int ntiles, int nsum,
                                                            const float* __restrict__ temperature,
                                                            const float* __restrict__ ca_scale,
                                                            float* __restrict__ inv_n, float* __restrict__ Ghat,
@@ -232,9 +259,9 @@ __global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restri
     const int hd = blockIdx.x, b = blockIdx.y;
     const long long O = dsa_osize(C, c, P);
     const float* base = part + (long long)b * ntiles * O;
-    auto tsum = [&](long long off) {
+    auto tsum = [&](long long off) {           // rows [0, nsum) hold the group sums (tile_group_sum_kernel)
         float s = 0.f;
-        for (int k = 0; k < ntiles; ++k) s += base[(long long)k * O + off];
+        for (int k = 0; k < nsum; ++k) s += base[(long long)k * O + off];
         return s;
     };
     for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
@@ -522,7 +549,7 @@ __global__ void __launch_bounds__(64) dsa_bwd_reduce_kernel(const bf16* __restri
 
 // grid (h, B): sums tile partials; softmax backward of the channel attention; emits
 // dKV [B][2][C][P] (dKP then dVP), dGhat [B][h][c][c], rqk [B][2][C] and accumulates dtemperature / dtemperature2.
-__global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __restrict__ part, int ntiles,
+__global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __restrict__ part, int ntiles, int nsum,
                                                                const float* __restrict__ temperature,
                                                                const float* __restrict__ Ghat,
                                                                const float* __restrict__ A,
@@ -540,7 +567,7 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
     const float* base = part + ((long long)b * H + hd) * ntiles * O;
     auto tsum = [&](long long off) {
         float s = 0.f;
-        for (int k = 0; k < ntiles; ++k) s += base[(long long)k * O + off];
+        for (int k = 0; k < nsum; ++k) s += base[(long long)k * O + off];
         return s;
     };
     for (int i = threadIdx.x; i < 2 * c * P; i += blockDim.x) {
@@ -671,31 +698,48 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     }
 }
 
-// dEF[n][p] = sum_b sum_ch ( k[b,n,ch] dKP[b][ch][p] + v_SA[b,n,ch] dVP[b][ch][p] ).  thread per (n, 4 p's).
+// dEF[n][p] = sum_b sum_ch ( k[b,n,ch] dKP[b][ch][p] + v_SA[b,n,ch] dVP[b][ch][p] ).  Thread per (4 tokens, 4 p's):
+// k / v_SA come in as 16 B (8-channel) loads, every dKP/dVP float4 (L1-resident) feeds 4 tokens.
 __global__ void __launch_bounds__(256) dsa_bwd_ef_kernel(const bf16* __restrict__ qkvv, long long ldq,
                                                          const float* __restrict__ dKV, float* __restrict__ dEF,
                                                          int B, int N, int C, int P) {
     const int P4 = P / 4;
     const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = gid / P4;
+    const long long n0 = (gid / P4) * 4;
     const int p = (int)(gid % P4) * 4;
-    if (n >= N) return;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 >= N) return;
+    float4 a[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = 0; b < B; ++b) {
-        const bf16* row = qkvv + ((long long)b * N + n) * ldq;
         const float* dkp = dKV + (long long)b * 2 * C * P;
         const float* dvp = dkp + (long long)C * P;
-        for (int ch = 0; ch < C; ++ch) {
-            const float k = __bfloat162float(row[C + ch]), v = __bfloat162float(row[3 * C + ch]);
-            const float4 x = *reinterpret_cast<const float4*>(&dkp[(long long)ch * P + p]);
-            const float4 y = *reinterpret_cast<const float4*>(&dvp[(long long)ch * P + p]);
-            a.x = fmaf(k, x.x, fmaf(v, y.x, a.x));
-            a.y = fmaf(k, x.y, fmaf(v, y.y, a.y));
-            a.z = fmaf(k, x.z, fmaf(v, y.z, a.z));
-            a.w = fmaf(k, x.w, fmaf(v, y.w, a.w));
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float kf[4][8], vf[4][8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const long long n = n0 + t < N ? n0 + t : N - 1;
+                const bf16* row = qkvv + ((long long)b * N + n) * ldq;
+                unpack8(ld8(row + C + c0), kf[t]);
+                unpack8(ld8(row + 3 * C + c0), vf[t]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(&dkp[(long long)(c0 + j) * P + p]);
+                const float4 y = *reinterpret_cast<const float4*>(&dvp[(long long)(c0 + j) * P + p]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    a[t].x = fmaf(kf[t][j], x.x, fmaf(vf[t][j], y.x, a[t].x));
+                    a[t].y = fmaf(kf[t][j], x.y, fmaf(vf[t][j], y.y, a[t].y));
+                    a[t].z = fmaf(kf[t][j], x.z, fmaf(vf[t][j], y.z, a[t].z));
+                    a[t].w = fmaf(kf[t][j], x.w, fmaf(vf[t][j], y.w, a[t].w));
+                }
+            }
         }
     }
-    *reinterpret_cast<float4*>(&dEF[n * P + p]) = a;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (n0 + t < N) *reinterpret_cast<float4*>(&dEF[(n0 + t) * P + p]) = a[t];
 }
 
 template <int CH, int P>
@@ -839,8 +883,9 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
     dsa_reduce_kernel<<<dim3(ntiles, B), 256, smem_r, st>>>((const bf16*)qkvv, ldq, EF, part, N, C, c, P, tn);
     float ds; uint32_t dth;
     drop_params(sa_drop, ds, dth);
-    dsa_finalize_kernel<<<dim3(H, B), 256, (c * c + 2 * c) * 4, st>>>(part, ntiles, temperature, ca_scale, inv_n, Ghat, A,
-                                                                     Ad, KV, C, c, P);
+    tile_group_sum(part, B, ntiles, 2LL * C + (long long)C * c + 2LL * C * P, st);
+    dsa_finalize_kernel<<<dim3(H, B), 256, (c * c + 2 * c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
+                                                                     ca_scale, inv_n, Ghat, A, Ad, KV, C, c, P);
     {
         auto run = [&]() -> int {
             DSA_DISPATCH(launch_apply, (const bf16*)qkvv, ldq, inv_n, Ad, KV, temperature2, xca, tsa, B, N, C, H, ds, dth,
@@ -885,8 +930,10 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
         if (rc != 0) return rc;
     }
     const int ntiles = (N + 63) / 64;
-    dsa_bwd_finalize_kernel<<<dim3(H, B), 256, (c * c + c) * 4, st>>>(part, ntiles, temperature, Ghat, A, ca_scale, dKV,
-                                                                     dGhat, rqk, dtemp, dtemp2, C, c, P);
+    tile_group_sum(part, B * H, ntiles, 2LL * c * P + (long long)c * c + c + 1, st);
+    dsa_bwd_finalize_kernel<<<dim3(H, B), 256, (c * c + c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
+                                                                     Ghat, A, ca_scale, dKV, dGhat, rqk, dtemp, dtemp2, C, c,
+                                                                     P);
     {
         auto run = [&]() -> int {
             DSA_DISPATCH(launch_bwd_apply, (const bf16*)qkvv, ldq, (const bf16*)dy, lddy, gamma, EF, inv_n, Ad, dGhat, rqk,
@@ -895,7 +942,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
         int rc = run();
         if (rc != 0) return rc;
     }
-    const long long tot = (long long)N * (P / 4);
+    const long long tot = (long long)((N + 3) / 4) * (P / 4);
     dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
     FCD_LAUNCH_CHECK();
 }

@@ -144,17 +144,19 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, floa
 
 // mode 0 instance (per b,c), 1 batch (per c over b), 2 group-of-2-channels (per b, c/2).
 // Writes mean[b][c], rstd[b][c]; for batch mode also updates running stats (momentum, unbiased var) if given.
-__global__ void norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
-                                     int B, int C, int nchunk, long long S, int mode, float eps,
-                                     float* __restrict__ running_mean, float* __restrict__ running_var, int crun,
-                                     float momentum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, int B, int C, int nchunk,
+                                                            long long S, int mode, float eps,
+                                                            float* __restrict__ running_mean,
+                                                            float* __restrict__ running_var, int crun, float momentum) {
+    // one WARP per (b, c): the lanes stride over the chunk partials (fixed order => deterministic), fp64 accumulation
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= B * C) return;
     const int b = i / C, c = i % C;
     double s = 0.0, q = 0.0, n = 0.0;
     auto add = [&](int bb, int cc) {
         const float* o = part + (long long)bb * nchunk * 2 * C;
-        for (int k = 0; k < nchunk; ++k) { s += o[(long long)k * 2 * C + cc]; q += o[(long long)k * 2 * C + C + cc]; }
+        for (int k = lane; k < nchunk; k += 32) { s += o[(long long)k * 2 * C + cc]; q += o[(long long)k * 2 * C + C + cc]; }
         n += (double)S;
     };
     if (mode == 0) {
@@ -165,6 +167,12 @@ __global__ void norm_finalize_kernel(const float* __restrict__ part, float* __re
         add(b, c & ~1);
         add(b, c | 1);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane != 0) return;
     const double m = s / n;
     double var = q / n - m * m;
     if (var < 0.0) var = 0.0;
@@ -305,16 +313,23 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
                                          float* __restrict__ coef, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta, int B, int C, int nchunk, long long S, int mode,
                                          int has2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per (b, c): lanes stride over the chunk partials, xor-shuffle totals (every lane ends with the sums)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= B * C) return;
     const int b = i / C, c = i % C;
     auto sum3 = [&](int bb, int cc, double& s0, double& s1, double& s2) {
         const float* o = part + (long long)bb * nchunk * 3 * C;
         s0 = s1 = s2 = 0.0;
-        for (int k = 0; k < nchunk; ++k) {
+        for (int k = lane; k < nchunk; k += 32) {
             s0 += o[(long long)k * 3 * C + cc];
             s1 += o[(long long)k * 3 * C + C + cc];
             s2 += o[(long long)k * 3 * C + 2 * C + cc];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
         }
     };
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, n = 0.0;   // group sums of gamma*ds, gamma*ds*xhat1, ds*xhat2
@@ -330,9 +345,12 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
     else { addgrp(b, c & ~1); addgrp(b, c | 1); }
     const double g = gamma1 ? (double)gamma1[c] : 1.0;
     float* o = coef + (long long)i * 6;
-    o[0] = (float)(g * rstd1[i]);
-    o[1] = (float)(rstd1[i] * (g0 / n));
-    o[2] = (float)(rstd1[i] * (g1 / n));
+    const bool writer = lane == 0;
+    if (writer) o[0] = (float)(g * rstd1[i]);
+    if (writer) {
+        o[1] = (float)(rstd1[i] * (g0 / n));
+        o[2] = (float)(rstd1[i] * (g1 / n));
+    }
     if (has2) {
         // second input never has affine parameters; its ds sum is the un-weighted one
         double u0 = 0.0, u2 = 0.0, nn = 0.0;
@@ -340,18 +358,22 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
         if (mode == 0) add2(b, c);
         else if (mode == 1) { for (int bb = 0; bb < B; ++bb) add2(bb, c); }
         else { add2(b, c & ~1); add2(b, c | 1); }
-        o[3] = rstd2[i];
-        o[4] = (float)(rstd2[i] * (u0 / nn));
-        o[5] = (float)(rstd2[i] * (u2 / nn));
-    } else {
+        if (writer) {
+            o[3] = rstd2[i];
+            o[4] = (float)(rstd2[i] * (u0 / nn));
+            o[5] = (float)(rstd2[i] * (u2 / nn));
+        }
+    } else if (writer) {
         o[3] = o[4] = o[5] = 0.f;
     }
     (void)g2;
     if (dgamma != nullptr && b == 0) {
         double dg = 0.0, db = 0.0;
         for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
-        dgamma[c] += (float)dg;
-        dbeta[c] += (float)db;
+        if (writer) {
+            dgamma[c] += (float)dg;
+            dbeta[c] += (float)db;
+        }
     }
 }
 
@@ -493,7 +515,7 @@ FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, B);
     norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk);
-    norm_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
+    norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
                                                              running_mean, running_var, crun, momentum);
     FCD_LAUNCH_CHECK();
 }
@@ -522,7 +544,7 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
     dim3 g1(nchunk, B);
     norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope);
-    norm_bwd_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, rstd1, rstd2, gamma1, coef, dgamma, dbeta, B,
+    norm_bwd_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, rstd1, rstd2, gamma1, coef, dgamma, dbeta, B,
                                                                  C, nchunk, S, mode, x2 != nullptr);
     dim3 g2(grid_for(S * (C / 8), nt, 8), B);
     norm_bwd_apply_kernel<<<g2, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
@@ -536,7 +558,7 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
 FCD_API int fcd_norm_finalize(const float* part, float* mean, float* rstd, int B, long long S, int C, int nchunk,
                               int mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                               cudaStream_t st) {
-    norm_finalize_kernel<<<(B * C + 127) / 128, 128, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
+    norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
                                                              running_mean, running_var, crun, momentum);
     FCD_LAUNCH_CHECK();
 }

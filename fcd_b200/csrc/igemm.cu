@@ -24,6 +24,8 @@ struct IGemmParams {
     int K, N;
     int kd, kh, kw, stride, pad, mode, out_mode, accumulate;
     int M, Cq;
+    int ksplit;        // > 1: blockIdx.z takes a slice of the (tap, k-chunk) loop and writes fp32 partials to ws
+    float* ws;         // [ksplit][M][N] fp32
 };
 
 namespace {
@@ -81,9 +83,13 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
 
     const int kchunks = p.K / BK;
     const int T = p.kd * p.kh * p.kw;
-    const int nk = T * kchunks;
+    const int nk_all = T * kchunks;
+    // split-K: this CTA runs iterations [it0, it0 + nk) of the flattened (tap, k-chunk) loop
+    const int it0 = (int)((long long)nk_all * blockIdx.z / p.ksplit);
+    const int nk = (int)((long long)nk_all * (blockIdx.z + 1) / p.ksplit) - it0;
 
-    auto load_stage = [&](int it, int slot) {
+    auto load_stage = [&](int it_local, int slot) {
+        const int it = it0 + it_local;
         const int t = it / kchunks, kc = it - t * kchunks;
         const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
         const uint32_t sa = smem_base + slot * STAGE_BYTES;
@@ -170,10 +176,26 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
     cp_async_wait<0>();
     __syncthreads();
 
+    const int g = lane >> 2, tq = lane & 3;
+    if (p.ksplit > 1) {
+        // ---- split-K epilogue: raw fp32 partial tile -> ws[z][m][n]; igemm_splitk_reduce_kernel finishes
+        float* w = p.ws + (long long)blockIdx.z * p.M * p.N;
+#pragma unroll
+        for (int nj = 0; nj < WN / 8; ++nj) {
+            const int col = n0 + wn * WN + nj * 8 + tq * 2;
+            if (col >= p.N) continue;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int row = m0 + wm * 32 + mi * 16 + g;
+                if (row < p.M) *reinterpret_cast<float2*>(&w[(long long)row * p.N + col]) = make_float2(acc[mi][nj][0], acc[mi][nj][1]);
+                if (row + 8 < p.M) *reinterpret_cast<float2*>(&w[(long long)(row + 8) * p.N + col]) = make_float2(acc[mi][nj][2], acc[mi][nj][3]);
+            }
+        }
+        return;
+    }
     // ---- epilogue: (+bias) -> bf16 tile in smem -> 16B coalesced rows (plain / accumulate / k2s2 scatter)
     constexpr int CLD = BN + 8;   // padded row (elements)
     bf16* ctile = reinterpret_cast<bf16*>(smem);
-    const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
     for (int nj = 0; nj < WN / 8; ++nj) {
         int col = wn * WN + nj * 8 + tq * 2;
@@ -236,9 +258,37 @@ int launch_igemm(const IGemmParams& p, cudaStream_t stream) {
         cudaFuncSetAttribute(igemm_kernel<BN, WN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.ksplit);
     igemm_kernel<BN, WN, BK><<<grid, NT, smem, stream>>>(p);
     return (int)cudaGetLastError();
+}
+
+// C[m][n] (+)= bias[n] + sum_z ws[z][m][n]  -> bf16 rows (fixed summation order: deterministic)
+__global__ void igemm_splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ C, long long ldc,
+                                           const float* __restrict__ bias, int M, int N, int ksplit, int accumulate) {
+    const int N8 = N / 8;
+    const long long total = (long long)M * N8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / N8;
+        const int n = (int)(i % N8) * 8;
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = bias ? bias[n + k] : 0.f;
+        for (int z = 0; z < ksplit; ++z) {
+            const float4* src = reinterpret_cast<const float4*>(ws + ((long long)z * M + m) * N + n);
+            const float4 u = src[0], v = src[1];
+            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w; a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+        }
+        bf16* dst = C + m * ldc + n;
+        if (accumulate) {
+            float b[8];
+            unpack8(ld8(dst), b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += b[k];
+        }
+        st8(dst, pack8(a));
+    }
 }
 
 }  // namespace
@@ -256,6 +306,7 @@ FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long
     p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
     p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
     p.mode = mode; p.out_mode = out_mode; p.accumulate = accumulate; p.Cq = Cq > 0 ? Cq : 1;
+    p.ksplit = 1; p.ws = nullptr;
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
@@ -265,4 +316,43 @@ FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long
     if (N <= 64 || (long long)((M + BM - 1) / BM) * ((N + 127) / 128) < 2 * fcd_num_sms())
         return k32 ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
     return k32 ? launch_igemm<128, 64, 32>(p, stream) : launch_igemm<128, 64, 16>(p, stream);
+}
+
+// Split-K variant for the deep, spatially tiny levels (e.g. 512->512 on 4^3 x batch 2: M = 128 rows but K = 13824):
+// the plain kernel would run the whole (tap, k-chunk) loop in a handful of CTAs.  fcd_igemm_ksplit proposes the
+// split (1 = use fcd_igemm); ws holds ksplit*M*N floats.  out_mode 0 only.
+FCD_API int fcd_igemm_ksplit(long long M, int N, int K, int T) {
+    if (M <= 0 || N % 8 || K % 16) return 1;
+    const int bk = (K % 32 == 0) ? 32 : 16;
+    const int nk = T * (K / bk);
+    const long long tiles = ((M + BM - 1) / BM) * ((N + 63) / 64);
+    if (tiles >= fcd_num_sms() || nk < 16) return 1;
+    long long ks = (2LL * fcd_num_sms() + tiles - 1) / tiles;
+    if (ks > nk / 4) ks = nk / 4;
+    if (ks > 64) ks = 64;
+    while (ks > 1 && ks * M * N * 4 > (256LL << 20)) --ks;
+    return ks < 2 ? 1 : (int)ks;
+}
+
+FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
+                             int Bn, int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh,
+                             int kw, int stride, int pad, int mode, int accumulate, float* ws, int ksplit,
+                             cudaStream_t stream) {
+    if (K % 16 != 0 || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0 || ksplit < 2 || ws == nullptr) return -1;
+    IGemmParams p;
+    p.A = (const bf16*)A; p.lda = lda; p.W = (const bf16*)W; p.C = (bf16*)C; p.ldc = ldc; p.bias = nullptr;
+    p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
+    p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+    p.mode = mode; p.out_mode = 0; p.accumulate = 0; p.Cq = 1;
+    p.ksplit = ksplit; p.ws = ws;
+    long long M = (long long)Bn * Dm * Hm * Wm;
+    if (M <= 0 || M > 0x7fffffffLL) return -1;
+    p.M = (int)M;
+    int rc = (K % 32 == 0) ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
+    if (rc != 0) return rc;
+    const long long total = M * (N / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 8 * fcd_num_sms()) blocks = 8 * fcd_num_sms();
+    igemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, (bf16*)C, ldc, bias, (int)M, N, ksplit, accumulate);
+    return (int)cudaGetLastError();
 }

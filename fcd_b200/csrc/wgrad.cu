@@ -162,23 +162,52 @@ int launch_wgrad(const WGradParams& p, cudaStream_t stream) {
 }
 
 // out[n*sn + kmap(k)*sk + t*st] = sum_split part[split][t][n][k];  kmap undoes the concat-segment padding.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int T, int N,
-                                    int K, int Np, int Kp, long long sn, long long sk, long long st, int kseg,
-                                    int ksegpad, int accumulate) {
+// Block = (256/ng) outputs x ng split groups (ng = 1, 2, 4, 8 chosen from nsplit): group g adds splits g, g+ng, ...
+// (coalesced rows, 4 loads in flight), the group sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                           int nsplit, int T, int N, int K, int Np, int Kp,
+                                                           long long sn, long long sk, long long st, int kseg,
+                                                           int ksegpad, int accumulate, int ng) {
+    __shared__ float sh[256];
+    const int per = 256 / ng;
+    const int li = threadIdx.x % per, g = threadIdx.x / per;
     const long long total = (long long)T * N * K;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int k = (int)(i % K);
-        long long r = i / K;
-        int n = (int)(r % N);
-        int t = (int)(r / N);
-        int kp = (k / kseg) * ksegpad + (k % kseg);
+    const long long sstride = (long long)T * Np * Kp;
+    for (long long i0 = blockIdx.x * (long long)per; i0 < total; i0 += (long long)gridDim.x * per) {
+        const long long i = i0 + li;
         float s = 0.f;
-        const long long off = ((long long)t * Np + n) * Kp + kp;
-        const long long sstride = (long long)T * Np * Kp;
-        for (int sp = 0; sp < nsplit; ++sp) s += part[sp * sstride + off];
-        const long long o = n * sn + k * sk + t * st;
-        out[o] = accumulate ? out[o] + s : s;
+        long long o = 0;
+        if (i < total) {
+            const int k = (int)(i % K);
+            const long long r = i / K;
+            const int n = (int)(r % N);
+            const int t = (int)(r / N);
+            const int kp = (k / kseg) * ksegpad + (k % kseg);
+            const float* src = part + ((long long)t * Np + n) * Kp + kp;
+            o = n * sn + k * sk + t * st;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int sp = g;
+            for (; sp + 3 * ng < nsplit; sp += 4 * ng) {
+                a0 += src[sp * sstride];
+                a1 += src[(sp + ng) * sstride];
+                a2 += src[(sp + 2 * ng) * sstride];
+                a3 += src[(sp + 3 * ng) * sstride];
+            }
+            for (; sp < nsplit; sp += ng) a0 += src[sp * sstride];
+            s = (a0 + a1) + (a2 + a3);
+        }
+        if (ng == 1) {
+            if (i < total) out[o] = accumulate ? out[o] + s : s;
+            continue;
+        }
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        if (g == 0 && i < total) {
+            float tot = 0.f;
+            for (int q = 0; q < ng; ++q) tot += sh[q * per + li];
+            out[o] = accumulate ? out[o] + tot : tot;
+        }
+        __syncthreads();
     }
 }
 
@@ -232,11 +261,15 @@ FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, i
                              long long sn, long long sk, long long st, int kseg, int ksegpad, int accumulate,
                              cudaStream_t stream) {
     long long total = (long long)T * N * K;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 4096) blocks = 4096;
+    // few outputs and many splits: several split groups per output; many outputs: one thread per output
+    int ng = 1;
+    while (ng < 8 && ng * 2 <= nsplit / 4 && total * ng < 256LL * 4 * fcd_num_sms()) ng *= 2;
+    const int per = 256 / ng;
+    int blocks = (int)((total + per - 1) / per);
+    if (blocks > 16 * fcd_num_sms()) blocks = 16 * fcd_num_sms();
     if (blocks < 1) blocks = 1;
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(part, out, nsplit, T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad,
-                                                    accumulate);
+                                                    accumulate, ng);
     FCD_LAUNCH_CHECK();
 }
 

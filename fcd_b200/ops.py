@@ -140,6 +140,19 @@ def _w32(weight):
     return w
 
 
+def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
+    """Legacy (mma.sync) implicit GEMM into contiguous rows of c; split-K when the output grid cannot fill the SMs."""
+    M = B * dst[0] * dst[1] * dst[2]
+    ks = _lib.lib().fcd_igemm_ksplit(M, N, K, k ** 3)
+    common = dict(A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), bias=bias, Bn=B, Ds=src[0], Hs=src[1], Ws=src[2], Dm=dst[0],
+                  Hm=dst[1], Wm=dst[2], K=K, N=N, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=mode, accumulate=0)
+    if ks > 1:
+        ws = torch.empty((ks, M, N), dtype=torch.float32, device=a.device)
+        call("fcd_igemm_splitk", ws=ws, ksplit=ks, **common)
+    else:
+        call("fcd_igemm", out_mode=0, Cq=0, **common)
+
+
 class ConvFn(Function):
     """nn.Conv3d (k in {1,3}, stride in {1,2}, pad = (k-1)//2 or given) and nn.Linear (k=1) on channels-last rows.
 
@@ -170,9 +183,7 @@ class ConvFn(Function):
                  nseg=nseg)
         else:
             wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
-            call("fcd_igemm", A=x, lda=ld(x), W=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, Ds=D, Hs=H, Ws=W,
-                 Dm=Do, Hm=Ho, Wm=Wo, K=Kp, N=Np, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=0, out_mode=0,
-                 accumulate=0, Cq=0)
+            _igemm(x, wp, y, _vpad(bias, Np), B, (D, H, W), (Do, Ho, Wo), Kp, Np, k, stride, pad, 0)
         ctx.save_for_backward(x, weight)
         ctx.cfg = (k, stride, pad, seg, segpad, bias is not None)
         return y
@@ -198,12 +209,12 @@ class ConvFn(Function):
                      flip=1, nseg=nseg)
             else:
                 wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
-                call("fcd_igemm", A=dy, lda=ld(dy), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=Do, Hs=Ho, Ws=Wo,
-                     Dm=D, Hm=H, Wm=W, K=Np, N=Kp, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=1, out_mode=0,
-                     accumulate=0, Cq=0)
+                _igemm(dy, wt, dx, None, B, (Do, Ho, Wo), (D, H, W), Np, Kp, k, stride, pad, 1)
         if ctx.needs_input_grad[1]:
             _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
             ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (USE_TC and k == 3 and stride == 1 and pad == 1) else 0
+            if ns > 0 and ((Kp + 31) // 32) * ((Np + 31) // 32) > 4:
+                ns = 0          # many thin slices over a small volume: the split-K mma.sync kernel is the better fit
             if ns > 0:
                 # tcgen05 path: 32- (or 16-) channel slices of x (shifted operand) against slices of dy
                 cs = 32 if Kp % 32 == 0 else 16

@@ -38,6 +38,11 @@ FCD_API int fcd_pack_weight(const float* src, void* dst, int T, int N, int K, in
 FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias, int Bn,
                       int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh, int kw, int stride,
                       int pad, int mode, int out_mode, int accumulate, int Cq, cudaStream_t stream);
+FCD_API int fcd_igemm_ksplit(long long M, int N, int K, int T);
+FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
+                             int Bn, int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh,
+                             int kw, int stride, int pad, int mode, int accumulate, float* ws, int ksplit,
+                             cudaStream_t stream);
 FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
                       int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
                       int nsplit, cudaStream_t stream);
