@@ -8,7 +8,7 @@ one "step" = forward + fused loss + backward + gradient all-reduce (N>1) + optim
   value : patches/s with the inputs resident in HBM (whole job, all ranks), CUDA-event timed, max over ranks.
   e2e   : the same metric through the public API with HOST (pinned) inputs: the H2D copy of the batch and the D2H
           read of the loss are inside every timed step.
-  roofline     : the conv kernel family (fcd_igemm + fcd_wgrad) measured with CUDA events inside one eager step.
+  roofline     : the tcgen05 conv kernel (and the whole conv family) measured with CUDA events inside one eager step.
   cpu_baseline : the CPU oracle (oracle/, kind "port": the reference's MONAI dependency is not installable here)
                  timed on the host cores on a bounded sample (rank 0, N=1 only).
   aux          : sliding-window inference vols/s on a synthetic 256x256x192 volume (configs[4]).
@@ -313,18 +313,30 @@ def main():
     e2e_value = patches / (ms_e2e / 1e3)
     final_loss = float(loss_host)
 
-    # ---- roofline of the conv family from the profiled eager step
-    conv = [v for k, v in agg.items() if k.split(":")[0] in ("fcd_igemm", "fcd_wgrad")]
-    conv_ms = sum(v["ms"] for v in conv)
-    conv_fl = sum(v["flops"] for v in conv)
+    # ---- roofline from the profiled eager step (CUDA events around every C-ABI call on the launching stream).
+    # Dominant kernel = the tcgen05/TMEM implicit-GEMM conv (forward + data gradient launches); the whole conv family
+    # (tcgen05 conv + tcgen05 wgrad + the mma.sync kernels of the deep levels, with their reduce kernels) beside it.
+    def fam(names):
+        sel = [v for k, v in agg.items() if k.split(":")[0] in names]
+        return sum(v["ms"] for v in sel), sum(v["flops"] for v in sel), sum(v["calls"] for v in sel)
+    tc_ms, tc_fl, tc_calls = fam(("fcd_conv3_tc",))
+    conv_ms, conv_fl, conv_calls = fam(("fcd_conv3_tc", "fcd_wgrad3_tc", "fcd_igemm", "fcd_igemm_splitk", "fcd_wgrad",
+                                        "fcd_wgrad_reduce", "fcd_pack_weight"))
     step_ms_eager = sum(v["ms"] for v in agg.values())
-    top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]
-    roof = {"bound": "tensor", "kernel": "fcd_igemm+fcd_wgrad (conv fwd/dgrad/wgrad family)",
-            "achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None, "peak": pk["tf_sust"],
-            "unit": "TFLOP/s", "frac": (conv_fl / (conv_ms * 1e-3) / 1e12 / pk["tf_sust"]) if conv_ms > 0 else None,
-            "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
-            "share_of_step": conv_ms / step_ms_eager if step_ms_eager > 0 else None,
-            "launches": sum(v["calls"] for v in conv),
+    top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:10]
+    tf = (lambda fl, ms: fl / (ms * 1e-3) / 1e12 if ms > 0 else None)
+    roof = {"bound": "tensor", "kernel": "fcd_conv3_tc (tcgen05/TMEM implicit-GEMM conv3x3x3, forward + data-gradient launches)",
+            "achieved": tf(tc_fl, tc_ms), "peak": pk["tf_sust"], "unit": "TFLOP/s",
+            "frac": (tf(tc_fl, tc_ms) / pk["tf_sust"]) if tc_ms > 0 else None,
+            "traffic": None,
+            "traffic_sample": {"launch": "16->16 @128^3 batch 2 (profiles/r01_ncu_conv3_tc_16x16.txt)",
+                               "dram_bytes": 228.4e6, "algorithmic_bytes": 268.4e6},
+            "peak_source": pk["source"] + " (sustained bf16)",
+            "share_of_step": tc_ms / step_ms_eager if step_ms_eager > 0 else None, "launches": tc_calls,
+            "conv_family": {"kernels": "fcd_conv3_tc + fcd_wgrad3_tc + fcd_igemm(_splitk) + fcd_wgrad(+reduce, pack)",
+                            "achieved": tf(conv_fl, conv_ms), "frac": (tf(conv_fl, conv_ms) / pk["tf_sust"]) if conv_ms > 0 else None,
+                            "share_of_step": conv_ms / step_ms_eager if step_ms_eager > 0 else None,
+                            "launches": conv_calls},
             "top_calls_ms": {k: round(v["ms"], 3) for k, v in top}}
     hbm = [v for k, v in agg.items() if k.split(":")[0] in ("fcd_norm_apply", "fcd_norm_stats", "fcd_norm_bwd")]
     hbm_ms = sum(v["ms"] for v in hbm)

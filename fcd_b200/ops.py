@@ -123,6 +123,55 @@ def _colsum(x, C):
 
 
 USE_TC = os.environ.get("FCD_TC", "1") != "0"     # tcgen05 conv path (debug switch; the default is on)
+WGRAD_OVERLAP = os.environ.get("FCD_WGRAD_OVERLAP", "1") != "0"
+
+
+class _SideWork:
+    """Weight gradients are not on the backward critical path (only the optimizer reads them), and on the deep
+    levels they are many small kernels that cannot fill 148 SMs.  They are launched on one side stream per device,
+    forked from the current stream, and joined by an autograd end-of-backward callback.  The operands are kept alive
+    until that join, so the caching allocator cannot hand their memory to main-stream work while the side stream
+    still reads it (no record_stream needed; works inside CUDA-graph capture as a fork/join branch)."""
+
+    def __init__(self):
+        self.streams = {}
+        self.pending = []
+        self.armed = False
+
+    def stream(self, dev):
+        st = self.streams.get(dev)
+        if st is None:
+            st = self.streams[dev] = torch.cuda.Stream(device=dev)
+        return st
+
+    def run(self, fn, *keep):
+        dev = keep[0].device
+        main = torch.cuda.current_stream(dev)
+        side = self.stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = fn()
+        self.pending.append((dev, main, keep))
+        if not self.armed:
+            self.armed = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.join)
+        return out
+
+    def join(self):
+        for dev, main, _ in self.pending:
+            main.wait_stream(self.stream(dev))
+        self.pending.clear()
+        self.armed = False
+
+
+_SIDE = _SideWork()
+
+
+def _off_critical_path(fn, *keep):
+    """Run fn() on the weight-gradient side stream (or inline when the overlap is switched off)."""
+    if WGRAD_OVERLAP and torch.is_tensor(keep[0]) and keep[0].is_cuda:
+        return _SIDE.run(fn, *keep)
+    return fn()
 _LAST_PART = [None]                               # fused InstanceNorm partials of the most recent ConvFn.forward
 
 
@@ -211,25 +260,34 @@ class ConvFn(Function):
                 wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
                 _igemm(dy, wt, dx, None, B, (Do, Ho, Wo), (D, H, W), Np, Kp, k, stride, pad, 1)
         if ctx.needs_input_grad[1]:
-            _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
-            ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (USE_TC and k == 3 and stride == 1 and pad == 1) else 0
-            if ns > 0 and ((Kp + 31) // 32) * ((Np + 31) // 32) > 4:
-                ns = 0          # many thin slices over a small volume: the split-K mma.sync kernel is the better fit
-            if ns > 0:
-                # tcgen05 path: 32- (or 16-) channel slices of x (shifted operand) against slices of dy
-                cs = 32 if Kp % 32 == 0 else 16
-                cu = 32 if Np % 32 == 0 else 16
-                part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
-                for n_off in range(0, Np, cu):
-                    for k_off in range(0, Kp, cs):
-                        call("fcd_wgrad3_tc", S=x[..., k_off:], lds=ld(x), U=dy[..., n_off:], ldu=ld(dy), part=part,
-                             ldn=Np, ldk=Kp, n_off=n_off, k_off=k_off, Bn=B, D=D, H=H, W=W, CS=cs, CU=cu)
+            def wgrad_work():
+                _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T,
+                               2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
+                ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (USE_TC and k == 3 and stride == 1 and pad == 1) else 0
+                if ns > 0 and ((Kp + 31) // 32) * ((Np + 31) // 32) > 4:
+                    ns = 0      # many thin slices over a small volume: the split-K mma.sync kernel is the better fit
+                if ns > 0:
+                    # tcgen05 path: 32- (or 16-) channel slices of x (shifted operand) against slices of dy
+                    cs = 32 if Kp % 32 == 0 else 16
+                    cu = 32 if Np % 32 == 0 else 16
+                    part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
+                    for n_off in range(0, Np, cu):
+                        for k_off in range(0, Kp, cs):
+                            call("fcd_wgrad3_tc", S=x[..., k_off:], lds=ld(x), U=dy[..., n_off:], ldu=ld(dy),
+                                 part=part, ldn=Np, ldk=Kp, n_off=n_off, k_off=k_off, Bn=B, D=D, H=H, W=W, CS=cs,
+                                 CU=cu)
+                else:
+                    part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
+                g = torch.empty_like(weight, dtype=torch.float32)
+                call("fcd_wgrad_reduce", part=part, out=g, nsplit=ns, T=T, N=Co, K=Ci, Np=Np, Kp=Kp, sn=Ci * T, sk=T,
+                     st=1, kseg=seg, ksegpad=segpad, accumulate=0)
+                return g.to(weight.dtype)
+            # overlap only when autograd will simply adopt the result as .grad (no accumulation kernel, no tensor
+            # hooks reading it on the main stream before the end-of-backward join)
+            if weight.is_leaf and weight.grad is None and not getattr(weight, "_backward_hooks", None):
+                dw = _off_critical_path(wgrad_work, dy, x)
             else:
-                part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
-            dw = torch.empty_like(weight, dtype=torch.float32)
-            call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=T, N=Co, K=Ci, Np=Np, Kp=Kp, sn=Ci * T, sk=T,
-                 st=1, kseg=seg, ksegpad=segpad, accumulate=0)
-            dw = dw.to(weight.dtype)
+                dw = wgrad_work()
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy, Co)
         return dx, dw, db, None, None, None, None
