@@ -116,11 +116,20 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, floa
 #pragma unroll
     for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
     const bf16* base = x + (long long)b * S * ld + c8 * 8;
-    for (long long s = s0 + r0; s < s1; s += rstep) {
-        float f[8];
-        unpack8(ld8(base + s * ld), f);
+    for (long long s = s0 + r0; s < s1; s += 4LL * rstep) {      // 4 independent 16 B loads in flight per thread
+        bf16x8 v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sum[k] += f[k]; sq[k] = fmaf(f[k], f[k], sq[k]); }
+        for (int u = 0; u < 4; ++u)
+            if (s + u * rstep < s1) v[u] = ld8_stream(base + (s + u * rstep) * ld);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (s + u * rstep < s1) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { sum[k] += f[k]; sq[k] = fmaf(f[k], f[k], sq[k]); }
+            }
+        }
     }
     __shared__ float sh[256 * 16];
 #pragma unroll
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restr
 
 // y = act( g1*(x1-mean1)*rstd1 + b1  [+ g2*(x2-mean2)*rstd2 + b2]  [+ r] ),  act(v) = v > 0 ? v : slope*v
 // mean/rstd are per (b,c); gamma/beta per c (nullptr => 1/0).  grid.y = B.
-__global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, const float* __restrict__ mean1,
+__global__ void __launch_bounds__(256, 2) norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, const float* __restrict__ mean1,
                                   const float* __restrict__ rstd1, const float* __restrict__ gamma1,
                                   const float* __restrict__ beta1, const bf16* __restrict__ x2, long long ld2,
                                   const float* __restrict__ mean2, const float* __restrict__ rstd2,
@@ -214,33 +223,52 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, co
             a2[k] = o2[k] = 0.f;
         }
     }
-    const long long total = S * C8;
-    for (long long i = gtid; i < total; i += gstride) {
-        const long long s = i / C8;
-        const long long row = (long long)b * S + s;
-        float f[8], v[8];
-        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
+    // rows r0, r0 + rstep, ... (gstride is a multiple of C8, so c8 is fixed per thread and no division is needed);
+    // 4 rows per iteration: all loads first (up to 12 independent 16 B loads in flight), then the math.
+    const long long r0 = gtid / C8, rstep = gstride / C8;
+    const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
+    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    const bf16* pr = res ? res + (long long)b * S * ldr + c8 * 8 : nullptr;
+    bf16* py = y + (long long)b * S * ldy + c8 * 8;
+    for (long long r = r0; r < S; r += 4 * rstep) {
+        bf16x8 u1[4], u2[4], ur[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaf(f[k], a1[k], o1[k]);
-        if (x2) {
-            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += fmaf(f[k], a2[k], o2[k]);
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + u * rstep;
+            if (rr < S) {
+                u1[u] = ld8_stream(p1 + rr * ld1);
+                if (p2) u2[u] = ld8_stream(p2 + rr * ld2);
+                if (pr) ur[u] = ld8_stream(pr + rr * ldr);
+            }
         }
-        if (res) {
-            unpack8(ld8(res + row * ldr + c8 * 8), f);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += f[k];
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + u * rstep;
+            if (rr >= S) break;
+            float f[8], v[8];
+            unpack8(u1[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaf(f[k], a1[k], o1[k]);
+            if (p2) {
+                unpack8(u2[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += fmaf(f[k], a2[k], o2[k]);
+            }
+            if (pr) {
+                unpack8(ur[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += f[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+            st8(py + rr * ldy, pack8(v));
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
-        st8(y + row * ldy + c8 * 8, pack8(v));
     }
 }
 
 // Backward statistics.  ds = dy * act'(y) (y = saved forward output; nullptr => no activation).
 // part[b][chunk][0..C) = sum ds, [C..2C) = sum ds*xhat1, [2C..3C) = sum ds*xhat2 (if x2).
-__global__ void norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
                                       const float* __restrict__ mean1, const float* __restrict__ rstd1,
                                       const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
@@ -259,22 +287,40 @@ __global__ void norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long ldd
         m2[k] = x2 ? mean2[b * C + c] : 0.f; i2[k] = x2 ? rstd2[b * C + c] : 0.f;
         a0[k] = a1[k] = a2[k] = 0.f;
     }
-    for (long long s = s0 + r0; s < s1; s += rstep) {
-        const long long row = (long long)b * S + s;
-        float g[8], f[8];
-        unpack8(ld8(dy + row * lddy + c8 * 8), g);
-        if (y) {
-            unpack8(ld8(y + row * ldy + c8 * 8), f);
+    const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
+    const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
+    const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
+    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    for (long long s = s0 + r0; s < s1; s += 2LL * rstep) {      // 2 rows x up to 4 streams of 16 B loads in flight
+        bf16x8 vg[2], vy[2], v1[2], v2[2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = f[k] > 0.f ? g[k] : g[k] * slope;
+        for (int u = 0; u < 2; ++u) {
+            const long long rr = s + u * rstep;
+            if (rr < s1) {
+                vg[u] = ld8_stream(pdy + rr * lddy);
+                if (py) vy[u] = ld8_stream(py + rr * ldy);
+                v1[u] = ld8_stream(p1 + rr * ld1);
+                if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
+            }
         }
-        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], (f[k] - m1[k]) * i1[k], a1[k]); }
-        if (x2) {
-            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
+        for (int u = 0; u < 2; ++u) {
+            if (s + u * rstep >= s1) break;
+            float g[8], f[8];
+            unpack8(vg[u], g);
+            if (py) {
+                unpack8(vy[u], f);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a2[k] = fmaf(g[k], (f[k] - m2[k]) * i2[k], a2[k]);
+                for (int k = 0; k < 8; ++k) g[k] = f[k] > 0.f ? g[k] : g[k] * slope;
+            }
+            unpack8(v1[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], (f[k] - m1[k]) * i1[k], a1[k]); }
+            if (p2) {
+                unpack8(v2[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a2[k] = fmaf(g[k], (f[k] - m2[k]) * i2[k], a2[k]);
+            }
         }
     }
     __shared__ float sh[256 * 24];
@@ -378,7 +424,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
 }
 
 // dx1 = k1*ds - k2 - k3*xhat1 ; dx2 likewise (optional) ; dres = ds (optional).  ds = dy*act'(y).
-__global__ void norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
                                       const float* __restrict__ mean1, const float* __restrict__ rstd1,
                                       const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
@@ -391,42 +437,71 @@ __global__ void norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long ldd
     const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long gstride = (long long)gridDim.x * blockDim.x;
     const int c8 = (int)(gtid % C8);
-    float m1[8], i1[8], m2[8], i2[8], k[8][6];
+    // dx_j = k0_j*ds - k1_j - k2_j*xhat_j  with xhat = (x - m)*i  ==>  dx_j = k0_j*ds - cB_j - cX_j*x
+    float kA1[8], cB1[8], cX1[8], kA2[8], cB2[8], cX2[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int c = c8 * 8 + q;
-        m1[q] = mean1[b * C + c]; i1[q] = rstd1[b * C + c];
-        m2[q] = x2 ? mean2[b * C + c] : 0.f; i2[q] = x2 ? rstd2[b * C + c] : 0.f;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) k[q][j] = coef[((long long)b * C + c) * 6 + j];
-    }
-    const long long total = S * C8;
-    for (long long i = gtid; i < total; i += gstride) {
-        const long long row = (long long)b * S + i / C8;
-        float g[8], f[8], o[8];
-        unpack8(ld8(dy + row * lddy + c8 * 8), g);
-        if (y) {
-            unpack8(ld8(y + row * ldy + c8 * 8), f);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) g[q] = f[q] > 0.f ? g[q] : g[q] * slope;
-        }
-        unpack8(ld8(x1 + row * ld1 + c8 * 8), f);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = k[q][0] * g[q] - k[q][1] - k[q][2] * ((f[q] - m1[q]) * i1[q]);
-        st8(dx1 + row * ldd1 + c8 * 8, pack8(o));
+        const float* kk = coef + ((long long)b * C + c) * 6;
+        const float m1 = mean1[b * C + c], i1 = rstd1[b * C + c];
+        kA1[q] = kk[0]; cX1[q] = kk[2] * i1; cB1[q] = kk[1] - kk[2] * i1 * m1;
         if (x2) {
-            unpack8(ld8(x2 + row * ld2 + c8 * 8), f);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = k[q][3] * g[q] - k[q][4] - k[q][5] * ((f[q] - m2[q]) * i2[q]);
-            st8(dx2 + row * ldd2 + c8 * 8, pack8(o));
+            const float m2 = mean2[b * C + c], i2 = rstd2[b * C + c];
+            kA2[q] = kk[3]; cX2[q] = kk[5] * i2; cB2[q] = kk[4] - kk[5] * i2 * m2;
+        } else {
+            kA2[q] = cX2[q] = cB2[q] = 0.f;
         }
-        if (dres) {
-            if (acc_res) {
-                unpack8(ld8(dres + row * lddr + c8 * 8), f);
+    }
+    const long long r0 = gtid / C8, rstep = gstride / C8;     // gstride is a multiple of C8: c8 fixed per thread
+    const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
+    const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
+    const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
+    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    bf16* q1 = dx1 + (long long)b * S * ldd1 + c8 * 8;
+    bf16* q2 = x2 ? dx2 + (long long)b * S * ldd2 + c8 * 8 : nullptr;
+    bf16* qr = dres ? dres + (long long)b * S * lddr + c8 * 8 : nullptr;
+    for (long long r = r0; r < S; r += 2 * rstep) {           // 2 rows x up to 5 streams of 16 B loads in flight
+        bf16x8 vg[2], vy[2], v1[2], v2[2], vr[2];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) g[q] += f[q];
+        for (int u = 0; u < 2; ++u) {
+            const long long rr = r + u * rstep;
+            if (rr < S) {
+                vg[u] = ld8_stream(pdy + rr * lddy);
+                if (py) vy[u] = ld8_stream(py + rr * ldy);
+                v1[u] = ld8_stream(p1 + rr * ld1);
+                if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
+                if (qr && acc_res) vr[u] = ld8(qr + rr * lddr);
             }
-            st8(dres + row * lddr + c8 * 8, pack8(g));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long rr = r + u * rstep;
+            if (rr >= S) break;
+            float g[8], f[8], o[8];
+            unpack8(vg[u], g);
+            if (py) {
+                unpack8(vy[u], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] = f[q] > 0.f ? g[q] : g[q] * slope;
+            }
+            unpack8(v1[u], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = fmaf(kA1[q], g[q], -fmaf(cX1[q], f[q], cB1[q]));
+            st8(q1 + rr * ldd1, pack8(o));
+            if (p2) {
+                unpack8(v2[u], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = fmaf(kA2[q], g[q], -fmaf(cX2[q], f[q], cB2[q]));
+                st8(q2 + rr * ldd2, pack8(o));
+            }
+            if (qr) {
+                if (acc_res) {
+                    unpack8(vr[u], f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] += f[q];
+                }
+                st8(qr + rr * lddr, pack8(g));
+            }
         }
     }
 }
