@@ -151,15 +151,23 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dln, long long lddl, cons
     }
 }
 
-// out0[c] = sum_k part[k][0][c], out1[c] = sum_k part[k][1][c]   (c < C)
-__global__ void pair_colsum_kernel(const float* __restrict__ part, int nblk, int Cp, int C, float* __restrict__ out0,
-                                   float* __restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// out0[c] = sum_k part[k][0][c], out1[c] = sum_k part[k][1][c]   (c < C).  One warp per column: lanes stride over
+// the nblk partial rows, fp64 accumulation, fixed shuffle order (deterministic).
+__global__ void __launch_bounds__(256) pair_colsum_kernel(const float* __restrict__ part, int nblk, int Cp, int C,
+                                                          float* __restrict__ out0, float* __restrict__ out1) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblk; ++k) { a += part[(long long)k * 2 * Cp + c]; b += part[(long long)k * 2 * Cp + Cp + c]; }
-    if (out0) out0[c] = (float)a;
-    if (out1) out1[c] = (float)b;
+    for (int k = lane; k < nblk; k += 32) { a += part[(long long)k * 2 * Cp + c]; b += part[(long long)k * 2 * Cp + Cp + c]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        if (out0) out0[c] = (float)a;
+        if (out1) out1[c] = (float)b;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ DSA forward
@@ -839,7 +847,7 @@ FCD_API int fcd_ln_bwd(const void* dln, long long lddl, const void* dtd, long lo
     const int nblk = fcd_ln_bwd_blocks(N, Cp);
     ln_bwd_kernel<<<nblk, 256, 0, st>>>((const bf16*)dln, lddl, (const bf16*)dtd, lddt, (const bf16*)t, ldt, mean, rstd,
                                         w, (bf16*)dx, lddx, dpos, part, B, N, C, LPT);
-    pair_colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nblk, Cp, C, dw, db);
+    pair_colsum_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nblk, Cp, C, dw, db);
     FCD_LAUNCH_CHECK();
 }
 
@@ -920,7 +928,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
     float ds; uint32_t dth;
     drop_params(sa_drop, ds, dth);
     dsa_dgamma_kernel<<<gblk, 256, 0, st>>>((const bf16*)dy, lddy, xca, tsa, gpart, rows, N, C, LPT);
-    pair_colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(gpart, gblk, Cp, C, dgamma, nullptr);
+    pair_colsum_kernel<<<(C + 7) / 8, 256, 0, st>>>(gpart, gblk, Cp, C, dgamma, nullptr);
     {
         auto run = [&]() -> int {
             DSA_DISPATCH(launch_bwd_reduce, (const bf16*)qkvv, ldq, (const bf16*)dy, lddy, gamma, inv_n, KV, temperature2,

@@ -117,6 +117,53 @@ __global__ void __launch_bounds__(256) outconv_bwd_kernel(const bf16* __restrict
     }
 }
 
+// Fast path for the shape every model of the hot path has (C = 16 feature channels, Co = 2 classes): thread per voxel,
+// the 2x16 dW and 2 dbias partial sums live in registers for the thread's whole voxel range (no per-voxel shuffles),
+// one warp-shuffle + shared-memory reduction per block at the end.  Same part[] layout as the generic kernel.
+__global__ void __launch_bounds__(256) outconv_bwd_c16o2_kernel(const bf16* __restrict__ x, long long ld,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ dout,
+                                                                bf16* __restrict__ dx, long long lddx,
+                                                                float* __restrict__ part, long long S,
+                                                                long long total) {
+    constexpr int C = 16, Co = 2, W1 = C + 1;
+    __shared__ float red[8][Co * W1];
+    float w0[C], w1[C], a0[C], a1[C], b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { w0[c] = w[c]; w1[c] = w[C + c]; a0[c] = a1[c] = 0.f; }
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        const long long b = v / S, s = v - b * S;
+        const float g0 = dout[(b * Co) * S + s], g1 = dout[(b * Co + 1) * S + s];
+        float f[C], o[C];
+        unpack8(ld8_stream(x + v * ld), f);
+        unpack8(ld8_stream(x + v * ld + 8), f + 8);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            o[c] = fmaf(g0, w0[c], g1 * w1[c]);
+            a0[c] = fmaf(g0, f[c], a0[c]);
+            a1[c] = fmaf(g1, f[c], a1[c]);
+        }
+        b0 += g0; b1 += g1;
+        st8(dx + v * lddx, pack8(o));
+        st8(dx + v * lddx + 8, pack8(o + 8));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float s0 = warp_sum(a0[c]), s1 = warp_sum(a1[c]);
+        if (lane == 0) { red[warp][c] = s0; red[warp][W1 + c] = s1; }
+    }
+    b0 = warp_sum(b0); b1 = warp_sum(b1);
+    if (lane == 0) { red[warp][C] = b0; red[warp][W1 + C] = b1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Co * W1; i += blockDim.x) {
+        float t = 0.f;
+        for (int wq = 0; wq < 8; ++wq) t += red[wq][i];
+        part[(long long)blockIdx.x * Co * W1 + i] = t;
+    }
+}
+
 __global__ void outconv_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int C, int Co,
                                           float* __restrict__ dw, float* __restrict__ db) {
     const int W1 = C + 1;
@@ -150,7 +197,10 @@ FCD_API int fcd_outconv_bwd(const void* x, long long ld, const float* w, const f
     if (C % 8 || C > OC_MAX_C || Co > OC_MAX_CO || Co < 1) return -1;
     const long long total = (long long)B * S;
     const int nblk = fcd_outconv_blocks();
-    outconv_bwd_kernel<<<nblk, 256, 0, st>>>((const bf16*)x, ld, w, dout, (bf16*)dx, lddx, part, S, total, C, Co);
+    if (C == 16 && Co == 2)
+        outconv_bwd_c16o2_kernel<<<nblk, 256, 0, st>>>((const bf16*)x, ld, w, dout, (bf16*)dx, lddx, part, S, total);
+    else
+        outconv_bwd_kernel<<<nblk, 256, 0, st>>>((const bf16*)x, ld, w, dout, (bf16*)dx, lddx, part, S, total, C, Co);
     outconv_bwd_reduce_kernel<<<1, 256, 0, st>>>(part, nblk, C, Co, dw, db);
     FCD_LAUNCH_CHECK();
 }

@@ -232,7 +232,53 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     }
 }
 
+// One launch packs MANY weights: the host keeps a table of pack jobs (one per conv layer and layout) and every block
+// finds its job by binary search over the jobs' first-block indices.  Same arithmetic as pack_weight_kernel.
+struct PackJob {
+    const float* src;
+    bf16* dst;
+    long long sn, sk, st, total;
+    int T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk0;
+    int pad_[2];
+};
+static_assert(sizeof(PackJob) == 96, "PackJob layout is mirrored by fcd_b200/ops.py");
+constexpr int PACK_EPB = 256 * 8;     // elements per block
+
+__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {                                   // last job with blk0 <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PackJob j = jobs[lo];
+    const long long base = (long long)(blockIdx.x - j.blk0) * PACK_EPB;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const long long i = base + u * 256 + threadIdx.x;
+        if (i >= j.total) break;
+        const int kp = (int)(i % j.Kp);
+        const long long r = i / j.Kp;
+        const int np_ = (int)(r % j.Np);
+        const int t = (int)(r / j.Np);
+        float v = 0.f;
+        const int seg = kp / j.ksegpad, within = kp % j.ksegpad;
+        const int k = seg * j.kseg + within;
+        const int nsg = np_ / j.nsegpad, nwithin = np_ % j.nsegpad;
+        const int n = nsg * j.nseg + nwithin;
+        if (nwithin < j.nseg && n < j.N && within < j.kseg && k < j.K) v = j.src[n * j.sn + k * j.sk + t * j.st];
+        j.dst[i] = __float2bfloat16(v);
+    }
+}
+
 }  // namespace
+
+// jobs: device array of `njobs` PackJob records (96 bytes each, see above), nblocks = sum over jobs of
+// ceil(total / 2048).  Replaces one fcd_pack_weight launch per layer and layout with one launch per forward.
+FCD_API int fcd_pack_weight_batched(const void* jobs, int njobs, int nblocks, cudaStream_t stream) {
+    if (njobs < 1 || nblocks < 1) return -1;
+    pack_weight_batched_kernel<<<nblocks, 256, 0, stream>>>((const PackJob*)jobs, njobs);
+    FCD_LAUNCH_CHECK();
+}
 
 // Weight gradient of Conv3d / ConvTranspose3d / Linear (autograd of the modules cited in igemm.cu).
 // `part` must hold nsplit*T*Np*Kp floats.  tiles_per_split = ceil(ceil(M/128)/nsplit).

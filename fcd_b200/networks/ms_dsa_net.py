@@ -59,6 +59,7 @@ class BaseUNet(nn.Module):
 
     def forward_cl(self, out):
         """Forward from a channels-last bf16 batch [B,D,H,W,16] (what fcd_sw_gather produces)."""
+        ops.prepack_weights(out.device)
         feats = []
         for i, enc in enumerate(self.encoders):
             out = enc(out)
@@ -148,6 +149,7 @@ class MS_DSA_NET(nn.Module):
 
     def forward_cl(self, x0):
         """Forward from a channels-last bf16 batch [B,D,H,W,16] (what fcd_sw_gather produces)."""
+        ops.prepack_weights(x0.device)
         if tuple(x0.shape[1:4]) != self.img_size:
             raise ValueError(f"MS_DSA_NET was built for patches of {self.img_size}, got {tuple(x0.shape[1:4])}")
         x1 = self.encoder1(x0)

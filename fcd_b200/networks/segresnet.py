@@ -158,6 +158,7 @@ class SegResNet(nn.Module):
 
     # -- forward ---------------------------------------------------------------------------------------------
     def encode(self, x):
+        ops.prepack_weights(x.device)
         x = ops.conv3d(x, self.convInit.conv.weight, None, 3)
         if self.dropout_prob is not None:
             x = ops.dropout3d(x, self.dropout.p, self.training)

@@ -80,14 +80,96 @@ def to_ncdhw(x: torch.Tensor, C: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ conv family
+class _PackCache:
+    """Packed bf16 copies of the parameters the mma.sync kernels read ([tap][Cout][Cin], zero padded).
+
+    A job is keyed by (parameter storage address, layout arguments) and stamped with the parameter's in-place
+    version counter, so a stale copy is never used: `get` re-packs (one small launch) whenever the stamp differs.
+    `refresh` re-packs EVERY known job in ONE launch (fcd_pack_weight_batched) and is called by the network at the
+    top of each forward: from the second step on the ~145 per-layer pack launches of a training step become one."""
+
+    JOB = None      # numpy dtype mirroring struct PackJob in csrc/wgrad.cu (96 bytes)
+
+    def __init__(self):
+        self.jobs = {}          # key -> [param_ref, args, dst, version]
+        self.table = {}         # device -> (njobs_at_build, jobs tensor, nblocks, keys)
+
+    @staticmethod
+    def _param_of(w):
+        base = w._base if w._is_view() else w
+        return base if isinstance(base, torch.nn.Parameter) else None
+
+    def get(self, w, args):
+        src = w.detach()
+        if src.dtype != torch.float32 or not src.is_contiguous():
+            src = src.float().contiguous()
+            owner = None
+        else:
+            owner = self._param_of(w)
+        T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
+        if owner is None:       # derived tensor (e.g. the permuted sub-pixel weight): pack into a fresh buffer
+            dst = torch.empty((T, Np, Kp), dtype=BF16, device=src.device)
+            self._pack(src, dst, args)
+            return dst
+        key = (src.data_ptr(), src.device.index) + tuple(args)
+        job = self.jobs.get(key)
+        if job is None:
+            job = self.jobs[key] = [owner, args, torch.empty((T, Np, Kp), dtype=BF16, device=src.device), -1]
+        if job[3] != owner._version or job[0] is not owner:
+            job[0] = owner
+            self._pack(src, job[2], args)
+            job[3] = owner._version
+        return job[2]
+
+    @staticmethod
+    def _pack(src, dst, args):
+        T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
+        call("fcd_pack_weight", src=src, dst=dst, T=T, N=N, K=K, Np=Np, Kp=Kp, sn=sn, sk=sk, st=st, kseg=kseg,
+             ksegpad=ksegpad, nseg=nseg, nsegpad=nsegpad)
+
+    def refresh(self, device):
+        """Re-pack every job of `device` whose parameter changed since it was packed, in one launch."""
+        import numpy as np
+        if not self.jobs:
+            return
+        keys = [k for k, j in self.jobs.items() if k[1] == device.index and j[0].data_ptr() == k[0]]
+        if not keys:
+            return
+        if all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
+            return
+        tab = self.table.get(device.index)
+        if tab is None or tab[0] != keys:
+            if _PackCache.JOB is None:
+                _PackCache.JOB = np.dtype({"names": ["src", "dst", "sn", "sk", "st", "total", "T", "N", "K", "Np", "Kp",
+                                                     "kseg", "ksegpad", "nseg", "nsegpad", "blk0"],
+                                           "formats": ["<u8", "<u8", "<i8", "<i8", "<i8", "<i8"] + ["<i4"] * 10,
+                                           "offsets": [0, 8, 16, 24, 32, 40] + [48 + 4 * i for i in range(10)],
+                                           "itemsize": 96})
+            rec = np.zeros(len(keys), dtype=_PackCache.JOB)
+            blk = 0
+            for i, k in enumerate(keys):
+                owner, args, dst, _ = self.jobs[k]
+                T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
+                total = T * Np * Kp
+                rec[i] = (k[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk)
+                blk += (total + 2047) // 2048
+            dev_tab = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+            tab = self.table[device.index] = (keys, dev_tab, blk)
+        call("fcd_pack_weight_batched", jobs=tab[1], njobs=len(keys), nblocks=tab[2])
+        for k in keys:
+            self.jobs[k][3] = self.jobs[k][0]._version
+
+
+_PACKS = _PackCache()
+
+
+def prepack_weights(device):
+    """Called by the networks at the top of forward(): refresh all cached packed weights in one launch."""
+    _PACKS.refresh(device)
+
+
 def pack_weight(w, T, N, K, Np, Kp, sn, sk, st, kseg=None, ksegpad=None, nseg=None, nsegpad=None):
-    w = w.detach()
-    if w.dtype != torch.float32 or not w.is_contiguous():
-        w = w.float().contiguous()
-    dst = torch.empty((T, Np, Kp), dtype=BF16, device=w.device)
-    call("fcd_pack_weight", src=w, dst=dst, T=T, N=N, K=K, Np=Np, Kp=Kp, sn=sn, sk=sk, st=st,
-         kseg=kseg or K, ksegpad=ksegpad or Kp, nseg=nseg or N, nsegpad=nsegpad or Np)
-    return dst
+    return _PACKS.get(w, (T, N, K, Np, Kp, sn, sk, st, kseg or K, ksegpad or Kp, nseg or N, nsegpad or Np))
 
 
 def _nsplit(M, Np, Kp, T):

@@ -35,6 +35,7 @@ FCD_API int fcd_ndhwc_to_ncdhw(const void* src, float* dst, int B, int C, long l
 FCD_API int fcd_pack_weight(const float* src, void* dst, int T, int N, int K, int Np, int Kp, long long sn,
                             long long sk, long long st, int kseg, int ksegpad, int nseg, int nsegpad,
                             cudaStream_t stream);
+FCD_API int fcd_pack_weight_batched(const void* jobs, int njobs, int nblocks, cudaStream_t stream);
 FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias, int Bn,
                       int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh, int kw, int stride,
                       int pad, int mode, int out_mode, int accumulate, int Cq, cudaStream_t stream);
