@@ -70,6 +70,10 @@ struct Cfg {
     static constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
     static_assert(TCOLS <= 512, "TMEM columns");
     static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;   // + barriers, tmem slot, stats scratch
+    // Small-Cout layers are limited by the latency-bound single-warp roles (one epilogue warp per SMSP needs ~1500
+    // cycles per plane against ~850 cycles of tensor work; ncu: tensor pipe 56 % active for 16->16, 93 % for 64->32),
+    // so two CTAs share an SM when shared memory and registers allow: their roles interleave.
+    static constexpr int CTAS_PER_SM = (COUT == 16 && 2 * SMEM <= 226 * 1024) ? 2 : 1;
     static_assert(NST >= 4, "need >= 4 halo-plane stages");
     static_assert(PLANE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "alignment");
 };
@@ -91,7 +95,7 @@ __device__ __forceinline__ Item decode(const ConvTcParams& p, int item) {
 }
 
 template <int CIN, int COUT, bool STATS, bool FLIP>
-__global__ void __launch_bounds__(NTHREADS, 1) conv3_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_tc_kernel(const ConvTcParams p) {
     using K = Cfg<CIN, COUT>;
     constexpr int NST = K::NST;
     constexpr int DEPTH = NST >= 6 ? 3 : NST - 3;   // cp.async groups in flight per producer lane (>= 1)
@@ -365,7 +369,7 @@ int launch2(const ConvTcParams& p, cudaStream_t stream) {
                              K::SMEM);
         configured = true;
     }
-    const int grid = min(p.nitems, fcd_num_sms());
+    const int grid = min(p.nitems, fcd_num_sms() * K::CTAS_PER_SM);
     conv3_tc_kernel<CIN, COUT, STATS, FLIP><<<grid, NTHREADS, K::SMEM, stream>>>(p);
     return (int)cudaGetLastError();
 }

@@ -56,6 +56,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
     // the ignored 4th plane of the last window reads past the S ring: the U ring sits right behind it
     static constexpr int SMEM = NS * PS_BYTES + NU * PU_BYTES + 1024;
+    static constexpr int CTAS_PER_SM = (2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;   // issue-bound: interleave two CTAs
     static_assert(PS_BYTES % 128 == 0 && PU_BYTES % 128 == 0, "alignment");
 };
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ Item decode(const WgradTcParams& p, int item, int DL)
 }
 
 template <int CS, int CU, int DL>
-__global__ void __launch_bounds__(NTHREADS, 1) wgrad3_tc_kernel(const WgradTcParams p) {
+__global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3_tc_kernel(const WgradTcParams p) {
     using K = Cfg<CS, CU, DL>;
     constexpr int NS = K::NS;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -282,7 +283,7 @@ FCD_API int fcd_wgrad3_tc_nsplit(int Bn, int D, int H, int W) {
     const int dl = pick_dl(Bn, D, H, W);
     if (dl == 0) return 0;
     const long long items = (long long)Bn * (H / TH) * (W / TW) * (D / dl);
-    return (int)(items < fcd_num_sms() ? items : fcd_num_sms());
+    return (int)(items < 2LL * fcd_num_sms() ? items : 2LL * fcd_num_sms());   // two CTAs per SM when they fit
 }
 
 // part[nsplit][27][ldn][ldk] fp32 (fcd_wgrad_reduce layout): this call fills the [n_off, n_off+CU) x [k_off, k_off+CS)
@@ -299,7 +300,7 @@ FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long
     p.ldn = ldn; p.ldk = ldk; p.n_off = n_off; p.k_off = k_off;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.nht = H / TH; p.nwt = W / TW; p.nseg = D / dl;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
-    const int grid = p.nitems < fcd_num_sms() ? p.nitems : fcd_num_sms();
+    const int grid = p.nitems < 2 * fcd_num_sms() ? p.nitems : 2 * fcd_num_sms();   // == fcd_wgrad3_tc_nsplit
 #define FCD_WG_CASE(A, B, L) if (CS == A && CU == B && dl == L) return launch<A, B, L>(p, grid, stream)
     FCD_WG_CASE(16, 16, 8); FCD_WG_CASE(16, 32, 8); FCD_WG_CASE(32, 16, 8); FCD_WG_CASE(32, 32, 8);
     FCD_WG_CASE(16, 16, 4); FCD_WG_CASE(16, 32, 4); FCD_WG_CASE(32, 16, 4); FCD_WG_CASE(32, 32, 4);
