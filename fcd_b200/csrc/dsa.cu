@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(256) dsa_reduce_kernel(const bf16* __restrict_
     float* out = part + ((long long)b * ntiles + tile) * dsa_osize(C, c, P);
     const int P4 = P / 4;
     const int n_kv = 2 * C * P4, n_g = C * c, n_s = 2 * C;
-    for (int it = threadIdx.x; it < n_kv + n_g + n_s; it += blockDim.x) {
+    // gridDim.z > 1 (small N, few token tiles): the blocks of one tile share the token tile and split the outputs
+    for (int it = blockIdx.z * blockDim.x + threadIdx.x; it < n_kv + n_g + n_s; it += blockDim.x * gridDim.z) {
         if (it < n_kv) {
             const int r = it / P4, p = (it % P4) * 4;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -435,8 +436,8 @@ __device__ __forceinline__ long long dsa_bsize(int c, int P) { return 2LL * c * 
 
 // Phase 1: thread per token (recompute the spatial softmax, form dlogits, write dqhat_sa); phase 2: the block
 // reduces the outer products over its TN tokens.
-template <int CH, int P>
-__global__ void __launch_bounds__(64) dsa_bwd_reduce_kernel(const bf16* __restrict__ qkvv, long long ldq,
+template <int CH, int P, int NT>
+__global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restrict__ qkvv, long long ldq,
                                                             const bf16* __restrict__ dy, long long lddy,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ inv_n,
@@ -457,9 +458,12 @@ __global__ void __launch_bounds__(64) dsa_bwd_reduce_kernel(const bf16* __restri
         sVP[i] = KV[((long long)b * 2 * C + C + hd * CH) * P + i];
     }
     __syncthreads();
+    // phase 1 runs on the first TN threads (one token each); all NT threads take part in the phase-2 reduction
+    // (NT = 64 when there are enough token tiles to fill the GPU, 256 on the deep levels with a handful of blocks)
+    const bool tok = threadIdx.x < TN;
     const int n = tile * TN + threadIdx.x;
-    float* my = sT + threadIdx.x * ROW;
-    if (n < N) {
+    float* my = sT + (tok ? threadIdx.x : 0) * ROW;
+    if (tok && n < N) {
         const bf16* row = qkvv + ((long long)b * N + n) * ldq;
         const float tau2 = temperature2[hd];
         float lg[P], raw[P];
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(64) dsa_bwd_reduce_kernel(const bf16* __restri
             dqh[((long long)b * N + n) * C + hd * CH + j] = a;
             my[2 * P + 4 * CH + j] = a * my[2 * P + CH + j];
         }
-    } else {
+    } else if (tok) {
         for (int i = 0; i < ROW; ++i) my[i] = 0.f;
     }
     __syncthreads();
@@ -706,6 +710,50 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     }
 }
 
+// Small-N variant (deep levels: N <= 1024 tokens but up to 256 channels): thread per (token, 4 p's, channel part);
+// the 8 parts of one output live in 8 adjacent lanes, split the channel loop and are added by xor-shuffles.
+__global__ void __launch_bounds__(256) dsa_bwd_ef_small_kernel(const bf16* __restrict__ qkvv, long long ldq,
+                                                               const float* __restrict__ dKV,
+                                                               float* __restrict__ dEF, int B, int N, int C, int P) {
+    const int P4 = P / 4;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int part = (int)(gid & 7);
+    const long long o = gid >> 3;
+    const long long n = o / P4;
+    const int p = (int)(o % P4) * 4;
+    const bool live = n < N;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        for (int b = 0; b < B; ++b) {
+            const float* dkp = dKV + (long long)b * 2 * C * P;
+            const float* dvp = dkp + (long long)C * P;
+            const bf16* row = qkvv + ((long long)b * N + n) * ldq;
+            for (int c0 = part * 8; c0 < C; c0 += 64) {
+                float kf[8], vf[8];
+                unpack8(ld8(row + C + c0), kf);
+                unpack8(ld8(row + 3 * C + c0), vf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 x = *reinterpret_cast<const float4*>(&dkp[(long long)(c0 + j) * P + p]);
+                    const float4 y = *reinterpret_cast<const float4*>(&dvp[(long long)(c0 + j) * P + p]);
+                    a.x = fmaf(kf[j], x.x, fmaf(vf[j], y.x, a.x));
+                    a.y = fmaf(kf[j], x.y, fmaf(vf[j], y.y, a.y));
+                    a.z = fmaf(kf[j], x.z, fmaf(vf[j], y.z, a.z));
+                    a.w = fmaf(kf[j], x.w, fmaf(vf[j], y.w, a.w));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, d);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, d);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, d);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, d);
+    }
+    if (live && part == 0) *reinterpret_cast<float4*>(&dEF[n * P + p]) = a;
+}
+
 // dEF[n][p] = sum_b sum_ch ( k[b,n,ch] dKP[b][ch][p] + v_SA[b,n,ch] dVP[b][ch][p] ).  Thread per (4 tokens, 4 p's):
 // k / v_SA come in as 16 B (8-channel) loads, every dKP/dVP float4 (L1-resident) feeds 4 tokens.
 __global__ void __launch_bounds__(256) dsa_bwd_ef_kernel(const bf16* __restrict__ qkvv, long long ldq,
@@ -768,10 +816,18 @@ int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long
                       int C, int H, float ds, uint32_t dth, unsigned long long seed, cudaStream_t st) {
     const int smem = (2 * CH * P + 64 * (2 * P + 5 * CH + 1)) * 4;
     static bool conf = false;
-    if (!conf) { cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
+    if (!conf) {
+        cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        conf = true;
+    }
     dim3 grid((N + 63) / 64, H, B);
-    dsa_bwd_reduce_kernel<CH, P><<<grid, 64, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N, C, ds,
-                                                         dth, seed);
+    if ((long long)grid.x * H * B >= 2LL * fcd_num_sms())
+        dsa_bwd_reduce_kernel<CH, P, 64><<<grid, 64, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N,
+                                                                C, ds, dth, seed);
+    else
+        dsa_bwd_reduce_kernel<CH, P, 256><<<grid, 256, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part,
+                                                                  N, C, ds, dth, seed);
     return (int)cudaGetLastError();
 }
 
@@ -888,7 +944,12 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
         cudaFuncSetAttribute(dsa_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r > 48 * 1024 ? smem_r : 48 * 1024);
         conf_r = smem_r;
     }
-    dsa_reduce_kernel<<<dim3(ntiles, B), 256, smem_r, st>>>((const bf16*)qkvv, ldq, EF, part, N, C, c, P, tn);
+    int zsplit = 1;
+    {
+        const long long items = 2LL * C * (P / 4) + (long long)C * c + 2LL * C;
+        while ((long long)ntiles * B * zsplit < 2LL * fcd_num_sms() && zsplit * 256LL < items) zsplit *= 2;
+    }
+    dsa_reduce_kernel<<<dim3(ntiles, B, zsplit), 256, smem_r, st>>>((const bf16*)qkvv, ldq, EF, part, N, C, c, P, tn);
     float ds; uint32_t dth;
     drop_params(sa_drop, ds, dth);
     tile_group_sum(part, B, ntiles, 2LL * C + (long long)C * c + 2LL * C * P, st);
@@ -950,7 +1011,12 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
         int rc = run();
         if (rc != 0) return rc;
     }
-    const long long tot = (long long)((N + 3) / 4) * (P / 4);
-    dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    if (N <= 1024) {
+        const long long tot = (long long)N * (P / 4) * 8;
+        dsa_bwd_ef_small_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    } else {
+        const long long tot = (long long)((N + 3) / 4) * (P / 4);
+        dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    }
     FCD_LAUNCH_CHECK();
 }
