@@ -135,10 +135,13 @@ class _PackCache:
         keys = [k for k, j in self.jobs.items() if k[1] == device.index and j[0].data_ptr() == k[0]]
         if not keys:
             return
-        if all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
-            return
+        # Inside CUDA-graph capture the launch must ALWAYS be recorded: the replayed graph has to re-pack from the
+        # parameters as they are at replay time, whatever the stamps say at capture time.
+        capturing = torch.cuda.is_current_stream_capturing()
         tab = self.table.get(device.index)
-        if tab is None or tab[0] != keys:
+        # (re)build the job table whenever the set of jobs changed -- and once more, eagerly, if it had to be built
+        # inside a capture (its memory then belongs to that graph's private pool)
+        if tab is None or tab[0] != keys or (tab[4] and not capturing):
             if _PackCache.JOB is None:
                 _PackCache.JOB = np.dtype({"names": ["src", "dst", "sn", "sk", "st", "total", "T", "N", "K", "Np", "Kp",
                                                      "kseg", "ksegpad", "nseg", "nsegpad", "blk0"],
@@ -153,8 +156,11 @@ class _PackCache:
                 total = T * Np * Kp
                 rec[i] = (k[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk)
                 blk += (total + 2047) // 2048
-            dev_tab = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
-            tab = self.table[device.index] = (keys, dev_tab, blk)
+            host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture
+            dev_tab = host.to(device, non_blocking=True)
+            tab = self.table[device.index] = (keys, dev_tab, blk, host, capturing)   # host: keep the pinned source alive
+        if not capturing and all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
+            return
         call("fcd_pack_weight_batched", jobs=tab[1], njobs=len(keys), nblocks=tab[2])
         for k in keys:
             self.jobs[k][3] = self.jobs[k][0]._version

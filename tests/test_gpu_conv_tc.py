@@ -143,3 +143,31 @@ def test_wgrad3_tc(ops, B, Ci, Co, D, H, W):
     y.backward(ops.to_channels_last(dy, ops.pad16(Co)))
     assert _lib.lib().fcd_wgrad_tc_error() == 0 and tc_error() == 0
     close(w2.grad, gw, rel=6e-3, what="tc wgrad")
+
+
+def test_packed_weights_follow_parameter_updates_inside_cuda_graph(ops):
+    """The mma.sync kernels read packed bf16 copies of the parameters (ops._PackCache).  A captured forward must
+    re-pack on every replay: update the weight in place between replays and the output has to follow."""
+    import torch.nn as nn
+    conv = nn.Conv3d(64, 64, 3, padding=1, bias=False).to("cuda")           # 64->64: legacy (packed-weight) path
+    x = ops.to_channels_last(rnd(1, 64, 4, 8, 8))
+
+    def fwd():
+        ops.prepack_weights(x.device)
+        return ops.conv3d(x, conv.weight, None, k=3)
+
+    with torch.no_grad():
+        for _ in range(2):
+            fwd()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = fwd()
+        g.replay()
+        torch.cuda.synchronize()
+        y0 = y.clone()
+        conv.weight.mul_(2.0)                                                # what an optimizer step does: in place
+        g.replay()
+        torch.cuda.synchronize()
+        close(y, 2.0 * y0.float(), rel=1e-2, mx=2e-2, what="graph replay after in-place weight update")
+        close(fwd(), y, rel=1e-6, mx=1e-6, what="eager after update")
