@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Callable, Sequence
 
 import torch
@@ -60,6 +61,53 @@ def _dist_info(group):
     return 0, 1
 
 
+class _GraphedWindowForward:
+    """CUDA graph of predictor.forward_cl for one window-batch shape (eval mode, no autograd).
+
+    An eager MS_DSA_NET forward is ~400 kernel launches of 5-30 us: the host cannot issue them as fast as a B200 retires
+    them.  The graph holds the static input the gather kernel writes into and the static logits the blend kernel
+    reads; parameters are read through their storage, so weight updates between evaluations are seen by replays."""
+
+    _cache = {}
+
+    def __init__(self, predictor, shape, device):
+        self.x = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up outside capture (lazy kernel attributes, pack tables)
+                self._fwd(predictor)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y = self._fwd(predictor)
+
+    def _fwd(self, predictor):
+        pred = predictor.forward_cl(self.x)
+        if isinstance(pred, (tuple, list)):
+            pred = pred[0]
+        return pred.detach().float().contiguous()
+
+    @classmethod
+    def get(cls, predictor, shape, device):
+        key = (id(predictor), tuple(shape), device.index)
+        g = cls._cache.get(key)
+        if g is None or g.owner() is not predictor:
+            if len(cls._cache) >= 8:
+                cls._cache.clear()
+            g = cls._cache[key] = cls(predictor, shape, device)
+            import weakref
+            g.owner = weakref.ref(predictor)
+        return g
+
+
+def _can_graph(predictor):
+    return (os.environ.get("FCD_SW_GRAPH", "1") != "0" and hasattr(predictor, "forward_cl")
+            and isinstance(predictor, torch.nn.Module) and not predictor.training and not torch.is_grad_enabled()
+            and not torch.cuda.is_current_stream_capturing())
+
+
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,
                              overlap: float = 0.25, mode: str = "constant", *, label_mode: str | None = None,
                              shard: bool = True, group=None, **unused):
@@ -81,6 +129,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     total = nw * B
     rank, world = _dist_info(group) if shard else (0, 1)
     fast = hasattr(predictor, "forward_cl")
+    graphed = fast and _can_graph(predictor)
     dev = inputs.device
     cp = ops.pad16(C)
     acc = None
@@ -97,11 +146,17 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
             by_img.setdefault(i // nw, []).append(wins[i % nw])
         for b, wl in by_img.items():
             if fast:
-                x_cl = torch.empty((len(wl), roi[0], roi[1], roi[2], cp), dtype=torch.bfloat16, device=dev)
+                shape = (len(wl), roi[0], roi[1], roi[2], cp)
+                gf = _GraphedWindowForward.get(predictor, shape, dev) if graphed else None
+                x_cl = gf.x if gf is not None else torch.empty(shape, dtype=torch.bfloat16, device=dev)
                 flat = (ctypes.c_int * (3 * len(wl)))(*[v for w in wl for v in w])
                 call("fcd_sw_gather", vol=inputs[b], dst=x_cl, C=C, Cp=cp, D=orig[0], H=orig[1], W=orig[2], r0=roi[0],
                      r1=roi[1], r2=roi[2], pz=pad_lo[0], py=pad_lo[1], px=pad_lo[2], starts_zyx=flat, nwin=len(wl))
-                pred = predictor.forward_cl(x_cl)
+                if gf is not None:
+                    gf.graph.replay()
+                    pred = gf.y
+                else:
+                    pred = predictor.forward_cl(x_cl)
             else:
                 padded = inputs[b:b + 1]
                 if size != tuple(orig):
