@@ -551,6 +551,24 @@ inline int grid_for(long long total, int block, int mult) {
     return (int)g;
 }
 
+// thread per 8-column chunk, serial over the (few) rows
+__global__ void colsum_wide_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, long long rows,
+                                   int C8) {
+    const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c8 >= C8) return;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    for (long long r = 0; r < rows; ++r) {
+        float f[8];
+        unpack8(ld8(x + r * ld + c8 * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[c8 * 8 + k] = a[k];
+}
+
 }  // namespace
 
 FCD_API int fcd_ncdhw_to_ndhwc(const float* src, void* dst, int B, int C, int Cp, long long S, cudaStream_t st) {
@@ -641,7 +659,11 @@ FCD_API int fcd_norm_finalize(const float* part, float* mean, float* rstd, int B
 // out[c] = sum over rows of x[row][c]  (bias gradients).  part: nchunk*2*C floats.
 FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, long long rows, int C, int nchunk,
                        cudaStream_t st) {
-    if (C % 8 || C / 8 > 256) return -1;
+    if (C % 8) return -1;
+    if (C / 8 > 256) {          // very wide rows (the VAE's fully connected layers: 8192 columns, a handful of rows)
+        colsum_wide_kernel<<<(C / 8 + 127) / 128, 128, 0, st>>>((const bf16*)x, ld, out, rows, C / 8);
+        FCD_LAUNCH_CHECK();
+    }
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, 1);
     norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk);

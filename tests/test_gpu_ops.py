@@ -436,3 +436,10 @@ def test_subpixel_upsample(ops, Ci, Co, mode):
     close(b2.grad, gb, rel=8e-3, what="subpixel db")
     if mode != "plain":
         close(ops.to_ncdhw(sc.grad, Co), gs, what="subpixel dskip")
+
+
+def test_colsum_wide_rows(ops):
+    """Bias gradient of the VAE's fully connected layers (segresnet_dsa.py:345-347): 8192 columns, batch-many rows."""
+    x = rnd(1, 1, 1, 3, 8192).to(torch.bfloat16).contiguous()
+    got = ops._colsum(x, 8192)
+    close(got, x.float().reshape(-1, 8192).sum(0), rel=1e-5, mx=1e-5, what="wide colsum")
