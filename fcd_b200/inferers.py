@@ -108,6 +108,11 @@ def _can_graph(predictor):
             and not torch.cuda.is_current_stream_capturing())
 
 
+def window_shard(total: int, rank: int, world: int):
+    """Indices (into the batch x window enumeration) that `rank` of `world` evaluates."""
+    return [i for i in range(total) if i % world == rank]
+
+
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,
                              overlap: float = 0.25, mode: str = "constant", *, label_mode: str | None = None,
                              shard: bool = True, group=None, **unused):
@@ -133,13 +138,12 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     dev = inputs.device
     cp = ops.pad16(C)
     acc = None
-    chunk_id = 0
-    for g in range(0, total, sw_batch_size):
-        idxs = list(range(g, min(g + sw_batch_size, total)))
-        mine = (chunk_id % world) == rank
-        chunk_id += 1
-        if not mine:
-            continue
+    # Sharding: WINDOWS (not chunks) are dealt round-robin to the ranks, then each rank batches its own windows in
+    # chunks of sw_batch_size -- 18 windows over 8 ranks is 3,3,2,2,2,2,2,2 instead of 2,1,...,1 chunks of two.
+    # Windows are independent in eval mode, so which windows share a predictor call does not change the result.
+    my_windows = window_shard(total, rank, world)
+    for g in range(0, len(my_windows), sw_batch_size):
+        idxs = my_windows[g:g + sw_batch_size]
         # split the chunk by image (B is 1 in the reference's evaluate loop)
         by_img = {}
         for i in idxs:

@@ -61,8 +61,11 @@ class GradAllReducer:
                 views.append(v)
         with torch.no_grad():
             torch._foreach_copy_(views, grads)
-            dist.all_reduce(self.flat, group=self.group)
-            self.flat.mul_(1.0 / self.world)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)   # mean inside NCCL: one pass less
+            else:
+                dist.all_reduce(self.flat, group=self.group)
+                self.flat.mul_(1.0 / self.world)
             torch._foreach_copy_(grads, views)
 
 

@@ -169,3 +169,13 @@ def test_grad_allreduce_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_ddp_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] is True and ret[1] is True
+
+
+def test_window_shard_partitions_windows():
+    """Sliding-window sharding: every window goes to exactly one rank, loads differ by at most one window."""
+    from fcd_b200.inferers import window_shard
+    for total in (1, 8, 18, 27):
+        for world in (1, 2, 4, 8):
+            parts = [window_shard(total, r, world) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(total))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
