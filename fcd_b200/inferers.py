@@ -153,9 +153,12 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
                 shape = (len(wl), roi[0], roi[1], roi[2], cp)
                 gf = _GraphedWindowForward.get(predictor, shape, dev) if graphed else None
                 x_cl = gf.x if gf is not None else torch.empty(shape, dtype=torch.bfloat16, device=dev)
-                flat = (ctypes.c_int * (3 * len(wl)))(*[v for w in wl for v in w])
-                call("fcd_sw_gather", vol=inputs[b], dst=x_cl, C=C, Cp=cp, D=orig[0], H=orig[1], W=orig[2], r0=roi[0],
-                     r1=roi[1], r2=roi[2], pz=pad_lo[0], py=pad_lo[1], px=pad_lo[2], starts_zyx=flat, nwin=len(wl))
+                for j0 in range(0, len(wl), 8):             # the gather kernel takes up to 8 window origins per launch
+                    sub = wl[j0:j0 + 8]
+                    flat = (ctypes.c_int * (3 * len(sub)))(*[v for w in sub for v in w])
+                    call("fcd_sw_gather", vol=inputs[b], dst=x_cl[j0:j0 + len(sub)], C=C, Cp=cp, D=orig[0], H=orig[1],
+                         W=orig[2], r0=roi[0], r1=roi[1], r2=roi[2], pz=pad_lo[0], py=pad_lo[1], px=pad_lo[2],
+                         starts_zyx=flat, nwin=len(sub))
                 if gf is not None:
                     gf.graph.replay()
                     pred = gf.y

@@ -192,3 +192,22 @@ def test_initialize_weights_and_checkpoint_roundtrip(tmp_path):
     x = torch.randn(1, 2, 64, 64, 64, device=DEV)
     with torch.no_grad():
         assert torch.equal(model(x), model2(x))
+
+
+def test_sliding_window_batching_is_invariant():
+    """sw_batch_size only changes how many windows share one predictor call (here 12 windows: one call of 12 -- more
+    than the gather kernel's 8 origins per launch -- vs six calls of 2): the blended logits must not change."""
+    import contextlib, io
+    import fcd_b200
+    from fcd_b200.inferers import sliding_window_inference
+    params = fcd_b200.get_default_params()
+    params.update(model_type="baseunet", patch_size=(32,) * 3, feature_size=4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, _ = fcd_b200.get_model(params)
+    model = model.to("cuda").eval()
+    vol = torch.randn((1, 2, 64, 48, 40), generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        a, la = sliding_window_inference(vol, 32, 12, model, overlap=0.5, label_mode="argmax")
+        b, lb = sliding_window_inference(vol, 32, 2, model, overlap=0.5, label_mode="argmax")
+    assert torch.equal(la, lb)
+    assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
