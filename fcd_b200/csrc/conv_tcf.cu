@@ -1,0 +1,359 @@
+// kd-FOLDED variant of the tcgen05 conv3x3x3 (conv_tc.cu) for Cout <= 32 -- the layers that hold most of the FLOPs.
+//
+// Observation: a halo-plane A tile with a fixed in-plane shift (kh,kw) is needed by THREE output planes -- plane p feeds
+// output z = p-1 with tap kd = 2, z = p with kd = 1, z = p+1 with kd = 0.  An M=128 x N=Cout instruction is bound by the
+// shared-memory fetch of its 4 KB A tile (31 cycles for 8 cycles of math at N = 16), so the three are issued as ONE
+// instruction of N = 3*Cout whose B operand is [W(2,kh,kw) | W(1,kh,kw) | W(0,kh,kw)] and whose D columns are the
+// accumulators of three CONSECUTIVE output planes, kept adjacent in a ring of R TMEM slots.  9*Cin/16 instructions per
+// plane instead of 27*Cin/16, same A traffic: 2.3x less tensor-pipe time for Cout = 16.
+//
+// Consequences: every instruction accumulates (a slot sees its first tap together with older slots' later taps), so the
+// epilogue hands a slot back ZEROED (tcgen05.st) after reading it; a slot is complete once the plane two below it has
+// been multiplied; slot ranges that wrap around the ring are issued as two instructions.  The three issuing warps own
+// one kh row of taps each and their own accumulator set (the epilogue adds the three sets), exactly as in conv_tc.cu.
+// Producers, halo-plane ring, weight staging from the fp32 parameter, fused statistics: as in conv_tc.cu.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int TH = 16, TW = 8, HH = TH + 2, HW = TW + 2, HV = HH * HW;
+constexpr int NPROD = 2, NMMA = 3;
+constexpr int NTHREADS = 32 * (NPROD + NMMA + 4);
+constexpr int R = 5;                      // accumulator ring slots (3 accumulating + slack for the epilogue)
+
+struct ConvTcfParams {
+    const bf16* A; long long lda;
+    const float* Wf; long long sn, sk, st;
+    int Nr, Kr, kseg, ksegpad, nsg, nsgpad;
+    bf16* C; long long ldc;
+    float* part;
+    int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
+};
+
+template <int CIN, int COUT>
+struct Cfg {
+    static constexpr int W_BYTES = 27 * CIN * COUT * 2;          // [khw][CIN/8][t = 2-kd][COUT][8]
+    static constexpr int KHW_BYTES = 3 * CIN * COUT * 2;
+    static constexpr int PLANE_BYTES = HV * CIN * 2;
+    static constexpr int LBO_A = HV * 16, SBO_A = HW * 16;
+    static constexpr int LBO_B = 3 * COUT * 16, SBO_B = 128;
+    static constexpr int BUDGET = 220 * 1024 - W_BYTES;
+    static constexpr int NST = BUDGET / PLANE_BYTES >= 6 ? 6 : BUDGET / PLANE_BYTES;
+    static constexpr int TCOLS = 3 * R * COUT;                   // [kh set][slot][COUT]
+    static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
+    static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;
+    static constexpr int CTAS_PER_SM = (COUT == 16 && 2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
+    static_assert(NST >= 4 && TCOLS <= 512, "resources");
+};
+
+struct Item { int n, h0, w0, d0, d1, p_lo, p_hi, chunk; };
+__device__ __forceinline__ Item decode(const ConvTcfParams& p, int item) {
+    Item it;
+    int wt = item % p.nwt; item /= p.nwt;
+    int ht = item % p.nht; item /= p.nht;
+    int seg = item % p.nseg; item /= p.nseg;
+    it.n = item; it.h0 = ht * TH; it.w0 = wt * TW;
+    it.d0 = seg * p.DL; it.d1 = min(it.d0 + p.DL, p.D);
+    it.p_lo = max(it.d0 - 1, 0); it.p_hi = min(it.d1, p.D - 1);
+    it.chunk = (seg * p.nht + ht) * p.nwt + wt;
+    return it;
+}
+
+template <int CIN, int COUT, bool STATS, bool FLIP>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_tcf_kernel(const ConvTcfParams p) {
+    using K = Cfg<CIN, COUT>;
+    constexpr int NST = K::NST;
+    constexpr int DEPTH = NST >= 6 ? 3 : NST - 3;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* wsm = smem;
+    unsigned char* ring = smem + K::W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::W_BYTES + NST * K::PLANE_BYTES);
+    // bars: [0,NST) FULL | [NST,2NST) EMPTY | [2NST,2NST+R) TFULL | [2NST+R,2NST+2R) TEMPTY
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 * R);
+    volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* red = reinterpret_cast<float*>(tmem_slot + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+    auto TFULL = [&](int s) { return bar0 + 8u * (2 * NST + s); };
+    auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + R + s); };
+
+    if (tid == 0) {
+        *dead = 0;
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), NMMA); }
+        for (int s = 0; s < R; ++s) { mbar_init(TFULL(s), NMMA); mbar_init(TEMPTY(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == NPROD) tmem_alloc<K::TMEM_COLS>(smem_u32(tmem_slot));
+    // weights: fp32 parameter -> bf16 smem [khw][k/8][t][n][8], t = 2 - kd (output planes ascending);
+    // FLIP (data gradient): the tap read is the mirrored one
+    {
+        constexpr int CHUNKS = 27 * COUT * (CIN / 8);
+        for (int i = tid; i < CHUNKS; i += NTHREADS) {
+            const int tap = i % 27;                              // logical tap of the correlation being computed
+            const int np_ = (i / 27) % COUT;
+            const int c8 = i / (27 * COUT);
+            const int src_tap = FLIP ? 26 - tap : tap;
+            const int kd = tap / 9, khw = tap % 9;
+            const int ns = np_ / p.nsgpad, nw = np_ % p.nsgpad;
+            const int n = ns * p.nsg + nw;
+            const bool nok = nw < p.nsg && n < p.Nr;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kp = c8 * 8 + j;
+                const int ks = kp / p.ksegpad, kwi = kp % p.ksegpad;
+                const int k = ks * p.kseg + kwi;
+                f[j] = (nok && kwi < p.kseg && k < p.Kr) ? __ldg(p.Wf + n * p.sn + k * p.sk + src_tap * p.st) : 0.f;
+            }
+            *reinterpret_cast<bf16x8*>(wsm + khw * K::KHW_BYTES + c8 * K::LBO_B + ((2 - kd) * COUT + np_) * 16) = pack8(f);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NPROD) {
+        // ===================================================================== producers (identical to conv_tc.cu)
+        constexpr int C8 = CIN / 8, VS = 32 * NPROD / C8, NJ = (HV + VS - 1) / VS;
+        const int pt = warp * 32 + lane;
+        const int c8 = pt % C8, v0 = pt / C8;
+        const uint32_t ring_u = smem_u32(ring);
+        uint32_t seq = 0, signaled = 0;
+        auto flush_to = [&](uint32_t upto) {
+            while (signaled < upto) { mbar_arrive(FULL(signaled % NST)); ++signaled; }
+        };
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const Item it = decode(p, item);
+            int off[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int v = v0 + j * VS;
+                const int hh = v / HW, ww = v - hh * HW;
+                const int h = it.h0 - 1 + hh, w = it.w0 - 1 + ww;
+                const bool ok = v < HV && h >= 0 && h < p.H && w >= 0 && w < p.W;
+                off[j] = ok ? (int)(((long long)h * p.W + w) * p.lda) + c8 * 8 : -1;
+            }
+            const long long plane_elems = (long long)p.H * p.W * p.lda;
+            for (int pl = it.p_lo; pl <= it.p_hi; ++pl, ++seq) {
+                const int s = seq % NST;
+                mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, dead, 1);
+                const bf16* plane = p.A + ((long long)it.n * p.D + pl) * plane_elems;
+                const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A + v0 * 16;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (j < NJ - 1 || v0 + j * VS < HV) {
+                        const bool ok = off[j] >= 0;
+                        cp_async16(dst0 + j * VS * 16, ok ? plane + off[j] : p.A, ok);
+                    }
+                }
+                cp_async_commit();
+                if (seq + 1 >= DEPTH) {
+                    cp_async_wait<DEPTH - 1>();
+                    fence_proxy_async();
+                    flush_to(seq + 2 - DEPTH);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        flush_to(seq);
+    } else if (warp < NPROD + NMMA) {
+        // ===================================================================== MMA issuers: warp kh owns taps (.,kh,.)
+        const int kh = warp - NPROD;
+        constexpr uint32_t A_HI = ((K::SBO_A >> 4) & 0x3fffu) | (1u << 14);
+        constexpr uint32_t B_HI = ((K::SBO_B >> 4) & 0x3fffu) | (1u << 14);
+        const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_A >> 4) << 16);
+        const uint32_t b_lo0 = ((smem_u32(wsm) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_B >> 4) << 16);
+        const uint32_t d_set = tmem_base + kh * R * COUT;
+        // n_out consecutive output slots starting at `slot`, whose first B row block is t0
+        auto issue = [&](uint32_t a_pl, int slot, int t0, int n_out) {
+            const uint32_t idesc = umma_idesc(128, n_out * COUT, 0, 0);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                for (int kc = 0; kc < CIN / 16; ++kc) {
+                    const uint32_t a_lo = a_pl + (((kh * HW + kw) * 16 + kc * 2 * K::LBO_A) >> 4);
+                    const uint32_t b_lo = b_lo0 + (((kh * 3 + kw) * K::KHW_BYTES + kc * 2 * K::LBO_B + t0 * COUT * 16) >> 4);
+                    umma_f16(d_set + slot * COUT, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, idesc, 1u);
+                }
+            }
+        };
+        uint32_t seq_base = 0, zc0 = 0;                        // plane sequence / output-plane counter at item start
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const Item it = decode(p, item);
+            const int nload = it.p_hi - it.p_lo + 1, DLi = it.d1 - it.d0;
+            int acq = 0, fin = 0;                              // outputs (local index) acquired / handed to the epilogue
+            for (int i = 0; i <= DLi + 1; ++i) {               // input plane z = d0 - 1 + i feeds outputs i-2, i-1, i
+                const int pl = it.d0 - 1 + i;
+                if (pl >= 0 && pl < p.D) {
+                    const uint32_t sq = seq_base + (pl - it.p_lo);
+                    mbar_wait(FULL(sq % NST), (sq / NST) & 1u, dead, 2);
+                    const int j_lo = max(i - 2, 0), j_hi = min(i, DLi - 1);
+                    while (acq <= j_hi) {                      // first touch of an output: its slot must be back, zeroed
+                        const uint32_t zc = zc0 + acq;
+                        mbar_wait(TEMPTY(zc % R), (zc / R) & 1u, dead, 3);
+                        ++acq;
+                    }
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_pl = a_lo0 + (sq % NST) * (K::PLANE_BYTES >> 4);
+                        const int t_lo = j_lo - (i - 2), n_out = j_hi - j_lo + 1;
+                        const int s_lo = (int)((zc0 + j_lo) % R);
+                        const int n1 = min(n_out, R - s_lo);
+                        issue(a_pl, s_lo, t_lo, n1);
+                        if (n_out > n1) issue(a_pl, 0, t_lo + n1, n_out - n1);      // the range wraps around the ring
+                        umma_commit(EMPTY(sq % NST));
+                    }
+                    __syncwarp();
+                }
+                const int fin_to = min(i - 2, DLi - 1);        // outputs <= i-2 have received all their planes
+                while (fin <= fin_to) {
+                    if (lane == 0) umma_commit(TFULL((zc0 + fin) % R));
+                    ++fin;
+                }
+                __syncwarp();
+            }
+            seq_base += nload;
+            zc0 += DLi;
+        }
+    } else {
+        // ===================================================================== epilogue (4 warps)
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int hh = r >> 3, ww = r & 7;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        // all accumulators start zeroed; completing phase 0 of every TEMPTY hands the slots to the MMA warps
+#pragma unroll 1
+        for (int c = 0; c < K::TCOLS; c += 16) tmem_st16_zero(trow + c);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            for (int s = 0; s < R; ++s) mbar_arrive(TEMPTY(s));
+        }
+        uint32_t zc = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            const Item it = decode(p, item);
+            float s1[STATS ? COUT : 1], s2[STATS ? COUT : 1];
+            if (STATS) {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) s1[c] = s2[c] = 0.f;
+            }
+            for (int od = it.d0; od < it.d1; ++od, ++zc) {
+                const int slot = zc % R;
+                mbar_wait(TFULL(slot), (zc / R) & 1u, dead, 4);
+                tc_fence_after();
+                uint32_t t[3][COUT];
+#pragma unroll
+                for (int set = 0; set < 3; ++set)
+#pragma unroll
+                    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(trow + (set * R + slot) * COUT + c0, t[set] + c0);
+                tmem_wait_ld();
+#pragma unroll
+                for (int set = 0; set < 3; ++set)
+#pragma unroll
+                    for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16_zero(trow + (set * R + slot) * COUT + c0);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(TEMPTY(slot));
+                bf16* dst = p.C + ((((long long)it.n * p.D + od) * p.H + it.h0 + hh) * p.W + it.w0 + ww) * p.ldc;
+#pragma unroll
+                for (int c0 = 0; c0 < COUT; c0 += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        f[k] = (__uint_as_float(t[0][c0 + k]) + __uint_as_float(t[1][c0 + k])) + __uint_as_float(t[2][c0 + k]);
+                    const bf16x8 pk = pack8(f);
+                    st8(dst + c0, pk);
+                    if (STATS) {
+                        float g[8];
+                        unpack8(pk, g);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { s1[c0 + k] += g[k]; s2[c0 + k] = fmaf(g[k], g[k], s2[c0 + k]); }
+                    }
+                }
+            }
+            if (STATS) {
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    const float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+                    if (lane == 0) { red[(q * 2 + 0) * COUT + c] = a; red[(q * 2 + 1) * COUT + c] = b; }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int e = tid - 32 * (NPROD + NMMA);
+                if (e < 2 * COUT) {
+                    const float tt = red[e] + red[2 * COUT + e] + red[4 * COUT + e] + red[6 * COUT + e];
+                    const long long nchunk = (long long)p.nht * p.nwt * p.nseg;
+                    p.part[((long long)it.n * nchunk + it.chunk) * 2 * COUT + e] = tt;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPROD) tmem_dealloc<K::TMEM_COLS>(tmem_base);
+}
+
+template <int CIN, int COUT, bool STATS, bool FLIP>
+int launch2(const ConvTcfParams& p, cudaStream_t stream) {
+    using K = Cfg<CIN, COUT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv3_tcf_kernel<CIN, COUT, STATS, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+        configured = true;
+    }
+    const int grid = min(p.nitems, fcd_num_sms() * K::CTAS_PER_SM);
+    conv3_tcf_kernel<CIN, COUT, STATS, FLIP><<<grid, NTHREADS, K::SMEM, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <int CIN, int COUT>
+int launch(const ConvTcfParams& p, int flip, cudaStream_t stream) {
+    if (p.part != nullptr)
+        return flip ? launch2<CIN, COUT, true, true>(p, stream) : launch2<CIN, COUT, true, false>(p, stream);
+    return flip ? launch2<CIN, COUT, false, true>(p, stream) : launch2<CIN, COUT, false, false>(p, stream);
+}
+
+}  // namespace
+
+// Same contract as fcd_conv3_tc (see conv_tc.cu / the header); takes K in {16,32,64} x N in {16,32}.  Returns -1 for
+// anything else so the caller can fall back to fcd_conv3_tc.
+FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
+                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
+                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream) {
+    if (H % TH || W % TW || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
+    if (!(K == 16 || K == 32 || K == 64) || !(N == 16 || N == 32)) return -1;
+    if (((uintptr_t)A & 15) || ((uintptr_t)C & 15) || kseg < 1 || ksegpad < 1 || nsg < 1 || nsgpad < 1) return -1;
+    ConvTcfParams p;
+    p.A = (const bf16*)A; p.lda = lda; p.Wf = Wf; p.sn = sn; p.sk = sk; p.st = st; p.Nr = Nr; p.Kr = Kr;
+    p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
+    p.C = (bf16*)C; p.ldc = ldc; p.part = part;
+    p.Bn = Bn; p.D = D; p.H = H; p.W = W;
+    p.nht = H / TH; p.nwt = W / TW; p.DL = (D + nseg - 1) / nseg;
+    p.nseg = (D + p.DL - 1) / p.DL;
+    if (p.nseg != nseg) return -1;
+    p.nitems = Bn * p.nht * p.nwt * p.nseg;
+#define FCD_TCF_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, flip, stream)
+    FCD_TCF_CASE(16, 16); FCD_TCF_CASE(32, 16); FCD_TCF_CASE(64, 16);
+    FCD_TCF_CASE(16, 32); FCD_TCF_CASE(32, 32); FCD_TCF_CASE(64, 32);
+#undef FCD_TCF_CASE
+    return -1;
+}
+
+FCD_API int fcd_tcf_error(void) {
+    int v = 0, zero = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    cudaMemcpyFromSymbol(&v, tc::g_error, sizeof(int));
+    cudaMemcpyToSymbol(tc::g_error, &zero, sizeof(int));
+    return v;
+}

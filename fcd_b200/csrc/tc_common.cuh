@@ -93,6 +93,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
+// store 16 consecutive fp32 columns of this thread's TMEM lane (used to zero accumulators)
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+        "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts (cute/atom/mma_traits_sm100.hpp):
 //   K-major :  ((8,m),(8,2)) : ((16 B, SBO),(2 B, LBO))   core matrix = 8 rows x 16 B, contiguous 128 B

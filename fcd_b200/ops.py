@@ -212,6 +212,12 @@ def _colsum(x, C):
 
 USE_TC = os.environ.get("FCD_TC", "1") != "0"     # tcgen05 conv path (debug switch; the default is on)
 WGRAD_OVERLAP = os.environ.get("FCD_WGRAD_OVERLAP", "1") != "0"
+USE_TCF = os.environ.get("FCD_TCF", "1") != "0"   # kd-folded tcgen05 conv for Cout <= 32 (csrc/conv_tcf.cu)
+
+
+def _conv3_entry(K, N):
+    """Entry point for a tcgen05 3x3x3 conv with K input / N output channels (both padded)."""
+    return "fcd_conv3_tcf" if (USE_TCF and N in (16, 32) and K in (16, 32, 64)) else "fcd_conv3_tc"
 
 
 class _SideWork:
@@ -315,7 +321,7 @@ class ConvFn(Function):
                 nchunk = (H // 16) * (W // 8) * nseg
                 part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
                 _LAST_PART[0] = (part, nchunk)
-            call("fcd_conv3_tc", A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
+            call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
                  nseg=nseg)
         else:
@@ -341,7 +347,7 @@ class ConvFn(Function):
             nseg = _tc_nseg(B, D, H, W, Np, Kp, k, stride, pad, None)
             if nseg > 0:
                 # dX = correlation of dY with the mirrored kernel: output channels = Cin (in concat segments)
-                call("fcd_conv3_tc", A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
+                call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
                      ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
                      flip=1, nseg=nseg)
             else:

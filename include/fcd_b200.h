@@ -62,6 +62,12 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream);
 FCD_API int fcd_tc_error(void);
+/* kd-folded variant for N in {16, 32}: one instruction of N = 3*Cout feeds three consecutive output planes from one A
+ * tile (csrc/conv_tcf.cu).  Same arguments and results as fcd_conv3_tc; -1 when the shape is not taken. */
+FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
+                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
+                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream);
+FCD_API int fcd_tcf_error(void);
 
 /* tcgen05/TMEM weight gradient of the same 3x3x3 stride-1 pad-1 convs (autograd of conv_blocks.py:393-416).  S: the
  * operand read shifted (conv input, CS channels from channel k_off), U: the unshifted one (output gradient, CU

@@ -22,7 +22,7 @@ def ops():
 
 def tc_error():
     from fcd_b200 import _lib
-    return _lib.lib().fcd_tc_error()
+    return _lib.lib().fcd_tc_error() or _lib.lib().fcd_tcf_error()
 
 
 TC_CASES = [
@@ -74,6 +74,27 @@ def test_conv3_tc_fwd_bwd(ops, B, Ci, Co, D, H, W):
     if Kp > Ci:
         assert float(xc.grad[..., Ci:].abs().max()) == 0.0
     close(w2.grad, gw, rel=6e-3, what="conv wgrad")
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", [(1, 16, 16, 7, 16, 8), (2, 32, 32, 12, 16, 16), (1, 64, 32, 6, 16, 8),
+                                            (1, 32, 16, 23, 16, 8)])
+def test_kd_folded_and_plain_tcgen05_kernels_agree(ops, B, Ci, Co, D, H, W):
+    """fcd_conv3_tcf (kd folded into N, accumulator ring, zeroing epilogue) vs fcd_conv3_tc (one accumulator per kd):
+    same products, fp32 accumulation in a different order."""
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=0.05, seed=1)
+    xc = ops.to_channels_last(x)
+    assert ops._conv3_entry(ops.pad16(Ci), ops.pad16(Co)) == "fcd_conv3_tcf"
+    y_f = ops.conv3d(xc, w, None, k=3)
+    ops.USE_TCF = False
+    try:
+        y_p = ops.conv3d(xc, w, None, k=3)
+    finally:
+        ops.USE_TCF = True
+    assert tc_error() == 0
+    close(y_f, y_p, rel=2e-3, mx=1e-2, what="kd-folded vs plain")
+    pf, pp = y_f._fcd_part[0].sum(1), y_p._fcd_part[0].sum(1)
+    close(pf, pp, rel=2e-3, mx=1e-2, what="fused statistics")
 
 
 def test_conv3_tc_matches_legacy_bitwise_layout(ops):
