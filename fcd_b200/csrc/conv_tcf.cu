@@ -11,6 +11,8 @@
 // epilogue hands a slot back ZEROED (tcgen05.st) after reading it; a slot is complete once the plane two below it has
 // been multiplied; slot ranges that wrap around the ring are issued as two instructions.  The three issuing warps own
 // one kh row of taps each and their own accumulator set (the epilogue adds the three sets), exactly as in conv_tc.cu.
+// (Measured: ONE issuing warp with one accumulator set -- lighter epilogue, 3 CTAs per SM -- is 1.5x SLOWER:
+// 0.189 vs 0.120 ms for 16->16 @128^3; the single issue stream / accumulate chain becomes the limiter again.)
 // Producers, halo-plane ring, weight staging from the fp32 parameter, fused statistics: as in conv_tc.cu.
 #include "tc_common.cuh"
 
