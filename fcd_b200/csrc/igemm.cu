@@ -356,3 +356,15 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
     igemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, (bf16*)C, ldc, bias, (int)M, N, ksplit, accumulate);
     return (int)cudaGetLastError();
 }
+
+// C[m][n] = bias[n] + sum_z ws[z][m][n] -> bf16 rows: the second half of every split-K conv (fcd_igemm_splitk calls it
+// itself; fcd_conv_gemm_tc leaves it to the caller).
+FCD_API int fcd_splitk_reduce(const float* ws, void* C, long long ldc, const float* bias, long long M, int N, int ksplit,
+                              int accumulate, cudaStream_t stream) {
+    if (N % 8 || ldc % 8 || ksplit < 1 || M < 1 || M > 0x7fffffffLL) return -1;
+    const long long total = M * (N / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 8 * fcd_num_sms()) blocks = 8 * fcd_num_sms();
+    igemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, (bf16*)C, ldc, bias, (int)M, N, ksplit, accumulate);
+    return (int)cudaGetLastError();
+}

@@ -212,6 +212,7 @@ def _colsum(x, C):
 
 USE_TC = os.environ.get("FCD_TC", "1") != "0"     # tcgen05 conv path (debug switch; the default is on)
 WGRAD_OVERLAP = os.environ.get("FCD_WGRAD_OVERLAP", "1") != "0"
+USE_GEMM_TC = os.environ.get("FCD_GEMM_TC", "1") != "0"   # tcgen05 split-K GEMM conv for the deep levels
 USE_TCF = os.environ.get("FCD_TCF", "1") != "0"   # kd-folded tcgen05 conv for Cout <= 32 (csrc/conv_tcf.cu)
 
 
@@ -286,6 +287,15 @@ def _w32(weight):
 def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
     """Legacy (mma.sync) implicit GEMM into contiguous rows of c; split-K when the output grid cannot fill the SMs."""
     M = B * dst[0] * dst[1] * dst[2]
+    if USE_TC and USE_GEMM_TC and k == 3 and stride == 1 and pad == 1 and bias is None and tuple(src) == tuple(dst):
+        ks = _lib.lib().fcd_conv_gemm_tc_ksplit(M, K, N)
+        if ks > 0:          # deep levels: tcgen05 split-K GEMM with streamed weights
+            ws = torch.empty((ks, M, N), dtype=torch.float32, device=a.device) if ks > 1 else None
+            call("fcd_conv_gemm_tc", A=a, lda=ld(a), Wp=wp, C=c, ldc=ld(c), ws=ws, Bn=B, D=dst[0], H=dst[1], W=dst[2],
+                 K=K, N=N, mode=mode, ksplit=ks)
+            if ks > 1:
+                call("fcd_splitk_reduce", ws=ws, C=c, ldc=ld(c), bias=None, M=M, N=N, ksplit=ks, accumulate=0)
+            return
     ks = _lib.lib().fcd_igemm_ksplit(M, N, K, k ** 3)
     common = dict(A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), bias=bias, Bn=B, Ds=src[0], Hs=src[1], Ws=src[2], Dm=dst[0],
                   Hm=dst[1], Wm=dst[2], K=K, N=N, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=mode, accumulate=0)

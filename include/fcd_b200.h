@@ -44,6 +44,15 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
                              int Bn, int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh,
                              int kw, int stride, int pad, int mode, int accumulate, float* ws, int ksplit,
                              cudaStream_t stream);
+FCD_API int fcd_splitk_reduce(const float* ws, void* C, long long ldc, const float* bias, long long M, int N, int ksplit,
+                              int accumulate, cudaStream_t stream);
+/* tcgen05 split-K GEMM form of the 3x3x3 stride-1 pad-1 convs of the DEEP levels (K, N multiples of 64; conv_blocks.py:
+ * 393-416 at encoder levels 3-6 / decoder / TransformerBlock.conv51): streamed packed weights, 128-voxel x up-to-256-
+ * channel tiles, (tap, k-chunk) loop split over gridDim.z.  mode 0 forward, 1 data gradient. */
+FCD_API int fcd_conv_gemm_tc_ksplit(long long M, int K, int N);
+FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void* C, long long ldc, float* ws, int Bn,
+                             int D, int H, int W, int K, int N, int mode, int ksplit, cudaStream_t stream);
+FCD_API int fcd_gemm_tc_error(void);
 FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
                       int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
                       int nsplit, cudaStream_t stream);

@@ -192,3 +192,36 @@ def test_packed_weights_follow_parameter_updates_inside_cuda_graph(ops):
         torch.cuda.synchronize()
         close(y, 2.0 * y0.float(), rel=1e-2, mx=2e-2, what="graph replay after in-place weight update")
         close(fwd(), y, rel=1e-6, mx=1e-6, what="eager after update")
+
+
+GEMM_TC_CASES = [
+    # B, Ci, Co, D, H, W      (K >= 128, N multiples of 64, >= 1024 voxels; small volumes -> split-K)
+    (2, 128, 256, 8, 8, 8),
+    (2, 256, 128, 8, 8, 8),
+    (2, 512, 512, 8, 8, 8),
+    (2, 128, 128, 16, 16, 16),
+    (1, 128, 64, 32, 32, 32),  # enough row tiles for ksplit 1: direct bf16 output
+    (1, 192, 64, 11, 10, 13),  # ragged volume: the last row tile is partial
+]
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", GEMM_TC_CASES)
+def test_conv_gemm_tc_fwd_bwd(ops, B, Ci, Co, D, H, W):
+    """Deep-level convs through the tcgen05 split-K GEMM kernel (forward + data gradient) vs torch fp32."""
+    from fcd_b200 import _lib
+    assert _lib.lib().fcd_conv_gemm_tc_ksplit(B * D * H * W, Ci, Co) > 0
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gw = torch.autograd.grad(ref, [xr, w], dy)
+    xc = cl(ops, x, True)
+    w2 = w.detach().clone().requires_grad_(True)
+    y = ops.conv3d(xc, w2, None, k=3)
+    assert _lib.lib().fcd_gemm_tc_error() == 0
+    close(ops.to_ncdhw(y, Co), ref, what="gemm_tc fwd")
+    y.backward(ops.to_channels_last(dy, Co))
+    assert _lib.lib().fcd_gemm_tc_error() == 0
+    close(ops.to_ncdhw(xc.grad, Ci), gx, what="gemm_tc dgrad")
+    close(w2.grad, gw, rel=6e-3, what="wgrad")
