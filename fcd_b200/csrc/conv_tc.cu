@@ -62,17 +62,16 @@ struct Cfg {
     static constexpr int LBO_B = COUT * 16, SBO_B = 128;
     static constexpr int BUDGET = 220 * 1024 - W_BYTES;
     static constexpr int NST = BUDGET / PLANE_BYTES >= 6 ? 6 : BUDGET / PLANE_BYTES;
-    // One UTCHMMA costs its issuing warp ~55 cycles (ptxas wraps it in an ELECT loop) against a 32-40 cycle
-    // shared-memory-bound execution for N = 16/32, so three warps issue -- warp kd owns the 9 taps of input plane
-    // z+kd-1 and its own TMEM accumulator; the epilogue adds the (valid) three.  Measured: splitting the taps of ONE
-    // issuing warp over 4 or 8 accumulators changes nothing (the accumulate chain is not the limiter).
+    // One issuing warp was the limiter (ptxas wraps every UTCHMMA in an ELECT loop; ncu showed the MMA warp busy issuing,
+    // never waiting), so three warps issue -- warp kd owns the 9 taps of input plane z+kd-1 and its own TMEM
+    // accumulator; the epilogue adds the (valid) three: 0.276 -> 0.223 ms for 16->16 @128^3.  Measured: splitting the
+    // taps of ONE issuing warp over 4 or 8 accumulators changes nothing (the accumulate chain is not the limiter).
     static constexpr int TCOLS = 2 * NMMA * COUT;
     static constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
     static_assert(TCOLS <= 512, "TMEM columns");
     static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;   // + barriers, tmem slot, stats scratch
-    // Small-Cout layers are limited by the latency-bound single-warp roles (one epilogue warp per SMSP needs ~1500
-    // cycles per plane against ~850 cycles of tensor work; ncu: tensor pipe 56 % active for 16->16, 93 % for 64->32),
-    // so two CTAs share an SM when shared memory and registers allow: their roles interleave.
+    // Small-Cout layers are limited by the latency-bound single-warp roles (one epilogue warp per SMSP), so two CTAs
+    // share an SM when shared memory and registers allow: their roles interleave (0.191 -> 0.166 ms for 16->16).
     static constexpr int CTAS_PER_SM = (COUT == 16 && 2 * SMEM <= 226 * 1024) ? 2 : 1;
     static_assert(NST >= 4, "need >= 4 halo-plane stages");
     static_assert(PLANE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "alignment");

@@ -1,11 +1,12 @@
 // kd-FOLDED variant of the tcgen05 conv3x3x3 (conv_tc.cu) for Cout <= 32 -- the layers that hold most of the FLOPs.
 //
 // Observation: a halo-plane A tile with a fixed in-plane shift (kh,kw) is needed by THREE output planes -- plane p feeds
-// output z = p-1 with tap kd = 2, z = p with kd = 1, z = p+1 with kd = 0.  An M=128 x N=Cout instruction is bound by the
-// shared-memory fetch of its 4 KB A tile (31 cycles for 8 cycles of math at N = 16), so the three are issued as ONE
+// output z = p-1 with tap kd = 2, z = p with kd = 1, z = p+1 with kd = 0.  The time of these small-N kernels follows the
+// NUMBER of tcgen05.mma instructions, not their N (an M=128 x N=16 x K=16 instruction carries 8 cycles of math but
+// costs several times that in fixed work: A-tile fetch, issue), so the three are issued as ONE
 // instruction of N = 3*Cout whose B operand is [W(2,kh,kw) | W(1,kh,kw) | W(0,kh,kw)] and whose D columns are the
 // accumulators of three CONSECUTIVE output planes, kept adjacent in a ring of R TMEM slots.  9*Cin/16 instructions per
-// plane instead of 27*Cin/16, same A traffic: 2.3x less tensor-pipe time for Cout = 16.
+// plane instead of 27*Cin/16, same A traffic: measured 1.4x (16->16) to 1.6x (32->16) faster.
 //
 // Consequences: every instruction accumulates (a slot sees its first tap together with older slots' later taps), so the
 // epilogue hands a slot back ZEROED (tcgen05.st) after reading it; a slot is complete once the plane two below it has
