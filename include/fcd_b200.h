@@ -87,6 +87,11 @@ FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long
                           int n_off, int k_off, int Bn, int D, int H, int W, int CS, int CU, cudaStream_t stream);
 FCD_API int fcd_wgrad_tc_error(void);
 
+/* measurement aid (not on the product path): cycles for back-to-back tcgen05.mma of shape M x N x 16, see
+ * csrc/umma_bench.cu and tools/umma_bench.py */
+FCD_API int fcd_umma_bench(int M, int N, int iters, int nissue, int same_acc, int ctas, long long* cycles,
+                           cudaStream_t stream);
+
 /* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382) ---- */
 FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int Wo, int C, cudaStream_t stream);
 FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,
