@@ -10,8 +10,8 @@
 //
 // Consequences: every instruction accumulates (a slot sees its first tap together with older slots' later taps), so the
 // epilogue hands a slot back ZEROED (tcgen05.st) after reading it; a slot is complete once the plane two below it has
-// been multiplied; slot ranges that wrap around the ring are issued as two instructions.  The three issuing warps own
-// one kh row of taps each and their own accumulator set (the epilogue adds the three sets), exactly as in conv_tc.cu.
+// been multiplied; slot ranges that wrap around the ring are issued as two instructions.  The three issuing warps take
+// turns on planes and own one accumulator set each (the epilogue adds the three sets).
 // (Measured: ONE issuing warp with one accumulator set -- lighter epilogue, 3 CTAs per SM -- is 1.5x SLOWER:
 // 0.189 vs 0.120 ms for 16->16 @128^3; the single issue stream / accumulate chain becomes the limiter again.)
 // Producers, halo-plane ring, weight staging from the fp32 parameter, fused statistics: as in conv_tc.cu.
@@ -25,6 +25,11 @@ constexpr int TH = 16, TW = 8, HH = TH + 2, HW = TW + 2, HV = HH * HW;
 constexpr int NPROD = 2, NMMA = 3;
 constexpr int NTHREADS = 32 * (NPROD + NMMA + 4);
 constexpr int R = 5;                      // accumulator ring slots (3 accumulating + slack for the epilogue)
+// Plane-done barriers: a multiple of NMMA (one warp owns every phase of a barrier) and more than the furthest the MMA
+// warps can run ahead of the epilogue's wait pointer -- TEMPTY keeps them within R = 5 outputs, i.e. within
+// 5 + 2 planes per item boundary crossed (<= 4 boundaries with 1-plane items) + 2 = 15 planes -- so a barrier can never
+// complete two phases before the epilogue has looked at the first.
+constexpr int NPB = 18;
 
 struct ConvTcfParams {
     const bf16* A; long long lda;
@@ -73,8 +78,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     unsigned char* wsm = smem;
     unsigned char* ring = smem + K::W_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::W_BYTES + NST * K::PLANE_BYTES);
-    // bars: [0,NST) FULL | [NST,2NST) EMPTY | [2NST,2NST+R) TFULL | [2NST+R,2NST+2R) TEMPTY
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 * R);
+    // bars: [0,NST) FULL | [NST,2NST) EMPTY | [2NST,2NST+NPB) PDONE | [2NST+NPB,2NST+NPB+R) TEMPTY
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + NPB + R);
     volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
     float* red = reinterpret_cast<float*>(tmem_slot + 4);
 
@@ -83,13 +88,14 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
-    auto TFULL = [&](int s) { return bar0 + 8u * (2 * NST + s); };
-    auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + R + s); };
+    auto PDONE = [&](int s) { return bar0 + 8u * (2 * NST + s); };
+    auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + NPB + s); };
 
     if (tid == 0) {
         *dead = 0;
-        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), NMMA); }
-        for (int s = 0; s < R; ++s) { mbar_init(TFULL(s), NMMA); mbar_init(TEMPTY(s), 4); }
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < NPB; ++s) mbar_init(PDONE(s), 1);
+        for (int s = 0; s < R; ++s) mbar_init(TEMPTY(s), 4);
         fence_barrier_init();
     }
     if (warp == NPROD) tmem_alloc<K::TMEM_COLS>(smem_u32(tmem_slot));
@@ -169,44 +175,56 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
         fence_proxy_async();
         flush_to(seq);
     } else if (warp < NPROD + NMMA) {
-        // ===================================================================== MMA issuers: warp kh owns taps (.,kh,.)
-        const int kh = warp - NPROD;
+        // ===================================================================== MMA issuers: the three warps take turns on
+        // PLANES (plane g -> warp g % 3): one warp pays a plane's waits / commits / bookkeeping once and issues all
+        // 9*CIN/16 instructions of it, while the other two work on the neighbouring planes.  Each warp accumulates
+        // into its own set of R slots (concurrent warps never share an accumulator); the epilogue adds the three sets.
+        const int me = warp - NPROD;
         constexpr uint32_t A_HI = ((K::SBO_A >> 4) & 0x3fffu) | (1u << 14);
         constexpr uint32_t B_HI = ((K::SBO_B >> 4) & 0x3fffu) | (1u << 14);
         const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_A >> 4) << 16);
         const uint32_t b_lo0 = ((smem_u32(wsm) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_B >> 4) << 16);
-        const uint32_t d_set = tmem_base + kh * R * COUT;
+        const uint32_t d_set = tmem_base + me * R * COUT;
         // n_out consecutive output slots starting at `slot`, whose first B row block is t0
         auto issue = [&](uint32_t a_pl, int slot, int t0, int n_out) {
             const uint32_t idesc = umma_idesc(128, n_out * COUT, 0, 0);
+            const uint32_t d = d_set + slot * COUT;
+            const uint32_t b_t = b_lo0 + ((t0 * COUT * 16) >> 4);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+            for (int khw = 0; khw < 9; ++khw) {
+                const int kh = khw / 3, kw = khw % 3;
 #pragma unroll
                 for (int kc = 0; kc < CIN / 16; ++kc) {
                     const uint32_t a_lo = a_pl + (((kh * HW + kw) * 16 + kc * 2 * K::LBO_A) >> 4);
-                    const uint32_t b_lo = b_lo0 + (((kh * 3 + kw) * K::KHW_BYTES + kc * 2 * K::LBO_B + t0 * COUT * 16) >> 4);
-                    umma_f16(d_set + slot * COUT, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, idesc, 1u);
+                    const uint32_t b_lo = b_t + ((khw * K::KHW_BYTES + kc * 2 * K::LBO_B) >> 4);
+                    umma_f16(d, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, idesc, 1u);
                 }
             }
         };
-        uint32_t seq_base = 0, zc0 = 0;                        // plane sequence / output-plane counter at item start
+        uint32_t seq_base = 0, zc0 = 0, pc0 = 0;               // loaded-plane sequence / output counter / plane counter
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const Item it = decode(p, item);
             const int nload = it.p_hi - it.p_lo + 1, DLi = it.d1 - it.d0;
-            int acq = 0, fin = 0;                              // outputs (local index) acquired / handed to the epilogue
             for (int i = 0; i <= DLi + 1; ++i) {               // input plane z = d0 - 1 + i feeds outputs i-2, i-1, i
+                const uint32_t g = pc0 + i;
+                if ((int)(g % NMMA) != me) continue;
                 const int pl = it.d0 - 1 + i;
-                if (pl >= 0 && pl < p.D) {
-                    const uint32_t sq = seq_base + (pl - it.p_lo);
+                const bool valid = pl >= 0 && pl < p.D;
+                const int j_lo = max(i - 2, 0), j_hi = min(i, DLi - 1);
+                uint32_t sq = 0;
+                if (valid) {
+                    sq = seq_base + (pl - it.p_lo);
                     mbar_wait(FULL(sq % NST), (sq / NST) & 1u, dead, 2);
-                    const int j_lo = max(i - 2, 0), j_hi = min(i, DLi - 1);
-                    while (acq <= j_hi) {                      // first touch of an output: its slot must be back, zeroed
-                        const uint32_t zc = zc0 + acq;
-                        mbar_wait(TEMPTY(zc % R), (zc / R) & 1u, dead, 3);
-                        ++acq;
-                    }
-                    tc_fence_after();
-                    if (lane == 0) {
+                }
+                // every output this plane touches must have been handed back (zeroed) by the epilogue; this also
+                // keeps a warp from running more than R outputs ahead, i.e. from lapping the PDONE phases
+                for (int j = j_lo; j <= j_hi; ++j) {
+                    const uint32_t zc = zc0 + j;
+                    mbar_wait(TEMPTY(zc % R), (zc / R) & 1u, dead, 3);
+                }
+                tc_fence_after();
+                if (lane == 0) {
+                    if (valid) {
                         const uint32_t a_pl = a_lo0 + (sq % NST) * (K::PLANE_BYTES >> 4);
                         const int t_lo = j_lo - (i - 2), n_out = j_hi - j_lo + 1;
                         const int s_lo = (int)((zc0 + j_lo) % R);
@@ -214,18 +232,16 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                         issue(a_pl, s_lo, t_lo, n1);
                         if (n_out > n1) issue(a_pl, 0, t_lo + n1, n_out - n1);      // the range wraps around the ring
                         umma_commit(EMPTY(sq % NST));
+                        umma_commit(PDONE(g % NPB));
+                    } else {
+                        mbar_arrive(PDONE(g % NPB));           // zero-padding plane: nothing to add
                     }
-                    __syncwarp();
-                }
-                const int fin_to = min(i - 2, DLi - 1);        // outputs <= i-2 have received all their planes
-                while (fin <= fin_to) {
-                    if (lane == 0) umma_commit(TFULL((zc0 + fin) % R));
-                    ++fin;
                 }
                 __syncwarp();
             }
             seq_base += nload;
             zc0 += DLi;
+            pc0 += DLi + 2;
         }
     } else {
         // ===================================================================== epilogue (4 warps)
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
         if (lane == 0) {
             for (int s = 0; s < R; ++s) mbar_arrive(TEMPTY(s));
         }
-        uint32_t zc = 0;
+        uint32_t zc = 0, pc0 = 0, pwaited = 0;              // outputs done / plane counter at item start / planes waited
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const Item it = decode(p, item);
             float s1[STATS ? COUT : 1], s2[STATS ? COUT : 1];
@@ -252,7 +268,12 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             }
             for (int od = it.d0; od < it.d1; ++od, ++zc) {
                 const int slot = zc % R;
-                mbar_wait(TFULL(slot), (zc / R) & 1u, dead, 4);
+                // output j = od - d0 is complete when planes j, j+1, j+2 of this item have been multiplied
+                const uint32_t need = pc0 + (uint32_t)(od - it.d0) + 3;
+                while (pwaited < need) {
+                    mbar_wait(PDONE(pwaited % NPB), (pwaited / NPB) & 1u, dead, 4);
+                    ++pwaited;
+                }
                 tc_fence_after();
                 uint32_t t[3][COUT];
 #pragma unroll
@@ -300,6 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            pc0 += (uint32_t)(it.d1 - it.d0) + 2;
         }
     }
     tc_fence_before();
