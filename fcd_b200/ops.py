@@ -367,10 +367,20 @@ class ConvFn(Function):
             def wgrad_work():
                 _lib.note_work("wgrad", 2.0 * B * Do * Ho * Wo * Co * Ci * T,
                                2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
-                ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (USE_TC and k == 3 and stride == 1 and pad == 1) else 0
+                std3 = USE_TC and k == 3 and stride == 1 and pad == 1
+                nsg = 0
+                if std3 and USE_GEMM_TC and Kp >= 64 and Np >= 64:
+                    nsg = _lib.lib().fcd_wgrad_gemm_tc_nsplit(B * D * H * W, Kp, Np)
+                ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (std3 and nsg == 0) else 0
                 if ns > 0 and ((Kp + 31) // 32) * ((Np + 31) // 32) > 4:
                     ns = 0      # many thin slices over a small volume: the split-K mma.sync kernel is the better fit
-                if ns > 0:
+                if nsg > 0:
+                    # deep levels (>= 64 channels both sides): tcgen05 GEMM with the voxels as the K dimension
+                    ns = nsg
+                    part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
+                    call("fcd_wgrad_gemm_tc", X=x, ldx=ld(x), dY=dy, ldy=ld(dy), part=part, Bn=B, D=D, H=H, W=W, Kp=Kp,
+                         Np=Np)
+                elif ns > 0:
                     # tcgen05 path: 32- (or 16-) channel slices of x (shifted operand) against slices of dy
                     cs = 32 if Kp % 32 == 0 else 16
                     cu = 32 if Np % 32 == 0 else 16

@@ -53,6 +53,12 @@ FCD_API int fcd_conv_gemm_tc_ksplit(long long M, int K, int N);
 FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void* C, long long ldc, float* ws, int Bn,
                              int D, int H, int W, int K, int N, int mode, int ksplit, cudaStream_t stream);
 FCD_API int fcd_gemm_tc_error(void);
+/* weight gradient of the same deep-level convs: voxels as the GEMM K dimension, 128 input channels x up to 256 output
+ * channels per CTA, one CTA per (tap, tile, voxel slice); part[nsplit][27][Np][Kp] is finished by fcd_wgrad_reduce. */
+FCD_API int fcd_wgrad_gemm_tc_nsplit(long long M, int Kp, int Np);
+FCD_API int fcd_wgrad_gemm_tc(const void* X, long long ldx, const void* dY, long long ldy, float* part, int Bn, int D,
+                              int H, int W, int Kp, int Np, cudaStream_t stream);
+FCD_API int fcd_wgrad_gemm_tc_error(void);
 FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
                       int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
                       int nsplit, cudaStream_t stream);

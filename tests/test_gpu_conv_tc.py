@@ -225,3 +225,21 @@ def test_conv_gemm_tc_fwd_bwd(ops, B, Ci, Co, D, H, W):
     assert _lib.lib().fcd_gemm_tc_error() == 0
     close(ops.to_ncdhw(xc.grad, Ci), gx, what="gemm_tc dgrad")
     close(w2.grad, gw, rel=6e-3, what="wgrad")
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", [(2, 64, 128, 8, 8, 8), (1, 128, 64, 16, 16, 16), (2, 256, 256, 4, 4, 4),
+                                            (2, 512, 512, 4, 4, 4), (1, 192, 320, 5, 6, 7), (1, 128, 64, 32, 32, 32)])
+def test_wgrad_gemm_tc(ops, B, Ci, Co, D, H, W):
+    """Deep-level weight gradient through the tcgen05 GEMM kernel (voxels as K, MN-major operands) vs torch autograd."""
+    from fcd_b200 import _lib
+    assert _lib.lib().fcd_wgrad_gemm_tc_nsplit(B * D * H * W, ops.pad16(Ci), ops.pad16(Co)) > 0
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    ref = F.conv3d(x, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    (gw,) = torch.autograd.grad(ref, [w], dy)
+    w2 = w.detach().clone().requires_grad_(True)
+    y = ops.conv3d(ops.to_channels_last(x), w2, None, k=3)
+    y.backward(ops.to_channels_last(dy, ops.pad16(Co)))
+    assert _lib.lib().fcd_wgrad_gemm_tc_error() == 0
+    close(w2.grad, gw, rel=6e-3, what="wgrad gemm_tc")
