@@ -99,13 +99,23 @@ class UnetResBlock(nn.Module):
         self.slope = _act_slope(act_name)
 
     def forward(self, inp, cin_seg=None):
+        if self.downsample and not isinstance(self.norm2, nn.InstanceNorm3d):
+            raise NotImplementedError("channel-changing UnetResBlock is built with instance norm by get_model")
+        branch = None
+        if self.downsample:
+            # The residual branch (1x1 conv + its InstanceNorm statistics: bandwidth-bound) is independent of the
+            # conv1 -> norm -> conv2 chain (tensor-bound) until the final add: it runs on a second stream, forked here
+            # and joined before the tail.  Autograd replays each node on its forward stream, so the branch's backward
+            # (1x1 data / weight gradient) overlaps the main chain's backward as well.
+            branch = ops.branch(inp.device)
+            with branch:
+                c3 = ops.conv3d(inp, self.conv3.conv.weight, self.conv3.conv.bias, 1, cin_seg=cin_seg)
+                ops.attach_stats(c3, "instance", self.norm2.eps)
         c1 = ops.conv3d(inp, self.conv1.conv.weight, self.conv1.conv.bias, 3, cin_seg=cin_seg)
         a1 = apply_norm(self.norm1, c1, slope=self.slope)
         c2 = ops.conv3d(a1, self.conv2.conv.weight, self.conv2.conv.bias, 3)
         if self.downsample:
-            c3 = ops.conv3d(inp, self.conv3.conv.weight, self.conv3.conv.bias, 1, cin_seg=cin_seg)
-            if not isinstance(self.norm2, nn.InstanceNorm3d):
-                raise NotImplementedError("channel-changing UnetResBlock is built with instance norm by get_model")
+            branch.join()
             return ops.norm_act(c2, c3, None, None, None, "instance", self.slope, self.norm2.eps)
         return apply_norm(self.norm2, c2, res=inp, slope=self.slope)
 

@@ -260,6 +260,43 @@ class _SideWork:
 
 
 _SIDE = _SideWork()
+BRANCH_OVERLAP = os.environ.get("FCD_BRANCH_OVERLAP", "1") != "0"
+_BRANCH_STREAMS = {}
+
+
+class branch:
+    """`with ops.branch(device): ...` runs the body on a second stream forked from the current one; `.join()` makes the
+    current stream wait for it.  Used for the independent residual branch of UnetResBlock (a no-op when switched off)."""
+
+    def __init__(self, device):
+        self.on = BRANCH_OVERLAP and device.type == "cuda"
+        if self.on:
+            self.main = torch.cuda.current_stream(device)
+            st = _BRANCH_STREAMS.get(device.index)
+            if st is None:
+                st = _BRANCH_STREAMS[device.index] = torch.cuda.Stream(device=device)
+            self.side = st
+            self.ctx = torch.cuda.stream(st)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+
+
+def attach_stats(x, mode, eps):
+    """Compute the norm statistics of x now (on the current stream) and attach them for the NormActFn that consumes x."""
+    x._fcd_meanrstd = _stats(rows(x), MODE[mode], float(eps))
 
 
 def _off_critical_path(fn, *keep):
@@ -564,7 +601,8 @@ class NormActFn(Function):
             mean1, rstd1 = _stats(x1, mode, eps)
         mean2 = rstd2 = None
         if x2 is not None:
-            mean2, rstd2 = _stats(x2, mode, eps)
+            pre = getattr(x2, "_fcd_meanrstd", None)        # computed on the residual-branch stream (ops.attach_stats)
+            mean2, rstd2 = pre if pre is not None else _stats(x2, mode, eps)
         y = _empty((B, D, H, W, C), x1)
         _lib.note_work(None, 0.0, 2.0 * B * S * C * (2 + (x2 is not None) + (res is not None)))
         call("fcd_norm_apply", x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1, gamma1=g, beta1=b, x2=x2,
