@@ -152,20 +152,33 @@ class MS_DSA_NET(nn.Module):
         ops.prepack_weights(x0.device)
         if tuple(x0.shape[1:4]) != self.img_size:
             raise ValueError(f"MS_DSA_NET was built for patches of {self.img_size}, got {tuple(x0.shape[1:4])}")
-        x1 = self.encoder1(x0)
-        x2 = self.encoder2(ops.max_pool2(x1))
-        x3 = self.encoder3(ops.max_pool2(x2))
-        x4 = self.encoder4(ops.max_pool2(x3))
-        x5 = self.encoder5(ops.max_pool2(x4))
-        x6 = self.encoder6(ops.max_pool2(x5))
-        ts = {}
-        for lvl, xi in ((3, x3), (4, x4), (5, x5), (6, x6)):
+        # The four transformer stacks (levels 3-6) are independent of each other and of the deeper encoder levels: stack i
+        # is forked onto its own stream as soon as x_i exists, while the encoder goes on; each is joined where the decoder
+        # needs it.  The deep stacks are chains of tiny latency-bound kernels, so they hide completely behind level 3.
+        # Autograd replays every node on its forward stream, so the backward pass overlaps the same way.
+        def stack(lvl, xi):
             t = getattr(self, f"patch_embedding{lvl}")(xi)
             for blk in getattr(self, f"trans{lvl}"):
                 t = blk(t)
-            ts[lvl] = t
+            return t
+
+        ts, br = {}, {}
+        x1 = self.encoder1(x0)
+        x2 = self.encoder2(ops.max_pool2(x1))
+        x = x2
+        for lvl in (3, 4, 5, 6):
+            x = getattr(self, f"encoder{lvl}")(ops.max_pool2(x))
+            if lvl < 6:
+                br[lvl] = ops.branch(x.device, key=lvl)
+                with br[lvl]:
+                    ts[lvl] = stack(lvl, x)
+            else:
+                ts[lvl] = stack(lvl, x)
+        br[5].join()
         y = self.decoder5(ts[6], ts[5])
+        br[4].join()
         y = self.decoder4(y, ts[4])
+        br[3].join()
         y = self.decoder3(y, ts[3])
         y = self.decoder2(y, x2)
         y = self.decoder1(y, x1)

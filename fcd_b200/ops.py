@@ -253,6 +253,10 @@ class _SideWork:
         return out
 
     def join(self):
+        # runs as an autograd end-of-backward callback, on the thread / stream that called backward(): that stream (the
+        # one the optimizer will use) and every stream a weight gradient was forked from wait for the side stream
+        for dev in {d for d, _, _ in self.pending}:
+            torch.cuda.current_stream(dev).wait_stream(self.stream(dev))
         for dev, main, _ in self.pending:
             main.wait_stream(self.stream(dev))
         self.pending.clear()
@@ -265,16 +269,17 @@ _BRANCH_STREAMS = {}
 
 
 class branch:
-    """`with ops.branch(device): ...` runs the body on a second stream forked from the current one; `.join()` makes the
-    current stream wait for it.  Used for the independent residual branch of UnetResBlock (a no-op when switched off)."""
+    """`with ops.branch(device, key): ...` runs the body on the side stream `key`, forked from the current stream;
+    `.join()` makes the current stream wait for it.  Used for the independent residual branch of UnetResBlock (key 0)
+    and the per-level transformer stacks of MS_DSA_NET (keys 3-5); a no-op when switched off."""
 
-    def __init__(self, device):
+    def __init__(self, device, key=0):
         self.on = BRANCH_OVERLAP and device.type == "cuda"
         if self.on:
             self.main = torch.cuda.current_stream(device)
-            st = _BRANCH_STREAMS.get(device.index)
+            st = _BRANCH_STREAMS.get((device.index, key))
             if st is None:
-                st = _BRANCH_STREAMS[device.index] = torch.cuda.Stream(device=device)
+                st = _BRANCH_STREAMS[(device.index, key)] = torch.cuda.Stream(device=device)
             self.side = st
             self.ctx = torch.cuda.stream(st)
 
