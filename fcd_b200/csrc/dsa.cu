@@ -317,7 +317,11 @@ __global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__
                                                         const float* __restrict__ temperature2,
                                                         float* __restrict__ xca, float* __restrict__ tsa, int N, int C,
                                                         float drop_scale, uint32_t drop_thresh,
-                                                        unsigned long long seed) {
+                                                        unsigned long long seed0,
+                                                        const long long* __restrict__ seed_dev) {
+    // seed_dev: device step counter (ticks once per training forward) mixed into the seed, so a captured CUDA graph
+    // draws a NEW mask on every replay while forward and backward of one step still agree
+    const unsigned long long seed = seed0 + (seed_dev ? (unsigned long long)(*seed_dev) * 0xD1B54A32D192ED03ULL : 0ULL);
     extern __shared__ float sm[];
     float* sKP = sm;                    // [CH][P]
     float* sVP = sm + CH * P;           // [CH][P]
@@ -445,7 +449,9 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
                                                             const float* __restrict__ temperature2,
                                                             float* __restrict__ dqh, float* __restrict__ part, int N,
                                                             int C, float drop_scale, uint32_t drop_thresh,
-                                                            unsigned long long seed) {
+                                                            unsigned long long seed0,
+                                                            const long long* __restrict__ seed_dev) {
+    const unsigned long long seed = seed0 + (seed_dev ? (unsigned long long)(*seed_dev) * 0xD1B54A32D192ED03ULL : 0ULL);
     constexpr int TN = 64;
     constexpr int ROW = 2 * P + 5 * CH + 1;
     extern __shared__ float sm[];
@@ -801,19 +807,20 @@ __global__ void __launch_bounds__(256) dsa_bwd_ef_kernel(const bf16* __restrict_
 template <int CH, int P>
 int launch_apply(const bf16* qkvv, long long ldq, const float* inv_n, const float* A, const float* KV,
                  const float* t2, float* xca, float* tsa, int B, int N, int C, int H, float ds, uint32_t dth,
-                 unsigned long long seed, cudaStream_t st) {
+                 unsigned long long seed, const long long* seed_dev, cudaStream_t st) {
     const int smem = (2 * CH * P + CH * CH + CH) * 4;
     static bool conf = false;
     if (!conf) { cudaFuncSetAttribute(dsa_apply_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
     dim3 grid((N + 127) / 128, H, B);
-    dsa_apply_kernel<CH, P><<<grid, 128, smem, st>>>(qkvv, ldq, inv_n, A, KV, t2, xca, tsa, N, C, ds, dth, seed);
+    dsa_apply_kernel<CH, P><<<grid, 128, smem, st>>>(qkvv, ldq, inv_n, A, KV, t2, xca, tsa, N, C, ds, dth, seed, seed_dev);
     return (int)cudaGetLastError();
 }
 
 template <int CH, int P>
 int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long lddy, const float* gamma,
                       const float* inv_n, const float* KV, const float* t2, float* dqh, float* part, int B, int N,
-                      int C, int H, float ds, uint32_t dth, unsigned long long seed, cudaStream_t st) {
+                      int C, int H, float ds, uint32_t dth, unsigned long long seed, const long long* seed_dev,
+                      cudaStream_t st) {
     const int smem = (2 * CH * P + 64 * (2 * P + 5 * CH + 1)) * 4;
     static bool conf = false;
     if (!conf) {
@@ -824,10 +831,10 @@ int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long
     dim3 grid((N + 63) / 64, H, B);
     if ((long long)grid.x * H * B >= 2LL * fcd_num_sms())
         dsa_bwd_reduce_kernel<CH, P, 64><<<grid, 64, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N,
-                                                                C, ds, dth, seed);
+                                                                C, ds, dth, seed, seed_dev);
     else
         dsa_bwd_reduce_kernel<CH, P, 256><<<grid, 256, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part,
-                                                                  N, C, ds, dth, seed);
+                                                                  N, C, ds, dth, seed, seed_dev);
     return (int)cudaGetLastError();
 }
 
@@ -929,7 +936,8 @@ static inline void drop_params(float p, float& scale, uint32_t& thresh) {
 // Saved for backward: inv_n [B][2][C], Ghat/A [B][H][c][c], KV [B][2][C][P], xca [B*N][C], tsa [B][c][H][N].
 FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const float* temperature,
                         const float* temperature2, const float* gamma, const void* t, long long ldt, void* y,
-                        long long ldy, const float* ca_scale, float sa_drop, long long seed, float* part, float* inv_n,
+                        long long ldy, const float* ca_scale, float sa_drop, long long seed, const long long* seed_dev,
+                        float* part, float* inv_n,
                         float* Ghat, float* A, float* Ad, float* KV, float* xca, float* tsa, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t st) {
     if (C % H || P % 4 || Cp % 8) return -1;
@@ -958,7 +966,7 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
     {
         auto run = [&]() -> int {
             DSA_DISPATCH(launch_apply, (const bf16*)qkvv, ldq, inv_n, Ad, KV, temperature2, xca, tsa, B, N, C, H, ds, dth,
-                         (unsigned long long)seed, st);
+                         (unsigned long long)seed, seed_dev, st);
         };
         int rc = run();
         if (rc != 0) return rc;
@@ -975,7 +983,8 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
 // work: dqh [B*N][C] fp32, dKV [B][2][C][P], dGhat [B][H][c][c], rqk [B][2][C], gpart 2*148*2*Cp floats.
 FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long long lddy, const float* EF,
                         const float* temperature, const float* temperature2, const float* gamma,
-                        const float* ca_scale, float sa_drop, long long seed, const float* inv_n, const float* Ghat,
+                        const float* ca_scale, float sa_drop, long long seed, const long long* seed_dev,
+                        const float* inv_n, const float* Ghat,
                         const float* A, const float* Ad, const float* KV, const float* xca, const float* tsa,
                         float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
                         long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
@@ -993,7 +1002,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
     {
         auto run = [&]() -> int {
             DSA_DISPATCH(launch_bwd_reduce, (const bf16*)qkvv, ldq, (const bf16*)dy, lddy, gamma, inv_n, KV, temperature2,
-                         dqh, part, B, N, C, H, ds, dth, (unsigned long long)seed, st);
+                         dqh, part, B, N, C, H, ds, dth, (unsigned long long)seed, seed_dev, st);
         };
         int rc = run();
         if (rc != 0) return rc;

@@ -150,6 +150,8 @@ class MS_DSA_NET(nn.Module):
     def forward_cl(self, x0):
         """Forward from a channels-last bf16 batch [B,D,H,W,16] (what fcd_sw_gather produces)."""
         ops.prepack_weights(x0.device)
+        if self.training:
+            ops.tick(x0.device)
         if tuple(x0.shape[1:4]) != self.img_size:
             raise ValueError(f"MS_DSA_NET was built for patches of {self.img_size}, got {tuple(x0.shape[1:4])}")
         # The four transformer stacks (levels 3-6) are independent of each other and of the deeper encoder levels: stack i

@@ -159,6 +159,8 @@ class SegResNet(nn.Module):
     # -- forward ---------------------------------------------------------------------------------------------
     def encode(self, x):
         ops.prepack_weights(x.device)
+        if self.training:
+            ops.tick(x.device)
         x = ops.conv3d(x, self.convInit.conv.weight, None, 3)
         if self.dropout_prob is not None:
             x = ops.dropout3d(x, self.dropout.p, self.training)

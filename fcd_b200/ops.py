@@ -792,6 +792,23 @@ def ln_pos(x, pos, w, b, C, eps=1e-5):
     return LNPosFn.apply(x, pos, w, b, C, eps)
 
 
+_STEP = {}
+
+
+def step_counter(device):
+    """int64 device counter, advanced once per training forward by `tick` (a captured, replayable op)."""
+    c = _STEP.get(device.index)
+    if c is None:
+        c = _STEP[device.index] = torch.zeros(1, dtype=torch.int64, device=device)
+    return c
+
+
+def tick(device):
+    """Advance the step counter; the networks call it at the top of a training forward.  In-kernel dropout mixes the
+    counter into its seed, so a CUDA-graph replay (whose kernel arguments are frozen) still draws new masks."""
+    step_counter(device).add_(1)
+
+
 class DSAFn(Function):
     """y = t + gamma * DSA(qkvv)  (conv_blocks.py:328-355 + line 77), qkvv = Linear(LayerNorm(t))."""
 
@@ -818,7 +835,8 @@ class DSAFn(Function):
         t2 = temperature2.detach().float().contiguous()
         g = gamma.detach().float().contiguous()
         call("fcd_dsa_fwd", qkvv=qkvv, ldq=ld(qkvv), EF=EFc, temperature=t1, temperature2=t2, gamma=g, t=t, ldt=ld(t),
-             y=y, ldy=Cp, ca_scale=ca_scale, sa_drop=float(sa_drop), seed=int(seed), part=part, inv_n=inv_n, Ghat=Ghat,
+             y=y, ldy=Cp, ca_scale=ca_scale, sa_drop=float(sa_drop), seed=int(seed),
+             seed_dev=step_counter(dev) if sa_drop > 0 else None, part=part, inv_n=inv_n, Ghat=Ghat,
              A=A, Ad=Ad, KV=KV, xca=xca, tsa=tsa, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
         ctx.save_for_backward(qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale)
         ctx.cfg = (C, H, P, float(sa_drop), int(seed), Cp, (B, D, Hs, W), tuple(temperature.shape))
@@ -846,7 +864,8 @@ class DSAFn(Function):
         dtemp2 = torch.zeros((H,), **f32)
         dgamma = torch.empty((C,), **f32)
         call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
-             gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
+             gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed,
+             seed_dev=step_counter(dev) if sa_drop > 0 else None, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
              xca=xca, tsa=tsa, part=part, dqh=dqh, dKV=dKV, dGhat=dGhat, rqk=rqk, gpart=gpart, dqkvv=dqkvv,
              lddq=dqkvv.shape[4], dEF=dEF, dtemp=dtemp, dtemp2=dtemp2, dgamma=dgamma, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
         return (dqkvv, dy, dEF, dtemp.view(tshape), dtemp2.view(tshape), dgamma, None, None, None, None, None, None)

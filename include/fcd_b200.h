@@ -160,17 +160,20 @@ FCD_API int fcd_ln_bwd(const void* dln, long long lddl, const void* dtd, long lo
 
 /* ---- DSA.forward, sa_type='parallel' (conv_blocks.py:328-355) fused with `x + gamma * dsa` (line 77).
  *      ca_scale: optional [B][H][c][c] dropout scale (0 or 1/(1-p)) for attn_drop; sa_drop/seed: in-kernel
- *      counter-based dropout of the [N,P] spatial attention map (attn_drop_2). ---- */
+ *      counter-based dropout of the [N,P] spatial attention map (attn_drop_2); seed_dev: optional DEVICE step counter
+ *      mixed into the seed, so that replays of a captured CUDA graph draw fresh masks. ---- */
 FCD_API int fcd_dsa_fwd_part_floats(int B, int N, int C, int H, int P);
 FCD_API int fcd_dsa_bwd_part_floats(int B, int N, int C, int H, int P);
 FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const float* temperature,
                         const float* temperature2, const float* gamma, const void* t, long long ldt, void* y,
-                        long long ldy, const float* ca_scale, float sa_drop, long long seed, float* part, float* inv_n,
+                        long long ldy, const float* ca_scale, float sa_drop, long long seed, const long long* seed_dev,
+                        float* part, float* inv_n,
                         float* Ghat, float* A, float* Ad, float* KV, float* xca, float* tsa, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t stream);
 FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long long lddy, const float* EF,
                         const float* temperature, const float* temperature2, const float* gamma,
-                        const float* ca_scale, float sa_drop, long long seed, const float* inv_n, const float* Ghat,
+                        const float* ca_scale, float sa_drop, long long seed, const long long* seed_dev,
+                        const float* inv_n, const float* Ghat,
                         const float* A, const float* Ad, const float* KV, const float* xca, const float* tsa,
                         float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
                         long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,

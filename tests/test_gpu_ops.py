@@ -405,6 +405,44 @@ def test_dsa_dropout_is_reproducible_and_unbiased(ops):
     close(g.grad, fd, rel=2e-2, mx=5e-2, what="dropout bwd mask")
 
 
+def test_dsa_dropout_mask_changes_across_graph_replays(ops):
+    """Kernel arguments are frozen in a captured CUDA graph, so the host seed alone would repeat the mask on every
+    replay; the device step counter (ops.tick, captured with the step) must give a new mask per replay while the
+    backward of a replay still sees that replay's forward mask."""
+    B, C, dims, P, H = 2, 32, (4, 4, 4), 64, 4
+    N = 64
+    qkvv = rnd(B, 4 * C, *dims, scale=0.5)
+    t = rnd(B, C, *dims, seed=2)
+    EF = rnd(N, P, scale=0.125, seed=3)
+    t1, t2 = rnd(H, 1, 1, scale=0.1, seed=4) + 1.0, rnd(H, 1, 1, scale=0.1, seed=5) + 1.0
+    gamma = (rnd(C, scale=0.1, seed=6) + 0.5).requires_grad_(True)
+    q, tt = ops.to_channels_last(qkvv, 4 * C), ops.to_channels_last(t)
+
+    def step():
+        ops.tick(q.device)
+        y = ops.dsa_attention(q, tt, EF, t1, t2, gamma, C, H, P, None, 0.1, 77)
+        (grad,) = torch.autograd.grad(y.float().sum(), gamma)
+        return y, grad
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y, grad = step()
+    outs = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        outs.append((y.clone(), grad.clone()))
+    assert not torch.equal(outs[0][0], outs[1][0]) and not torch.equal(outs[1][0], outs[2][0])
+    for yy, gg in outs:
+        fd = (yy.float() - tt.float())[..., :C].sum(dim=(0, 1, 2, 3)) / gamma.detach()
+        close(gg, fd, rel=2e-2, mx=5e-2, what="replayed dropout bwd mask")
+
+
 @pytest.mark.parametrize("Ci,Co,mode", [(16, 16, "add"), (32, 16, "concat"), (8, 4, "concat"), (16, 8, "plain")])
 def test_subpixel_upsample(ops, Ci, Co, mode):
     B, D, H, W = 2, 4, 5, 6
