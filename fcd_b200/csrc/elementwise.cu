@@ -65,7 +65,8 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
 
 // Gradient goes to the FIRST maximal element in (z,y,x) scan order, as ATen's max_pool3d backward does.
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
-                                    const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int Do, int Ho, int Wo,
+                                    const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                    const bf16* __restrict__ add, long long ldadd, int B, int Do, int Ho, int Wo,
                                     int C8, int accumulate) {
     const long long total = (long long)B * Do * Ho * Wo * C8;
     const int Hi = Ho * 2, Wi = Wo * 2;
@@ -90,13 +91,17 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
             long long vox = ((b * (Do * 2) + oz * 2 + (t >> 2)) * Hi + oy * 2 + ((t >> 1) & 1)) * Wi + ox * 2 + (t & 1);
             float f[8], o[8];
             unpack8(ld8(x + vox * C + c8 * 8), f);
+            // add: the gradient of the pooled tensor's OTHER consumer (skip connection), rows of pitch ldadd: the sum
+            // autograd would otherwise form with a strided add kernel is made here, in the pass that writes dx anyway
             if (accumulate) unpack8(ld8(dx + vox * C + c8 * 8), o);
+            else if (add) unpack8(ld8(add + vox * ldadd + c8 * 8), o);
+            const bool base = accumulate || add != nullptr;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 bool hit = (!done[k]) && (f[k] == m[k]);
                 float v = hit ? g[k] : 0.f;
                 done[k] = done[k] || hit;
-                o[k] = accumulate ? o[k] + v : v;
+                o[k] = base ? o[k] + v : v;
             }
             st8(dx + vox * C + c8 * 8, pack8(o));
         }
@@ -590,12 +595,14 @@ FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int 
     FCD_LAUNCH_CHECK();
 }
 
-FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,
-                             int C, int accumulate, cudaStream_t st) {
+FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, const void* add, long long ldadd,
+                             int B, int Do, int Ho, int Wo, int C, int accumulate, cudaStream_t st) {
     if (C % 8) return -1;
     long long total = (long long)B * Do * Ho * Wo * (C / 8);
+    if (add && (ldadd % 8 || ((uintptr_t)add & 15) || accumulate)) return -1;
     maxpool2_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy,
-                                                                 (bf16*)dx, B, Do, Ho, Wo, C / 8, accumulate);
+                                                                 (bf16*)dx, (const bf16*)add, ldadd, B, Do, Ho, Wo,
+                                                                 C / 8, accumulate);
     FCD_LAUNCH_CHECK();
 }
 

@@ -41,6 +41,7 @@ struct WgradTcParams {
     const bf16* U; long long ldu;
     float* part;                          // [grid][27][ldn][ldk] fp32
     int ldn, ldk, n_off, k_off;
+    int nks;                              // blockIdx.y = slice: k slice (y % nks) of CS channels, n slice (y / nks) of CU
     int Bn, D, H, W, nht, nwt, nseg, nitems;
 };
 
@@ -104,6 +105,11 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const long long plane_s = (long long)p.H * p.W * p.lds, plane_u = (long long)p.H * p.W * p.ldu;
+    // all channel slices of one conv in ONE launch (they were one launch each: 16-CTA grids, serial on the side stream)
+    const int ksl = blockIdx.y % p.nks, nsl = blockIdx.y / p.nks;
+    const bf16* const Sp = p.S + ksl * CS;
+    const bf16* const Up = p.U + nsl * CU;
+    const int n_off = p.n_off + nsl * CU, k_off = p.k_off + ksl * CS;
 
     if (warp < NPS) {
         // ===================================================================== S producers: halo planes d0-1 .. d0+DL
@@ -132,13 +138,13 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
                 mbar_wait(EMPTY_S(s), ph ^ 1u, dead, 1);
                 const int pl = it.d0 - 1 + i;
                 const bool inside = pl >= 0 && pl < p.D;    // planes outside the volume are zero-filled
-                const bf16* plane = p.S + ((long long)it.n * p.D + (inside ? pl : 0)) * plane_s;
+                const bf16* plane = Sp + ((long long)it.n * p.D + (inside ? pl : 0)) * plane_s;
                 const uint32_t dst0 = ring_u + s * K::PS_BYTES + c8 * K::SBO_A + v0 * 16;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     if (j < NJ - 1 || v0 + j * VS < HV) {
                         const bool ok = inside && off[j] >= 0;
-                        cp_async16(dst0 + j * VS * 16, ok ? plane + off[j] : p.S, ok);
+                        cp_async16(dst0 + j * VS * 16, ok ? plane + off[j] : Sp, ok);
                     }
                 }
                 cp_async_commit();
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
         };
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             const Item it = decode(p, item, DL);
-            const bf16* col = p.U + (((long long)it.n * p.D + it.d0) * p.H + it.h0) * p.W * p.ldu + (long long)it.w0 * p.ldu + c8 * 8;
+            const bf16* col = Up + (((long long)it.n * p.D + it.d0) * p.H + it.h0) * p.W * p.ldu + (long long)it.w0 * p.ldu + c8 * 8;
             for (int j = 0; j < DL; ++j, ++seq) {
                 const int s = seq % NU;
                 const uint32_t ph = (seq / NU) & 1u;
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
             if (lane < CS) {
 #pragma unroll
                 for (int n = 0; n < CU; ++n)
-                    out[((long long)t * p.ldn + p.n_off + n) * p.ldk + p.k_off + lane] = __uint_as_float(v[n]);
+                    out[((long long)t * p.ldn + n_off + n) * p.ldk + k_off + lane] = __uint_as_float(v[n]);
             }
         }
     }
@@ -257,14 +263,14 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
 }
 
 template <int CS, int CU, int DL>
-int launch(const WgradTcParams& p, int grid, cudaStream_t stream) {
+int launch(const WgradTcParams& p, int grid, int nslices, cudaStream_t stream) {
     using K = Cfg<CS, CU, DL>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(wgrad3_tc_kernel<CS, CU, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
         configured = true;
     }
-    wgrad3_tc_kernel<CS, CU, DL><<<grid, NTHREADS, K::SMEM, stream>>>(p);
+    wgrad3_tc_kernel<CS, CU, DL><<<dim3(grid, nslices), NTHREADS, K::SMEM, stream>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -286,22 +292,25 @@ FCD_API int fcd_wgrad3_tc_nsplit(int Bn, int D, int H, int W) {
     return (int)(items < 2LL * fcd_num_sms() ? items : 2LL * fcd_num_sms());   // two CTAs per SM when they fit
 }
 
-// part[nsplit][27][ldn][ldk] fp32 (fcd_wgrad_reduce layout): this call fills the [n_off, n_off+CU) x [k_off, k_off+CS)
-// block of every tap in every partial.  S: shifted operand rows (pitch lds, already offset to channel k_off),
-// U: unshifted operand rows (pitch ldu, offset to channel n_off).  CS, CU in {16, 32}.
+// part[nsplit][27][ldn][ldk] fp32 (fcd_wgrad_reduce layout): this call fills the [n_off, n_off+nns*CU) x
+// [k_off, k_off+nks*CS) block of every tap in every partial, one CTA row (blockIdx.y) per CU x CS slice.
+// S: shifted operand rows (pitch lds, already offset to channel k_off), U: unshifted operand rows (pitch ldu, offset to
+// channel n_off).  CS, CU in {16, 32}.
 FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long ldu, float* part, int ldn, int ldk,
-                          int n_off, int k_off, int Bn, int D, int H, int W, int CS, int CU, cudaStream_t stream) {
+                          int n_off, int k_off, int nns, int nks, int Bn, int D, int H, int W, int CS, int CU,
+                          cudaStream_t stream) {
     const int dl = pick_dl(Bn, D, H, W);
     if (dl == 0 || lds % 8 || ldu % 8 || ((uintptr_t)S & 15) || ((uintptr_t)U & 15)) return -1;
     if (!(CS == 16 || CS == 32) || !(CU == 16 || CU == 32)) return -1;
-    if (n_off + CU > ldn || k_off + CS > ldk) return -1;
+    if (nns < 1 || nks < 1 || (long long)nns * nks > 65535) return -1;
+    if (n_off + nns * CU > ldn || k_off + nks * CS > ldk) return -1;
     WgradTcParams p;
     p.S = (const bf16*)S; p.lds = lds; p.U = (const bf16*)U; p.ldu = ldu; p.part = part;
-    p.ldn = ldn; p.ldk = ldk; p.n_off = n_off; p.k_off = k_off;
+    p.ldn = ldn; p.ldk = ldk; p.n_off = n_off; p.k_off = k_off; p.nks = nks;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.nht = H / TH; p.nwt = W / TW; p.nseg = D / dl;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
     const int grid = p.nitems < 2 * fcd_num_sms() ? p.nitems : 2 * fcd_num_sms();   // == fcd_wgrad3_tc_nsplit
-#define FCD_WG_CASE(A, B, L) if (CS == A && CU == B && dl == L) return launch<A, B, L>(p, grid, stream)
+#define FCD_WG_CASE(A, B, L) if (CS == A && CU == B && dl == L) return launch<A, B, L>(p, grid, nns * nks, stream)
     FCD_WG_CASE(16, 16, 8); FCD_WG_CASE(16, 32, 8); FCD_WG_CASE(32, 16, 8); FCD_WG_CASE(32, 32, 8);
     FCD_WG_CASE(16, 16, 4); FCD_WG_CASE(16, 32, 4); FCD_WG_CASE(32, 16, 4); FCD_WG_CASE(32, 32, 4);
 #undef FCD_WG_CASE

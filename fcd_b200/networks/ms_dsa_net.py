@@ -165,12 +165,14 @@ class MS_DSA_NET(nn.Module):
             return t
 
         ts, br = {}, {}
-        x1 = self.encoder1(x0)
-        x2 = self.encoder2(ops.max_pool2(x1))
-        x = x2
+        # every encoder output has two consumers (the pool to the next level + the decoder skip / the transformer
+        # stack): pool_and_skip sums their gradients inside the pool's backward pass
+        xp, x1 = ops.pool_and_skip(self.encoder1(x0))
+        xp, x2 = ops.pool_and_skip(self.encoder2(xp))
         for lvl in (3, 4, 5, 6):
-            x = getattr(self, f"encoder{lvl}")(ops.max_pool2(x))
+            x = getattr(self, f"encoder{lvl}")(xp)
             if lvl < 6:
+                xp, x = ops.pool_and_skip(x)
                 br[lvl] = ops.branch(x.device, key=lvl)
                 with br[lvl]:
                     ts[lvl] = stack(lvl, x)

@@ -155,7 +155,7 @@ class _PackCache:
                 T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
                 total = T * Np * Kp
                 rec[i] = (k[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk)
-                blk += (total + 2047) // 2048
+                blk += ((Np + 7) // 8) * ((Kp + 63) // 64)      # one block per 8 x 64 tile (csrc/wgrad.cu)
             host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture
             dev_tab = host.to(device, non_blocking=True)
             tab = self.table[device.index] = (keys, dev_tab, blk, host, capturing)   # host: keep the pinned source alive
@@ -228,16 +228,23 @@ class _SideWork:
     until that join, so the caching allocator cannot hand their memory to main-stream work while the side stream
     still reads it (no record_stream needed; works inside CUDA-graph capture as a fork/join branch)."""
 
+    NSTREAMS = int(os.environ.get("FCD_WGRAD_STREAMS", "3"))
+
     def __init__(self):
         self.streams = {}
         self.pending = []
         self.armed = False
+        self.turn = 0
 
     def stream(self, dev):
-        st = self.streams.get(dev)
-        if st is None:
-            st = self.streams[dev] = torch.cuda.Stream(device=dev)
-        return st
+        # consecutive weight gradients take turns on a few side streams: the small ones (16-CTA grids, partial-sum
+        # reductions) then overlap each other instead of queueing behind one another (measured: the single side
+        # stream was still draining ~1 ms of them after the main stream had finished its backward)
+        sts = self.streams.get(dev)
+        if sts is None:
+            sts = self.streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.NSTREAMS))]
+        self.turn += 1
+        return sts[self.turn % len(sts)]
 
     def run(self, fn, *keep):
         dev = keep[0].device
@@ -254,13 +261,16 @@ class _SideWork:
 
     def join(self):
         # runs as an autograd end-of-backward callback, on the thread / stream that called backward(): that stream (the
-        # one the optimizer will use) and every stream a weight gradient was forked from wait for the side stream
+        # one the optimizer will use) and every stream a weight gradient was forked from wait for the side streams
         for dev in {d for d, _, _ in self.pending}:
-            torch.cuda.current_stream(dev).wait_stream(self.stream(dev))
-        for dev, main, _ in self.pending:
-            main.wait_stream(self.stream(dev))
+            for st in self.streams[dev]:
+                torch.cuda.current_stream(dev).wait_stream(st)
+        for dev, main in {(d, m) for d, m, _ in self.pending}:
+            for st in self.streams[dev]:
+                main.wait_stream(st)
         self.pending.clear()
         self.armed = False
+        self.turn = 0
 
 
 _SIDE = _SideWork()
@@ -317,6 +327,17 @@ def _tc_nseg(B, D, H, W, K, N, k, stride, pad, bias):
     if not USE_TC or k != 3 or stride != 1 or pad != 1 or bias is not None:
         return 0
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, N)
+
+
+def _tc_nslice_nseg(B, D, H, W, K, N, k, stride, pad, bias, cin_seg, Co, Ci):
+    """64 -> 64 channels on a large volume (encoder3.conv2 at 32^3): the 27 x 64 x 64 weights do not fit beside the halo
+    planes, so the conv runs as TWO kd-folded 64 -> 32 convs writing the two halves of the output rows (measured
+    ~2 x 20 us against 128 us for the mma.sync kernel).  Returns the d-segment count of one half, 0 if not applicable."""
+    if not (USE_TC and USE_TCF and k == 3 and stride == 1 and pad == 1 and bias is None and cin_seg is None):
+        return 0
+    if not (K == 64 and N == 64 and Co == 64 and Ci == 64 and B * D * H * W >= 32768):
+        return 0
+    return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, 64, 32)
 
 
 def _w32(weight):
@@ -376,6 +397,13 @@ class ConvFn(Function):
             call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
                  nseg=nseg)
+        elif _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci) > 0:
+            ns2 = _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci)
+            w32 = _w32(weight)
+            for i in range(2):
+                call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
+                     ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp,
+                     N=32, flip=0, nseg=ns2)
         else:
             wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
             _igemm(x, wp, y, _vpad(bias, Np), B, (D, H, W), (Do, Ho, Wo), Kp, Np, k, stride, pad, 0)
@@ -402,6 +430,13 @@ class ConvFn(Function):
                 call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
                      ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
                      flip=1, nseg=nseg)
+            elif _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None if seg == Ci else 1, Co, Ci) > 0:
+                ns2 = _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None, Co, Ci)
+                w32 = _w32(weight).view(-1)
+                for i in range(2):
+                    call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
+                         kseg=Co, ksegpad=Np, nsg=32, nsgpad=32, C=dx[..., 32 * i:], ldc=Kp, part=None, Bn=B, D=D, H=H,
+                         W=W, K=Np, N=32, flip=1, nseg=ns2)
             else:
                 wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
                 _igemm(dy, wt, dx, None, B, (Do, Ho, Wo), (D, H, W), Np, Kp, k, stride, pad, 1)
@@ -414,8 +449,6 @@ class ConvFn(Function):
                 if std3 and USE_GEMM_TC and Kp >= 64 and Np >= 64:
                     nsg = _lib.lib().fcd_wgrad_gemm_tc_nsplit(B * D * H * W, Kp, Np)
                 ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (std3 and nsg == 0) else 0
-                if ns > 0 and ((Kp + 31) // 32) * ((Np + 31) // 32) > 4:
-                    ns = 0      # many thin slices over a small volume: the split-K mma.sync kernel is the better fit
                 if nsg > 0:
                     # deep levels (>= 64 channels both sides): tcgen05 GEMM with the voxels as the K dimension
                     ns = nsg
@@ -427,11 +460,8 @@ class ConvFn(Function):
                     cs = 32 if Kp % 32 == 0 else 16
                     cu = 32 if Np % 32 == 0 else 16
                     part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
-                    for n_off in range(0, Np, cu):
-                        for k_off in range(0, Kp, cs):
-                            call("fcd_wgrad3_tc", S=x[..., k_off:], lds=ld(x), U=dy[..., n_off:], ldu=ld(dy),
-                                 part=part, ldn=Np, ldk=Kp, n_off=n_off, k_off=k_off, Bn=B, D=D, H=H, W=W, CS=cs,
-                                 CU=cu)
+                    call("fcd_wgrad3_tc", S=x, lds=ld(x), U=dy, ldu=ld(dy), part=part, ldn=Np, ldk=Kp, n_off=0, k_off=0,
+                         nns=Np // cu, nks=Kp // cs, Bn=B, D=D, H=H, W=W, CS=cs, CU=cu)
                 else:
                     part, ns = _wgrad(dy, x, (D, H, W), (Do, Ho, Wo), Np, Kp, k, stride, pad)
                 g = torch.empty_like(weight, dtype=torch.float32)
@@ -542,12 +572,53 @@ class MaxPool2Fn(Function):
         dy = rows(dy).contiguous()
         B, D, H, W, C = x.shape
         dx = torch.empty_like(x)
-        call("fcd_maxpool2_bwd", x=x, y=y, dy=dy, dx=dx, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2, C=C, accumulate=0)
+        call("fcd_maxpool2_bwd", x=x, y=y, dy=dy, dx=dx, add=None, ldadd=0, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2, C=C,
+             accumulate=0)
         return dx
 
 
 def max_pool2(x):
     return MaxPool2Fn.apply(x)
+
+
+class PoolSkipFn(Function):
+    """x -> (max_pool2(x), x): the encoder output feeds the next level through the pool AND a second consumer (decoder
+    skip / transformer stack, ms_dsa_net.py:378-390).  Routing both uses through one node lets the backward form
+    dx = pool_bwd(d_pooled) + d_skip in the pool's own pass instead of autograd's separate (strided) add kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = rows(x)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        B, D, H, W, C = x.shape
+        y = _empty((B, D // 2, H // 2, W // 2, C), x)
+        call("fcd_maxpool2_fwd", x=x, y=y, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2, C=C)
+        ctx.save_for_backward(x, y)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, y = ctx.saved_tensors
+        B, D, H, W, C = x.shape
+        if dy is None:
+            return dskip
+        dy = rows(dy).contiguous()
+        add, ldadd = None, 0
+        if dskip is not None:
+            add = rows(dskip)                 # usually the right half of the decoder's concat-buffer gradient
+            if add.data_ptr() % 16 or ld(add) % 8:
+                add = add.contiguous()
+            ldadd = ld(add)
+        dx = torch.empty_like(x)
+        call("fcd_maxpool2_bwd", x=x, y=y, dy=dy, dx=dx, add=add, ldadd=ldadd, B=B, Do=D // 2, Ho=H // 2, Wo=W // 2,
+             C=C, accumulate=0)
+        return dx
+
+
+def pool_and_skip(x):
+    """(max_pool2(x), alias of x for the second consumer) with a fused backward, see PoolSkipFn."""
+    return PoolSkipFn.apply(x)
 
 
 # ------------------------------------------------------------------------------------------------ normalisation

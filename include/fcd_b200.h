@@ -86,11 +86,13 @@ FCD_API int fcd_tcf_error(void);
 
 /* tcgen05/TMEM weight gradient of the same 3x3x3 stride-1 pad-1 convs (autograd of conv_blocks.py:393-416).  S: the
  * operand read shifted (conv input, CS channels from channel k_off), U: the unshifted one (output gradient, CU
- * channels from n_off); CS, CU in {16, 32}, wider layers are cut into slices by the caller.  Each of the
- * fcd_wgrad3_tc_nsplit() CTAs writes one partial part[cta][27][ldn][ldk] block; fcd_wgrad_reduce sums them. */
+ * channels from n_off); CS, CU in {16, 32}; wider layers are cut into nns x nks slices of CU x CS channels that run as
+ * CTA rows of the same launch.  CTA column c of the fcd_wgrad3_tc_nsplit() columns writes its slice of the partial
+ * part[c][27][ldn][ldk]; fcd_wgrad_reduce sums the partials. */
 FCD_API int fcd_wgrad3_tc_nsplit(int Bn, int D, int H, int W);
 FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long ldu, float* part, int ldn, int ldk,
-                          int n_off, int k_off, int Bn, int D, int H, int W, int CS, int CU, cudaStream_t stream);
+                          int n_off, int k_off, int nns, int nks, int Bn, int D, int H, int W, int CS, int CU,
+                          cudaStream_t stream);
 FCD_API int fcd_wgrad_tc_error(void);
 
 /* measurement aid (not on the product path): cycles for back-to-back tcgen05.mma of shape M x N x 16, see
@@ -98,10 +100,11 @@ FCD_API int fcd_wgrad_tc_error(void);
 FCD_API int fcd_umma_bench(int M, int N, int iters, int nissue, int same_acc, int ctas, long long* cycles,
                            cudaStream_t stream);
 
-/* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382) ---- */
+/* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382).  bwd: add (optional, rows of pitch ldadd) is the gradient
+ *      x receives from its other consumer (the skip connection, ms_dsa_net.py:386-390): dx = pool_bwd(dy) + add. ---- */
 FCD_API int fcd_maxpool2_fwd(const void* x, void* y, int B, int Do, int Ho, int Wo, int C, cudaStream_t stream);
-FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int Do, int Ho, int Wo,
-                             int C, int accumulate, cudaStream_t stream);
+FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, const void* add, long long ldadd,
+                             int B, int Do, int Ho, int Wo, int C, int accumulate, cudaStream_t stream);
 
 /* ---- InstanceNorm3d / BatchNorm3d / GroupNorm(2 ch per group) fused with LeakyReLU/ReLU and the residual add
  *      (conv_blocks.py:439-452, 56; ms_dsa_net.py:217; MONAI ResBlock).  mode: 0 instance, 1 batch,

@@ -145,6 +145,8 @@ WG_CASES = [
     (1, 2, 16, 8, 16, 16),
     (1, 24, 12, 4, 16, 8),
     (2, 32, 16, 16, 128, 128),    # enough columns for 8-plane items (DL = 8)
+    (1, 96, 48, 4, 16, 8),        # 3 x 3 slices (32-wide k, 16-wide n) as CTA rows of one launch
+    (2, 128, 32, 8, 16, 16),      # 4 k slices
 ]
 
 
@@ -164,6 +166,30 @@ def test_wgrad3_tc(ops, B, Ci, Co, D, H, W):
     y.backward(ops.to_channels_last(dy, ops.pad16(Co)))
     assert _lib.lib().fcd_wgrad_tc_error() == 0 and tc_error() == 0
     close(w2.grad, gw, rel=6e-3, what="tc wgrad")
+
+
+def test_conv_64_to_64_runs_as_two_kd_folded_halves(ops):
+    """64 -> 64 channels on >= 32768 voxels (encoder3.conv2): two fcd_conv3_tcf launches write the two halves of the
+    output rows, forward and data gradient; result vs torch."""
+    from fcd_b200 import _lib
+    B, Ci, Co, D, H, W = 1, 64, 64, 32, 32, 32
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, w, None, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gw = torch.autograd.grad(ref, [xr, w], dy)
+    xc = cl(ops, x, True)
+    w2 = w.detach().clone().requires_grad_(True)
+    before = _lib.LAUNCHES
+    y = ops.conv3d(xc, w2, None, k=3)
+    assert _lib.LAUNCHES == before + 2, "expected the two-half tcgen05 path"
+    assert tc_error() == 0
+    close(ops.to_ncdhw(y, Co), ref, what="64->64 fwd")
+    y.backward(ops.to_channels_last(dy, Co))
+    assert tc_error() == 0
+    close(ops.to_ncdhw(xc.grad, Ci), gx, what="64->64 dgrad")
+    close(w2.grad, gw, rel=6e-3, what="64->64 wgrad")
 
 
 def test_packed_weights_follow_parameter_updates_inside_cuda_graph(ops):

@@ -147,6 +147,30 @@ def test_maxpool(ops):
     close(ops.to_ncdhw(xc.grad, 16), gx, rel=0, mx=0, what="maxpool bwd")
 
 
+def test_pool_and_skip_sums_both_gradients_in_the_pool_pass(ops):
+    """ops.pool_and_skip: (max_pool(x), x) with dx = pool_bwd(d_pooled) + d_skip formed inside the pool's backward
+    kernel; the skip gradient arrives as the right half of a concat-buffer gradient (a strided channel slice)."""
+    x = rnd(2, 16, 8, 6, 16)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool3d(xr, 2, 2)
+    dy = rnd(*ref.shape, seed=3)
+    dcat = rnd(2, 32, 8, 6, 16, seed=4).to(torch.bfloat16).float()
+    (gx,) = torch.autograd.grad([ref, xr * 1.0], [xr], [dy, dcat[:, 16:]], retain_graph=True)
+    xc = cl(ops, x, True)
+    y, skip = ops.pool_and_skip(xc)
+    assert skip.data_ptr() == xc.data_ptr()
+    close(ops.to_ncdhw(y, 16), ref, rel=0, mx=0, what="pool fwd")
+    dcat_cl = ops.to_channels_last(dcat, 32)
+    torch.autograd.backward([y, skip], [ops.to_channels_last(dy, 16), dcat_cl[..., 16:]])
+    close(ops.to_ncdhw(xc.grad, 16), gx, rel=4e-3, mx=4e-2, what="pool+skip bwd")
+    # only one consumer used
+    xc2 = cl(ops, x, True)
+    y2, _ = ops.pool_and_skip(xc2)
+    y2.backward(ops.to_channels_last(dy, 16))
+    (gp,) = torch.autograd.grad(ref, [xr], dy)
+    close(ops.to_ncdhw(xc2.grad, 16), gp, rel=0, mx=0, what="pool-only bwd")
+
+
 @pytest.mark.parametrize("C,slope", [(16, 0.01), (32, 0.0), (4, 1.0), (64, 0.01)])
 def test_instance_norm_act(ops, C, slope):
     x = rnd(2, C, 6, 8, 10, scale=2.0) + 0.5
