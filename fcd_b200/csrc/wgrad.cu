@@ -244,55 +244,97 @@ struct PackJob {
 static_assert(sizeof(PackJob) == 96, "PackJob layout is mirrored by fcd_b200/ops.py");
 constexpr int PACK_NB = 8, PACK_KB = 64;      // one block packs an 8 (n) x 64 (k) tile of every tap
 
+__device__ __forceinline__ uint32_t pack_bf16x2_raw(bf16 lo, bf16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// Tile body for a compile-time tap count (index math by constants; the per-row segment maps come from shared memory).
+template <int T>
+__device__ __forceinline__ void pack_tile(const PackJob& j, int n0, int k0, const int* nmap, const int* kmap, bf16* tile) {
+    constexpr int TP = T | 1;                           // odd pitch: conflict-free in both passes
+    constexpr int NE = PACK_NB * PACK_KB * T;
+    const float* __restrict__ src = j.src;
+    const int sn = (int)j.sn, sk = (int)j.sk, st = (int)j.st;
+    if (j.sn < j.sk) {                                  // n is the faster source axis (data-gradient packs)
+        for (int e = threadIdx.x; e < NE; e += 256) {
+            const int t = e % T, r = e / T;
+            const int nn = r % PACK_NB, kk = r / PACK_NB;
+            const int n = nmap[nn], k = kmap[kk];
+            const float v = (n >= 0 && k >= 0) ? __ldg(src + n * sn + k * sk + t * st) : 0.f;
+            tile[(nn * PACK_KB + kk) * TP + t] = __float2bfloat16(v);
+        }
+    } else {
+        for (int e = threadIdx.x; e < NE; e += 256) {
+            const int t = e % T, r = e / T;
+            const int kk = r % PACK_KB, nn = r / PACK_KB;
+            const int n = nmap[nn], k = kmap[kk];
+            const float v = (n >= 0 && k >= 0) ? __ldg(src + n * sn + k * sk + t * st) : 0.f;
+            tile[(nn * PACK_KB + kk) * TP + t] = __float2bfloat16(v);
+        }
+    }
+    __syncthreads();
+    // 8 consecutive k per thread: one 16-byte store (Kp % 8 == 0, so an 8-group is entirely inside or outside)
+    constexpr int NG = PACK_NB * (PACK_KB / 8) * T;
+    for (int g = threadIdx.x; g < NG; g += 256) {
+        const int k8 = g % (PACK_KB / 8), r = g / (PACK_KB / 8);
+        const int nn = r % PACK_NB, t = r / PACK_NB;
+        const int np_ = n0 + nn, kp = k0 + k8 * 8;
+        if (np_ >= j.Np || kp >= j.Kp) continue;
+        const bf16* tp = tile + (nn * PACK_KB + k8 * 8) * TP + t;
+        uint4 o;
+        o.x = pack_bf16x2_raw(tp[0], tp[TP]);
+        o.y = pack_bf16x2_raw(tp[2 * TP], tp[3 * TP]);
+        o.z = pack_bf16x2_raw(tp[4 * TP], tp[5 * TP]);
+        o.w = pack_bf16x2_raw(tp[6 * TP], tp[7 * TP]);
+        *reinterpret_cast<uint4*>(j.dst + ((long long)t * j.Np + np_) * j.Kp + kp) = o;
+    }
+}
+
 // The source is fp32 [.., T] with the tap index fastest and either k (forward packs: sk == T) or n (data-gradient
-// packs: sn == T) next: a block reads its tile as long contiguous runs in whichever order the source has (the first
-// version read with a 27-float stride: 8x DRAM over-fetch, 362 us for MS_DSA_NET's 174 MB of weights), transposes
-// through shared memory and writes 128-byte runs of the packed [T][Np][Kp] bf16 layout.
+// packs: sn == T) next.  A block reads its tile as long contiguous runs in whichever order the source has,
+// transposes through shared memory and writes 128-byte runs of the packed [T][Np][Kp] bf16 layout.  (The first
+// version computed ~6 runtime integer divisions per element and was instruction-bound: 362 us for MS_DSA_NET's
+// 87 M packed elements, at the head of every step.)
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
-    __shared__ bf16 tile[27 * PACK_NB * PACK_KB];        // [nn][kk][T | 1]: tap fastest, odd pitch (conflict-free both ways)
+    __shared__ __align__(16) bf16 tile[27 * PACK_NB * PACK_KB];
+    __shared__ int kmap[PACK_KB], nmap[PACK_NB];
+    __shared__ PackJob sj;
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {                                   // last job with blk0 <= blockIdx.x
         const int mid = (lo + hi + 1) >> 1;
         if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
     }
-    const PackJob j = jobs[lo];
+    if (threadIdx.x < sizeof(PackJob) / 4)
+        reinterpret_cast<int*>(&sj)[threadIdx.x] = reinterpret_cast<const int*>(jobs + lo)[threadIdx.x];
+    __syncthreads();
+    const PackJob& j = sj;
     const int kt = (j.Kp + PACK_KB - 1) / PACK_KB;
     const int b = blockIdx.x - j.blk0;
     const int n0 = (b / kt) * PACK_NB, k0 = (b % kt) * PACK_KB;
-    const int T = j.T;
-    const int ne = PACK_NB * PACK_KB * T;
-    const int TP = T | 1;
-    const bool n_inner = (j.sn < j.sk);                 // which of n / k is the faster source axis
-    for (int e = threadIdx.x; e < ne; e += 256) {
-        const int t = e % T;
-        const int r = e / T;
-        int nn, kk;
-        if (n_inner) { nn = r % PACK_NB; kk = r / PACK_NB; } else { kk = r % PACK_KB; nn = r / PACK_KB; }
-        const int np_ = n0 + nn, kp = k0 + kk;
-        float v = 0.f;
-        if (np_ < j.Np && kp < j.Kp) {
-            const int seg = kp / j.ksegpad, within = kp % j.ksegpad;
-            const int k = seg * j.kseg + within;
-            const int nsg = np_ / j.nsegpad, nwithin = np_ % j.nsegpad;
-            const int n = nsg * j.nseg + nwithin;
-            if (nwithin < j.nseg && n < j.N && within < j.kseg && k < j.K) v = __ldg(j.src + n * j.sn + k * j.sk + t * j.st);
-        }
-        tile[(nn * PACK_KB + kk) * TP + t] = __float2bfloat16(v);
+    if (threadIdx.x < PACK_KB) {                        // padded k -> source k (or -1): concat-segment map
+        const int kp = k0 + threadIdx.x;
+        const int seg = kp / j.ksegpad, within = kp % j.ksegpad;
+        const int k = seg * j.kseg + within;
+        kmap[threadIdx.x] = (kp < j.Kp && within < j.kseg && k < j.K) ? k : -1;
+    } else if (threadIdx.x < PACK_KB + PACK_NB) {
+        const int nn = threadIdx.x - PACK_KB, np_ = n0 + nn;
+        const int nsg = np_ / j.nsegpad, nwithin = np_ % j.nsegpad;
+        const int n = nsg * j.nseg + nwithin;
+        nmap[nn] = (np_ < j.Np && nwithin < j.nseg && n < j.N) ? n : -1;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < ne; e += 256) {
-        const int kk = e % PACK_KB;
-        const int r = e / PACK_KB;
-        const int nn = r % PACK_NB, t = r / PACK_NB;
-        const int np_ = n0 + nn, kp = k0 + kk;
-        if (np_ < j.Np && kp < j.Kp) j.dst[((long long)t * j.Np + np_) * j.Kp + kp] = tile[(nn * PACK_KB + kk) * TP + t];
+    switch (j.T) {
+        case 27: pack_tile<27>(j, n0, k0, nmap, kmap, tile); break;
+        case 8: pack_tile<8>(j, n0, k0, nmap, kmap, tile); break;
+        case 1: pack_tile<1>(j, n0, k0, nmap, kmap, tile); break;
+        default: break;                                 // the host only builds jobs with T in {1, 8, 27}
     }
 }
 
 }  // namespace
 
 // jobs: device array of `njobs` PackJob records (96 bytes each, see above), nblocks = sum over jobs of
-// ceil(Np / 8) * ceil(Kp / 64); T <= 27.  Replaces one fcd_pack_weight launch per layer and layout with one launch per forward.
+// ceil(Np / 8) * ceil(Kp / 64); T in {1, 8, 27}; Kp % 8 == 0 and dst 16-byte aligned.  Replaces one fcd_pack_weight launch per layer and layout with one launch per forward.
 FCD_API int fcd_pack_weight_batched(const void* jobs, int njobs, int nblocks, cudaStream_t stream) {
     if (njobs < 1 || nblocks < 1) return -1;
     pack_weight_batched_kernel<<<nblocks, 256, 0, stream>>>((const PackJob*)jobs, njobs);

@@ -154,6 +154,7 @@ class _PackCache:
                 owner, args, dst, _ = self.jobs[k]
                 T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
                 total = T * Np * Kp
+                assert T in (1, 8, 27) and Kp % 8 == 0 and dst.data_ptr() % 16 == 0, "fcd_pack_weight_batched contract"
                 rec[i] = (k[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk)
                 blk += ((Np + 7) // 8) * ((Kp + 63) // 64)      # one block per 8 x 64 tile (csrc/wgrad.cu)
             host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture

@@ -192,6 +192,35 @@ def test_conv_64_to_64_runs_as_two_kd_folded_halves(ops):
     close(w2.grad, gw, rel=6e-3, what="64->64 wgrad")
 
 
+def test_batched_weight_pack_matches_single_pack(ops):
+    """fcd_pack_weight_batched (tiled transposition, one launch for every layer) against fcd_pack_weight, job by job:
+    forward and data-gradient orientations, ragged channel counts, concat segments, 1x1x1 / 2x2x2 / 3x3x3 taps."""
+    import torch.nn as nn
+    dev = torch.device("cuda:0")
+    cache = ops._PackCache()
+    specs = []       # (param, args)
+    g = torch.Generator().manual_seed(5)
+    for Co, Ci, T in [(16, 2, 27), (64, 64, 27), (72, 40, 27), (128, 256, 1), (24, 136, 8), (256, 128, 27)]:
+        w = nn.Parameter(torch.randn(Co, Ci, T, generator=g).to(dev))
+        Np, Kp = ops.pad16(Co), ops.pad16(Ci)
+        specs.append((w, (T, Co, Ci, Np, Kp, Ci * T, T, 1, Ci, Kp, Co, Np)))                 # forward pack
+        specs.append((w, (T, Ci, Co, Kp, Np, T, Ci * T, 1, Co, Np, Ci, Kp)))                 # data-gradient pack
+    w = nn.Parameter(torch.randn(32, 24, 27, generator=g).to(dev))                              # concat: 2 x 12 -> 2 x 16
+    specs.append((w, (27, 32, 24, 32, 32, 24 * 27, 27, 1, 12, 16, 32, 32)))
+    specs.append((w, (27, 24, 32, 32, 32, 27, 24 * 27, 1, 32, 32, 12, 16)))
+    single = [cache.get(w, a).clone() for w, a in specs]
+    with torch.no_grad():
+        for w, _ in specs:
+            w.add_(0.0)                                  # bump the version stamps: refresh() must re-pack everything
+    for job in cache.jobs.values():
+        job[2].fill_(7.0)
+    cache.refresh(dev)
+    torch.cuda.synchronize()
+    for (w, a), ref in zip(specs, single):
+        got = cache.get(w, a)
+        assert torch.equal(got, ref), f"batched pack differs for args {a}"
+
+
 def test_packed_weights_follow_parameter_updates_inside_cuda_graph(ops):
     """The mma.sync kernels read packed bf16 copies of the parameters (ops._PackCache).  A captured forward must
     re-pack on every replay: update the weight in place between replays and the output has to follow."""
