@@ -404,7 +404,10 @@ __global__ void dsa_combine_kernel(const bf16* __restrict__ t, long long ldt, co
 // dgamma partials: part[blk][0][c] = sum_rows dy * (xca + tsa_flat).
 __global__ void dsa_dgamma_kernel(const bf16* __restrict__ dy, long long lddy, const float* __restrict__ xca,
                                   const float* __restrict__ tsa, float* __restrict__ part, long long rows, int N,
-                                  int C, int LPT) {
+                                  int C, int LPT, float* __restrict__ dtemp, float* __restrict__ dtemp2, int H) {
+    // first kernel of fcd_dsa_bwd: also clears the two accumulators dsa_bwd_finalize_kernel adds into (saves the
+    // caller two fill launches per block on a latency-bound chain)
+    if (blockIdx.x == 0 && (int)threadIdx.x < H) { dtemp[threadIdx.x] = 0.f; dtemp2[threadIdx.x] = 0.f; }
     const int chunk = threadIdx.x % LPT, r0 = threadIdx.x / LPT, rstep = blockDim.x / LPT;
     float acc[8];
 #pragma unroll
@@ -923,12 +926,29 @@ FCD_API int fcd_dsa_bwd_part_floats(int B, int N, int C, int H, int P) {
     return (int)((long long)B * H * ((N + 63) / 64) * (2LL * c * P + (long long)c * c + c + 1));
 }
 
+// Bernoulli keep-mask scaled by 1/(1-p) for the O(B*C) channel dropouts (nn.Dropout3d conv_blocks.py:57, attn_drop
+// conv_blocks.py:347): one launch instead of torch's rand / compare / cast / divide chain.
+__global__ void keep_scale_kernel(float* __restrict__ out, int n, float scale, uint32_t thresh, unsigned long long seed0,
+                                  const long long* __restrict__ seed_dev) {
+    const unsigned long long seed = seed0 + (seed_dev ? (unsigned long long)(*seed_dev) * 0xD1B54A32D192ED03ULL : 0ULL);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sa_keep(seed, (unsigned long long)i, thresh) ? scale : 0.f;
+}
+
 static inline void drop_params(float p, float& scale, uint32_t& thresh) {
     if (p <= 0.f) { scale = 1.f; thresh = 0; return; }
     scale = 1.f / (1.f - p);
     double t = (double)p * 4294967296.0;
     thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
     if (thresh == 0) thresh = 1;
+}
+
+FCD_API int fcd_keep_scale(float* out, int n, float p, long long seed, const long long* seed_dev, cudaStream_t st) {
+    if (n < 1 || p < 0.f || p >= 1.f) return -1;
+    float ds; uint32_t dth;
+    drop_params(p, ds, dth);
+    keep_scale_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, n, ds, dth, (unsigned long long)seed, seed_dev);
+    FCD_LAUNCH_CHECK();
 }
 
 // DSA.forward (conv_blocks.py:328-355) + `x + gamma * dsa` (conv_blocks.py:77).
@@ -979,7 +999,7 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
 }
 
 // Backward of fcd_dsa_fwd w.r.t. qkvv, EF, temperature(2), gamma.  (dt = dy passes straight to fcd_ln_bwd.)
-// dtemp / dtemp2 [H] are ACCUMULATED (zero them first); dgamma [C], dEF [N][P] are overwritten.
+// dtemp / dtemp2 [H], dgamma [C], dEF [N][P] are overwritten (H <= 256).
 // work: dqh [B*N][C] fp32, dKV [B][2][C][P], dGhat [B][H][c][c], rqk [B][2][C], gpart 2*148*2*Cp floats.
 FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long long lddy, const float* EF,
                         const float* temperature, const float* temperature2, const float* gamma,
@@ -989,7 +1009,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
                         float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
                         long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t st) {
-    if (C % H || P % 4 || Cp % 8) return -1;
+    if (C % H || P % 4 || Cp % 8 || H > 256) return -1;
     const int c = C / H;
     const int LPT = Cp / 8;
     if (LPT > 32 || (LPT & (LPT - 1))) return -1;
@@ -997,7 +1017,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
     const int gblk = 2 * fcd_num_sms();
     float ds; uint32_t dth;
     drop_params(sa_drop, ds, dth);
-    dsa_dgamma_kernel<<<gblk, 256, 0, st>>>((const bf16*)dy, lddy, xca, tsa, gpart, rows, N, C, LPT);
+    dsa_dgamma_kernel<<<gblk, 256, 0, st>>>((const bf16*)dy, lddy, xca, tsa, gpart, rows, N, C, LPT, dtemp, dtemp2, H);
     pair_colsum_kernel<<<(C + 7) / 8, 256, 0, st>>>(gpart, gblk, Cp, C, dgamma, nullptr);
     {
         auto run = [&]() -> int {

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
 
 // Turn the backward partial sums into per-(b,c) coefficients:
 //   dx_j = k1_j * ds - k2_j - k3_j * xhat_j     (j = 1, 2)
-// with k1 = gamma*rstd, k2 = rstd*mean_grp(gamma*ds), k3 = rstd*mean_grp(gamma*ds*xhat); also dgamma/dbeta (+=).
+// with k1 = gamma*rstd, k2 = rstd*mean_grp(gamma*ds), k3 = rstd*mean_grp(gamma*ds*xhat); also dgamma/dbeta (written, not accumulated).
 // coef[b][c][0..2] for input 1, coef[b][c][3..5] for input 2.
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ rstd1,
                                          const float* __restrict__ rstd2, const float* __restrict__ gamma1,
@@ -422,8 +422,8 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const f
         double dg = 0.0, db = 0.0;
         for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
         if (writer) {
-            dgamma[c] += (float)dg;
-            dbeta[c] += (float)db;
+            dgamma[c] = (float)dg;
+            dbeta[c] = (float)db;
         }
     }
 }

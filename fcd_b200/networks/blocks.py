@@ -16,7 +16,7 @@ import torch.nn as nn
 from .. import ops
 
 LRELU_SLOPE = 0.01
-_host_rng = random.Random(0x5eed)
+_host_rng = random.Random(0x5eed + int(__import__("os").environ.get("RANK", "0")))   # per-rank mask streams
 
 
 class Convolution(nn.Sequential):
@@ -191,7 +191,7 @@ class DSA(nn.Module):
         if self.training:
             if self.attn_drop.p > 0:
                 pk = self.attn_drop.p
-                ca_scale = (torch.rand((B, H, c, c), device=t.device) >= pk).float() / (1.0 - pk)
+                ca_scale = ops.keep_scale((B, H, c, c), pk, t.device)
             if self.attn_drop_2.p > 0:
                 sa_p = float(self.attn_drop_2.p)
                 seed = _host_rng.getrandbits(62)     # host-side counter RNG: no device sync

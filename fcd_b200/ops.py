@@ -627,7 +627,9 @@ MODE = {"instance": 0, "batch": 1, "group2": 2}
 
 
 def _nchunk(B, S):
-    return int(max(1, min(592 // max(B, 1), S // 512)))
+    # slabs of >= 64 rows: the deep levels (512 or 64 rows per sample) are latency chains, a one-block reduction of 512
+    # rows cost 16 us there; the big tensors still get 2 x SMs blocks
+    return int(max(1, min(592 // max(B, 1), S // 64)))
 
 
 def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0.1):
@@ -704,8 +706,8 @@ class NormActFn(Function):
         dres = torch.empty_like(dx1) if (has_res and ctx.needs_input_grad[2]) else None
         dgamma = dbeta = None
         if has_affine:
-            dgamma = torch.zeros((C,), dtype=torch.float32, device=x1.device)
-            dbeta = torch.zeros((C,), dtype=torch.float32, device=x1.device)
+            dgamma = torch.empty((C,), dtype=torch.float32, device=x1.device)
+            dbeta = torch.empty((C,), dtype=torch.float32, device=x1.device)
         nin = 2 + (y is not None) + (x2 is not None)
         _lib.note_work(None, 0.0, 2.0 * B * S * C * (2 * nin + 1 + (x2 is not None) + (dres is not None)))
         call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1,
@@ -932,8 +934,8 @@ class DSAFn(Function):
         gpart = torch.empty((512, 2, Cp), **f32)
         dqkvv = torch.empty_like(qkvv, memory_format=torch.contiguous_format)
         dEF = torch.empty((N, P), **f32)
-        dtemp = torch.zeros((H,), **f32)
-        dtemp2 = torch.zeros((H,), **f32)
+        dtemp = torch.empty((H,), **f32)
+        dtemp2 = torch.empty((H,), **f32)
         dgamma = torch.empty((C,), **f32)
         call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
              gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed,
@@ -947,6 +949,30 @@ def dsa_attention(qkvv, t, EF, temperature, temperature2, gamma, C, H, P, ca_sca
     return DSAFn.apply(qkvv, t, EF, temperature, temperature2, gamma, C, H, P, ca_scale, sa_drop, seed)
 
 
+_ZEROS = {}
+_host_rng = __import__("random").Random(0x0d15ea5e + int(os.environ.get("RANK", "0")))   # per-rank mask streams
+
+
+def _const_zeros(shape, device):
+    """A shared, never-written fp32 zero tensor (the 'mean' of a pure per-channel scale): no fill launch per call."""
+    key = (tuple(shape), device.index)
+    z = _ZEROS.get(key)
+    if z is None:
+        if torch.cuda.is_current_stream_capturing():     # would land in the graph's private pool: do not cache
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        z = _ZEROS[key] = torch.zeros(shape, dtype=torch.float32, device=device)
+    return z
+
+
+def keep_scale(shape, p, device):
+    """Bernoulli(1-p) keep mask / (1-p), fp32 `shape`: ONE kernel (fcd_keep_scale) keyed by a host-drawn seed and the
+    device step counter, so CUDA-graph replays draw fresh masks (see `tick`)."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    call("fcd_keep_scale", out=out, n=out.numel(), p=float(p), seed=_host_rng.getrandbits(62),
+         seed_dev=step_counter(device))
+    return out
+
+
 class ChannelScaleFn(Function):
     """y[b,...,c] = x[b,...,c] * scale[b,c]: nn.Dropout3d (conv_blocks.py:57; segresnet_dsa.py:197-198) with a
     host-drawn O(B*C) Bernoulli mask."""
@@ -955,7 +981,7 @@ class ChannelScaleFn(Function):
     def forward(ctx, x, scale):
         x = rows(x)
         B, D, H, W, C = x.shape
-        zero = torch.zeros_like(scale)
+        zero = _const_zeros(scale.shape, x.device)
         y = _empty((B, D, H, W, C), x)
         call("fcd_norm_apply", x1=x, ld1=ld(x), mean1=zero, rstd1=scale, gamma1=None, beta1=None, x2=None, ld2=0,
              mean2=None, rstd2=None, res=None, ldr=0, y=y, ldy=C, B=B, S=D * H * W, C=C, slope=1.0)
@@ -973,8 +999,7 @@ def dropout3d(x, p, training):
     if not training or p <= 0.0:
         return x
     B, C = x.shape[0], x.shape[4]
-    keep = (torch.rand((B, C), device=x.device) >= p).float() / (1.0 - p)
-    return ChannelScaleFn.apply(x, keep)
+    return ChannelScaleFn.apply(x, keep_scale((B, C), p, x.device))
 
 
 # ------------------------------------------------------------------------------------------------ sub-pixel upsample

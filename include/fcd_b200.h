@@ -161,6 +161,10 @@ FCD_API int fcd_ln_bwd(const void* dln, long long lddl, const void* dtd, long lo
                        const float* mean, const float* rstd, const float* w, void* dx, long long lddx, float* dpos,
                        float* part, float* dw, float* db, int B, int N, int C, int Cp, cudaStream_t stream);
 
+/* ---- nn.Dropout3d / nn.Dropout channel masks (conv_blocks.py:57, 347): out[i] = keep_i / (1 - p), keep_i a counter-based
+ *      Bernoulli(1-p) bit of (seed, *seed_dev, i); seed_dev as for fcd_dsa_fwd. ---- */
+FCD_API int fcd_keep_scale(float* out, int n, float p, long long seed, const long long* seed_dev, cudaStream_t stream);
+
 /* ---- DSA.forward, sa_type='parallel' (conv_blocks.py:328-355) fused with `x + gamma * dsa` (line 77).
  *      ca_scale: optional [B][H][c][c] dropout scale (0 or 1/(1-p)) for attn_drop; sa_drop/seed: in-kernel
  *      counter-based dropout of the [N,P] spatial attention map (attn_drop_2); seed_dev: optional DEVICE step counter
