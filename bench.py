@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--model", default="ms_dsa_net")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one gradient all-reduce after backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches timed for the CPU baseline")
@@ -191,7 +192,7 @@ def main():
     model = model.to(dev).train()
     loss_fn = fcd_b200.CombinedLoss(params, dev)
     opt = torch.optim.AdamW(model.parameters(), lr=params["lr"], weight_decay=params["weight_decay"], fused=True)
-    reducer = parallel.GradAllReducer(model.parameters())
+    reducer = parallel.GradAllReducer(model.parameters(), overlap=not args.no_overlap)
     reducer.sync_params()
     B = args.batch
     n_pool = 4
@@ -260,7 +261,7 @@ def main():
         else:
             opt.zero_grad(set_to_none=True)
             loss = fwd_bwd()
-        reducer.allreduce()
+        reducer.allreduce(early_in_graph=graph is not None and reducer.early_captured)
         opt.step()
         return loss
 
@@ -445,7 +446,10 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model} train step: fwd + DiceCELoss + bwd + AdamW, 2ch {args.patch}^3 patches, "
                                f"batch {B}/GPU, dropout p=0.1 active", "global_batch": B * world,
-                   "parallelism": f"dp{world}", "cuda_graph": graph_ok, "l2": "inputs_exceed_l2"},
+                   "parallelism": f"dp{world}", "cuda_graph": graph_ok, "l2": "inputs_exceed_l2",
+                   **({"grad_allreduce": ("2 buckets, early bucket overlapped with backward"
+                                          if (reducer.overlap and reducer.early_launches) else "1 bucket after backward")}
+                      if world > 1 else {})},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": gpu_launches * args.steps, "gpu_launches_per_step": gpu_launches,

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "fcd_b200.h")
-LIBPATH = os.path.join(_HERE, "libfcd_b200.so")
+LIBPATH = os.environ.get("FCD_B200_LIB") or os.path.join(_HERE, "libfcd_b200.so")
 
 _CT = {
     "int": ctypes.c_int,

@@ -172,6 +172,7 @@ _PACKS = _PackCache()
 
 def prepack_weights(device):
     """Called by the networks at the top of forward(): refresh all cached packed weights in one launch."""
+    _FWD_STREAMS.pop(device.index, None)
     _PACKS.refresh(device)
 
 
@@ -236,6 +237,7 @@ class _SideWork:
         self.pending = []
         self.armed = False
         self.turn = 0
+        self.used = []          # (device, stream) pairs with work since the last join
 
     def stream(self, dev):
         # consecutive weight gradients take turns on a few side streams: the small ones (16-CTA grids, partial-sum
@@ -255,6 +257,8 @@ class _SideWork:
         with torch.cuda.stream(side):
             out = fn()
         self.pending.append((dev, main, keep))
+        if not any(st is side for _, st in self.used):
+            self.used.append((dev, side))
         if not self.armed:
             self.armed = True
             torch.autograd.Variable._execution_engine.queue_callback(self.join)
@@ -270,11 +274,24 @@ class _SideWork:
             for st in self.streams[dev]:
                 main.wait_stream(st)
         self.pending.clear()
+        self.used.clear()
         self.armed = False
         self.turn = 0
 
 
 _SIDE = _SideWork()
+
+
+_FWD_STREAMS = {}      # device index -> branch streams the latest forward used (its backward runs on them again)
+
+
+def producer_streams(device):
+    """Every side stream that may hold pending work of the current forward/backward pass: the weight-gradient streams
+    used so far in this backward and the branch streams of the latest forward.  A consumer that runs INSIDE the
+    backward pass on its own stream (the overlapped gradient all-reduce) waits for these."""
+    out = [st for d, st in _SIDE.used if d == device]
+    out += list(_FWD_STREAMS.get(device.index, ()))
+    return out
 BRANCH_OVERLAP = os.environ.get("FCD_BRANCH_OVERLAP", "1") != "0"
 _BRANCH_STREAMS = {}
 
@@ -298,6 +315,9 @@ class branch:
         if self.on:
             self.side.wait_stream(self.main)
             self.ctx.__enter__()
+            used = _FWD_STREAMS.setdefault(self.side.device.index, [])
+            if not any(st is self.side for st in used):
+                used.append(self.side)
         return self
 
     def __exit__(self, *exc):

@@ -141,18 +141,31 @@ def _ddp_worker(rank, world, port, ret):
         red = GradAllReducer(net.parameters())
         red.sync_params(src=0)
         w0 = [p.detach().clone() for p in net.parameters()]
-        x = torch.full((4, 5), float(rank + 1))
-        net(x).sum().backward()
-        local = [p.grad.clone() for p in net.parameters()]
-        red.allreduce()
-        gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
-        for g, lst in zip(local, gathered):
-            dist.all_gather(lst, g)
-        ok = all(torch.allclose(p.grad, sum(lst) / world, atol=1e-6) for p, lst in zip(net.parameters(), gathered))
         ws = [[torch.zeros_like(w) for _ in range(world)] for w in w0]
         for w, lst in zip(w0, ws):
             dist.all_gather(lst, w)
         same = all(torch.equal(lst[0], lst[1]) for lst in ws)
+
+        def averaged_ok(reducer, scale):
+            net.zero_grad(set_to_none=True)
+            x = torch.full((4, 5), float(rank + 1) * scale)
+            local_net = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+            h = torch.nn.functional.linear(x, local_net[0], local_net[1])
+            torch.nn.functional.linear(h, local_net[2], local_net[3]).sum().backward()
+            local = [p.grad for p in local_net]                   # this rank's own gradients, untouched by hooks
+            net(x).sum().backward()
+            reducer.allreduce()
+            gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+            for g, lst in zip(local, gathered):
+                dist.all_gather(lst, g)
+            return all(torch.allclose(p.grad, sum(lst) / world, atol=1e-6) for p, lst in zip(net.parameters(), gathered))
+
+        ok = averaged_ok(red, 1.0)
+        # two buckets, the early one launched from inside backward: step 1 observes the readiness order, steps 2-3 overlap
+        red2 = GradAllReducer(net.parameters(), overlap=True, early_fraction=0.3)
+        ok = ok and averaged_ok(red2, 1.0)
+        planned = red2.overlap and red2._early is not None and 0 < len(red2._early[0]) < 4
+        ok = ok and planned and averaged_ok(red2, 2.0) and averaged_ok(red2, 3.0) and red2.early_launches == 2
         ret[rank] = bool(ok and same)
     finally:
         dist.destroy_process_group()
