@@ -24,6 +24,77 @@ __device__ __forceinline__ bool sa_keep(unsigned long long seed, unsigned long l
     return (uint32_t)(z >> 32) >= thresh;
 }
 
+// acc[0..P) += s * row[0..P) and dot(v, row) with `row` a 16-byte aligned shared-memory row read as float4: every lane
+// reads the same address (broadcast), and a scalar read per FMA made these kernels LDS-issue bound (1 LDS : 1 FFMA).
+template <int P>
+__device__ __forceinline__ void fma_row(float* acc, float s, const float* row) {
+#pragma unroll
+    for (int p = 0; p < P; p += 4) {
+        const float4 k = *reinterpret_cast<const float4*>(row + p);
+        acc[p] = fmaf(s, k.x, acc[p]);
+        acc[p + 1] = fmaf(s, k.y, acc[p + 1]);
+        acc[p + 2] = fmaf(s, k.z, acc[p + 2]);
+        acc[p + 3] = fmaf(s, k.w, acc[p + 3]);
+    }
+}
+template <int P>
+__device__ __forceinline__ float dot_row(const float* v, const float* row) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int p = 0; p < P; p += 4) {
+        const float4 k = *reinterpret_cast<const float4*>(row + p);
+        a0 = fmaf(v[p], k.x, a0);
+        a1 = fmaf(v[p + 1], k.y, a1);
+        a0 = fmaf(v[p + 2], k.z, a0);
+        a1 = fmaf(v[p + 3], k.w, a1);
+    }
+    return a0 + a1;
+}
+
+// Per-token row segments (one head's CH channels) as 16-byte accesses: a thread's segment is contiguous but the
+// threads of a warp sit on different rows, so a scalar access touches 32 sectors for 2-4 bytes each (and a scalar
+// bf16 store is a partial-sector write); CH % 8 == 0 on every MS_DSA_NET level.
+template <int CH>
+__device__ __forceinline__ void ld_seg_bf16(const bf16* p, float* out) {
+    if constexpr (CH % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < CH; k += 8) unpack8(ld8(p + k), out + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) out[k] = __bfloat162float(p[k]);
+    }
+}
+template <int CH>
+__device__ __forceinline__ void st_seg_bf16(bf16* p, const float* in) {
+    if constexpr (CH % 8 == 0) {
+#pragma unroll
+        for (int k = 0; k < CH; k += 8) st8(p + k, pack8(in + k));
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) p[k] = __float2bfloat16(in[k]);
+    }
+}
+template <int CH>
+__device__ __forceinline__ void ld_seg_f32(const float* p, float* out) {
+    if constexpr (CH % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < CH; k += 4) *reinterpret_cast<float4*>(out + k) = *reinterpret_cast<const float4*>(p + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) out[k] = p[k];
+    }
+}
+template <int CH>
+__device__ __forceinline__ void st_seg_f32(float* p, const float* in) {
+    if constexpr (CH % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < CH; k += 4) *reinterpret_cast<float4*>(p + k) = *reinterpret_cast<const float4*>(in + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) p[k] = in[k];
+    }
+}
+
 __device__ __forceinline__ float group_sum(float v, int width) {
     for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -177,7 +248,7 @@ __device__ __forceinline__ long long dsa_osize(int C, int c, int P) { return 2LL
 __global__ void __launch_bounds__(256) dsa_reduce_kernel(const bf16* __restrict__ qkvv, long long ldq,
                                                          const float* __restrict__ EF, float* __restrict__ part,
                                                          int N, int C, int c, int P, int TN) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int W3 = 3 * C;                       // [q | k | v_SA] per token
     float* sQ = sm;                             // [TN][3C]
     float* sE = sm + (long long)TN * W3;        // [TN][P]
@@ -262,7 +333,7 @@ __global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restri
                                                            float* __restrict__ inv_n, float* __restrict__ Ghat,
                                                            float* __restrict__ A, float* __restrict__ Ad,
                                                            float* __restrict__ KV, int C, int c, int P) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* sG = sm;               // [c][c]
     float* sN = sm + c * c;       // [2][c]
     const int hd = blockIdx.x, b = blockIdx.y;
@@ -322,7 +393,7 @@ __global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__
     // seed_dev: device step counter (ticks once per training forward) mixed into the seed, so a captured CUDA graph
     // draws a NEW mask on every replay while forward and backward of one step still agree
     const unsigned long long seed = seed0 + (seed_dev ? (unsigned long long)(*seed_dev) * 0xD1B54A32D192ED03ULL : 0ULL);
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* sKP = sm;                    // [CH][P]
     float* sVP = sm + CH * P;           // [CH][P]
     float* sA = sm + 2 * CH * P;        // [CH][CH]
@@ -342,11 +413,12 @@ __global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__
     float lg[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) lg[p] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < CH; ++j) {
-        const float qh = __bfloat162float(row[hd * CH + j]) * sIq[j];
+    constexpr int CK = CH % 8 == 0 ? 8 : CH;              // channels per 16-byte row segment
+    for (int j0 = 0; j0 < CH; j0 += CK) {
+        float q[CK];
+        ld_seg_bf16<CK>(row + hd * CH + j0, q);
 #pragma unroll
-        for (int p = 0; p < P; ++p) lg[p] = fmaf(qh, sKP[j * P + p], lg[p]);
+        for (int jj = 0; jj < CK; ++jj) fma_row<P>(lg, q[jj] * sIq[j0 + jj], sKP + (j0 + jj) * P);
     }
     float mx = -INFINITY;
 #pragma unroll
@@ -362,19 +434,21 @@ __global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__
         inv *= drop_scale;
     }
     for (int j = 0; j < CH; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; ++p) a = fmaf(lg[p], sVP[j * P + p], a);
+        const float a = dot_row<P>(lg, sVP + j * P);
         tsa[(((long long)b * CH + j) * H + hd) * N + n] = a * inv;
     }
     float v[CH];
+    ld_seg_bf16<CH>(row + 2 * C + hd * CH, v);
+    for (int i0 = 0; i0 < CH; i0 += CK) {
+        float o[CK];
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = __bfloat162float(row[2 * C + hd * CH + j]);
-    for (int i = 0; i < CH; ++i) {
-        float a = 0.f;
+        for (int ii = 0; ii < CK; ++ii) {
+            float a = 0.f;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) a = fmaf(sA[i * CH + j], v[j], a);
-        xca[((long long)b * N + n) * C + hd * CH + i] = a;
+            for (int j = 0; j < CH; ++j) a = fmaf(sA[(i0 + ii) * CH + j], v[j], a);
+            o[ii] = a;
+        }
+        st_seg_f32<CK>(xca + ((long long)b * N + n) * C + hd * CH + i0, o);
     }
 }
 
@@ -456,8 +530,8 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
                                                             const long long* __restrict__ seed_dev) {
     const unsigned long long seed = seed0 + (seed_dev ? (unsigned long long)(*seed_dev) * 0xD1B54A32D192ED03ULL : 0ULL);
     constexpr int TN = 64;
-    constexpr int ROW = 2 * P + 5 * CH + 1;
-    extern __shared__ float sm[];
+    constexpr int ROW = (2 * P + 5 * CH + 1 + 3) & ~3;      // multiple of 4 floats: rows are float4-addressable
+    extern __shared__ __align__(16) float sm[];
     float* sKP = sm;                        // [CH][P]
     float* sVP = sm + CH * P;               // [CH][P]
     float* sT = sm + 2 * CH * P;            // [TN][ROW]: a[P] | dlog[P] | dxs[CH] | qh[CH] | dxca[CH] | vca[CH] | r1[CH] | dt2
@@ -475,18 +549,31 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
     if (tok && n < N) {
         const bf16* row = qkvv + ((long long)b * N + n) * ldq;
         const float tau2 = temperature2[hd];
-        float lg[P], raw[P];
+        // live per-thread arrays: lg[P] and da[P] only
+        float lg[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) lg[p] = 0.f;
-        for (int j = 0; j < CH; ++j) {
-            const float qh = __bfloat162float(row[hd * CH + j]) * inv_n[(long long)b * 2 * C + hd * CH + j];
-            my[2 * P + CH + j] = qh;
+        // the token's row segments arrive as 16-byte loads and are parked in its shared-memory row; the channel loops
+        // below stay rolled (unrolling them lets the compiler hoist every KP/VP row: 255 registers + KBs of spills)
+        constexpr int CK = CH % 8 == 0 ? 8 : CH;          // channels per 16-byte row segment
+        for (int j0 = 0; j0 < CH; j0 += CK) {
+            float q8[CK], g8[CK], v8[CK];
+            ld_seg_bf16<CK>(row + hd * CH + j0, q8);
+            ld_seg_bf16<CK>(dy + ((long long)b * N + n) * lddy + hd * CH + j0, g8);
+            ld_seg_bf16<CK>(row + 2 * C + hd * CH + j0, v8);
 #pragma unroll
-            for (int p = 0; p < P; ++p) lg[p] = fmaf(qh, sKP[j * P + p], lg[p]);
+            for (int jj = 0; jj < CK; ++jj) {
+                const int j = j0 + jj;
+                my[2 * P + CH + j] = q8[jj] * inv_n[(long long)b * 2 * C + hd * CH + j];
+                my[2 * P + 2 * CH + j] = gamma[hd * CH + j] * g8[jj];
+                my[2 * P + 3 * CH + j] = v8[jj];
+            }
         }
+#pragma unroll 1
+        for (int j = 0; j < CH; ++j) fma_row<P>(lg, my[2 * P + CH + j], sKP + j * P);
         float mx = -INFINITY;
 #pragma unroll
-        for (int p = 0; p < P; ++p) { raw[p] = lg[p]; lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
+        for (int p = 0; p < P; ++p) { lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
         float den = 0.f;
 #pragma unroll
         for (int p = 0; p < P; ++p) { lg[p] = __expf(lg[p] - mx); den += lg[p]; }
@@ -496,6 +583,7 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
         float da[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) da[p] = 0.f;
+#pragma unroll 1
         for (int j = 0; j < CH; ++j) {
             // gradient of the scrambled x_SA element: flat index f -> (n', ch')
             const long long f = ((long long)j * H + hd) * N + n;
@@ -503,68 +591,124 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
             const int ch2 = (int)(f % C);
             const float dxs = gamma[ch2] * __bfloat162float(dy[((long long)b * N + n2) * lddy + ch2]);
             my[2 * P + j] = dxs;
-#pragma unroll
-            for (int p = 0; p < P; ++p) da[p] = fmaf(dxs, sVP[j * P + p], da[p]);
-            const int chc = hd * CH + j;
-            my[2 * P + 2 * CH + j] = gamma[chc] * __bfloat162float(dy[((long long)b * N + n) * lddy + chc]);
-            my[2 * P + 3 * CH + j] = __bfloat162float(row[2 * C + chc]);
+            fma_row<P>(da, dxs, sVP + j * P);
         }
         float s = 0.f;
-        float keepf[P];
-        if (drop_thresh) {
-            const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P;
+        const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P;
 #pragma unroll
-            for (int p = 0; p < P; ++p) keepf[p] = sa_keep(seed, e0 + p, drop_thresh) ? drop_scale : 0.f;
-        } else {
+        for (int p = 0; p < P; p += 4) {
+            float4 kept;
+            float* kv = reinterpret_cast<float*>(&kept);
 #pragma unroll
-            for (int p = 0; p < P; ++p) keepf[p] = 1.f;
+            for (int u = 0; u < 4; ++u) {
+                const float kf = drop_thresh ? (sa_keep(seed, e0 + p + u, drop_thresh) ? drop_scale : 0.f) : 1.f;
+                da[p + u] *= kf;
+                s = fmaf(lg[p + u], da[p + u], s);
+                kv[u] = lg[p + u] * kf;                                   // dropped-out attention row (for dVP)
+            }
+            *reinterpret_cast<float4*>(my + p) = kept;
         }
 #pragma unroll
-        for (int p = 0; p < P; ++p) { da[p] *= keepf[p]; s = fmaf(lg[p], da[p], s); }
+        for (int p = 0; p < P; p += 4) {
+            float4 d4;
+            float* dv = reinterpret_cast<float*>(&d4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dv[u] = lg[p + u] * (da[p + u] - s);
+                da[p + u] = dv[u];                                        // reuse as dlog
+            }
+            *reinterpret_cast<float4*>(my + P + p) = d4;
+        }
+        // dt2 = sum_p dlog[p] * raw[p] with raw[p] = sum_j qh[j] KP[j][p]  ==  sum_j qh[j] * (sum_p dlog[p] KP[j][p])
         float dt2 = 0.f;
+        constexpr int C4 = CH % 4 == 0 ? 4 : 1;           // dqh leaves as float4 stores
+#pragma unroll 1
+        for (int j0 = 0; j0 < CH; j0 += C4) {
+            float o[C4];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const float dl = lg[p] * (da[p] - s);
-            my[p] = lg[p] * keepf[p];
-            my[P + p] = dl;
-            dt2 = fmaf(dl, raw[p], dt2);
-            da[p] = dl;                                                   // reuse as dlog
+            for (int jj = 0; jj < C4; ++jj) {
+                const int j = j0 + jj;
+                float a = dot_row<P>(da, sKP + j * P);
+                const float qh = my[2 * P + CH + j];
+                dt2 = fmaf(qh, a, dt2);
+                a *= tau2;
+                o[jj] = a;
+                my[2 * P + 4 * CH + j] = a * qh;
+            }
+            st_seg_f32<C4>(dqh + ((long long)b * N + n) * C + hd * CH + j0, o);
         }
-        my[ROW - 1] = dt2;
-        for (int j = 0; j < CH; ++j) {
-            float a = 0.f;
-#pragma unroll
-            for (int p = 0; p < P; ++p) a = fmaf(da[p], sKP[j * P + p], a);
-            a *= tau2;
-            dqh[((long long)b * N + n) * C + hd * CH + j] = a;
-            my[2 * P + 4 * CH + j] = a * my[2 * P + CH + j];
-        }
+        my[2 * P + 5 * CH] = dt2;
     } else if (tok) {
         for (int i = 0; i < ROW; ++i) my[i] = 0.f;
     }
     __syncthreads();
     float* out = part + (((long long)b * H + hd) * ntiles + tile) * dsa_bsize(CH, P);
     const float tau2 = temperature2[hd];
-    const int n_vp = CH * P, n_a = CH * CH;
-    for (int it = threadIdx.x; it < 2 * n_vp + n_a + CH + 1; it += blockDim.x) {
-        float a = 0.f;
-        if (it < n_vp) {                                   // dVP[j][p] = sum a[p] dxs[j]
-            const int j = it / P, p = it % P;
-            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + p], sT[q * ROW + 2 * P + j], a);
-        } else if (it < 2 * n_vp) {                        // dKP[j][p] = tau2 sum qh[j] dlog[p]
-            const int j = (it - n_vp) / P, p = (it - n_vp) % P;
-            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + CH + j], sT[q * ROW + P + p], a);
-            a *= tau2;
-        } else if (it < 2 * n_vp + n_a) {                  // dA[i][j] = sum dxca[i] vca[j]
-            const int i = (it - 2 * n_vp) / CH, j = (it - 2 * n_vp) % CH;
-            for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + 2 * CH + i], sT[q * ROW + 2 * P + 3 * CH + j], a);
-        } else if (it < 2 * n_vp + n_a + CH) {             // R1[j]
-            const int j = it - 2 * n_vp - n_a;
-            for (int q = 0; q < TN; ++q) a += sT[q * ROW + 2 * P + 4 * CH + j];
-        } else {
-            for (int q = 0; q < TN; ++q) a += sT[q * ROW + ROW - 1];
+    constexpr int n_vp = CH * P, n_a = CH * CH;
+    if constexpr (CH % 4 == 0) {
+        // outer-product reductions over the TN tokens as 4 x 4 register tiles: two float4 reads per 16 FMAs
+        // (the scalar version issued two LDS per FMA and dominated the kernel)
+        constexpr int JT = CH / 4, PT = P / 4, NVP = JT * PT, NA = JT * JT;
+        for (int ti = threadIdx.x; ti < 2 * NVP + NA; ti += blockDim.x) {
+            int offA, offB, ldo;
+            float scale = 1.f;
+            float* o;
+            if (ti < NVP) {                                // dVP[j][p] = sum a[p] dxs[j]
+                const int j4 = ti / PT, p4 = ti % PT;
+                offA = 2 * P + 4 * j4; offB = 4 * p4; o = out + 4 * j4 * P + 4 * p4; ldo = P;
+            } else if (ti < 2 * NVP) {                     // dKP[j][p] = tau2 sum qh[j] dlog[p]
+                const int u = ti - NVP, j4 = u / PT, p4 = u % PT;
+                offA = 2 * P + CH + 4 * j4; offB = P + 4 * p4; o = out + n_vp + 4 * j4 * P + 4 * p4; ldo = P;
+                scale = tau2;
+            } else {                                       // dA[i][j] = sum dxca[i] vca[j]
+                const int u = ti - 2 * NVP, i4 = u / JT, j4 = u % JT;
+                offA = 2 * P + 2 * CH + 4 * i4; offB = 2 * P + 3 * CH + 4 * j4; o = out + 2 * n_vp + 4 * i4 * CH + 4 * j4;
+                ldo = CH;
+            }
+            float acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < TN; ++q) {
+                const float4 av = *reinterpret_cast<const float4*>(sT + q * ROW + offA);
+                const float4 bv = *reinterpret_cast<const float4*>(sT + q * ROW + offB);
+                const float ar[4] = {av.x, av.y, av.z, av.w}, bc[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], bc[c], acc[r][c]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[r * ldo + c] = acc[r][c] * scale;
         }
-        out[it] = a;
+        for (int it = threadIdx.x; it < CH + 1; it += blockDim.x) {        // R1[j], dt2
+            float a = 0.f;
+            for (int q = 0; q < TN; ++q) a += sT[q * ROW + 2 * P + 4 * CH + it];
+            out[2 * n_vp + n_a + it] = a;
+        }
+    } else {
+        for (int it = threadIdx.x; it < 2 * n_vp + n_a + CH + 1; it += blockDim.x) {
+            float a = 0.f;
+            if (it < n_vp) {                                   // dVP[j][p] = sum a[p] dxs[j]
+                const int j = it / P, p = it % P;
+                for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + p], sT[q * ROW + 2 * P + j], a);
+            } else if (it < 2 * n_vp) {                        // dKP[j][p] = tau2 sum qh[j] dlog[p]
+                const int j = (it - n_vp) / P, p = (it - n_vp) % P;
+                for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + CH + j], sT[q * ROW + P + p], a);
+                a *= tau2;
+            } else if (it < 2 * n_vp + n_a) {                  // dA[i][j] = sum dxca[i] vca[j]
+                const int i = (it - 2 * n_vp) / CH, j = (it - 2 * n_vp) % CH;
+                for (int q = 0; q < TN; ++q) a = fmaf(sT[q * ROW + 2 * P + 2 * CH + i], sT[q * ROW + 2 * P + 3 * CH + j], a);
+            } else {                                           // R1[j], dt2
+                const int j = it - 2 * n_vp - n_a;
+                for (int q = 0; q < TN; ++q) a += sT[q * ROW + 2 * P + 4 * CH + j];
+            }
+            out[it] = a;
+        }
     }
 }
 
@@ -579,7 +723,7 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
                                                                float* __restrict__ dGhat, float* __restrict__ rqk,
                                                                float* __restrict__ dtemp, float* __restrict__ dtemp2,
                                                                int C, int c, int P) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* sdA = sm;                 // [c][c] -> dGhat
     float* sR1 = sm + c * c;         // [c]
     __shared__ float sred[256];
@@ -652,7 +796,7 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
                                                             const float* __restrict__ dKV,
                                                             const float* __restrict__ dqh, bf16* __restrict__ dqkvv,
                                                             long long lddq, int N, int C) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* sdKP = sm;                     // [CH][P]
     float* sdVP = sm + CH * P;            // [CH][P]
     float* sA = sm + 2 * CH * P;          // [CH][CH]
@@ -679,43 +823,61 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     const long long r = (long long)b * N + n;
     const bf16* row = qkvv + r * ldq;
     bf16* drow = dqkvv + r * lddq;
+    constexpr int CK = CH % 8 == 0 ? 8 : CH;              // channels per 16-byte row segment
     float qh[CH], kh[CH];
+    ld_seg_bf16<CH>(row + hd * CH, qh);
+    ld_seg_bf16<CH>(row + C + hd * CH, kh);
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-        qh[j] = __bfloat162float(row[hd * CH + j]) * sV[j];
-        kh[j] = __bfloat162float(row[C + hd * CH + j]) * sV[CH + j];
+    for (int j = 0; j < CH; ++j) { qh[j] *= sV[j]; kh[j] *= sV[CH + j]; }
+    // dq, one row segment at a time (the segment's own q values are re-read: no dynamic register indexing)
+    for (int i0 = 0; i0 < CH; i0 += CK) {
+        float o[CK], q8[CK];
+        ld_seg_f32<CK>(dqh + r * C + hd * CH + i0, o);
+        ld_seg_bf16<CK>(row + hd * CH + i0, q8);
+#pragma unroll
+        for (int ii = 0; ii < CK; ++ii) {
+            const int i = i0 + ii;
+            float a = o[ii];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) a = fmaf(sdG[i * CH + j], kh[j], a);
+            o[ii] = (a - q8[ii] * sV[i] * sV[2 * CH + i]) * sV[i];
+        }
+        st_seg_bf16<CK>(drow + hd * CH + i0, o);
     }
-    float ef[P];
+    {
+        float ef[P];
+        ld_seg_f32<P>(EF + (long long)n * P, ef);
+        for (int j0 = 0; j0 < CH; j0 += CK) {
+            float o[CK], f[CK], k8[CK];
+            ld_seg_bf16<CK>(row + C + hd * CH + j0, k8);
 #pragma unroll
-    for (int p = 0; p < P; ++p) ef[p] = EF[(long long)n * P + p];
-    for (int i = 0; i < CH; ++i) {
-        // dq
-        float a = dqh[r * C + hd * CH + i];
+            for (int jj = 0; jj < CK; ++jj) {
+                const int j = j0 + jj;
+                float a = 0.f;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) a = fmaf(sdG[i * CH + j], kh[j], a);
-        a = (a - qh[i] * sV[2 * CH + i]) * sV[i];
-        drow[hd * CH + i] = __float2bfloat16(a);
-    }
-    for (int j = 0; j < CH; ++j) {
-        // dk
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) a = fmaf(sdG[i * CH + j], qh[i], a);
-        a = (a - kh[j] * sV[3 * CH + j]) * sV[CH + j];
-        float e = 0.f, f = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; ++p) { e = fmaf(sdKP[j * P + p], ef[p], e); f = fmaf(sdVP[j * P + p], ef[p], f); }
-        drow[C + hd * CH + j] = __float2bfloat16(a + e);
-        drow[3 * C + hd * CH + j] = __float2bfloat16(f);
+                for (int i = 0; i < CH; ++i) a = fmaf(sdG[i * CH + j], qh[i], a);
+                a = (a - k8[jj] * sV[CH + j] * sV[3 * CH + j]) * sV[CH + j];
+                o[jj] = a + dot_row<P>(ef, sdKP + j * P);                 // dk (+ its EF term)
+                f[jj] = dot_row<P>(ef, sdVP + j * P);                     // dv_SA
+            }
+            st_seg_bf16<CK>(drow + C + hd * CH + j0, o);
+            st_seg_bf16<CK>(drow + 3 * C + hd * CH + j0, f);
+        }
     }
     // dv_CA[j] = sum_i A[i][j] dxca[i]   (reuse qh as dxca)
+    ld_seg_bf16<CH>(dy + r * lddy + hd * CH, qh);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) qh[i] = gamma[hd * CH + i] * __bfloat162float(dy[r * lddy + hd * CH + i]);
-    for (int j = 0; j < CH; ++j) {
-        float a = 0.f;
+    for (int i = 0; i < CH; ++i) qh[i] *= gamma[hd * CH + i];
+    for (int j0 = 0; j0 < CH; j0 += CK) {
+        float o[CK];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) a = fmaf(sA[i * CH + j], qh[i], a);
-        drow[2 * C + hd * CH + j] = __float2bfloat16(a);
+        for (int jj = 0; jj < CK; ++jj) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) a = fmaf(sA[i * CH + j0 + jj], qh[i], a);
+            o[jj] = a;
+        }
+        st_seg_bf16<CK>(drow + 2 * C + hd * CH + j0, o);
     }
 }
 
@@ -824,7 +986,7 @@ int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long
                       const float* inv_n, const float* KV, const float* t2, float* dqh, float* part, int B, int N,
                       int C, int H, float ds, uint32_t dth, unsigned long long seed, const long long* seed_dev,
                       cudaStream_t st) {
-    const int smem = (2 * CH * P + 64 * (2 * P + 5 * CH + 1)) * 4;
+    const int smem = (2 * CH * P + 64 * ((2 * P + 5 * CH + 1 + 3) & ~3)) * 4;
     static bool conf = false;
     if (!conf) {
         cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
