@@ -254,35 +254,71 @@ __global__ void __launch_bounds__(256) dsa_reduce_kernel(const bf16* __restrict_
     float* sE = sm + (long long)TN * W3;        // [TN][P]
     const int b = blockIdx.y, tile = blockIdx.x;
     const int n0 = tile * TN;
-    for (int i = threadIdx.x; i < TN * W3; i += blockDim.x) {
-        const int n = i / W3, col = i % W3;
-        float v = 0.f;
+    // token rows as 16-byte loads (C % 8 == 0 is checked by the host wrapper; ldq % 8 == 0)
+    const int W8 = W3 / 8;
+    for (int i = threadIdx.x; i < TN * W8; i += blockDim.x) {
+        const int n = i / W8, col = (i % W8) * 8;
+        float v[8];
         if (n0 + n < N) {
             const int src = col < 2 * C ? col : col + C;        // skip v_CA (third slot)
-            v = __bfloat162float(qkvv[((long long)b * N + n0 + n) * ldq + src]);
+            unpack8(ld8(qkvv + ((long long)b * N + n0 + n) * ldq + src), v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
         }
-        sQ[i] = v;
+        *reinterpret_cast<float4*>(&sQ[n * W3 + col]) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(&sQ[n * W3 + col + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    for (int i = threadIdx.x; i < TN * P; i += blockDim.x) {
-        const int n = i / P;
-        sE[i] = (n0 + n < N) ? EF[(long long)(n0 + n) * P + (i % P)] : 0.f;
+    const int P4 = P / 4;
+    for (int i = threadIdx.x; i < TN * P4; i += blockDim.x) {
+        const int n = i / P4;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + n < N) e = *reinterpret_cast<const float4*>(&EF[(long long)(n0 + n) * P + (i % P4) * 4]);
+        *reinterpret_cast<float4*>(&sE[i * 4]) = e;
     }
     __syncthreads();
     const int ntiles = gridDim.x;
     float* out = part + ((long long)b * ntiles + tile) * dsa_osize(C, c, P);
-    const int P4 = P / 4;
-    const int n_kv = 2 * C * P4, n_g = C * c, n_s = 2 * C;
+    // Outputs as 4 x 4 register tiles (two float4 reads per 16 FMAs; one scalar + one float4 read per 4 FMAs made the
+    // kernel LDS-bound): [k | v_SA] rows x P columns, then the per-head q k^T blocks when c % 4 == 0, then the norms.
+    const bool g_tiled = (c % 4) == 0;
+    const int c4 = c / 4;
+    const int n_kv = (2 * C / 4) * P4;
+    const int n_g = g_tiled ? (C / c) * c4 * c4 : C * c;
+    const int n_s = 2 * C;
     // gridDim.z > 1 (small N, few token tiles): the blocks of one tile share the token tile and split the outputs
     for (int it = blockIdx.z * blockDim.x + threadIdx.x; it < n_kv + n_g + n_s; it += blockDim.x * gridDim.z) {
-        if (it < n_kv) {
-            const int r = it / P4, p = (it % P4) * 4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int n = 0; n < TN; ++n) {
-                const float kv = sQ[n * W3 + C + r];
-                const float4 e = *reinterpret_cast<const float4*>(&sE[n * P + p]);
-                a.x = fmaf(kv, e.x, a.x); a.y = fmaf(kv, e.y, a.y); a.z = fmaf(kv, e.z, a.z); a.w = fmaf(kv, e.w, a.w);
+        if (it < n_kv || (g_tiled && it < n_kv + n_g)) {
+            int offA, offB, ldo, strideB;
+            float* o;
+            if (it < n_kv) {
+                const int r4 = it / P4, p4 = it % P4;
+                offA = C + 4 * r4; offB = TN * W3 + 4 * p4; strideB = P;           // B operand lives in sE
+                o = out + 2 * C + (long long)C * c + (long long)(4 * r4) * P + 4 * p4; ldo = P;
+            } else {
+                const int g = it - n_kv;
+                const int j4 = g % c4, i4 = (g / c4) % c4, hd = g / (c4 * c4);
+                offA = hd * c + 4 * i4; offB = C + hd * c + 4 * j4; strideB = W3;
+                o = out + 2 * C + (long long)hd * c * c + (long long)(4 * i4) * c + 4 * j4; ldo = c;
             }
-            *reinterpret_cast<float4*>(&out[2 * C + (long long)C * c + (long long)r * P + p]) = a;
+            float acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+#pragma unroll 4
+            for (int n = 0; n < TN; ++n) {
+                const float4 av = *reinterpret_cast<const float4*>(&sm[n * W3 + offA]);
+                const float4 bv = *reinterpret_cast<const float4*>(&sm[offB + n * strideB]);
+                const float ar[4] = {av.x, av.y, av.z, av.w}, bc[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(ar[r], bc[q], acc[r][q]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                *reinterpret_cast<float4*>(&o[(long long)r * ldo]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         } else if (it < n_kv + n_g) {
             const int g = it - n_kv;
             const int j = g % c, i = (g / c) % c, hd = g / (c * c);
@@ -1122,7 +1158,7 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
                         float* part, float* inv_n,
                         float* Ghat, float* A, float* Ad, float* KV, float* xca, float* tsa, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t st) {
-    if (C % H || P % 4 || Cp % 8) return -1;
+    if (C % H || P % 4 || Cp % 8 || C % 8) return -1;
     const int c = C / H;
     const int LPT = Cp / 8;
     if (LPT > 32 || (LPT & (LPT - 1))) return -1;
@@ -1136,7 +1172,7 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
     }
     int zsplit = 1;
     {
-        const long long items = 2LL * C * (P / 4) + (long long)C * c + 2LL * C;
+        const long long items = (2LL * C / 4) * (P / 4) + ((c % 4) ? (long long)C * c : (long long)C * c / 16) + 2LL * C;
         while ((long long)ntiles * B * zsplit < 2LL * fcd_num_sms() && zsplit * 256LL < items) zsplit *= 2;
     }
     dsa_reduce_kernel<<<dim3(ntiles, B, zsplit), 256, smem_r, st>>>((const bf16*)qkvv, ldq, EF, part, N, C, c, P, tn);
