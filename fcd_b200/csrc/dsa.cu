@@ -380,6 +380,15 @@ __global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restri
         for (int k = 0; k < nsum; ++k) s += base[(long long)k * O + off];
         return s;
     };
+    // the K/V projection copy is split over the gridDim.z blocks of this (head, sample); block z == 0 also does the
+    // small-matrix part (on the deep levels this kernel is a link of a latency chain: 8 blocks took ~35 us)
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < 2 * c * P; i += blockDim.x * gridDim.z) {
+        const int which = i / (c * P), rem = i % (c * P);
+        const int j = rem / P, p = rem % P;
+        const long long r = (long long)which * C + hd * c + j;
+        KV[((long long)b * 2 * C + r) * P + p] = tsum(2LL * C + (long long)C * c + r * P + p);
+    }
+    if (blockIdx.z != 0) return;
     for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
         const int which = i / c, j = i % c;
         const float s = tsum((long long)which * C + hd * c + j);
@@ -388,25 +397,23 @@ __global__ void __launch_bounds__(256) dsa_finalize_kernel(const float* __restri
         inv_n[((long long)b * 2 + which) * C + hd * c + j] = inv;
     }
     for (int i = threadIdx.x; i < c * c; i += blockDim.x) sG[i] = tsum(2LL * C + (long long)hd * c * c + i);
-    for (int i = threadIdx.x; i < 2 * c * P; i += blockDim.x) {
-        const int which = i / (c * P), rem = i % (c * P);
-        const int j = rem / P, p = rem % P;
-        const long long r = (long long)which * C + hd * c + j;
-        KV[((long long)b * 2 * C + r) * P + p] = tsum(2LL * C + (long long)C * c + r * P + p);
-    }
     __syncthreads();
     const float tau = temperature[hd];
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    // softmax rows: one warp per row, lanes over the columns
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = warp; i < c; i += nwarp) {
         float mx = -INFINITY;
-        for (int j = 0; j < c; ++j) {
+        for (int j = lane; j < c; j += 32) {
             const float g = sG[i * c + j] * sN[i] * sN[c + j];
             sG[i * c + j] = g;
             mx = fmaxf(mx, g * tau);
         }
+        mx = warp_max(mx);
         float den = 0.f;
-        for (int j = 0; j < c; ++j) den += __expf(sG[i * c + j] * tau - mx);
+        for (int j = lane; j < c; j += 32) den += __expf(sG[i * c + j] * tau - mx);
+        den = warp_sum(den);
         const long long o = (((long long)b * gridDim.x + hd) * c + i) * c;
-        for (int j = 0; j < c; ++j) {
+        for (int j = lane; j < c; j += 32) {
             Ghat[o + j] = sG[i * c + j];
             const float a = __expf(sG[i * c + j] * tau - mx) / den;
             A[o + j] = a;
@@ -771,12 +778,14 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
         for (int k = 0; k < nsum; ++k) s += base[(long long)k * O + off];
         return s;
     };
-    for (int i = threadIdx.x; i < 2 * c * P; i += blockDim.x) {
+    // the dKV copy is split over the gridDim.z blocks; block z == 0 also does the small-matrix part
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < 2 * c * P; i += blockDim.x * gridDim.z) {
         const int which = i / (c * P), rem = i % (c * P);          // partial: 0 dVP, 1 dKP
         const int j = rem / P, p = rem % P;
         const int dst_which = which == 0 ? 1 : 0;                   // dKV: 0 dKP, 1 dVP
         dKV[(((long long)b * 2 + dst_which) * C + hd * c + j) * P + p] = tsum(i);
     }
+    if (blockIdx.z != 0) return;
     for (int i = threadIdx.x; i < c * c; i += blockDim.x) {
         const float v = tsum(2LL * c * P + i);
         sdA[i] = ca_scale ? v * ca_scale[((long long)b * H + hd) * c * c + i] : v;
@@ -788,11 +797,14 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
     const float tau = temperature[hd];
     const long long o = ((long long)b * H + hd) * c * c;
     float dtau = 0.f;
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    // softmax backward rows: one warp per row, lanes over the columns (coalesced A / Ghat reads)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = warp; i < c; i += nwarp) {
         float s = 0.f;
-        for (int j = 0; j < c; ++j) s = fmaf(A[o + i * c + j], sdA[i * c + j], s);
-        float rq = sR1[i];
-        for (int j = 0; j < c; ++j) {
+        for (int j = lane; j < c; j += 32) s = fmaf(A[o + i * c + j], sdA[i * c + j], s);
+        s = warp_sum(s);
+        float rq = 0.f;
+        for (int j = lane; j < c; j += 32) {
             const float dS = A[o + i * c + j] * (sdA[i * c + j] - s);     // d(tau * Ghat)
             const float gh = Ghat[o + i * c + j];
             dtau = fmaf(dS, gh, dtau);
@@ -801,13 +813,24 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
             dGhat[o + i * c + j] = dg;
             rq = fmaf(dg, gh, rq);
         }
-        rqk[((long long)b * 2) * C + hd * c + i] = rq;
+        rq = warp_sum(rq);
+        if (lane == 0) rqk[((long long)b * 2) * C + hd * c + i] = rq + sR1[i];
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+    // rk[j] = sum_i dGhat[i][j] Ghat[i][j]: the row range is split over blockDim / c thread groups
+    {
+        const int j = threadIdx.x % c, k = threadIdx.x / c, K = blockDim.x / c;     // c <= 256 (host check)
         float rk = 0.f;
-        for (int i = 0; i < c; ++i) rk = fmaf(sdA[i * c + j], Ghat[o + i * c + j], rk);
-        rqk[((long long)b * 2 + 1) * C + hd * c + j] = rk;
+        if (k < K)
+            for (int i = k; i < c; i += K) rk = fmaf(sdA[i * c + j], Ghat[o + i * c + j], rk);
+        __shared__ float sp[256];              // [K][c] partials, K * c <= 256
+        if (k < K) sp[k * c + j] = rk;
+        __syncthreads();
+        if ((int)threadIdx.x < c) {
+            float r = 0.f;
+            for (int kk = 0; kk < K; ++kk) r += sp[kk * c + threadIdx.x];
+            rqk[((long long)b * 2 + 1) * C + hd * c + threadIdx.x] = r;
+        }
     }
     sred[threadIdx.x] = dtau;
     __syncthreads();
@@ -1078,6 +1101,12 @@ int launch_bwd_apply(const bf16* qkvv, long long ldq, const bf16* dy, long long 
         return -1;                                                               \
     } while (0)
 
+// blocks per (head, sample) of the finalize kernels: ~512 copied K/V projection elements per block
+int finalize_zsplit(int c, int P) {
+    int z = (2 * c * P + 511) / 512;
+    return z < 1 ? 1 : (z > 16 ? 16 : z);
+}
+
 int dsa_tile_tokens(int C, int P) {
     int tn = 64;
     while (tn > 8 && (long long)tn * (3 * C + P) * 4 > 60 * 1024) tn >>= 1;
@@ -1179,7 +1208,7 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
     float ds; uint32_t dth;
     drop_params(sa_drop, ds, dth);
     tile_group_sum(part, B, ntiles, 2LL * C + (long long)C * c + 2LL * C * P, st);
-    dsa_finalize_kernel<<<dim3(H, B), 256, (c * c + 2 * c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
+    dsa_finalize_kernel<<<dim3(H, B, finalize_zsplit(c, P)), 256, (c * c + 2 * c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
                                                                      ca_scale, inv_n, Ghat, A, Ad, KV, C, c, P);
     {
         auto run = [&]() -> int {
@@ -1207,7 +1236,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
                         float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
                         long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t st) {
-    if (C % H || P % 4 || Cp % 8 || H > 256) return -1;
+    if (C % H || P % 4 || Cp % 8 || H > 256 || C / H > 256) return -1;
     const int c = C / H;
     const int LPT = Cp / 8;
     if (LPT > 32 || (LPT & (LPT - 1))) return -1;
@@ -1227,7 +1256,7 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
     }
     const int ntiles = (N + 63) / 64;
     tile_group_sum(part, B * H, ntiles, 2LL * c * P + (long long)c * c + c + 1, st);
-    dsa_bwd_finalize_kernel<<<dim3(H, B), 256, (c * c + c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
+    dsa_bwd_finalize_kernel<<<dim3(H, B, finalize_zsplit(c, P)), 256, (c * c + c) * 4, st>>>(part, ntiles, tile_rows_after_sum(ntiles), temperature,
                                                                      Ghat, A, ca_scale, dKV, dGhat, rqk, dtemp, dtemp2, C, c,
                                                                      P);
     {
