@@ -95,6 +95,12 @@ __device__ __forceinline__ void st_seg_f32(float* p, const float* in) {
     }
 }
 
+// block-cooperative global -> shared copy of n floats (n % 4 == 0, both 16-byte aligned) as float4
+__device__ __forceinline__ void stage_f4(float* dst, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
+}
+
 __device__ __forceinline__ float group_sum(float v, int width) {
     for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -442,11 +448,10 @@ __global__ void __launch_bounds__(128) dsa_apply_kernel(const bf16* __restrict__
     float* sA = sm + 2 * CH * P;        // [CH][CH]
     float* sIq = sA + CH * CH;          // [CH]
     const int hd = blockIdx.y, b = blockIdx.z, H = gridDim.y;
-    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
-        sKP[i] = KV[((long long)b * 2 * C + hd * CH) * P + i];
-        sVP[i] = KV[((long long)b * 2 * C + C + hd * CH) * P + i];
-    }
-    for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) sA[i] = A[((long long)b * H + hd) * CH * CH + i];
+    stage_f4(sKP, KV + ((long long)b * 2 * C + hd * CH) * P, CH * P);
+    stage_f4(sVP, KV + ((long long)b * 2 * C + C + hd * CH) * P, CH * P);
+    if constexpr (CH % 2 == 0) stage_f4(sA, A + ((long long)b * H + hd) * CH * CH, CH * CH);
+    else for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) sA[i] = A[((long long)b * H + hd) * CH * CH + i];
     for (int i = threadIdx.x; i < CH; i += blockDim.x) sIq[i] = inv_n[(long long)b * 2 * C + hd * CH + i];
     __syncthreads();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,10 +584,8 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
     float* sVP = sm + CH * P;               // [CH][P]
     float* sT = sm + 2 * CH * P;            // [TN][ROW]: a[P] | dlog[P] | dxs[CH] | qh[CH] | dxca[CH] | vca[CH] | r1[CH] | dt2
     const int tile = blockIdx.x, hd = blockIdx.y, b = blockIdx.z, H = gridDim.y, ntiles = gridDim.x;
-    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
-        sKP[i] = KV[((long long)b * 2 * C + hd * CH) * P + i];
-        sVP[i] = KV[((long long)b * 2 * C + C + hd * CH) * P + i];
-    }
+    stage_f4(sKP, KV + ((long long)b * 2 * C + hd * CH) * P, CH * P);
+    stage_f4(sVP, KV + ((long long)b * 2 * C + C + hd * CH) * P, CH * P);
     __syncthreads();
     // phase 1 runs on the first TN threads (one token each); all NT threads take part in the phase-2 reduction
     // (NT = 64 when there are enough token tiles to fill the GPU, 256 on the deep levels with a handful of blocks)
@@ -842,8 +845,10 @@ __global__ void __launch_bounds__(256) dsa_bwd_finalize_kernel(const float* __re
     }
 }
 
-// thread per (token, head): gradients of q, k, v_CA, v_SA -> dqkvv rows (bf16).
-template <int CH, int P>
+// thread per (token, head): gradients of q, k, v_CA, v_SA -> dqkvv rows (bf16).  SPLIT (deep levels, a few hundred
+// tokens): CH/8 adjacent threads share a token and each produces one 8-channel segment of every output, which cuts the
+// serial FMA chain of the latency-bound small-N launches by CH/8.
+template <int CH, int P, bool SPLIT>
 __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restrict__ qkvv, long long ldq,
                                                             const bf16* __restrict__ dy, long long lddy,
                                                             const float* __restrict__ gamma,
@@ -862,13 +867,16 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     float* sdG = sA + CH * CH;            // [CH][CH]
     float* sV = sdG + CH * CH;            // inv_nq | inv_nk | rq | rk : [4][CH]
     const int hd = blockIdx.y, b = blockIdx.z, H = gridDim.y;
-    for (int i = threadIdx.x; i < CH * P; i += blockDim.x) {
-        sdKP[i] = dKV[((long long)b * 2 * C + hd * CH) * P + i];
-        sdVP[i] = dKV[((long long)b * 2 * C + C + hd * CH) * P + i];
-    }
-    for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) {
-        sA[i] = A[((long long)b * H + hd) * CH * CH + i];
-        sdG[i] = dGhat[((long long)b * H + hd) * CH * CH + i];
+    stage_f4(sdKP, dKV + ((long long)b * 2 * C + hd * CH) * P, CH * P);
+    stage_f4(sdVP, dKV + ((long long)b * 2 * C + C + hd * CH) * P, CH * P);
+    if constexpr (CH % 2 == 0) {
+        stage_f4(sA, A + ((long long)b * H + hd) * CH * CH, CH * CH);
+        stage_f4(sdG, dGhat + ((long long)b * H + hd) * CH * CH, CH * CH);
+    } else {
+        for (int i = threadIdx.x; i < CH * CH; i += blockDim.x) {
+            sA[i] = A[((long long)b * H + hd) * CH * CH + i];
+            sdG[i] = dGhat[((long long)b * H + hd) * CH * CH + i];
+        }
     }
     for (int i = threadIdx.x; i < CH; i += blockDim.x) {
         sV[i] = inv_n[(long long)b * 2 * C + hd * CH + i];
@@ -877,7 +885,9 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
         sV[3 * CH + i] = rqk[(long long)b * 2 * C + C + hd * CH + i];
     }
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int NSEG = (SPLIT && CH % 8 == 0) ? CH / 8 : 1;     // threads per token
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) / NSEG;
+    const int seg = threadIdx.x % NSEG;
     if (n >= N) return;
     const long long r = (long long)b * N + n;
     const bf16* row = qkvv + r * ldq;
@@ -889,7 +899,8 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
 #pragma unroll
     for (int j = 0; j < CH; ++j) { qh[j] *= sV[j]; kh[j] *= sV[CH + j]; }
     // dq, one row segment at a time (the segment's own q values are re-read: no dynamic register indexing)
-    for (int i0 = 0; i0 < CH; i0 += CK) {
+    const int c_lo = NSEG > 1 ? seg * CK : 0, c_hi = NSEG > 1 ? c_lo + CK : CH;      // this thread's output channels
+    for (int i0 = c_lo; i0 < c_hi; i0 += CK) {
         float o[CK], q8[CK];
         ld_seg_f32<CK>(dqh + r * C + hd * CH + i0, o);
         ld_seg_bf16<CK>(row + hd * CH + i0, q8);
@@ -906,7 +917,7 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     {
         float ef[P];
         ld_seg_f32<P>(EF + (long long)n * P, ef);
-        for (int j0 = 0; j0 < CH; j0 += CK) {
+        for (int j0 = c_lo; j0 < c_hi; j0 += CK) {
             float o[CK], f[CK], k8[CK];
             ld_seg_bf16<CK>(row + C + hd * CH + j0, k8);
 #pragma unroll
@@ -927,7 +938,7 @@ __global__ void __launch_bounds__(128) dsa_bwd_apply_kernel(const bf16* __restri
     ld_seg_bf16<CH>(dy + r * lddy + hd * CH, qh);
 #pragma unroll
     for (int i = 0; i < CH; ++i) qh[i] *= gamma[hd * CH + i];
-    for (int j0 = 0; j0 < CH; j0 += CK) {
+    for (int j0 = c_lo; j0 < c_hi; j0 += CK) {
         float o[CK];
 #pragma unroll
         for (int jj = 0; jj < CK; ++jj) {
@@ -1069,10 +1080,22 @@ int launch_bwd_apply(const bf16* qkvv, long long ldq, const bf16* dy, long long 
                      cudaStream_t st) {
     const int smem = (2 * CH * P + 2 * CH * CH + 4 * CH) * 4;
     static bool conf = false;
-    if (!conf) { cudaFuncSetAttribute(dsa_bwd_apply_kernel<CH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); conf = true; }
-    dim3 grid((N + 127) / 128, H, B);
-    dsa_bwd_apply_kernel<CH, P><<<grid, 128, smem, st>>>(qkvv, ldq, dy, lddy, gamma, EF, inv_n, A, dGhat, rqk, dKV,
-                                                         dqh, dqkvv, lddq, N, C);
+    if (!conf) {
+        cudaFuncSetAttribute(dsa_bwd_apply_kernel<CH, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(dsa_bwd_apply_kernel<CH, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        conf = true;
+    }
+    // few tokens (deep levels): one thread per (token, 8-channel segment)
+    constexpr int NSEG = CH % 8 == 0 ? CH / 8 : 1;
+    if (NSEG > 1 && (long long)N * H * B < 64LL * fcd_num_sms()) {
+        dim3 grid((N * NSEG + 127) / 128, H, B);
+        dsa_bwd_apply_kernel<CH, P, true><<<grid, 128, smem, st>>>(qkvv, ldq, dy, lddy, gamma, EF, inv_n, A, dGhat, rqk,
+                                                                   dKV, dqh, dqkvv, lddq, N, C);
+    } else {
+        dim3 grid((N + 127) / 128, H, B);
+        dsa_bwd_apply_kernel<CH, P, false><<<grid, 128, smem, st>>>(qkvv, ldq, dy, lddy, gamma, EF, inv_n, A, dGhat, rqk,
+                                                                    dKV, dqh, dqkvv, lddq, N, C);
+    }
     return (int)cudaGetLastError();
 }
 
