@@ -1248,6 +1248,21 @@ FCD_API int fcd_dsa_fwd(const void* qkvv, long long ldq, const float* EF, const 
     FCD_LAUNCH_CHECK();
 }
 
+// dEF [N][P] = sum over samples and channels of k (x) dKP + v_SA (x) dVP: a PARAMETER gradient that nothing else in
+// the backward pass reads, so the host may launch it on a side stream (dKV from fcd_dsa_bwd must stay alive until then).
+FCD_API int fcd_dsa_bwd_ef(const void* qkvv, long long ldq, const float* dKV, float* dEF, int B, int N, int C, int P,
+                           cudaStream_t st) {
+    if (P % 4 || dEF == nullptr) return -1;
+    if (N <= 1024) {
+        const long long tot = (long long)N * (P / 4) * 8;
+        dsa_bwd_ef_small_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    } else {
+        const long long tot = (long long)((N + 3) / 4) * (P / 4);
+        dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
+    }
+    FCD_LAUNCH_CHECK();
+}
+
 // Backward of fcd_dsa_fwd w.r.t. qkvv, EF, temperature(2), gamma.  (dt = dy passes straight to fcd_ln_bwd.)
 // dtemp / dtemp2 [H], dgamma [C], dEF [N][P] are overwritten (H <= 256).
 // work: dqh [B*N][C] fp32, dKV [B][2][C][P], dGhat [B][H][c][c], rqk [B][2][C], gpart 2*148*2*Cp floats.
@@ -1290,12 +1305,6 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
         int rc = run();
         if (rc != 0) return rc;
     }
-    if (N <= 1024) {
-        const long long tot = (long long)N * (P / 4) * 8;
-        dsa_bwd_ef_small_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
-    } else {
-        const long long tot = (long long)((N + 3) / 4) * (P / 4);
-        dsa_bwd_ef_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)qkvv, ldq, dKV, dEF, B, N, C, P);
-    }
-    FCD_LAUNCH_CHECK();
+    if (dEF == nullptr) FCD_LAUNCH_CHECK();        // the caller runs fcd_dsa_bwd_ef itself (off the critical path)
+    return fcd_dsa_bwd_ef(qkvv, ldq, dKV, dEF, B, N, C, P, st);
 }

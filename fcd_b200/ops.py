@@ -934,6 +934,7 @@ class DSAFn(Function):
              A=A, Ad=Ad, KV=KV, xca=xca, tsa=tsa, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
         ctx.save_for_backward(qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale)
         ctx.cfg = (C, H, P, float(sa_drop), int(seed), Cp, (B, D, Hs, W), tuple(temperature.shape))
+        ctx.ef_param = EF if isinstance(EF, torch.nn.Parameter) else None
         return y
 
     @staticmethod
@@ -953,15 +954,26 @@ class DSAFn(Function):
         rqk = torch.empty((B, 2, C), **f32)
         gpart = torch.empty((512, 2, Cp), **f32)
         dqkvv = torch.empty_like(qkvv, memory_format=torch.contiguous_format)
-        dEF = torch.empty((N, P), **f32)
         dtemp = torch.empty((H,), **f32)
         dtemp2 = torch.empty((H,), **f32)
         dgamma = torch.empty((C,), **f32)
+        # dEF is a parameter gradient nothing else in backward reads: like the conv weight gradients it leaves the
+        # critical path (the transformer stacks are latency chains) when autograd will simply adopt it as .grad
+        EFp = ctx.ef_param
+        ef_side = (EFp is not None and EFp.is_leaf and EFp.grad is None
+                   and not getattr(EFp, "_backward_hooks", None))
+        dEF = None if ef_side else torch.empty((N, P), **f32)
         call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
              gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed,
              seed_dev=step_counter(dev) if sa_drop > 0 else None, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
              xca=xca, tsa=tsa, part=part, dqh=dqh, dKV=dKV, dGhat=dGhat, rqk=rqk, gpart=gpart, dqkvv=dqkvv,
              lddq=dqkvv.shape[4], dEF=dEF, dtemp=dtemp, dtemp2=dtemp2, dgamma=dgamma, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
+        if ef_side:
+            def ef_work():
+                out = torch.empty((N, P), **f32)
+                call("fcd_dsa_bwd_ef", qkvv=qkvv, ldq=ld(qkvv), dKV=dKV, dEF=out, B=B, N=N, C=C, P=P)
+                return out
+            dEF = _off_critical_path(ef_work, qkvv, dKV)
         return (dqkvv, dy, dEF, dtemp.view(tshape), dtemp2.view(tshape), dgamma, None, None, None, None, None, None)
 
 

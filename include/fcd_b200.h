@@ -185,6 +185,10 @@ FCD_API int fcd_dsa_bwd(const void* qkvv, long long ldq, const void* dy, long lo
                         float* part, float* dqh, float* dKV, float* dGhat, float* rqk, float* gpart, void* dqkvv,
                         long long lddq, float* dEF, float* dtemp, float* dtemp2, float* dgamma, int B, int N, int C,
                         int Cp, int H, int P, cudaStream_t stream);
+/* dEF alone (fcd_dsa_bwd with dEF == NULL skips it): a parameter gradient, launchable on a side stream once
+ * fcd_dsa_bwd has produced dKV [B][2][C][P]. */
+FCD_API int fcd_dsa_bwd_ef(const void* qkvv, long long ldq, const float* dKV, float* dEF, int B, int N, int C, int P,
+                           cudaStream_t stream);
 
 /* ---- MONAI SubpixelUpsample tail: pixelshuffle x2 + pad(1,0)x3 + AvgPool3d(2,1) (+ skip add / concat write)
  *      (conv_blocks.py:727-735, 771; segresnet_dsa.py:133-141, 217).  src channels are ordered tap*Cq + c. ---- */
