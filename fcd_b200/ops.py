@@ -361,6 +361,15 @@ def _tc_nslice_nseg(B, D, H, W, K, N, k, stride, pad, bias, cin_seg, Co, Ci):
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, 64, 32)
 
 
+USE_PW = os.environ.get("FCD_USE_PW", "1") != "0"
+
+
+def _pw_ok(M, K, N, k, stride, pad, bias):
+    """1x1x1 stride-1 conv without bias on a big volume with <= 32 channels each side: the pointwise kernel."""
+    return bool(USE_PW and k == 1 and stride == 1 and pad == 0 and bias is None
+                and _lib.lib().fcd_pw_conv_ok(M, K, N))
+
+
 def _w32(weight):
     w = weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
@@ -425,6 +434,9 @@ class ConvFn(Function):
                 call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                      ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp,
                      N=32, flip=0, nseg=ns2)
+        elif _pw_ok(B * D * H * W, Kp, Np, k, stride, pad, bias):
+            call("fcd_pw_conv", A=x, lda=ld(x), Wf=_w32(weight), sn=Ci, sk=1, Nr=Co, Kr=Ci, kseg=seg, ksegpad=segpad,
+                 nsg=Co, nsgpad=Np, C=y, ldc=Np, M=B * D * H * W, K=Kp, N=Np)
         else:
             wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
             _igemm(x, wp, y, _vpad(bias, Np), B, (D, H, W), (Do, Ho, Wo), Kp, Np, k, stride, pad, 0)
@@ -458,6 +470,10 @@ class ConvFn(Function):
                     call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
                          kseg=Co, ksegpad=Np, nsg=32, nsgpad=32, C=dx[..., 32 * i:], ldc=Kp, part=None, Bn=B, D=D, H=H,
                          W=W, K=Np, N=32, flip=1, nseg=ns2)
+            elif _pw_ok(B * D * H * W, Np, Kp, k, stride, pad, None):
+                # dX rows = dY rows x W: the same pointwise kernel with the weight read transposed
+                call("fcd_pw_conv", A=dy, lda=ld(dy), Wf=_w32(weight), sn=1, sk=Ci, Nr=Ci, Kr=Co, kseg=Co, ksegpad=Np,
+                     nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, M=B * D * H * W, K=Np, N=Kp)
             else:
                 wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
                 _igemm(dy, wt, dx, None, B, (Do, Ho, Wo), (D, H, W), Np, Kp, k, stride, pad, 1)

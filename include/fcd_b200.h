@@ -84,6 +84,14 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
                           int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream);
 FCD_API int fcd_tcf_error(void);
 
+/* Pointwise (1x1x1, stride 1, no bias) conv on >= 65536 voxels with 16/32 (padded) channels each side: UnetResBlock's
+ * residual conv3 (conv_blocks.py:420-424) on the two top levels, forward and data gradient (A = dY, sn = 1, sk = Cin).
+ * W(n, k) = Wf[n*sn + k*sk] for real n < Nr, k < Kr under the concat-segment maps of fcd_pack_weight. */
+FCD_API int fcd_pw_conv_ok(long long M, int K, int N);
+FCD_API int fcd_pw_conv(const void* A, long long lda, const float* Wf, long long sn, long long sk, int Nr, int Kr,
+                        int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, long long M, int K, int N,
+                        cudaStream_t stream);
+
 /* tcgen05/TMEM weight gradient of the same 3x3x3 stride-1 pad-1 convs (autograd of conv_blocks.py:393-416).  S: the
  * operand read shifted (conv input, CS channels from channel k_off), U: the unshifted one (output gradient, CU
  * channels from n_off); CS, CU in {16, 32}; wider layers are cut into nns x nks slices of CU x CS channels that run as

@@ -429,6 +429,35 @@ def test_dsa_dropout_is_reproducible_and_unbiased(ops):
     close(g.grad, fd, rel=2e-2, mx=5e-2, what="dropout bwd mask")
 
 
+def test_keep_scale_masks(ops):
+    """fcd_keep_scale (nn.Dropout3d / attn_drop masks in one launch): values in {0, 1/(1-p)}, unbiased, a new mask per
+    call and per step-counter tick, and dropout3d's backward applies the forward's mask."""
+    dev = torch.device("cuda:0")
+    p = 0.25
+    m = ops.keep_scale((64, 1024), p, dev)
+    vals = torch.unique(m)
+    assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.0 / (1.0 - p)) < 1e-6
+    assert abs(float(m.mean()) - 1.0) < 2e-2
+    m2 = ops.keep_scale((64, 1024), p, dev)
+    assert not torch.equal(m, m2)
+    # same host seed, different device step counter -> different mask (what a CUDA-graph replay sees)
+    out_a = torch.empty(4096, device=dev)
+    out_b = torch.empty(4096, device=dev)
+    from fcd_b200 import _lib
+    _lib.call("fcd_keep_scale", out=out_a, n=4096, p=p, seed=1234, seed_dev=ops.step_counter(dev))
+    ops.tick(dev)
+    _lib.call("fcd_keep_scale", out=out_b, n=4096, p=p, seed=1234, seed_dev=ops.step_counter(dev))
+    assert not torch.equal(out_a, out_b)
+    out_c = torch.empty(4096, device=dev)
+    _lib.call("fcd_keep_scale", out=out_c, n=4096, p=p, seed=1234, seed_dev=ops.step_counter(dev))
+    assert torch.equal(out_b, out_c)
+    x = cl(ops, rnd(2, 16, 4, 4, 8), True)
+    y = ops.dropout3d(x, 0.5, True)
+    y.backward(torch.ones_like(y))
+    scale = (y.float().abs().sum(dim=(1, 2, 3)) > 0).float() * 2.0          # per (b, c): kept channels carry 1/(1-p) = 2
+    close(x.grad.float(), scale[:, None, None, None, :].expand_as(x.grad), rel=0, mx=0, what="dropout3d bwd mask")
+
+
 def test_dsa_dropout_mask_changes_across_graph_replays(ops):
     """Kernel arguments are frozen in a captured CUDA graph, so the host seed alone would repeat the mask on every
     replay; the device step counter (ops.tick, captured with the step) must give a new mask per replay while the
