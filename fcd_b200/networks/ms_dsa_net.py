@@ -60,12 +60,17 @@ class BaseUNet(nn.Module):
     def forward_cl(self, out):
         """Forward from a channels-last bf16 batch [B,D,H,W,16] (what fcd_sw_gather produces)."""
         ops.prepack_weights(out.device)
+        if self.training:
+            ops.tick(out.device)
         feats = []
         for i, enc in enumerate(self.encoders):
             out = enc(out)
-            feats.append(out)
             if i != self.depth - 1:
-                out = ops.max_pool2(out)
+                # pool + skip through one node: the two gradients are summed inside the pool's backward kernel
+                out, skip = ops.pool_and_skip(out)
+                feats.append(skip)
+            else:
+                feats.append(out)
         for i, dec in enumerate(self.decoders):
             out = dec(out, feats[-(i + 2)])
         return ops.out_conv(out, self.final_conv.weight, self.final_conv.bias)
