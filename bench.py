@@ -222,6 +222,13 @@ def main():
         reducer.allreduce()
         opt.step()
     torch.cuda.synchronize()
+    # per-launch durations for the roofline object: one eager step with CUDA events around every C-ABI call, with the
+    # stream overlap (side-stream weight gradients, branch streams) switched OFF so that every launch is timed alone
+    # on its launching stream -- inside the overlapped step a launch shares the SMs with other streams' kernels
+    from fcd_b200 import ops as _ops
+    saved_overlap = (_ops.WGRAD_OVERLAP, _ops.BRANCH_OVERLAP)
+    _ops.WGRAD_OVERLAP = _ops.BRANCH_OVERLAP = False
+    reducer.enabled = False
     prof = _lib.Profiler()
     _lib.set_profiler(prof)
     opt.zero_grad(set_to_none=True)
@@ -229,6 +236,9 @@ def main():
     _lib.set_profiler(None)
     agg = prof.summary()
     gpu_launches = prof.launches
+    _ops.WGRAD_OVERLAP, _ops.BRANCH_OVERLAP = saved_overlap
+    reducer.enabled = True
+    reducer.allreduce()
     opt.step()
 
     # ---- CUDA graph of forward + loss + backward (static input buffers, static gradient tensors)
@@ -361,6 +371,7 @@ def main():
                                "note": "ncu's hmma cycles-active counter is a work counter on this part (DESIGN.md "
                                        "3.1): utilisation is quoted from FLOPs / CUDA-event time only"},
             "peak_source": pk["source"] + " (sustained bf16)",
+            "timing": "CUDA events around each launch in one serialized eager step (stream overlap off)",
             "share_of_step": tc_ms / step_ms_eager if step_ms_eager > 0 else None, "launches": tc_calls,
             "conv_family": {"kernels": "fcd_conv3_tc + fcd_wgrad3_tc + fcd_igemm(_splitk) + fcd_wgrad(+reduce, pack)",
                             "achieved": tf(conv_fl, conv_ms), "frac": (tf(conv_fl, conv_ms) / pk["tf_sust"]) if conv_ms > 0 else None,
