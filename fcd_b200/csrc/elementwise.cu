@@ -294,7 +294,12 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
     }
     const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
     const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
-    const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
+    // x1 == nullptr: xhat1 is RECONSTRUCTED from the saved output, xhat1 = act^-1(y) - xhat2 (no affine, no residual,
+    // slope > 0: the host checks), so the backward never reads (and the forward never keeps) the conv output x1:
+    // one 2E-byte stream less in each of the two passes of this HBM-bound pair
+    const bool recon = (x1 == nullptr);
+    const float inv_slope = 1.f / slope;
+    const bf16* p1 = recon ? nullptr : x1 + (long long)b * S * ld1 + c8 * 8;
     const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
     for (long long s = s0 + r0; s < s1; s += 2LL * rstep) {      // 2 rows x up to 4 streams of 16 B loads in flight
         bf16x8 vg[2], vy[2], v1[2], v2[2];
@@ -304,28 +309,41 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
             if (rr < s1) {
                 vg[u] = ld8_stream(pdy + rr * lddy);
                 if (py) vy[u] = ld8_stream(py + rr * ldy);
-                v1[u] = ld8_stream(p1 + rr * ld1);
+                if (p1) v1[u] = ld8_stream(p1 + rr * ld1);
                 if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
             }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (s + u * rstep >= s1) break;
-            float g[8], f[8];
+            float g[8], f[8], xh[8];
             unpack8(vg[u], g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xh[k] = 0.f;
             if (py) {
                 unpack8(vy[u], f);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) g[k] = f[k] > 0.f ? g[k] : g[k] * slope;
+                for (int k = 0; k < 8; ++k) {
+                    g[k] = f[k] > 0.f ? g[k] : g[k] * slope;
+                    xh[k] = f[k] > 0.f ? f[k] : f[k] * inv_slope;          // pre-activation sum (used when recon)
+                }
             }
-            unpack8(v1[u], f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], (f[k] - m1[k]) * i1[k], a1[k]); }
             if (p2) {
                 unpack8(v2[u], f);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a2[k] = fmaf(g[k], (f[k] - m2[k]) * i2[k], a2[k]);
+                for (int k = 0; k < 8; ++k) {
+                    const float x2h = (f[k] - m2[k]) * i2[k];
+                    a2[k] = fmaf(g[k], x2h, a2[k]);
+                    xh[k] -= x2h;
+                }
             }
+            if (p1) {
+                unpack8(v1[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xh[k] = (f[k] - m1[k]) * i1[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], xh[k], a1[k]); }
         }
     }
     __shared__ float sh[256 * 24];
@@ -449,7 +467,8 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
         const int c = c8 * 8 + q;
         const float* kk = coef + ((long long)b * C + c) * 6;
         const float m1 = mean1[b * C + c], i1 = rstd1[b * C + c];
-        kA1[q] = kk[0]; cX1[q] = kk[2] * i1; cB1[q] = kk[1] - kk[2] * i1 * m1;
+        if (x1) { kA1[q] = kk[0]; cX1[q] = kk[2] * i1; cB1[q] = kk[1] - kk[2] * i1 * m1; }
+        else { kA1[q] = kk[0]; cX1[q] = kk[2]; cB1[q] = kk[1]; }      // reconstructed xhat1 is used directly
         if (x2) {
             const float m2 = mean2[b * C + c], i2 = rstd2[b * C + c];
             kA2[q] = kk[3]; cX2[q] = kk[5] * i2; cB2[q] = kk[4] - kk[5] * i2 * m2;
@@ -460,7 +479,14 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
     const long long r0 = gtid / C8, rstep = gstride / C8;     // gstride is a multiple of C8: c8 fixed per thread
     const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
     const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
-    const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
+    const bf16* p1 = x1 ? x1 + (long long)b * S * ld1 + c8 * 8 : nullptr;      // nullptr: reconstruct xhat1 from y
+    const float inv_slope = 1.f / slope;
+    float m2v[8], i2v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        m2v[q] = x2 ? mean2[b * C + c8 * 8 + q] : 0.f;
+        i2v[q] = x2 ? rstd2[b * C + c8 * 8 + q] : 0.f;
+    }
     const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
     bf16* q1 = dx1 + (long long)b * S * ldd1 + c8 * 8;
     bf16* q2 = x2 ? dx2 + (long long)b * S * ldd2 + c8 * 8 : nullptr;
@@ -473,7 +499,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
             if (rr < S) {
                 vg[u] = ld8_stream(pdy + rr * lddy);
                 if (py) vy[u] = ld8_stream(py + rr * ldy);
-                v1[u] = ld8_stream(p1 + rr * ld1);
+                if (p1) v1[u] = ld8_stream(p1 + rr * ld1);
                 if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
                 if (qr && acc_res) vr[u] = ld8(qr + rr * lddr);
             }
@@ -482,23 +508,31 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
         for (int u = 0; u < 2; ++u) {
             const long long rr = r + u * rstep;
             if (rr >= S) break;
-            float g[8], f[8], o[8];
+            float g[8], f[8], o[8], xh[8];
             unpack8(vg[u], g);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xh[q] = 0.f;
             if (py) {
                 unpack8(vy[u], f);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) g[q] = f[q] > 0.f ? g[q] : g[q] * slope;
+                for (int q = 0; q < 8; ++q) {
+                    g[q] = f[q] > 0.f ? g[q] : g[q] * slope;
+                    xh[q] = f[q] > 0.f ? f[q] : f[q] * inv_slope;
+                }
             }
-            unpack8(v1[u], f);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = fmaf(kA1[q], g[q], -fmaf(cX1[q], f[q], cB1[q]));
-            st8(q1 + rr * ldd1, pack8(o));
             if (p2) {
                 unpack8(v2[u], f);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = fmaf(kA2[q], g[q], -fmaf(cX2[q], f[q], cB2[q]));
+                for (int q = 0; q < 8; ++q) {
+                    o[q] = fmaf(kA2[q], g[q], -fmaf(cX2[q], f[q], cB2[q]));
+                    xh[q] -= (f[q] - m2v[q]) * i2v[q];
+                }
                 st8(q2 + rr * ldd2, pack8(o));
             }
+            if (p1) unpack8(v1[u], xh);                               // the real x1 (cX1/cB1 fold mean and rstd in)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = fmaf(kA1[q], g[q], -fmaf(cX1[q], xh[q], cB1[q]));
+            st8(q1 + rr * ldd1, pack8(o));
             if (qr) {
                 if (acc_res) {
                     unpack8(vr[u], f);
@@ -640,6 +674,8 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
                          long long lddr, int acc_res, int B, long long S, int C, int nchunk, int mode, float slope,
                          cudaStream_t st) {
     if (C % 8 || C / 8 > 256) return -1;
+    // x1 == NULL: xhat1 is reconstructed from y (see norm_bwd_stats_kernel); only without affine and residual terms
+    if (x1 == nullptr && (y == nullptr || !(slope > 0.f) || gamma1 != nullptr || dres != nullptr)) return -1;
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 g1(nchunk, B);
     norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,

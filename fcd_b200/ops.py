@@ -689,6 +689,9 @@ def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0
     return mean, rstd
 
 
+NORM_RECON = os.environ.get("FCD_NORM_RECON", "1") != "0"
+
+
 class NormActFn(Function):
     """y = act( norm(x1)*gamma + beta  [+ norm(x2)]  [+ res] ),  act = LeakyReLU(slope) (slope=1: identity, 0: ReLU).
 
@@ -723,7 +726,11 @@ class NormActFn(Function):
         call("fcd_norm_apply", x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1, gamma1=g, beta1=b, x2=x2,
              ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2, res=res,
              ldr=ld(res) if res is not None else 0, y=y, ldy=C, B=B, S=S, C=C, slope=slope)
-        ctx.save_for_backward(x1, x2, y if slope != 1.0 else None, mean1, rstd1, mean2, rstd2, g)
+        # Without affine / residual terms and with an invertible activation the normalised input is recoverable from
+        # the saved output (xhat1 = act^-1(y) - xhat2): the backward then never reads x1, and x1 (a conv output) is
+        # not kept alive for it -- one tensor stream less in both passes of the HBM-bound backward, and less memory.
+        recon = NORM_RECON and gamma is None and res is None and 0.0 < slope != 1.0
+        ctx.save_for_backward(None if recon else x1, x2, y if slope != 1.0 else None, mean1, rstd1, mean2, rstd2, g)
         ctx.cfg = (mode, slope, res is not None, gamma is not None, None if gamma is None else gamma.numel())
         return y
 
@@ -732,21 +739,24 @@ class NormActFn(Function):
         x1, x2, y, mean1, rstd1, mean2, rstd2, g = ctx.saved_tensors
         mode, slope, has_res, has_affine, ntrue = ctx.cfg
         dy = rows(dy)
-        B, D, H, W, C = x1.shape
+        shape_src = x1 if x1 is not None else y
+        B, D, H, W, C = shape_src.shape
+        dev = shape_src.device
         S = D * H * W
         nchunk = _nchunk(B, S)
-        part = torch.empty((B, nchunk, 3, C), dtype=torch.float32, device=x1.device)
-        coef = torch.empty((B, C, 6), dtype=torch.float32, device=x1.device)
-        dx1 = torch.empty((B, D, H, W, C), dtype=BF16, device=x1.device)
+        part = torch.empty((B, nchunk, 3, C), dtype=torch.float32, device=dev)
+        coef = torch.empty((B, C, 6), dtype=torch.float32, device=dev)
+        dx1 = torch.empty((B, D, H, W, C), dtype=BF16, device=dev)
         dx2 = torch.empty_like(dx1) if x2 is not None else None
         dres = torch.empty_like(dx1) if (has_res and ctx.needs_input_grad[2]) else None
         dgamma = dbeta = None
         if has_affine:
-            dgamma = torch.empty((C,), dtype=torch.float32, device=x1.device)
-            dbeta = torch.empty((C,), dtype=torch.float32, device=x1.device)
-        nin = 2 + (y is not None) + (x2 is not None)
+            dgamma = torch.empty((C,), dtype=torch.float32, device=dev)
+            dbeta = torch.empty((C,), dtype=torch.float32, device=dev)
+        nin = 1 + (x1 is not None) + (y is not None) + (x2 is not None)
         _lib.note_work(None, 0.0, 2.0 * B * S * C * (2 * nin + 1 + (x2 is not None) + (dres is not None)))
-        call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=x1, ld1=ld(x1), mean1=mean1, rstd1=rstd1,
+        call("fcd_norm_bwd", dy=dy, lddy=ld(dy), y=y, ldy=C, x1=x1, ld1=ld(x1) if x1 is not None else 0, mean1=mean1,
+             rstd1=rstd1,
              gamma1=g if has_affine else None, x2=x2, ld2=ld(x2) if x2 is not None else 0, mean2=mean2, rstd2=rstd2,
              part=part, coef=coef, dgamma=dgamma, dbeta=dbeta, dx1=dx1, ldd1=C, dx2=dx2, ldd2=C, dres=dres, lddr=C,
              acc_res=0, B=B, S=S, C=C, nchunk=nchunk, mode=mode, slope=slope)

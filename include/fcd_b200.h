@@ -116,7 +116,9 @@ FCD_API int fcd_maxpool2_bwd(const void* x, const void* y, const void* dy, void*
 
 /* ---- InstanceNorm3d / BatchNorm3d / GroupNorm(2 ch per group) fused with LeakyReLU/ReLU and the residual add
  *      (conv_blocks.py:439-452, 56; ms_dsa_net.py:217; MONAI ResBlock).  mode: 0 instance, 1 batch,
- *      2 group-of-2. ---- */
+ *      2 group-of-2. ---- 
+ * fcd_norm_bwd with x1 == NULL: xhat1 is reconstructed from the saved output, xhat1 = act^-1(y) - xhat2 (requires y, slope > 0, no
+ * gamma1, no dres): the conv output x1 is then neither read by the backward nor kept by the forward. */
 FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean, float* rstd, int B, long long S,
                            int C, int nchunk, int mode, float eps, float* running_mean, float* running_var,
                            int crun, float momentum, cudaStream_t stream);

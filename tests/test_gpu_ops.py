@@ -147,6 +147,35 @@ def test_maxpool(ops):
     close(ops.to_ncdhw(xc.grad, 16), gx, rel=0, mx=0, what="maxpool bwd")
 
 
+@pytest.mark.parametrize("two", [False, True])
+def test_norm_backward_reconstructs_xhat_from_the_output(ops, two):
+    """Without affine / residual terms and with LeakyReLU the backward does not read (or keep) x1: xhat1 = act^-1(y) -
+    xhat2.  Same gradients as the path that reads x1, and as torch."""
+    C, slope = 16, 0.01
+    x1 = (rnd(2, C, 6, 8, 10, scale=2.0) + 0.5).to(torch.bfloat16).float()
+    x2 = (rnd(2, C, 6, 8, 10, scale=1.5, seed=5) - 0.3).to(torch.bfloat16).float()
+    r1, r2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    z = F.instance_norm(r1, eps=1e-5) + (F.instance_norm(r2, eps=1e-5) if two else 0.0)
+    ref = F.leaky_relu(z, slope)
+    dy = rnd(*ref.shape, seed=3)
+    grads_ref = torch.autograd.grad(ref, [r1, r2] if two else [r1], dy)
+    out = {}
+    for recon in (True, False):
+        ops.NORM_RECON = recon
+        try:
+            c1, c2 = cl(ops, x1, True), cl(ops, x2, True)
+            y = ops.norm_act(c1, c2 if two else None, None, None, None, "instance", slope)
+            y.backward(ops.to_channels_last(dy, C))
+            out[recon] = (ops.to_ncdhw(c1.grad, C), ops.to_ncdhw(c2.grad, C) if two else None)
+        finally:
+            ops.NORM_RECON = True
+    close(out[True][0], grads_ref[0], rel=1.5e-2, mx=6e-2, what="recon dx1 vs torch")
+    close(out[True][0], out[False][0], rel=1.5e-2, mx=6e-2, what="recon dx1 vs x1 path")
+    if two:
+        close(out[True][1], grads_ref[1], rel=1.5e-2, mx=6e-2, what="recon dx2 vs torch")
+        close(out[True][1], out[False][1], rel=1.5e-2, mx=6e-2, what="recon dx2 vs x1 path")
+
+
 def test_pool_and_skip_sums_both_gradients_in_the_pool_pass(ops):
     """ops.pool_and_skip: (max_pool(x), x) with dx = pool_bwd(d_pooled) + d_skip formed inside the pool's backward
     kernel; the skip gradient arrives as the right half of a concat-buffer gradient (a strided channel slice)."""

@@ -61,6 +61,16 @@ for B, S, C in [(2, 128, 16), (2, 64, 32), (2, 32, 64)]:
                             ldd1=C, dx2=dx2, ldd2=C, dres=None, lddr=0, acc_res=0, B=B, S=S ** 3, C=C, nchunk=nchunk,
                             mode=0, slope=0.01))
     report("norm_bwd (2 inputs) " + tag, ms, (4 + 4 + 2) * 2 * E)
+    ms = bench(lambda: call("fcd_norm_bwd", dy=dy, lddy=C, y=y, ldy=C, x1=None, ld1=0, mean1=mean, rstd1=rstd, gamma1=None,
+                            x2=None, ld2=0, mean2=None, rstd2=None, part=part, coef=coef, dgamma=None, dbeta=None, dx1=dx1,
+                            ldd1=C, dx2=None, ldd2=0, dres=None, lddr=0, acc_res=0, B=B, S=S ** 3, C=C, nchunk=nchunk,
+                            mode=0, slope=0.01))
+    report("norm_bwd (1 input, xhat from y) " + tag, ms, (2 + 2 + 1) * 2 * E)
+    ms = bench(lambda: call("fcd_norm_bwd", dy=dy, lddy=C, y=y, ldy=C, x1=None, ld1=0, mean1=mean, rstd1=rstd, gamma1=None,
+                            x2=x2, ld2=C, mean2=mean, rstd2=rstd, part=part, coef=coef, dgamma=None, dbeta=None, dx1=dx1,
+                            ldd1=C, dx2=dx2, ldd2=C, dres=None, lddr=0, acc_res=0, B=B, S=S ** 3, C=C, nchunk=nchunk,
+                            mode=0, slope=0.01))
+    report("norm_bwd (2 inputs, xhat1 from y) " + tag, ms, (3 + 3 + 2) * 2 * E)
     if S >= 64:
         yp = torch.empty(B, S // 2, S // 2, S // 2, C, dtype=torch.bfloat16, device=dev)
         ms = bench(lambda: call("fcd_maxpool2_fwd", x=x, y=yp, B=B, Do=S // 2, Ho=S // 2, Wo=S // 2, C=C))
