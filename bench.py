@@ -418,15 +418,19 @@ def main():
                     vol_d.copy_(vol, non_blocking=True)
                     sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5, label_mode="argmax")
                 barrier()
-                n_vol = 5
+                n_vol = 8
+                import time as _time
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                per_vol = []
                 e0.record()
                 for _ in range(n_vol):
+                    t0 = _time.perf_counter()
                     vol_d.copy_(vol, non_blocking=True)                        # H2D of the volume (pinned)
                     _, lab = sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5,
                                                       label_mode="argmax")
                     lab_h.copy_(lab, non_blocking=True)                        # D2H of the label map (pinned)
                     torch.cuda.current_stream().synchronize()
+                    per_vol.append(round((_time.perf_counter() - t0) * 1e3, 2))
                 e1.record()
                 barrier()
             ms = e0.elapsed_time(e1)
@@ -437,7 +441,7 @@ def main():
             aux = {"metric": "ms_dsa_net_sliding_window_vols_per_s", "value": n_vol / (ms / 1e3), "unit": "vols/s",
                    "workload": "2ch 256x256x192, roi 128^3, overlap 0.5, 18 windows sharded over ranks (all windows "
                                "of a rank in one forward), H2D volume + D2H uint8 label map inside the timed region",
-                   "fg_fraction": float(lab_h.float().mean())}
+                   "ms_per_vol_rank0": per_vol, "fg_fraction": float(lab_h.float().mean())}
         except Exception as e:
             aux = {"error": f"{type(e).__name__}: {e}"[:300]}
 
