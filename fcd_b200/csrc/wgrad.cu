@@ -255,7 +255,49 @@ __device__ __forceinline__ void pack_tile(const PackJob& j, int n0, int k0, cons
     constexpr int NE = PACK_NB * PACK_KB * T;
     const float* __restrict__ src = j.src;
     const int sn = (int)j.sn, sk = (int)j.sk, st = (int)j.st;
-    if (j.sn < j.sk) {                                  // n is the faster source axis (data-gradient packs)
+    // Interior tiles of 3x3x3 weights (all 8 n and 64 k real and contiguous in the source: the bulk of the bytes) are
+    // read as float4 with almost no index math; ragged / segmented tiles take the generic element loop below.
+    bool fast = false;
+    if constexpr (T == 27) {
+        fast = st == 1 && kmap[0] >= 0 && kmap[PACK_KB - 1] == kmap[0] + PACK_KB - 1 && nmap[0] >= 0 &&
+               nmap[PACK_NB - 1] == nmap[0] + PACK_NB - 1;
+        if (fast && sk == T) {                          // k next to the taps: 8 runs of 64 * 27 floats
+            fast = (sn % 4) == 0 && ((reinterpret_cast<uintptr_t>(src + (long long)nmap[0] * sn + kmap[0] * T)) & 15) == 0;
+            if (fast) {
+                constexpr int RUN = PACK_KB * T;        // == the shared-memory pitch of one n (TP == T)
+                for (int nn = 0; nn < PACK_NB; ++nn) {
+                    const float* base = src + (long long)(nmap[0] + nn) * sn + kmap[0] * T;
+                    for (int i = threadIdx.x * 4; i < RUN; i += 1024) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(base + i));
+                        uint2 o;
+                        o.x = pack_bf16x2_raw(__float2bfloat16(v.x), __float2bfloat16(v.y));
+                        o.y = pack_bf16x2_raw(__float2bfloat16(v.z), __float2bfloat16(v.w));
+                        *reinterpret_cast<uint2*>(tile + nn * RUN + i) = o;
+                    }
+                }
+            }
+        } else if (fast && sn == T) {                   // n next to the taps: 64 runs of 8 * 27 floats
+            fast = (sk % 4) == 0 && ((reinterpret_cast<uintptr_t>(src + (long long)kmap[0] * sk + nmap[0] * T)) & 15) == 0;
+            if (fast) {
+                constexpr int RUN4 = PACK_NB * T / 4;   // float4 per run (216 / 4)
+                for (int idx = threadIdx.x; idx < PACK_KB * RUN4; idx += 256) {
+                    const int kk = idx / RUN4, j0 = (idx % RUN4) * 4;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)(kmap[0] + kk) * sk + nmap[0] * T + j0));
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int jj = j0 + u, nn = jj / T, t = jj % T;
+                        tile[(nn * PACK_KB + kk) * TP + t] = __float2bfloat16(vv[u]);
+                    }
+                }
+            }
+        } else {
+            fast = false;
+        }
+    }
+    if (fast) {
+        // tile filled above
+    } else if (j.sn < j.sk) {                           // n is the faster source axis (data-gradient packs)
         for (int e = threadIdx.x; e < NE; e += 256) {
             const int t = e % T, r = e / T;
             const int nn = r % PACK_NB, kk = r / PACK_NB;
