@@ -414,12 +414,18 @@ def main():
             # forward (18 at N=1, 3 at N=8) -- the deep levels are latency-bound, so they amortise over the batch
             sw_bs = 18
             with torch.no_grad():
-                for _ in range(2):
+                for _ in range(4):            # warm-up runs the timed body (incl. the pinned D2H and the sync)
                     vol_d.copy_(vol, non_blocking=True)
-                    sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5, label_mode="argmax")
+                    _, lab = sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5,
+                                                      label_mode="argmax")
+                    lab_h.copy_(lab, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
                 barrier()
                 n_vol = 8
+                import gc
                 import time as _time
+                gc.collect()
+                gc.disable()          # a generational collection inside the loop showed up as a 7-80 ms stall on one volume
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 per_vol = []
                 e0.record()
@@ -432,6 +438,7 @@ def main():
                     torch.cuda.current_stream().synchronize()
                     per_vol.append(round((_time.perf_counter() - t0) * 1e3, 2))
                 e1.record()
+                gc.enable()
                 barrier()
             ms = e0.elapsed_time(e1)
             if world > 1:
