@@ -93,6 +93,7 @@ class _PackCache:
     def __init__(self):
         self.jobs = {}          # key -> [param_ref, args, dst, version]
         self.table = {}         # device -> (njobs_at_build, jobs tensor, nblocks, keys)
+        self.dirty = {}         # device -> a grad-enabled forward ran since the last pack (see refresh)
 
     @staticmethod
     def _param_of(w):
@@ -160,8 +161,15 @@ class _PackCache:
             host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture
             dev_tab = host.to(device, non_blocking=True)
             tab = self.table[device.index] = (keys, dev_tab, blk, host, capturing)   # host: keep the pinned source alive
-        if not capturing and all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
+        # The version stamps cannot be trusted across an optimizer step: torch's FUSED optimizers update the
+        # parameters in place without bumping `_version`.  So a grad-enabled forward always re-packs (an optimizer step
+        # may have happened since the last one, 0.12 ms), and marks the copies dirty for the first no-grad forward
+        # that follows (evaluation right after training); only no-grad forwards with clean, unchanged parameters skip.
+        grad_mode = torch.is_grad_enabled()
+        if not capturing and not grad_mode and not self.dirty.get(device.index, False) \
+                and all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
             return
+        self.dirty[device.index] = grad_mode
         call("fcd_pack_weight_batched", jobs=tab[1], njobs=len(keys), nblocks=tab[2])
         for k in keys:
             self.jobs[k][3] = self.jobs[k][0]._version

@@ -276,6 +276,41 @@ def test_batched_weight_pack_matches_single_pack(ops):
         assert torch.equal(got, ref), f"batched pack differs for args {a}"
 
 
+def test_packed_weights_follow_a_fused_optimizer_step_in_eager_mode(ops):
+    """torch's fused optimizers update parameters WITHOUT bumping `_version`, so the packed bf16 copies cannot rely on
+    the version stamps: every grad-enabled forward of a network re-packs, and so does the first no-grad forward after
+    training.  A 1x1 conv on the implicit-GEMM path (packed weights) must see the updated weights."""
+    import torch.nn as nn
+    dev = torch.device("cuda:0")
+    conv = nn.Conv3d(64, 64, 1, bias=False).to(dev)
+    opt = torch.optim.AdamW(conv.parameters(), lr=0.05, fused=True)
+    x = ops.to_channels_last(rnd(1, 64, 4, 8, 8))
+
+    def fwd():
+        ops.prepack_weights(dev)                          # what every network does at the top of forward()
+        return ops.conv3d(x, conv.weight, None, k=1)
+
+    y0 = fwd()
+    v0 = conv.weight._version
+    y0.float().square().mean().backward()
+    opt.step()
+    w_new = conv.weight.detach().clone()
+    y1 = fwd()                                            # grad-enabled forward after the step
+    ref = F.conv3d(ops.to_ncdhw(x, 64), w_new.to(torch.bfloat16).float())
+    close(ops.to_ncdhw(y1, 64), ref, what="forward after fused optimizer step")
+    assert not torch.equal(y0, y1)
+    y1.float().square().mean().backward()
+    opt.step()
+    w_new2 = conv.weight.detach().clone()
+    with torch.no_grad():
+        y2 = fwd()                                        # evaluation right after training
+        y3 = fwd()
+    ref2 = F.conv3d(ops.to_ncdhw(x, 64), w_new2.to(torch.bfloat16).float())
+    close(ops.to_ncdhw(y2, 64), ref2, what="no-grad forward after fused optimizer step")
+    assert torch.equal(y2, y3)
+    print("fused AdamW bumped _version:", conv.weight._version != v0)
+
+
 def test_packed_weights_follow_parameter_updates_inside_cuda_graph(ops):
     """The mma.sync kernels read packed bf16 copies of the parameters (ops._PackCache).  A captured forward must
     re-pack on every replay: update the weight in place between replays and the output has to follow."""
