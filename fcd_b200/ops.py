@@ -94,6 +94,7 @@ class _PackCache:
         self.jobs = {}          # key -> [param_ref, args, dst, version]
         self.table = {}         # device -> (njobs_at_build, jobs tensor, nblocks, keys)
         self.dirty = {}         # device -> a grad-enabled forward ran since the last pack (see refresh)
+        self.covered = set()    # job keys that are part of a batched table
 
     @staticmethod
     def _param_of(w):
@@ -116,7 +117,9 @@ class _PackCache:
         job = self.jobs.get(key)
         if job is None:
             job = self.jobs[key] = [owner, args, torch.empty((T, Np, Kp), dtype=BF16, device=src.device), -1]
-        if job[3] != owner._version or job[0] is not owner:
+        # jobs the batched refresh does not cover yet (first forward of a network, ops used without a network) are
+        # re-packed on every use: their version stamp alone would miss a fused optimizer's update (see refresh)
+        if key not in self.covered or job[3] != owner._version or job[0] is not owner:
             job[0] = owner
             self._pack(src, job[2], args)
             job[3] = owner._version
@@ -161,6 +164,7 @@ class _PackCache:
             host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture
             dev_tab = host.to(device, non_blocking=True)
             tab = self.table[device.index] = (keys, dev_tab, blk, host, capturing)   # host: keep the pinned source alive
+            self.covered = {k for t in self.table.values() for k in t[0]}
         # The version stamps cannot be trusted across an optimizer step: torch's FUSED optimizers update the
         # parameters in place without bumping `_version`.  So a grad-enabled forward always re-packs (an optimizer step
         # may have happened since the last one, 0.12 ms), and marks the copies dirty for the first no-grad forward
