@@ -220,3 +220,79 @@ def test_sliding_window_batching_is_invariant():
     assert flips <= 5e-3
     if margin.numel():
         assert float(margin.max()) <= 2e-2 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_training_steps_eager_equal_cuda_graph(fused):
+    """Three optimizer steps of MS_DSA_NET run eagerly (kernels launched one by one, weight gradients / residual
+    branches / transformer stacks on their side streams) must leave the same parameters as three replays of the
+    captured CUDA graph of the same step.  Every kernel is deterministic, so the two schedules may only differ through
+    a capture-specific bug (stale packed weights, an unjoined stream, an argument frozen at capture time).  Run with
+    torch's fused AdamW (no `_version` bump) and the foreach one."""
+    import fcd_b200
+    from fcd_b200 import synthetic
+
+    def make():
+        params = fcd_b200.get_default_params()
+        params.update(model_type="ms_dsa_net", patch_size=(64,) * 3, loss="DiceCELoss")
+        torch.manual_seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model, params = fcd_b200.get_model(params)
+        model.apply(synthetic.initialize_weights)
+        model = model.to(DEV).train()
+        for m in model.modules():            # dropout seeds are host-drawn per eager step but frozen in a graph
+            if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+                m.p = 0.0
+        return model, fcd_b200.CombinedLoss(params, torch.device(DEV))
+
+    x, y = synthetic.make_batch(2, 2, 64, seed=3, device=torch.device(DEV))
+
+    def run(graphed):
+        model, loss_fn = make()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=fused)
+        losses = []
+
+        def fwd_bwd():
+            loss = loss_fn(model(x), y)
+            loss.backward()
+            return loss.detach()
+
+        if not graphed:
+            for _ in range(4):
+                opt.zero_grad(set_to_none=True)
+                losses.append(float(fwd_bwd()))
+                opt.step()
+        else:
+            opt.zero_grad(set_to_none=True)
+            losses.append(float(fwd_bwd()))             # step 0 eagerly (allocates the optimizer state)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):               # a throw-away warm-up on a side stream, then restore
+                state = [p.detach().clone() for p in model.parameters()]
+                bufs = [b.detach().clone() for b in model.buffers()]
+                fwd_bwd()
+                opt.zero_grad(set_to_none=True)
+                with torch.no_grad():
+                    for p, s in zip(model.parameters(), state):
+                        p.copy_(s)
+                    for b, s in zip(model.buffers(), bufs):
+                        b.copy_(s)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                static_loss = fwd_bwd()
+            for _ in range(3):
+                g.replay()
+                losses.append(float(static_loss))
+                opt.step()
+        torch.cuda.synchronize()
+        return losses, torch.cat([p.detach().flatten().float() for p in model.parameters()])
+
+    le, pe = run(False)
+    lg, pg = run(True)
+    assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
+    err = float((pe - pg).norm() / pe.norm())
+    assert err <= 1e-6, f"parameters after 4 steps differ between eager and graph execution: rel {err:.3e}"
