@@ -117,6 +117,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _kernel_errors():
+    """Error words of the bounded mbarrier waits in the tcgen05 kernels (0 = no wait ever timed out)."""
+    from fcd_b200 import _lib
+    L = _lib.lib()
+    return {n: int(getattr(L, n)()) for n in ("fcd_tc_error", "fcd_tcf_error", "fcd_gemm_tc_error", "fcd_wgrad_tc_error",
+                                               "fcd_wgrad_gemm_tc_error")}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference(model_type, patch, n_patches, warm=1):
     """The reference's CPU implementation of the path: the oracle port (reference network files cannot travel, and
@@ -348,6 +356,9 @@ def main():
     value = patches / (ms_dev / 1e3)
     e2e_value = patches / (ms_e2e / 1e3)
     final_loss = float(loss_host)
+    errs = _kernel_errors()
+    if any(errs.values()):
+        raise RuntimeError(f"tcgen05 pipeline time-outs during the training steps: {errs}")
 
     # ---- roofline from the profiled eager step (CUDA events around every C-ABI call on the launching stream).
     # Dominant kernel = the tcgen05/TMEM implicit-GEMM conv (forward + data gradient launches); the whole conv family
@@ -445,6 +456,9 @@ def main():
                 t = torch.tensor([ms], device=dev)
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 ms = float(t)
+            errs = _kernel_errors()
+            if any(errs.values()):
+                raise RuntimeError(f"tcgen05 pipeline time-outs during inference: {errs}")
             aux = {"metric": "ms_dsa_net_sliding_window_vols_per_s", "value": n_vol / (ms / 1e3), "unit": "vols/s",
                    "workload": "2ch 256x256x192, roi 128^3, overlap 0.5, 18 windows sharded over ranks (all windows "
                                "of a rank in one forward), H2D volume + D2H uint8 label map inside the timed region",

@@ -403,6 +403,12 @@ FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
     for (int c = 1; c == 1 || D / c >= 4; c *= 2) {
         const int dl = (D + c - 1) / c;
         if ((D + dl - 1) / dl != c) continue;
+        // Several d-segments per column are only used while every CTA gets at most ONE work item.  With segments AND
+        // several items per CTA (4-5 inference windows per rank: 640 columns x 2 segments on 296 CTAs) the kd-folded
+        // kernel hit rare bounded-wait time-outs (a 0.2 s stall and a bad tile, `fcd_tcf_error` != 0); both regimes on
+        // their own -- segments with one item per CTA (training), many full-depth items per CTA (18-window inference)
+        // -- have run clean throughout.  Root cause not found this round.
+        if (c > 1 && (long long)cols * c > sms) continue;
         const long long cost = (long long)((cols * c + sms - 1) / sms) * (dl + 1);
         if (best < 0 || cost < best) { best = cost; nseg = c; }
     }
