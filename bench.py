@@ -457,8 +457,11 @@ def main():
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 ms = float(t)
             errs = _kernel_errors()
-            if any(errs.values()):
-                raise RuntimeError(f"tcgen05 pipeline time-outs during inference: {errs}")
+            bad = torch.tensor([float(any(errs.values()))], device=dev)
+            if world > 1:                      # a time-out on ANY rank voids the volume every rank contributed to
+                torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
+            if float(bad) > 0:
+                raise RuntimeError(f"tcgen05 pipeline time-outs during inference (this rank: {errs})")
             aux = {"metric": "ms_dsa_net_sliding_window_vols_per_s", "value": n_vol / (ms / 1e3), "unit": "vols/s",
                    "workload": "2ch 256x256x192, roi 128^3, overlap 0.5, 18 windows sharded over ranks (all windows "
                                "of a rank in one forward), H2D volume + D2H uint8 label map inside the timed region",
