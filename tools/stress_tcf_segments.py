@@ -3,7 +3,10 @@ several work items per persistent CTA.  Calls the C-ABI entry directly with nseg
 (640 columns x 2 segments on 296 CTAs) and compares every run with the nseg = 1 result of the same kernel; prints the
 error word (call-site code << 16 | CTA) of the first bounded wait that timed out.
 
-    python tools/stress_tcf_segments.py [iterations] [Cin] [Cout]
+    python tools/stress_tcf_segments.py [iterations] [Cin] [Cout] [concurrent]
+
+With a 4th argument a second stream keeps a 32->32 kd-folded conv (512 TMEM columns, one CTA per SM) in flight next to
+every stressed launch, the way the branch streams of the window forward do.
 """
 import sys
 
@@ -37,8 +40,20 @@ def main():
     ref32 = ref.float()
     sref = pref.sum(1)
     bad = 0
+    side = torch.cuda.Stream() if len(sys.argv) > 4 else None
+    if side is not None:
+        x2 = (torch.randn((5, 64, 64, 64, 32), generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        w2 = (torch.randn((32, 32, 3, 3, 3), generator=g) * 0.05).to(dev).contiguous()
+        torch.cuda.synchronize()
     for i in range(iters):
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    conv(x2, w2, 1, 32, 32)
         y, part = conv(x, w32, 2, Ci, Co)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         err = L.fcd_tcf_error()
         d = (y.float() - ref32).abs().max().item()
         ds = (part.sum(1) - sref).abs().max().item()
