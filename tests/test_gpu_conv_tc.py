@@ -388,3 +388,25 @@ def test_wgrad_gemm_tc(ops, B, Ci, Co, D, H, W):
     y.backward(ops.to_channels_last(dy, ops.pad16(Co)))
     assert _lib.lib().fcd_wgrad_gemm_tc_error() == 0
     close(w2.grad, gw, rel=6e-3, what="wgrad gemm_tc")
+
+
+def test_depth_segments_only_with_one_item_per_cta(ops):
+    """`fcd_conv3_tc_nseg` never combines several d-segments per column with several work items per CTA (the open
+    defect of DESIGN.md section 9, item 0): nseg > 1 only while columns x nseg <= SM count.  The 4-5 window batches of
+    sharded sliding-window inference (640 columns at 128^3) must therefore run full-depth columns; the small training
+    levels keep their segments."""
+    from fcd_b200 import _lib
+    L = _lib.lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for B in (1, 2, 3, 4, 5, 9, 18):
+        for S in (16, 32, 64, 128):
+            for K, N in ((16, 16), (32, 16), (32, 32), (64, 32)):
+                nseg = L.fcd_conv3_tc_nseg(B, S, S, S, K, N)
+                cols = B * (S // 16) * (S // 8)
+                assert nseg >= 1
+                assert nseg == 1 or cols * nseg <= sms, (B, S, K, N, nseg)
+                assert S // nseg >= 4
+    assert L.fcd_conv3_tc_nseg(5, 128, 128, 128, 16, 16) == 1
+    assert L.fcd_conv3_tc_nseg(4, 128, 128, 128, 32, 16) == 1
+    assert L.fcd_conv3_tc_nseg(2, 64, 64, 64, 32, 32) == 2          # training level 2: 64 columns x 2 segments
+    assert L.fcd_conv3_tc_nseg(2, 32, 32, 32, 64, 32) > 1           # training level 3 keeps its segments
