@@ -3,10 +3,12 @@ several work items per persistent CTA.  Calls the C-ABI entry directly with nseg
 (640 columns x 2 segments on 296 CTAs) and compares every run with the nseg = 1 result of the same kernel; prints the
 error word (call-site code << 16 | CTA) of the first bounded wait that timed out.
 
-    python tools/stress_tcf_segments.py [iterations] [Cin] [Cout] [concurrent]
+    python tools/stress_tcf_segments.py [iterations] [Cin] [Cout] [concurrent|-] [size] [nseg]
 
 With a 4th argument a second stream keeps a 32->32 kd-folded conv (512 TMEM columns, one CTA per SM) in flight next to
-every stressed launch, the way the branch streams of the window forward do.
+every stressed launch, the way the branch streams of the window forward do.  size / nseg (default 128 / 2) select the
+other shapes a 4-5 window batch used to run with several short items per CTA: 64 8 (160 columns x 8 segments of 8
+planes) and 32 8 (40 columns x 8 segments of 4 planes) -- NOT yet run on a GPU (round-1 budget spent).
 """
 import sys
 
@@ -30,9 +32,11 @@ def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     Ci = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     Co = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    S = int(sys.argv[5]) if len(sys.argv) > 5 else 128
+    nseg = int(sys.argv[6]) if len(sys.argv) > 6 else 2
     dev = torch.device("cuda", 0)
     g = torch.Generator(device="cpu").manual_seed(0)
-    x = (torch.randn((5, 128, 128, 128, ops.pad16(Ci)), generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    x = (torch.randn((5, S, S, S, ops.pad16(Ci)), generator=g) * 0.5).to(torch.bfloat16).to(dev)
     w32 = (torch.randn((Co, Ci, 3, 3, 3), generator=g) * 0.05).to(dev).contiguous()
     L = _lib.lib()
     ref, pref = conv(x, w32, 1, Ci, Co)
@@ -40,7 +44,7 @@ def main():
     ref32 = ref.float()
     sref = pref.sum(1)
     bad = 0
-    side = torch.cuda.Stream() if len(sys.argv) > 4 else None
+    side = torch.cuda.Stream() if len(sys.argv) > 4 and sys.argv[4] != "-" else None
     if side is not None:
         x2 = (torch.randn((5, 64, 64, 64, 32), generator=g) * 0.5).to(torch.bfloat16).to(dev)
         w2 = (torch.randn((32, 32, 3, 3, 3), generator=g) * 0.05).to(dev).contiguous()
@@ -51,7 +55,7 @@ def main():
             with torch.cuda.stream(side):
                 for _ in range(3):
                     conv(x2, w2, 1, 32, 32)
-        y, part = conv(x, w32, 2, Ci, Co)
+        y, part = conv(x, w32, nseg, Ci, Co)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         err = L.fcd_tcf_error()
@@ -61,7 +65,7 @@ def main():
             bad += 1
             print(f"iter {i}: error word {err:#x} (wait site {err >> 16}, CTA {err & 0xffff}), max |dy| {d:.4g}, "
                   f"max |dstats| {ds:.4g}", flush=True)
-    print(f"{iters} iterations of {Ci}->{Co} @ 5 x 128^3, nseg 2: {bad} bad", flush=True)
+    print(f"{iters} iterations of {Ci}->{Co} @ 5 x {S}^3, nseg {nseg}: {bad} bad", flush=True)
 
 
 if __name__ == "__main__":
