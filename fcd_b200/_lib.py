@@ -30,13 +30,17 @@ KERNELS_PER_CALL = {
 }
 
 
+RESTYPES = {}
+
+
 def parse_header(path: str = HEADER):
     """Return {name: [(param_name, ctype), ...]} for every FCD_API prototype in the header."""
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"FCD_API\s+int\s+(\w+)\s*\(([^)]*)\)\s*;", text):
-        name, args = m.group(1), m.group(2).strip()
+    for m in re.finditer(r"FCD_API\s+(int|long long)\s+(\w+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(2), m.group(3).strip()
+        RESTYPES[name] = _CT[m.group(1)]
         params = []
         if args and args != "void":
             for a in args.split(","):
@@ -66,7 +70,7 @@ def lib():
         _lib = ctypes.CDLL(LIBPATH)
         for name, params in PROTOS.items():
             fn = getattr(_lib, name)       # raises AttributeError if the .so lacks a declared symbol
-            fn.restype = ctypes.c_int
+            fn.restype = RESTYPES[name]
             fn.argtypes = [ct for _, ct in params]
     return _lib
 
@@ -150,6 +154,37 @@ def call(name: str, **kw):
     if rc != 0:
         raise RuntimeError(f"{name} failed with code {rc}" + (" (unsupported shape)" if rc == -1 else " (CUDA error)"))
     return rc
+
+
+STATUS_INTS = 48
+KERNEL_NAMES = {1: "fcd_conv3_tc", 2: "fcd_conv3_tcf", 3: "fcd_conv_gemm_tc", 4: "fcd_wgrad3_tc", 5: "fcd_wgrad_gemm_tc"}
+
+
+def status(clear: bool = True) -> dict:
+    """The device status block (include/fcd_b200.h, fcd_status) as a dict; word 0 != 0 means a bounded pipeline wait of a
+    tcgen05 kernel timed out since the last clear.  Synchronises the device."""
+    buf = (ctypes.c_int * STATUS_INTS)()
+    fn = lib().fcd_status
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    word = fn(ctypes.cast(buf, ctypes.c_void_p), 1 if clear else 0)
+    v = list(buf)
+    return dict(word=word, kernel=KERNEL_NAMES.get(v[1], v[1]), site=v[2], cta=v[3], thread=v[4], bar=v[5],
+                parity=v[6], item=v[7], grid=v[8], cta_y=v[9], progress=v[16:48])
+
+
+class PipelineError(RuntimeError):
+    pass
+
+
+def check_errors(clear: bool = True) -> None:
+    """Raise if any tcgen05 kernel hit a bounded-wait time-out since the last clear (results may hold a bad tile; the
+    fused loss / sliding-window finalize kernels have already turned them into NaN).  Synchronises the device."""
+    st = status(clear)
+    if st["word"] != 0:
+        raise PipelineError(
+            f"fcd_b200: a tcgen05 pipeline wait timed out (error word {st['word']:#x}): kernel {st['kernel']}, wait site "
+            f"{st['site']}, CTA {st['cta']}/{st['grid']} thread {st['thread']}, item {st['item']}, mbarrier smem "
+            f"{st['bar']:#x} parity {st['parity']}, progress {st['progress']}")
 
 
 def query(name: str) -> int:

@@ -1,0 +1,331 @@
+// GPU post-processing of the predicted FCD mask: utils/utils_common.py:10-33 `post_process_segment` as called by
+// ModelTrainer.post_process (train.py:167-182), bit-exact against the scipy calls the reference makes:
+//   1. binary_opening(mask, iterations=1)            6-connected cross, border_value 0 (erosion, then dilation)
+//   2. binary_fill_holes(., structure=ones((5,5,5)))  = complement of the background reachable from OUTSIDE the volume
+//                                                       by steps of Chebyshev length <= 2 through background voxels
+//   3. label(., structure=ones((3,3,3)))              26-connected components numbered in raster order of first voxel
+//   4. sizes per label (label 0 = background, size 0); l_min == -1 -> l_min = max size; keep labels with size >= l_min
+//      (QUIRKS kept: the background is "kept" too when 0 >= l_min, e.g. l_min = -1 on an empty mask -> all ones; a
+//      volume without any background voxel yields all zeros because the reference indexes sizes by position)
+//   5. output_msk = 1 on kept labels, output_lab = 1, 2, ... in label order over the kept ones.
+// Everything runs on the stream without a host round trip (the reference does D2H -> scipy on one core -> H2D).
+//
+// Connected components: label-equivalence union-find with atomicMin (roots are the smallest linear index of their set,
+// which is exactly scipy's numbering order), row-run initialisation by warp ballot.  The fill-holes reachability is the
+// same machinery on the background: two background voxels are adjacent when their Chebyshev distance is <= 2.  A
+// distance-2 edge whose midpoint is background is implied by two distance-1 edges, so only voxels with a foreground
+// voxel in their 3x3x3 neighbourhood walk the 62 forward neighbours of the 5x5x5 cube; the rest walk 13.  The search is
+// confined to the bounding box of the foreground (every voxel outside it reaches the volume border along an axis), whose
+// 2-voxel inner shell plays the role of scipy's border_value = 1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+
+struct Dims { int D, H, W; long long N; };
+
+// misc ints in the workspace
+enum { M_ZLO = 0, M_YLO, M_XLO, M_ZHI, M_YHI, M_XHI, M_MAXSIZE, M_ANYBG, M_LMIN, M_BGKEPT, M_COUNT = 16 };
+
+__device__ __forceinline__ bool in_val(const float* pf, const unsigned char* pu, long long i, float thr) {
+    return pf != nullptr ? (pf[i] > thr) : (pu[i] != 0);
+}
+
+__global__ void pp_init_misc(int* misc, Dims d) {
+    if (threadIdx.x == 0) {
+        misc[M_ZLO] = d.D; misc[M_YLO] = d.H; misc[M_XLO] = d.W;
+        misc[M_ZHI] = -1; misc[M_YHI] = -1; misc[M_XHI] = -1;
+        misc[M_MAXSIZE] = 0; misc[M_ANYBG] = 0; misc[M_LMIN] = 0; misc[M_BGKEPT] = 0;
+    }
+}
+
+// eroded[v] = mask at v and at its 6 face neighbours, all inside the volume (border_value 0)
+__global__ void pp_erode(const float* __restrict__ pf, const unsigned char* __restrict__ pu, float thr,
+                         unsigned char* __restrict__ er, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const long long sy = d.W, sz = (long long)d.W * d.H;
+    bool v = in_val(pf, pu, i, thr) && x > 0 && x < d.W - 1 && y > 0 && y < d.H - 1 && z > 0 && z < d.D - 1;
+    if (v)
+        v = in_val(pf, pu, i - 1, thr) && in_val(pf, pu, i + 1, thr) && in_val(pf, pu, i - sy, thr) &&
+            in_val(pf, pu, i + sy, thr) && in_val(pf, pu, i - sz, thr) && in_val(pf, pu, i + sz, thr);
+    er[i] = v ? 1 : 0;
+}
+
+// opened[v] = eroded at v or at any in-volume face neighbour; also the bounding box of the opened foreground
+__global__ void pp_dilate_bbox(const unsigned char* __restrict__ er, unsigned char* __restrict__ op, int* misc, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    bool v = false;
+    int x = 0, y = 0, z = 0;
+    if (i < d.N) {
+        x = (int)(i % d.W); y = (int)((i / d.W) % d.H); z = (int)(i / ((long long)d.W * d.H));
+        const long long sy = d.W, sz = (long long)d.W * d.H;
+        v = er[i] || (x > 0 && er[i - 1]) || (x < d.W - 1 && er[i + 1]) || (y > 0 && er[i - sy]) ||
+            (y < d.H - 1 && er[i + sy]) || (z > 0 && er[i - sz]) || (z < d.D - 1 && er[i + sz]);
+        op[i] = v ? 1 : 0;
+    }
+    // block-level bounding box, one atomic set per block that holds foreground
+    __shared__ int sh[6];
+    if (threadIdx.x < 3) sh[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) sh[threadIdx.x] = -1;
+    __syncthreads();
+    if (v) {
+        atomicMin(&sh[0], z); atomicMin(&sh[1], y); atomicMin(&sh[2], x);
+        atomicMax(&sh[3], z); atomicMax(&sh[4], y); atomicMax(&sh[5], x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && sh[threadIdx.x] != 0x7fffffff) atomicMin(&misc[threadIdx.x], sh[threadIdx.x]);
+    else if (threadIdx.x >= 3 && threadIdx.x < 6 && sh[threadIdx.x] >= 0) atomicMax(&misc[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------- union-find
+__device__ __forceinline__ int uf_find(const int* L, int a) {
+    int p;
+    while ((p = __ldcg(L + a)) != a) a = p;
+    return a;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) {
+            const int old = atomicMin(L + b, a);
+            done = old == b;
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(L + a, b);
+            done = old == a;
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+// active(v): BG = false -> foreground voxel of `m`;  BG = true -> background voxel of `m` inside the bounding box
+template <bool BG>
+__device__ __forceinline__ bool uf_active(const unsigned char* m, const int* misc, long long i, int z, int y, int x) {
+    if (!BG) return m[i] != 0;
+    return m[i] == 0 && z >= misc[M_ZLO] && z <= misc[M_ZHI] && y >= misc[M_YLO] && y <= misc[M_YHI] &&
+           x >= misc[M_XLO] && x <= misc[M_XHI];
+}
+
+// L[v] = start of v's run of active voxels inside its 32-voxel x segment (-1 for inactive voxels)
+template <bool BG>
+__global__ void uf_init(const unsigned char* __restrict__ m, const int* __restrict__ misc, int* __restrict__ L, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool a = false;
+    int x = 0;
+    if (i < d.N) {
+        x = (int)(i % d.W);
+        const int y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+        a = uf_active<BG>(m, misc, i, z, y, x);
+    }
+    // a run may not cross a row end: lanes whose x is 0 start a new row
+    const unsigned act = __ballot_sync(0xffffffffu, a);
+    const unsigned row0 = __ballot_sync(0xffffffffu, x == 0);
+    if (i >= d.N) return;
+    if (!a) { L[i] = -1; return; }
+    // breaks below or at my lane: inactive lanes, and row starts (a row start at lane k breaks between k-1 and k)
+    const unsigned below = (lane == 31) ? 0xffffffffu : ((1u << (lane + 1)) - 1u);
+    const unsigned inactive = ~act & below;                       // inactive lanes <= lane (mine is active)
+    const unsigned starts = row0 & below;                         // row starts <= lane
+    int s0 = inactive ? (32 - __clz(inactive)) : 0;               // first lane after the last inactive one
+    const int s1 = starts ? (31 - __clz(starts)) : 0;             // the last row start itself
+    if (s1 > s0) s0 = s1;
+    L[i] = (int)(i - (lane - s0));
+}
+
+template <bool BG>
+__global__ void uf_merge(const unsigned char* __restrict__ m, const int* __restrict__ misc, int* __restrict__ L, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    if (!uf_active<BG>(m, misc, i, z, y, x)) return;
+    int R = 1;
+    if (BG) {
+        // walk the 5x5x5 forward half only when a foreground voxel sits in my 3x3x3 neighbourhood
+        bool near = false;
+        for (int dz = -1; dz <= 1 && !near; ++dz)
+            for (int dy = -1; dy <= 1 && !near; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int zz = z + dz, yy = y + dy, xx = x + dx;
+                    if (zz < 0 || zz >= d.D || yy < 0 || yy >= d.H || xx < 0 || xx >= d.W) continue;
+                    if (m[((long long)zz * d.H + yy) * d.W + xx] != 0) { near = true; break; }
+                }
+        R = near ? 2 : 1;
+    }
+    for (int dz = 0; dz <= R; ++dz)
+        for (int dy = (dz == 0 ? 0 : -R); dy <= R; ++dy)
+            for (int dx = ((dz == 0 && dy == 0) ? 1 : -R); dx <= R; ++dx) {
+                const int zz = z + dz, yy = y + dy, xx = x + dx;
+                if (zz >= d.D || yy < 0 || yy >= d.H || xx < 0 || xx >= d.W) continue;
+                const long long j = ((long long)zz * d.H + yy) * d.W + xx;
+                if (!uf_active<BG>(m, misc, j, zz, yy, xx)) continue;
+                if (dz == 0 && dy == 0 && dx == 1 && (i & 31) != 31) continue;   // same run segment: joined by uf_init
+                uf_union(L, (int)i, (int)j);
+            }
+}
+
+__global__ void uf_flatten(int* __restrict__ L, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    if (L[i] >= 0) L[i] = uf_find(L, (int)i);
+}
+
+// fill-holes: roots of background sets that touch the 2-voxel inner shell of the bounding box are reachable
+__global__ void fh_seed(const int* __restrict__ L, const int* __restrict__ misc, int* __restrict__ reach, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    const int r = L[i];
+    if (r < 0) return;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    if (z <= misc[M_ZLO] + 1 || z >= misc[M_ZHI] - 1 || y <= misc[M_YLO] + 1 || y >= misc[M_YHI] - 1 ||
+        x <= misc[M_XLO] + 1 || x >= misc[M_XHI] - 1)
+        reach[r] = 1;
+}
+// filled = opened | (background voxel inside the box whose set is not reachable); also: is there any background left
+__global__ void fh_fill(const unsigned char* __restrict__ op, const int* __restrict__ L, const int* __restrict__ reach,
+                        unsigned char* __restrict__ filled, int* misc, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    bool bg = false;
+    if (i < d.N) {
+        const int r = L[i];
+        const bool f = op[i] != 0 || (r >= 0 && reach[r] == 0);
+        filled[i] = f ? 1 : 0;
+        bg = !f;
+    }
+    if (__syncthreads_or(bg) && threadIdx.x == 0) misc[M_ANYBG] = 1;
+}
+
+__global__ void cc_count(const int* __restrict__ L, int* __restrict__ cnt, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    const int r = L[i];
+    if (r >= 0) atomicAdd(cnt + r, 1);
+}
+__global__ void cc_max(const int* __restrict__ L, const int* __restrict__ cnt, int* misc, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    int v = 0;
+    if (i < d.N && L[i] == (int)i) v = cnt[i];
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(&misc[M_MAXSIZE], v);
+}
+__global__ void cc_resolve(int* misc, int l_min) {
+    if (threadIdx.x == 0) {
+        const int lm = l_min == -1 ? misc[M_MAXSIZE] : l_min;
+        misc[M_LMIN] = lm;
+        misc[M_BGKEPT] = (misc[M_ANYBG] != 0 && 0 >= lm) ? 1 : 0;
+    }
+}
+
+// kept-root flags -> exclusive ranks (raster order of the roots = scipy's label order), three passes
+__device__ __forceinline__ int kept_root(const int* L, const int* cnt, const int* misc, long long i, long long N) {
+    return (i < N && L[i] == (int)i && misc[M_ANYBG] != 0 && cnt[i] >= misc[M_LMIN]) ? 1 : 0;
+}
+__global__ void rank_block_sums(const int* __restrict__ L, const int* __restrict__ cnt, const int* __restrict__ misc,
+                                int* __restrict__ bsum, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    const int f = kept_root(L, cnt, misc, i, d.N);
+    const int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = c;
+}
+__global__ void rank_scan_sums(int* __restrict__ bsum, int nb) {      // one block of 1024 threads, exclusive scan in place
+    __shared__ int sh[1024];
+    const int per = (nb + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, nb);
+    int s = 0;
+    for (int k = lo; k < hi; ++k) s += bsum[k];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - s;
+    for (int k = lo; k < hi; ++k) { const int v = bsum[k]; bsum[k] = run; run += v; }
+}
+// cnt[root] <- 1-based output label of a kept root (after the background's, if that is kept), 0 for dropped roots
+__global__ void rank_apply(const int* __restrict__ L, int* __restrict__ cnt, const int* __restrict__ misc,
+                           const int* __restrict__ bsum, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    const int f = kept_root(L, cnt, misc, i, d.N);
+    __shared__ int wsum[TB / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    int before = bsum[blockIdx.x] + __popc(b & ((1u << lane) - 1u));
+    for (int k = 0; k < w; ++k) before += wsum[k];
+    if (i < d.N && L[i] == (int)i) cnt[i] = f ? before + 1 + misc[M_BGKEPT] : 0;
+}
+__global__ void pp_output(const int* __restrict__ L, const int* __restrict__ cnt, const int* __restrict__ misc,
+                          float* __restrict__ out_mask, float* __restrict__ out_lab, Dims d) {
+    const long long i = blockIdx.x * (long long)TB + threadIdx.x;
+    if (i >= d.N) return;
+    const int r = L[i];
+    int lab;
+    if (r >= 0) lab = cnt[r];
+    else lab = misc[M_BGKEPT] ? 1 : 0;
+    if (out_mask != nullptr) out_mask[i] = lab > 0 ? 1.f : 0.f;
+    if (out_lab != nullptr) out_lab[i] = (float)lab;
+}
+
+inline long long align256(long long v) { return (v + 255) / 256 * 256; }
+
+}  // namespace
+
+// workspace bytes for a D x H x W volume: two uint8 masks, labels, per-root counters, block sums, misc
+FCD_API long long fcd_post_process_ws_bytes(int D, int H, int W) {
+    const long long N = (long long)D * H * W;
+    const long long nb = (N + TB - 1) / TB;
+    return 2 * align256(N) + 2 * align256(4 * N) + align256(4 * nb) + 256;
+}
+
+// pred_f (fp32 [D][H][W], mask = pred_f > threshold) or pred_u8 (uint8 [D][H][W], mask = != 0): exactly one non-NULL.
+// out_mask / out_lab: fp32 [D][H][W] (either may be NULL).  l_min as the reference's params['min_region_size'].
+FCD_API int fcd_post_process(const float* pred_f, const void* pred_u8, float threshold, int l_min, float* out_mask,
+                             float* out_lab, int D, int H, int W, void* ws, long long ws_bytes, cudaStream_t st) {
+    if (D < 1 || H < 1 || W < 1 || (pred_f == nullptr) == (pred_u8 == nullptr) || ws == nullptr) return -1;
+    const long long N = (long long)D * H * W;
+    if (N >= 0x7fffffffLL || ws_bytes < fcd_post_process_ws_bytes(D, H, W) || ((uintptr_t)ws & 255)) return -1;
+    const long long nb = (N + TB - 1) / TB;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    unsigned char* m0 = base;                       // eroded, later the filled mask
+    unsigned char* m1 = m0 + align256(N);           // opened mask
+    int* L = reinterpret_cast<int*>(m1 + align256(N));
+    int* cnt = L + align256(4 * N) / 4;
+    int* bsum = cnt + align256(4 * N) / 4;
+    int* misc = bsum + align256(4 * nb) / 4;
+    const Dims d{D, H, W, N};
+    const int grid = (int)nb;
+    pp_init_misc<<<1, 32, 0, st>>>(misc, d);
+    pp_erode<<<grid, TB, 0, st>>>(pred_f, static_cast<const unsigned char*>(pred_u8), threshold, m0, d);
+    pp_dilate_bbox<<<grid, TB, 0, st>>>(m0, m1, misc, d);
+    // fill holes: union-find over the background inside the foreground's bounding box
+    cudaMemsetAsync(cnt, 0, 4 * N, st);
+    uf_init<true><<<grid, TB, 0, st>>>(m1, misc, L, d);
+    uf_merge<true><<<grid, TB, 0, st>>>(m1, misc, L, d);
+    uf_flatten<<<grid, TB, 0, st>>>(L, d);
+    fh_seed<<<grid, TB, 0, st>>>(L, misc, cnt, d);
+    fh_fill<<<grid, TB, 0, st>>>(m1, L, cnt, m0, misc, d);
+    // 26-connected components of the filled mask
+    cudaMemsetAsync(cnt, 0, 4 * N, st);
+    uf_init<false><<<grid, TB, 0, st>>>(m0, misc, L, d);
+    uf_merge<false><<<grid, TB, 0, st>>>(m0, misc, L, d);
+    uf_flatten<<<grid, TB, 0, st>>>(L, d);
+    cc_count<<<grid, TB, 0, st>>>(L, cnt, d);
+    cc_max<<<grid, TB, 0, st>>>(L, cnt, misc, d);
+    cc_resolve<<<1, 32, 0, st>>>(misc, l_min);
+    rank_block_sums<<<grid, TB, 0, st>>>(L, cnt, misc, bsum, d);
+    rank_scan_sums<<<1, 1024, 0, st>>>(bsum, (int)nb);
+    rank_apply<<<grid, TB, 0, st>>>(L, cnt, misc, bsum, d);
+    pp_output<<<grid, TB, 0, st>>>(L, cnt, misc, out_mask, out_lab, d);
+    FCD_LAUNCH_CHECK();
+}

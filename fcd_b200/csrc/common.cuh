@@ -8,6 +8,9 @@
 
 #define FCD_LAUNCH_CHECK() return (int)cudaGetLastError()
 
+// device address of the library-wide status block of the current device (csrc/status.cu); word 0 = sticky error word
+int* fcd_status_dev();
+
 typedef __nv_bfloat16 bf16;
 
 struct __align__(16) bf16x8 {

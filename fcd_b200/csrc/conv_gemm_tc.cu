@@ -30,6 +30,7 @@ struct GemmTcParams {
     bf16* C; long long ldc;               // ksplit == 1
     float* ws;                            // ksplit > 1: [ksplit][M][N] fp32
     int Bn, D, H, W, K, N, M, mode, ksplit;
+    int* status;
 };
 
 template <int BN>
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * K::STAGE);
     // bars: [0,NST) FULL | [NST,2NST) EMPTY | [2NST] DONE
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
-    volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t bar0 = smem_u32(bars);
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
     auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
     const uint32_t DONE = bar0 + 8u * (2 * NST);
     if (tid == 0) {
-        *dead = 0;
+        wait_ctx_init(ctx, p.status, 3);
         for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPRODW); mbar_init(EMPTY(s), 1); }
         mbar_init(DONE, 1);
         fence_barrier_init();
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
             const int it = it0 + i;
             const int tap = it / kchunks, kc = it - tap * kchunks;
             const int s = i % NST;
-            mbar_wait(EMPTY(s), ((i / NST) & 1u) ^ 1u, dead, 1);
+            mbar_wait(EMPTY(s), ((i / NST) & 1u) ^ 1u, ctx, 1);
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
             // forward: src = m + tap - 1; data gradient (stride 1): src = m + 1 - tap
             const int sz = p.mode == 0 ? z + kd - 1 : z + 1 - kd;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
         const uint32_t b_lo0 = (((smem_u32(smem) + K::A_BYTES) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_B >> 4) << 16);
         for (int i = 0; i < nk; ++i) {
             const int s = i % NST;
-            mbar_wait(FULL(s), (i / NST) & 1u, dead, 2);
+            mbar_wait(FULL(s), (i / NST) & 1u, ctx, 2);
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
     }
 
     // ===================================================================== drain: warps 0-3, thread = output row
-    mbar_wait(DONE, 0, dead, 3);
+    mbar_wait(DONE, 0, ctx, 3);
     tc_fence_after();
     if (warp < 4) {
         const int row = warp * 32 + lane;
@@ -231,16 +232,8 @@ FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void*
     p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.K = K; p.N = N; p.mode = mode; p.ksplit = ksplit;
     const long long M = (long long)Bn * D * H * W;
     if (M > 0x7fffffffLL) return -1;
-    p.M = (int)M;
+    p.M = (int)M; p.status = fcd_status_dev();
     if (bn == 256) return launch<256>(p, stream);
     if (bn == 128) return launch<128>(p, stream);
     return launch<64>(p, stream);
-}
-
-FCD_API int fcd_gemm_tc_error(void) {
-    int v = 0, zero = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    cudaMemcpyFromSymbol(&v, tc::g_error, sizeof(int));
-    cudaMemcpyToSymbol(tc::g_error, &zero, sizeof(int));
-    return v;
 }

@@ -38,6 +38,7 @@ struct ConvTcfParams {
     bf16* C; long long ldc;
     float* part;
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
+    int* status;
 };
 
 template <int CIN, int COUT>
@@ -80,8 +81,11 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::W_BYTES + NST * K::PLANE_BYTES);
     // bars: [0,NST) FULL | [NST,2NST) EMPTY | [2NST,2NST+NPB) PDONE | [2NST+NPB,2NST+NPB+R) TEMPTY
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + NPB + R);
-    volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
-    float* red = reinterpret_cast<float*>(tmem_slot + 4);
+    WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
+    float* red = reinterpret_cast<float*>(ctx + 1);
+    // ctx->prog (debug record of a timed-out wait): [0] producer plane seq, [1] its item; [2+me] MMA warp's plane
+    // counter g, [5+me] its item, [8+me] (wait site << 24 | sq or zc); [11+q] epilogue outputs done, [15+q] planes
+    // waited, [19+q] its item; [23] nitems, [24] nseg, [25] DL
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + NPB + s); };
 
     if (tid == 0) {
-        *dead = 0;
+        wait_ctx_init(ctx, p.status, 2);
+        ctx->prog[23] = p.nitems; ctx->prog[24] = p.nseg; ctx->prog[25] = p.DL;
         for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPROD); mbar_init(EMPTY(s), 1); }
         for (int s = 0; s < NPB; ++s) mbar_init(PDONE(s), 1);
         for (int s = 0; s < R; ++s) mbar_init(TEMPTY(s), 4);
@@ -153,7 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             const long long plane_elems = (long long)p.H * p.W * p.lda;
             for (int pl = it.p_lo; pl <= it.p_hi; ++pl, ++seq) {
                 const int s = seq % NST;
-                mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, dead, 1);
+                if (pt == 0) { prog_set(ctx, 0, (int)seq); prog_set(ctx, 1, item); }
+                mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, ctx, 1, item);
                 const bf16* plane = p.A + ((long long)it.n * p.D + pl) * plane_elems;
                 const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A + v0 * 16;
 #pragma unroll
@@ -212,15 +218,18 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 const bool valid = pl >= 0 && pl < p.D;
                 const int j_lo = max(i - 2, 0), j_hi = min(i, DLi - 1);
                 uint32_t sq = 0;
+                if (lane == 0) { prog_set(ctx, 2 + me, (int)g); prog_set(ctx, 5 + me, item); }
                 if (valid) {
                     sq = seq_base + (pl - it.p_lo);
-                    mbar_wait(FULL(sq % NST), (sq / NST) & 1u, dead, 2);
+                    if (lane == 0) prog_set(ctx, 8 + me, (2 << 24) | (int)(sq & 0xffffff));
+                    mbar_wait(FULL(sq % NST), (sq / NST) & 1u, ctx, 2, item);
                 }
                 // every output this plane touches must have been handed back (zeroed) by the epilogue; this also
                 // keeps a warp from running more than R outputs ahead, i.e. from lapping the PDONE phases
                 for (int j = j_lo; j <= j_hi; ++j) {
                     const uint32_t zc = zc0 + j;
-                    mbar_wait(TEMPTY(zc % R), (zc / R) & 1u, dead, 3);
+                    if (lane == 0) prog_set(ctx, 8 + me, (3 << 24) | (int)(zc & 0xffffff));
+                    mbar_wait(TEMPTY(zc % R), (zc / R) & 1u, ctx, 3, item);
                 }
                 tc_fence_after();
                 if (lane == 0) {
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                         if (n_out > n1) issue(a_pl, 0, t_lo + n1, n_out - n1);      // the range wraps around the ring
                         umma_commit(EMPTY(sq % NST));
                         umma_commit(PDONE(g % NPB));
+                        prog_set(ctx, 8 + me, (7 << 24) | (int)(g & 0xffffff));
                     } else {
                         mbar_arrive(PDONE(g % NPB));           // zero-padding plane: nothing to add
                     }
@@ -270,8 +280,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 const int slot = zc % R;
                 // output j = od - d0 is complete when planes j, j+1, j+2 of this item have been multiplied
                 const uint32_t need = pc0 + (uint32_t)(od - it.d0) + 3;
+                if (lane == 0) { prog_set(ctx, 11 + q, (int)zc); prog_set(ctx, 15 + q, (int)pwaited); prog_set(ctx, 19 + q, item); }
                 while (pwaited < need) {
-                    mbar_wait(PDONE(pwaited % NPB), (pwaited / NPB) & 1u, dead, 4);
+                    mbar_wait(PDONE(pwaited % NPB), (pwaited / NPB) & 1u, ctx, 4, item);
                     ++pwaited;
                 }
                 tc_fence_after();
@@ -368,17 +379,10 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     p.nseg = (D + p.DL - 1) / p.DL;
     if (p.nseg != nseg) return -1;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
+    p.status = fcd_status_dev();
 #define FCD_TCF_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, flip, stream)
     FCD_TCF_CASE(16, 16); FCD_TCF_CASE(32, 16); FCD_TCF_CASE(64, 16);
     FCD_TCF_CASE(16, 32); FCD_TCF_CASE(32, 32); FCD_TCF_CASE(64, 32);
 #undef FCD_TCF_CASE
     return -1;
-}
-
-FCD_API int fcd_tcf_error(void) {
-    int v = 0, zero = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    cudaMemcpyFromSymbol(&v, tc::g_error, sizeof(int));
-    cudaMemcpyToSymbol(tc::g_error, &zero, sizeof(int));
-    return v;
 }

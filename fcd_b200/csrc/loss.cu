@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) tv_fwd_kernel(const float* __res
 
 // res[0]=total, [1]=dice N, [2]=dice Dn, [3]=CE weight sum, [4..6]=tv_z,tv_y,tv_x, [7]=dice, [8]=ce|focal, [9]=tv
 __global__ void loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ tvpart, int nblk,
-                                     LossCfg cfg, int B, int D, int H, int W, float* __restrict__ res) {
+                                     LossCfg cfg, int B, int D, int H, int W, float* __restrict__ res,
+                                     const int* __restrict__ status) {
     __shared__ double sh[9];
     if (threadIdx.x < 9) {
         double s = 0.0;
@@ -147,6 +148,9 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, const float
             }
         }
         double total = (cfg.kind == 0 ? dice : cfg.lambda_dice * dice + cfg.lambda_2 * second) + cfg.tv_w * tvsum;
+        // a tcgen05 pipeline wait timed out somewhere upstream (status word, csrc/status.cu): the activations this loss
+        // was computed from may contain a bad tile -- report NaN instead of a plausible number
+        if (status != nullptr && *reinterpret_cast<const volatile int*>(status) != 0) total = nan("");
         res[0] = (float)total; res[1] = (float)N; res[2] = (float)Dn; res[3] = (float)sh[4];
         res[4] = (float)tv[0]; res[5] = (float)tv[1]; res[6] = (float)tv[2];
         res[7] = (float)dice; res[8] = (float)second; res[9] = (float)tvsum;
@@ -281,7 +285,8 @@ FCD_API int fcd_loss_fwd(const float* pred, const float* target, int B, int D, i
     loss_fwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pred, target, S, B, cfg, (tv && tv_exclude) ? keep : nullptr,
                                                           tv ? pbuf : nullptr, part);
     if (tv) tv_fwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pbuf, B, D, H, W, tv_norm, tvpart);
-    loss_finalize_kernel<<<1, 32, 0, st>>>(part, tv ? tvpart : nullptr, LOSS_BLOCKS, cfg, B, D, H, W, res);
+    loss_finalize_kernel<<<1, 32, 0, st>>>(part, tv ? tvpart : nullptr, LOSS_BLOCKS, cfg, B, D, H, W, res,
+                                           fcd_status_dev());
     FCD_LAUNCH_CHECK();
 }
 

@@ -1,18 +1,35 @@
-// Blackwell (sm_100a) building blocks shared by the tcgen05 kernels: mbarrier, TMA (cp.async.bulk.tensor),
-// TMEM allocation / loads, UMMA shared-memory + instruction descriptors, tcgen05.mma / commit.
+// Blackwell (sm_100a) building blocks shared by the tcgen05 kernels: mbarrier, TMEM allocation / loads / stores,
+// UMMA shared-memory + instruction descriptors, tcgen05.mma / commit.
 //
 // Every wait is BOUNDED: a pipeline bug must not hang the GPU.  A wait that exceeds kWaitCycles sets the CTA-wide
-// `dead` flag (all later waits fall through at once) and a global error word the host can read (fcd_tc_error).
+// `dead` flag (all later waits fall through at once) and the library-wide status block (csrc/status.cu): the sticky
+// error word the loss / sliding-window finalize kernels turn into NaN, plus a debug record naming the wait
+// (fcd_status).
 #pragma once
-#include <cuda.h>
-
 #include "common.cuh"
 
 namespace tc {
 
 constexpr long long kWaitCycles = 400000000LL;   // ~0.2 s at 1.9 GHz; a healthy wait here is < 100 us
 
-static __device__ int g_error = 0;   // per translation unit; sticky: 0 ok, else (code << 16 | blockIdx) of the first timed-out wait
+// Per-CTA wait context (shared memory).  `dead`: a wait of this CTA timed out, all later waits fall through.
+// `status`: the library-wide device status block (csrc/status.cu, fcd_status): word 0 is the sticky error word
+// (kernel id << 24 | wait site << 16 | CTA), words 1.. the debug record of the FIRST timed-out wait, including a copy of
+// `prog` -- progress counters every role of the CTA keeps up to date, so the record shows where each role stood.
+constexpr int kProgInts = 32;
+struct WaitCtx {
+    int dead;
+    int kernel_id;
+    int* status;
+    int prog[kProgInts];
+};
+__device__ __forceinline__ void wait_ctx_init(WaitCtx* c, int* status, int kernel_id) {   // one thread, before the CTA sync
+    c->dead = 0;
+    c->kernel_id = kernel_id;
+    c->status = status;
+    for (int i = 0; i < kProgInts; ++i) c->prog[i] = -1;
+}
+__device__ __forceinline__ void prog_set(WaitCtx* c, int i, int v) { reinterpret_cast<volatile int*>(c->prog)[i] = v; }
 
 // ---------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -41,31 +58,29 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait.  `dead` is a CTA-shared int; `code` identifies the call site in the error word.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* dead, int code) {
+// Bounded wait.  `code` identifies the call site in the error word; `info` is free-form (item / counter) for the record.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, WaitCtx* ctx, int code, int info) {
+    reinterpret_cast<volatile int*>(&ctx->dead)[0] = 1;
+    int* st = ctx->status;
+    if (st == nullptr) return;
+    const int word = (ctx->kernel_id << 24) | (code << 16) | (int)(blockIdx.x & 0xffff);
+    if (atomicCAS(st, 0, word) == 0) {
+        st[1] = ctx->kernel_id; st[2] = code; st[3] = (int)blockIdx.x; st[4] = (int)threadIdx.x;
+        st[5] = (int)bar; st[6] = (int)parity; st[7] = info; st[8] = (int)gridDim.x; st[9] = (int)blockIdx.y;
+        for (int i = 0; i < kProgInts; ++i) st[16 + i] = reinterpret_cast<volatile int*>(ctx->prog)[i];
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, WaitCtx* ctx, int code, int info = 0) {
     if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try(bar, parity)) {
-        if (*dead) return;
+        if (reinterpret_cast<volatile int*>(&ctx->dead)[0]) return;
         if (clock64() - t0 > kWaitCycles) {
-            *dead = 1;
-            atomicCAS(&g_error, 0, (code << 16) | (int)(blockIdx.x & 0xffff));
+            mbar_timeout(bar, parity, ctx, code, info);
             return;
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------- TMA
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
-        "%7}], [%2];" ::"r"(dst),
-        "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- TMEM
@@ -159,23 +174,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // all tcgen05.mma issued so far by this thread complete -> one arrive on `bar` (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------- host: tensor maps
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static inline EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
 }
 
 }  // namespace tc

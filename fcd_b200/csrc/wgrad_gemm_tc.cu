@@ -26,6 +26,7 @@ struct WgemmParams {
     const bf16* dY; long long ldy;
     float* part;
     int Bn, D, H, W, Kp, Np, M, ktiles, ntiles, msplit, mper;
+    int* status;
 };
 
 template <int BN>
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_gemm_tc_kernel(const WgemmP
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * K::STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
-    volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t bar0 = smem_u32(bars);
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_gemm_tc_kernel(const WgemmP
     auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
     const uint32_t DONE = bar0 + 8u * (2 * NST);
     if (tid == 0) {
-        *dead = 0;
+        wait_ctx_init(ctx, p.status, 5);
         for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 32 * NPRODW); mbar_init(EMPTY(s), 1); }
         mbar_init(DONE, 1);
         fence_barrier_init();
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_gemm_tc_kernel(const WgemmP
         };
         for (int i = 0; i < nstage; ++i) {
             const int s = i % NST;
-            mbar_wait(EMPTY(s), ((i / NST) & 1u) ^ 1u, dead, 1);
+            mbar_wait(EMPTY(s), ((i / NST) & 1u) ^ 1u, ctx, 1);
             const int m = m_begin + i * BKV + r;
             const bool row_ok = m < m_end;
             int x = m % p.W, q = m / p.W;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_gemm_tc_kernel(const WgemmP
         const uint32_t b_lo0 = (((smem_u32(smem) + K::A_BYTES) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO >> 4) << 16);
         for (int i = 0; i < nstage; ++i) {
             const int s = i % NST;
-            mbar_wait(FULL(s), (i / NST) & 1u, dead, 2);
+            mbar_wait(FULL(s), (i / NST) & 1u, ctx, 2);
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_gemm_tc_kernel(const WgemmP
     }
 
     // ===================================================================== drain: TMEM lane = input channel k of the tile
-    mbar_wait(DONE, 0, dead, 3);
+    mbar_wait(DONE, 0, ctx, 3);
     tc_fence_after();
     if (warp < 4) {
         const int k = warp * 32 + lane;
@@ -215,17 +216,9 @@ FCD_API int fcd_wgrad_gemm_tc(const void* X, long long ldx, const void* dY, long
     WgemmParams p;
     p.X = (const bf16*)X; p.ldx = ldx; p.dY = (const bf16*)dY; p.ldy = ldy; p.part = part;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.Kp = Kp; p.Np = Np; p.M = (int)M;
-    p.ktiles = (Kp + BMK - 1) / BMK; p.ntiles = Np / bn;
+    p.ktiles = (Kp + BMK - 1) / BMK; p.ntiles = Np / bn; p.status = fcd_status_dev();
     plan(M, Kp, Np, p.msplit, p.mper);
     if (bn == 256) return launch<256>(p, stream);
     if (bn == 128) return launch<128>(p, stream);
     return launch<64>(p, stream);
-}
-
-FCD_API int fcd_wgrad_gemm_tc_error(void) {
-    int v = 0, zero = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    cudaMemcpyFromSymbol(&v, tc::g_error, sizeof(int));
-    cudaMemcpyToSymbol(tc::g_error, &zero, sizeof(int));
-    return v;
 }

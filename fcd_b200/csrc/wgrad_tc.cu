@@ -43,6 +43,7 @@ struct WgradTcParams {
     int ldn, ldk, n_off, k_off;
     int nks;                              // blockIdx.y = slice: k slice (y % nks) of CS channels, n slice (y / nks) of CU
     int Bn, D, H, W, nht, nwt, nseg, nitems;
+    int* status;
 };
 
 template <int CS, int CU, int DL>
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::PS_BYTES + NU * K::PU_BYTES);
     // bars: [0,NS) FULL_S | [NS,2NS) EMPTY_S | [2NS,2NS+NU) FULL_U | [2NS+NU,2NS+2NU) EMPTY_U | [2NS+2NU] DONE
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NU + 1);
-    volatile int* dead = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
     const uint32_t DONE = bar0 + 8u * (2 * NS + 2 * NU);
 
     if (tid == 0) {
-        *dead = 0;
+        wait_ctx_init(ctx, p.status, 4);
         for (int s = 0; s < NS; ++s) { mbar_init(FULL_S(s), 32 * NPS); mbar_init(EMPTY_S(s), NMMA); }
         for (int s = 0; s < NU; ++s) { mbar_init(FULL_U(s), 32); mbar_init(EMPTY_U(s), NMMA); }
         mbar_init(DONE, NMMA);
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
             for (int i = 0; i < NS; ++i, ++seq) {
                 const int s = seq % NS;                     // == i
                 const uint32_t ph = (seq / NS) & 1u;
-                mbar_wait(EMPTY_S(s), ph ^ 1u, dead, 1);
+                mbar_wait(EMPTY_S(s), ph ^ 1u, ctx, 1);
                 const int pl = it.d0 - 1 + i;
                 const bool inside = pl >= 0 && pl < p.D;    // planes outside the volume are zero-filled
                 const bf16* plane = Sp + ((long long)it.n * p.D + (inside ? pl : 0)) * plane_s;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
             for (int j = 0; j < DL; ++j, ++seq) {
                 const int s = seq % NU;
                 const uint32_t ph = (seq / NU) & 1u;
-                mbar_wait(EMPTY_U(s), ph ^ 1u, dead, 5);
+                mbar_wait(EMPTY_U(s), ph ^ 1u, ctx, 5);
                 const bf16* plane = col + (long long)j * plane_u;
                 const uint32_t dst0 = ring_u + s * K::PU_BYTES + c8 * K::SBO_B + v0 * 16;
 #pragma unroll
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
             const uint32_t sph = nitem & 1u;                 // every S slot is used exactly once per item
             int waited = 0;
             for (int j = 0; j < DL; ++j, ++useq) {
-                while (waited < j + 3) { mbar_wait(FULL_S(waited), sph, dead, 2); ++waited; }
+                while (waited < j + 3) { mbar_wait(FULL_S(waited), sph, ctx, 2); ++waited; }
                 const int us = useq % NU;
-                mbar_wait(FULL_U(us), (useq / NU) & 1u, dead, 6);
+                mbar_wait(FULL_U(us), (useq / NU) & 1u, ctx, 6);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_pl = a_lo0 + j * (K::PS_BYTES >> 4) + ((kh * HW * 16) >> 4);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
     }
 
     // ===================================================================== dump: one partial dW per CTA
-    mbar_wait(DONE, 0, dead, 7);
+    mbar_wait(DONE, 0, ctx, 7);
     tc_fence_after();
     __syncthreads();
     if (warp < 3) {
@@ -308,19 +309,11 @@ FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long
     p.S = (const bf16*)S; p.lds = lds; p.U = (const bf16*)U; p.ldu = ldu; p.part = part;
     p.ldn = ldn; p.ldk = ldk; p.n_off = n_off; p.k_off = k_off; p.nks = nks;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.nht = H / TH; p.nwt = W / TW; p.nseg = D / dl;
-    p.nitems = Bn * p.nht * p.nwt * p.nseg;
+    p.nitems = Bn * p.nht * p.nwt * p.nseg; p.status = fcd_status_dev();
     const int grid = p.nitems < 2 * fcd_num_sms() ? p.nitems : 2 * fcd_num_sms();   // == fcd_wgrad3_tc_nsplit
 #define FCD_WG_CASE(A, B, L) if (CS == A && CU == B && dl == L) return launch<A, B, L>(p, grid, nns * nks, stream)
     FCD_WG_CASE(16, 16, 8); FCD_WG_CASE(16, 32, 8); FCD_WG_CASE(32, 16, 8); FCD_WG_CASE(32, 32, 8);
     FCD_WG_CASE(16, 16, 4); FCD_WG_CASE(16, 32, 4); FCD_WG_CASE(32, 16, 4); FCD_WG_CASE(32, 32, 4);
 #undef FCD_WG_CASE
     return -1;
-}
-
-FCD_API int fcd_wgrad_tc_error(void) {
-    int v = 0, zero = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    cudaMemcpyFromSymbol(&v, tc::g_error, sizeof(int));
-    cudaMemcpyToSymbol(tc::g_error, &zero, sizeof(int));
-    return v;
 }

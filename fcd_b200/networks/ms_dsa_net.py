@@ -178,7 +178,7 @@ class MS_DSA_NET(nn.Module):
             x = getattr(self, f"encoder{lvl}")(xp)
             if lvl < 6:
                 xp, x = ops.pool_and_skip(x)
-                br[lvl] = ops.branch(x.device, key=lvl)
+                br[lvl] = ops.branch(x.device, key=lvl).hold(x)     # x is rebound below; the side stream still reads it
                 with br[lvl]:
                     ts[lvl] = stack(lvl, x)
             else:

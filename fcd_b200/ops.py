@@ -86,15 +86,25 @@ class _PackCache:
     A job is keyed by (parameter storage address, layout arguments) and stamped with the parameter's in-place
     version counter, so a stale copy is never used: `get` re-packs (one small launch) whenever the stamp differs.
     `refresh` re-packs EVERY known job in ONE launch (fcd_pack_weight_batched) and is called by the network at the
-    top of each forward: from the second step on the ~145 per-layer pack launches of a training step become one."""
+    top of each forward: from the second step on the ~145 per-layer pack launches of a training step become one.
+
+    The batched launch reads a device job table.  CUDA graphs (the training-step graph, the graphed window forward)
+    bake the table's ADDRESS and their job count into the launch, so the table lives in ONE fixed-capacity device
+    buffer (and one pinned host mirror) that is only ever updated in place, and jobs are only ever APPENDED: the first
+    n entries a graph was captured with stay the same jobs for as long as the buffer lives.  Whenever that cannot be
+    kept -- capacity exceeded, a job evicted because its parameter died (k-fold loops building model after model), or
+    the buffer had to be allocated inside a capture -- a new buffer is made and `epoch` is bumped; holders of captured
+    graphs compare epochs (`ops.pack_table_epoch`) and re-capture.  Jobs hold their parameter by weak reference."""
 
     JOB = None      # numpy dtype mirroring struct PackJob in csrc/wgrad.cu (96 bytes)
+    CAPACITY = 2048
 
     def __init__(self):
-        self.jobs = {}          # key -> [param_ref, args, dst, version]
-        self.table = {}         # device -> (njobs_at_build, jobs tensor, nblocks, keys)
+        self.jobs = {}          # key -> [weakref(param), args, dst, version]
+        self.table = {}         # device -> dict(keys, dev, host, nblocks, in_capture, capacity)
         self.dirty = {}         # device -> a grad-enabled forward ran since the last pack (see refresh)
         self.covered = set()    # job keys that are part of a batched table
+        self.epoch = {}         # device -> table generation (see class docstring)
 
     @staticmethod
     def _param_of(w):
@@ -102,6 +112,7 @@ class _PackCache:
         return base if isinstance(base, torch.nn.Parameter) else None
 
     def get(self, w, args):
+        import weakref
         src = w.detach()
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.float().contiguous()
@@ -115,12 +126,15 @@ class _PackCache:
             return dst
         key = (src.data_ptr(), src.device.index) + tuple(args)
         job = self.jobs.get(key)
+        if job is not None and job[0]() is not owner:
+            # the address was recycled for another parameter: the old job is dead
+            self._evict([key], src.device.index)
+            job = None
         if job is None:
-            job = self.jobs[key] = [owner, args, torch.empty((T, Np, Kp), dtype=BF16, device=src.device), -1]
+            job = self.jobs[key] = [weakref.ref(owner), args, torch.empty((T, Np, Kp), dtype=BF16, device=src.device), -1]
         # jobs the batched refresh does not cover yet (first forward of a network, ops used without a network) are
         # re-packed on every use: their version stamp alone would miss a fused optimizer's update (see refresh)
-        if key not in self.covered or job[3] != owner._version or job[0] is not owner:
-            job[0] = owner
+        if key not in self.covered or job[3] != owner._version:
             self._pack(src, job[2], args)
             job[3] = owner._version
         return job[2]
@@ -131,55 +145,97 @@ class _PackCache:
         call("fcd_pack_weight", src=src, dst=dst, T=T, N=N, K=K, Np=Np, Kp=Kp, sn=sn, sk=sk, st=st, kseg=kseg,
              ksegpad=ksegpad, nseg=nseg, nsegpad=nsegpad)
 
+    def _evict(self, keys, dev_index):
+        for k in keys:
+            self.jobs.pop(k, None)
+            self.covered.discard(k)
+        tab = self.table.get(dev_index)
+        if tab is not None and any(k in tab["keys"] for k in keys):
+            # entries would have to move: retire the buffer (graphs that baked it in keep it alive through `retired`)
+            self._retire(dev_index)
+
+    def _retire(self, dev_index):
+        tab = self.table.pop(dev_index, None)
+        if tab is not None:
+            self.retired = getattr(self, "retired", [])[-3:] + [tab]    # a few generations stay alive for old graphs
+            self.covered -= set(tab["keys"])
+        self.epoch[dev_index] = self.epoch.get(dev_index, 0) + 1
+
+    def _record(self, key, blk0):
+        _, args, dst, _ = self.jobs[key]
+        T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
+        total = T * Np * Kp
+        assert T in (1, 8, 27) and Kp % 8 == 0 and dst.data_ptr() % 16 == 0, "fcd_pack_weight_batched contract"
+        return (key[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk0), \
+            ((Np + 7) // 8) * ((Kp + 63) // 64)          # one block per 8 x 64 tile (csrc/wgrad.cu)
+
     def refresh(self, device):
         """Re-pack every job of `device` whose parameter changed since it was packed, in one launch."""
         import numpy as np
         if not self.jobs:
             return
-        keys = [k for k, j in self.jobs.items() if k[1] == device.index and j[0].data_ptr() == k[0]]
+        di = device.index
+        dead = [k for k, j in self.jobs.items() if k[1] == di and (j[0]() is None or j[0]().data_ptr() != k[0])]
+        if dead:
+            self._evict(dead, di)
+        keys = [k for k in self.jobs if k[1] == di]
         if not keys:
             return
+        if _PackCache.JOB is None:
+            _PackCache.JOB = np.dtype({"names": ["src", "dst", "sn", "sk", "st", "total", "T", "N", "K", "Np", "Kp",
+                                                 "kseg", "ksegpad", "nseg", "nsegpad", "blk0"],
+                                       "formats": ["<u8", "<u8", "<i8", "<i8", "<i8", "<i8"] + ["<i4"] * 10,
+                                       "offsets": [0, 8, 16, 24, 32, 40] + [48 + 4 * i for i in range(10)],
+                                       "itemsize": 96})
         # Inside CUDA-graph capture the launch must ALWAYS be recorded: the replayed graph has to re-pack from the
         # parameters as they are at replay time, whatever the stamps say at capture time.
         capturing = torch.cuda.is_current_stream_capturing()
-        tab = self.table.get(device.index)
-        # (re)build the job table whenever the set of jobs changed -- and once more, eagerly, if it had to be built
-        # inside a capture (its memory then belongs to that graph's private pool)
-        if tab is None or tab[0] != keys or (tab[4] and not capturing):
-            if _PackCache.JOB is None:
-                _PackCache.JOB = np.dtype({"names": ["src", "dst", "sn", "sk", "st", "total", "T", "N", "K", "Np", "Kp",
-                                                     "kseg", "ksegpad", "nseg", "nsegpad", "blk0"],
-                                           "formats": ["<u8", "<u8", "<i8", "<i8", "<i8", "<i8"] + ["<i4"] * 10,
-                                           "offsets": [0, 8, 16, 24, 32, 40] + [48 + 4 * i for i in range(10)],
-                                           "itemsize": 96})
-            rec = np.zeros(len(keys), dtype=_PackCache.JOB)
-            blk = 0
-            for i, k in enumerate(keys):
-                owner, args, dst, _ = self.jobs[k]
-                T, N, K, Np, Kp, sn, sk, st, kseg, ksegpad, nseg, nsegpad = args
-                total = T * Np * Kp
-                assert T in (1, 8, 27) and Kp % 8 == 0 and dst.data_ptr() % 16 == 0, "fcd_pack_weight_batched contract"
-                rec[i] = (k[0], dst.data_ptr(), sn, sk, st, total, T, N, K, Np, Kp, kseg, ksegpad, nseg, nsegpad, blk)
-                blk += ((Np + 7) // 8) * ((Kp + 63) // 64)      # one block per 8 x 64 tile (csrc/wgrad.cu)
-            host = torch.from_numpy(rec.view(np.uint8).copy()).pin_memory()   # pinned: legal inside graph capture
-            dev_tab = host.to(device, non_blocking=True)
-            tab = self.table[device.index] = (keys, dev_tab, blk, host, capturing)   # host: keep the pinned source alive
-            self.covered = {k for t in self.table.values() for k in t[0]}
+        tab = self.table.get(di)
+        if tab is not None and (len(keys) > tab["capacity"] or (tab["in_capture"] and not capturing)):
+            self._retire(di)            # too small, or its memory belongs to a graph's private pool
+            tab = None
+        if tab is None:
+            cap = max(self.CAPACITY, 2 * len(keys))
+            host = torch.zeros(cap * 96, dtype=torch.uint8).pin_memory()
+            tab = self.table[di] = dict(keys=[], dev=torch.zeros(cap * 96, dtype=torch.uint8, device=device), host=host,
+                                        nblocks=0, in_capture=capturing, capacity=cap)
+            self.epoch.setdefault(di, 0)
+        known = tab["keys"]
+        if known != keys:
+            # jobs are only ever appended (dict order = insertion order; evictions retire the whole buffer)
+            assert keys[:len(known)] == known, "pack job table: jobs may only be appended"
+            rec = np.zeros(len(keys) - len(known), dtype=_PackCache.JOB)
+            blk = tab["nblocks"]
+            for i, k in enumerate(keys[len(known):]):
+                rec[i], nb = self._record(k, blk)
+                blk += nb
+            lo, hi = len(known) * 96, len(keys) * 96
+            tab["host"][lo:hi].copy_(torch.from_numpy(rec.view(np.uint8).copy()))
+            tab["dev"][lo:hi].copy_(tab["host"][lo:hi], non_blocking=True)     # pinned source: legal inside capture
+            tab["keys"] = list(keys)
+            tab["nblocks"] = blk
+            self.covered |= set(keys)
         # The version stamps cannot be trusted across an optimizer step: torch's FUSED optimizers update the
         # parameters in place without bumping `_version`.  So a grad-enabled forward always re-packs (an optimizer step
         # may have happened since the last one, 0.12 ms), and marks the copies dirty for the first no-grad forward
         # that follows (evaluation right after training); only no-grad forwards with clean, unchanged parameters skip.
         grad_mode = torch.is_grad_enabled()
-        if not capturing and not grad_mode and not self.dirty.get(device.index, False) \
-                and all(self.jobs[k][3] == self.jobs[k][0]._version for k in keys):
+        if not capturing and not grad_mode and not self.dirty.get(di, False) \
+                and all(self.jobs[k][3] == self.jobs[k][0]()._version for k in keys):
             return
-        self.dirty[device.index] = grad_mode
-        call("fcd_pack_weight_batched", jobs=tab[1], njobs=len(keys), nblocks=tab[2])
+        self.dirty[di] = grad_mode
+        call("fcd_pack_weight_batched", jobs=tab["dev"], njobs=len(keys), nblocks=tab["nblocks"])
         for k in keys:
-            self.jobs[k][3] = self.jobs[k][0]._version
+            self.jobs[k][3] = self.jobs[k][0]()._version
 
 
 _PACKS = _PackCache()
+
+
+def pack_table_epoch(device):
+    """Generation of the batched weight-pack job table of `device`; a CUDA graph captured under another generation reads
+    a retired table and must be captured again (see _PackCache)."""
+    return _PACKS.epoch.get(device.index, 0)
 
 
 def prepack_weights(device):
@@ -322,6 +378,14 @@ class branch:
                 st = _BRANCH_STREAMS[(device.index, key)] = torch.cuda.Stream(device=device)
             self.side = st
             self.ctx = torch.cuda.stream(st)
+        self.held = []
+
+    def hold(self, *tensors):
+        """Keep main-stream tensors the branch reads alive until `join`: without autograd (eval / no_grad, graphed
+        window forward) nothing else references them, and the caching allocator would hand their memory to later
+        main-stream work while the side stream may still be reading it."""
+        self.held.extend(tensors)
+        return self
 
     def __enter__(self):
         if self.on:
@@ -340,6 +404,7 @@ class branch:
     def join(self):
         if self.on:
             self.main.wait_stream(self.side)
+        self.held.clear()
 
 
 def attach_stats(x, mode, eps):
@@ -935,10 +1000,25 @@ def step_counter(device):
     return c
 
 
+_STEP_SNAP = {}
+
+
 def tick(device):
     """Advance the step counter; the networks call it at the top of a training forward.  In-kernel dropout mixes the
-    counter into its seed, so a CUDA-graph replay (whose kernel arguments are frozen) still draws new masks."""
-    step_counter(device).add_(1)
+    counter into its seed, so a CUDA-graph replay (whose kernel arguments are frozen) still draws new masks.
+
+    The value is also copied into a fresh one-element tensor (`step_snapshot`): kernels that must regenerate a forward
+    mask in BACKWARD (DSA spatial-attention dropout) read the snapshot of THEIR forward, so a second training forward
+    before that backward (two forwards then one backward, a grad-enabled validation pass) cannot change their mask."""
+    c = step_counter(device)
+    c.add_(1)
+    _STEP_SNAP[device.index] = c.clone()
+
+
+def step_snapshot(device):
+    """The step-counter value of the latest training forward on `device` (see `tick`)."""
+    snap = _STEP_SNAP.get(device.index)
+    return snap if snap is not None else step_counter(device)
 
 
 class DSAFn(Function):
@@ -966,18 +1046,19 @@ class DSAFn(Function):
         t1 = temperature.detach().float().contiguous()
         t2 = temperature2.detach().float().contiguous()
         g = gamma.detach().float().contiguous()
+        snap = step_snapshot(dev) if sa_drop > 0 else None      # the backward regenerates the mask from the SAME value
         call("fcd_dsa_fwd", qkvv=qkvv, ldq=ld(qkvv), EF=EFc, temperature=t1, temperature2=t2, gamma=g, t=t, ldt=ld(t),
              y=y, ldy=Cp, ca_scale=ca_scale, sa_drop=float(sa_drop), seed=int(seed),
-             seed_dev=step_counter(dev) if sa_drop > 0 else None, part=part, inv_n=inv_n, Ghat=Ghat,
+             seed_dev=snap, part=part, inv_n=inv_n, Ghat=Ghat,
              A=A, Ad=Ad, KV=KV, xca=xca, tsa=tsa, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
-        ctx.save_for_backward(qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale)
+        ctx.save_for_backward(qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale, snap)
         ctx.cfg = (C, H, P, float(sa_drop), int(seed), Cp, (B, D, Hs, W), tuple(temperature.shape))
         ctx.ef_param = EF if isinstance(EF, torch.nn.Parameter) else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale = ctx.saved_tensors
+        qkvv, EFc, t1, t2, g, inv_n, Ghat, A, Ad, KV, xca, tsa, ca_scale, snap = ctx.saved_tensors
         C, H, P, sa_drop, seed, Cp, (B, D, Hs, W), tshape = ctx.cfg
         N = D * Hs * W
         c = C // H
@@ -1003,7 +1084,7 @@ class DSAFn(Function):
         dEF = None if ef_side else torch.empty((N, P), **f32)
         call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
              gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed,
-             seed_dev=step_counter(dev) if sa_drop > 0 else None, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
+             seed_dev=snap, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
              xca=xca, tsa=tsa, part=part, dqh=dqh, dKV=dKV, dGhat=dGhat, rqk=rqk, gpart=gpart, dqkvv=dqkvv,
              lddq=dqkvv.shape[4], dEF=dEF, dtemp=dtemp, dtemp2=dtemp2, dgamma=dgamma, B=B, N=N, C=C, Cp=Cp, H=H, P=P)
         if ef_side:

@@ -25,6 +25,20 @@
 #define FCD_API
 #endif
 
+/* ---- status block: every pipeline wait of the tcgen05 kernels is bounded; the first wait that times out writes the
+ * sticky error word (kernel id << 24 | wait site << 16 | CTA; kernel ids: 1 fcd_conv3_tc, 2 fcd_conv3_tcf,
+ * 3 fcd_conv_gemm_tc, 4 fcd_wgrad3_tc, 5 fcd_wgrad_gemm_tc) and a debug record into a device-resident block of
+ * FCD_STATUS_INTS ints: [0] error word, [1] kernel id, [2] wait site, [3] CTA, [4] thread, [5] mbarrier shared
+ * address, [6] parity waited for, [7] work item, [8] grid size, [9] blockIdx.y, [16..48) the CTA's per-role progress
+ * counters (meaning documented at the top of each kernel).  fcd_loss_fwd and fcd_sw_finalize read word 0 on the device
+ * and turn a non-zero value into NaN results (the reference has no such failure mode: train.py:374-382 would simply
+ * hang or crash), so a fault cannot pass silently.  fcd_status copies the block to host_out[FCD_STATUS_INTS] (NULL:
+ * skip), clears it when `clear` != 0, and returns word 0; it synchronises the device.  The per-kernel *_error
+ * accessors below are aliases: value-and-clear of the same word. ---- */
+#define FCD_STATUS_INTS 48
+FCD_API int fcd_status(int* host_out, int clear);
+FCD_API int fcd_status_device_ptr(void** out);
+
 /* ---- layout (train.py:367-370 feeds fp32 NCDHW batches; the model returns NCDHW logits, train.py:374) ---- */
 FCD_API int fcd_ncdhw_to_ndhwc(const float* src, void* dst, int B, int C, int Cp, long long S, cudaStream_t stream);
 FCD_API int fcd_ndhwc_to_ncdhw(const void* src, float* dst, int B, int C, long long ld, long long S,
@@ -103,10 +117,6 @@ FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long
                           cudaStream_t stream);
 FCD_API int fcd_wgrad_tc_error(void);
 
-/* measurement aid (not on the product path): cycles for back-to-back tcgen05.mma of shape M x N x 16, see
- * csrc/umma_bench.cu and tools/umma_bench.py */
-FCD_API int fcd_umma_bench(int M, int N, int iters, int nissue, int same_acc, int ctas, long long* cycles,
-                           cudaStream_t stream);
 
 /* ---- torch.max_pool3d(x, 2, 2) (ms_dsa_net.py:92, 378-382).  bwd: add (optional, rows of pitch ldadd) is the gradient
  *      x receives from its other consumer (the skip connection, ms_dsa_net.py:386-390): dx = pool_bwd(dy) + add. ---- */
@@ -216,10 +226,29 @@ FCD_API int fcd_mse_bwd(const float* a, const float* b, long long n, const float
  *      train.py:185,209-211 / get_transforms.py:142-154).  starts_zyx is a HOST array of nwin*3 ints. ---- */
 FCD_API int fcd_sw_gather(const float* vol, void* dst, int C, int Cp, int D, int H, int W, int r0, int r1, int r2,
                           int pz, int py, int px, const int* starts_zyx, int nwin, cudaStream_t stream);
-FCD_API int fcd_sw_blend(const float* pred, float* out, int C, int r0, int r1, int r2, int Dp, int Hp, int Wp, int z0,
-                         int y0, int x0, cudaStream_t stream);
+/* blend: out[c*sc + (z0+z)*sz + (y0+y)*Wp + (x0+x)] += pred[c][z][y][x] (fp32, one launch per window: the reference's
+ * window order).  The accumulation volume is channel-major [C][Dp][Hp][Wp] (sc = Dp*Hp*Wp, sz = Hp*Wp) or plane-major
+ * [Dp][C][Hp][Wp] (sc = Hp*Wp, sz = C*Hp*Wp), the layout whose D-slabs are contiguous for the multi-GPU reduce-scatter.
+ * finalize: unpadded planes z in [z_lo, z_hi): v = acc / (cz*cy*cx) (per-axis coverage counts, padded frame), written
+ * to dst (optional, [C][out_planes][H][W], plane z - out_z0) and turned into the label map (mode 1: softmax >= 0.5 per
+ * channel, float; mode 2: argmax, uint8; same plane addressing); acc plane 0 is padded plane acc_z0. */
+FCD_API int fcd_sw_blend(const float* pred, float* out, int C, int r0, int r1, int r2, int Wp, long long sc,
+                         long long sz, int z0, int y0, int x0, cudaStream_t stream);
 FCD_API int fcd_sw_finalize(const float* acc, const int* cz, const int* cy, const int* cx, float* dst, float* label_f,
-                            void* label_u8, int C, int D, int H, int W, int Dp, int Hp, int Wp, int pz, int py, int px,
-                            int z_lo, int z_hi, int mode, cudaStream_t stream);
+                            void* label_u8, int C, int H, int W, int Wp, long long sc, long long sz, int pz, int py,
+                            int px, int z_lo, int z_hi, int acc_z0, int out_z0, int out_planes, int mode,
+                            cudaStream_t stream);
+
+/* ---- post-processing of the predicted mask: utils/utils_common.py:10-33 post_process_segment as called by
+ *      ModelTrainer.post_process (train.py:167-182), on the device and bit-exact against the reference's scipy calls:
+ *      binary_opening (6-connected, 1 iteration) -> binary_fill_holes(structure = ones 5^3) -> label(structure = ones
+ *      3^3, numbered in raster order) -> keep components with >= l_min voxels (l_min = -1: the largest; the reference's
+ *      quirks for empty / full masks and l_min <= 0 are kept).  Input: pred_f (fp32 [D][H][W], mask = pred_f >
+ *      threshold, train.py:173) or pred_u8 (uint8, mask = != 0), exactly one non-NULL.  Outputs (either may be NULL):
+ *      out_mask, out_lab fp32 [D][H][W] = output_msk / output_lab of the reference.  ws: fcd_post_process_ws_bytes()
+ *      bytes of device scratch, 256-byte aligned.  No host synchronisation. ---- */
+FCD_API long long fcd_post_process_ws_bytes(int D, int H, int W);
+FCD_API int fcd_post_process(const float* pred_f, const void* pred_u8, float threshold, int l_min, float* out_mask,
+                             float* out_lab, int D, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream);
 
 #endif /* FCD_B200_H */

@@ -1,9 +1,20 @@
 """Cycles per tcgen05.mma (M x N x 16, bf16, operands in shared memory, no-swizzle K-major) on this B200.
 python tools/umma_bench.py"""
+import ctypes
+import os
+import subprocess
 import sys
 import torch
-sys.path.insert(0, ".")
-from fcd_b200 import _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libumma_bench.so")
+if not os.path.exists(SO):        # measurement aid, deliberately NOT part of the product library
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
+                           "-Xcompiler", "-fPIC", "-I", os.path.join(HERE, "..", "include"),
+                           os.path.join(HERE, "umma_bench.cu"), "-o", SO])
+LIB = ctypes.CDLL(SO)
+LIB.fcd_umma_bench.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]
 
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 ITERS = 4096
@@ -11,7 +22,8 @@ ITERS = 4096
 
 def run(M, N, nissue, same, ctas=1):
     for _ in range(2):
-        _lib.call("fcd_umma_bench", M=M, N=N, iters=ITERS, nissue=nissue, same_acc=same, ctas=ctas, cycles=out)
+        rc = LIB.fcd_umma_bench(M, N, ITERS, nissue, same, ctas, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, rc
     torch.cuda.synchronize()
     return float(out.item()) / (ITERS * nissue)
 
