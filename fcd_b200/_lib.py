@@ -60,6 +60,22 @@ PROTOS = parse_header()
 _lib = None
 
 
+def _check_fresh():
+    """The .so must have been built from the sources next to it: a stale library silently tests / benches old kernels.
+    Rebuild when nvcc is there (seconds), fail loudly otherwise."""
+    from . import build as _build
+    try:
+        fresh = os.path.exists(_build.STAMP) and open(_build.STAMP).read().strip() == _build._digest()
+    except OSError:
+        fresh = True            # sources not shipped (binary-only deployment): nothing to compare with
+    if fresh or os.environ.get("FCD_B200_LIB"):
+        return
+    import shutil
+    if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
+        raise RuntimeError(f"{LIBPATH} is older than fcd_b200/csrc: rebuild it with `python -m fcd_b200.build`")
+    _build.build()
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -67,6 +83,7 @@ def lib():
             raise RuntimeError(
                 f"{LIBPATH} is missing: build it with `python -m fcd_b200.build` (nvcc, sm_100a). "
                 "fcd_b200 has no CPU or library fallback.")
+        _check_fresh()
         _lib = ctypes.CDLL(LIBPATH)
         for name, params in PROTOS.items():
             fn = getattr(_lib, name)       # raises AttributeError if the .so lacks a declared symbol

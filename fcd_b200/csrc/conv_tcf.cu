@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + NPB + R);
     WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
     float* red = reinterpret_cast<float*>(ctx + 1);
-    // ctx->prog (debug record of a timed-out wait): [0] producer plane seq, [1] its item; [2+me] MMA warp's plane
-    // counter g, [5+me] its item, [8+me] (wait site << 24 | sq or zc); [11+q] epilogue outputs done, [15+q] planes
-    // waited, [19+q] its item; [23] nitems, [24] nseg, [25] DL
+    // ctx->prog (debug record of a timed-out wait): [0] / [26] producer warp 0 / 1 plane seq, [1] / [27] its item;
+    // [2+me] MMA warp's plane counter g, [5+me] its item, [8+me] (wait site << 24 | sq or zc; site 7 = issued g);
+    // [11+q] epilogue outputs done, [15+q] plane it waits for (| 0x40000000: past the waits), [19+q] its item;
+    // [23] nitems, [24] nseg, [25] DL
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             const long long plane_elems = (long long)p.H * p.W * p.lda;
             for (int pl = it.p_lo; pl <= it.p_hi; ++pl, ++seq) {
                 const int s = seq % NST;
-                if (pt == 0) { prog_set(ctx, 0, (int)seq); prog_set(ctx, 1, item); }
-                mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, ctx, 1, item);
+                if (lane == 0) { prog_set(ctx, warp == 0 ? 0 : 26, (int)seq); prog_set(ctx, warp == 0 ? 1 : 27, item); }
+                mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, ctx, 1, (int)seq);
                 const bf16* plane = p.A + ((long long)it.n * p.D + pl) * plane_elems;
                 const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A + v0 * 16;
 #pragma unroll
@@ -280,11 +281,13 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 const int slot = zc % R;
                 // output j = od - d0 is complete when planes j, j+1, j+2 of this item have been multiplied
                 const uint32_t need = pc0 + (uint32_t)(od - it.d0) + 3;
-                if (lane == 0) { prog_set(ctx, 11 + q, (int)zc); prog_set(ctx, 15 + q, (int)pwaited); prog_set(ctx, 19 + q, item); }
+                if (lane == 0) { prog_set(ctx, 11 + q, (int)zc); prog_set(ctx, 19 + q, item); }
                 while (pwaited < need) {
-                    mbar_wait(PDONE(pwaited % NPB), (pwaited / NPB) & 1u, ctx, 4, item);
+                    if (lane == 0) prog_set(ctx, 15 + q, (int)pwaited);
+                    mbar_wait(PDONE(pwaited % NPB), (pwaited / NPB) & 1u, ctx, 4, (int)pwaited);
                     ++pwaited;
                 }
+                if (lane == 0) prog_set(ctx, 15 + q, (int)pwaited | 0x40000000);      // past the waits of this output
                 tc_fence_after();
                 uint32_t t[3][COUT];
 #pragma unroll

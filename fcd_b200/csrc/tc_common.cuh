@@ -29,7 +29,11 @@ __device__ __forceinline__ void wait_ctx_init(WaitCtx* c, int* status, int kerne
     c->status = status;
     for (int i = 0; i < kProgInts; ++i) c->prog[i] = -1;
 }
-__device__ __forceinline__ void prog_set(WaitCtx* c, int i, int v) { reinterpret_cast<volatile int*>(c->prog)[i] = v; }
+// progress words freeze once a wait of the CTA has timed out (the other roles then fall through their waits and run
+// ahead: the record must show where they stood, not where they got to afterwards)
+__device__ __forceinline__ void prog_set(WaitCtx* c, int i, int v) {
+    if (reinterpret_cast<volatile int*>(&c->dead)[0] == 0) reinterpret_cast<volatile int*>(c->prog)[i] = v;
+}
 
 // ---------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

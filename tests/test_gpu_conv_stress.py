@@ -52,6 +52,8 @@ STRESS_CASES = [
     (5, 32, 16, 128, 2, 0, 300),
     (5, 16, 16, 128, 2, 1, 100),      # data-gradient orientation of the same
     (5, 32, 32, 64, 8, 0, 300),       # 160 columns x 8 segments of 8 planes: 2-9 SHORT items per CTA
+    (4, 64, 32, 64, 8, 0, 600),       # decoder2.conv1 of a 4-window batch: the shape round 2's reproducer timed out in
+    (5, 64, 32, 64, 8, 0, 300),
     (5, 16, 32, 64, 8, 0, 200),
     (5, 64, 32, 32, 8, 0, 300),       # 40 columns x 8 segments of FOUR planes, 4-stage ring (DEPTH 1), one CTA per SM
     (5, 64, 32, 32, 8, 1, 100),

@@ -145,23 +145,23 @@ def test_sliding_window_bit_exact(name, B, size, roi, ov, bs, fast):
 
 
 def test_sliding_window_model_vs_oracle():
-    """A real network (BaseUNet fs 4 on 32^3 windows, bf16 kernels) against the fp32 CPU oracle network through the
+    """A real network (BaseUNet fs 4 on 64^3 windows, bf16 kernels) against the fp32 CPU oracle network through the
     oracle's sliding window: bf16 tolerance on the logits, label flips only on near-ties."""
     import contextlib
     import io
     import fcd_b200
     from oracle import nets as onets
     params = fcd_b200.get_default_params()
-    params.update(model_type="baseunet", patch_size=(32,) * 3, feature_size=4)
+    params.update(model_type="baseunet", patch_size=(64,) * 3, feature_size=4)
     with contextlib.redirect_stdout(io.StringIO()):
         model, _ = fcd_b200.get_model(params)
     sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=1)
     model.load_state_dict(sd)
     model = model.to(DEV).eval()
-    x = synth.image(1, 2, (64, 48, 40), seed=3)
+    x = synth.image(1, 2, (96, 64, 80), seed=3)
     with torch.no_grad():
-        ref = oinf.sliding_window_inference(x, 32, 4, lambda t: onets.forward("baseunet", sd, t, False, {}), 0.5)
-        out, lab = _sw()(x.to(DEV), 32, 4, model, overlap=0.5, label_mode="argmax")
+        ref = oinf.sliding_window_inference(x, 64, 3, lambda t: onets.forward("baseunet", sd, t, False, {}), 0.5)
+        out, lab = _sw()(x.to(DEV), 64, 3, model, overlap=0.5, label_mode="argmax")
     rel = float((out.cpu().double() - ref.double()).norm() / ref.double().norm())
     ref_lab = oinf.label_map(ref, "argmax")
     flip = lab.cpu().long() != ref_lab

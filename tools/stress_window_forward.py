@@ -11,6 +11,7 @@ running on another stream (SM pressure: fewer CTAs of a launch resident at once,
 Prints `RESULT ok` or `RESULT FAILED`."""
 import contextlib
 import io
+import os
 import sys
 import time
 
@@ -61,7 +62,10 @@ def main():
                     for _ in range(busy):
                         a = torch.tanh(a @ a * 1e-4)
             t0 = time.perf_counter()
-            gf.graph.replay()
+            if os.environ.get("MODE", "graph") == "eager":      # the same forward launched kernel by kernel
+                gf.y.copy_(gf._fwd(model))
+            else:
+                gf.graph.replay()
             torch.cuda.synchronize()
             times.append((time.perf_counter() - t0) * 1e3)
             st = _lib.status()
