@@ -406,14 +406,12 @@ FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
     for (int c = 1; c == 1 || D / c >= 4; c *= 2) {
         const int dl = (D + c - 1) / c;
         if ((D + dl - 1) / dl != c) continue;
-        // Several d-segments per column are only used while every CTA gets at most ONE work item.  With segments AND
-        // several items per CTA (4-5 inference windows per rank: 640 columns x 2 segments on 296 CTAs) the kd-folded
-        // kernel hit rare bounded-wait time-outs (a 0.2 s stall and a bad tile, `fcd_tcf_error` != 0); both regimes on
-        // their own -- segments with one item per CTA (training), many full-depth items per CTA (18-window inference)
-        // -- have run clean throughout.  Root cause not found this round.
-        // FCD_NSEG_UNRESTRICTED=1 lifts the restriction (reproducer / stress runs only).
-        static const bool unrestricted = getenv("FCD_NSEG_UNRESTRICTED") != nullptr;
-        if (!unrestricted && c > 1 && (long long)cols * c > sms) continue;
+        // (Round 1 restricted c > 1 to one work item per CTA because segments AND several items per CTA hit rare
+        // time-outs; the cause -- an aliased FULL-barrier parity wait at item boundaries with one padding plane,
+        // conv_tcf.cu -- is fixed, tests/test_gpu_conv_stress.py covers the regime.  FCD_NSEG_RESTRICTED=1 restores
+        // the old choice for A/B timing.)
+        static const bool restricted = getenv("FCD_NSEG_RESTRICTED") != nullptr;
+        if (restricted && c > 1 && (long long)cols * c > sms) continue;
         const long long cost = (long long)((cols * c + sms - 1) / sms) * (dl + 1);
         if (best < 0 || cost < best) { best = cost; nseg = c; }
     }

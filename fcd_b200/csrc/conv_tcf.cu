@@ -15,6 +15,8 @@
 // (Measured: ONE issuing warp with one accumulator set -- lighter epilogue, 3 CTAs per SM -- is 1.5x SLOWER:
 // 0.189 vs 0.120 ms for 16->16 @128^3; the single issue stream / accumulate chain becomes the limiter again.)
 // Producers, halo-plane ring, weight staging from the fp32 parameter, fused statistics: as in conv_tc.cu.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -39,6 +41,7 @@ struct ConvTcfParams {
     float* part;
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
     int* status;
+    int dbg_delay_ns, dbg_single_full_wait;   // reproducer switches (FCD_TCF_PRODUCER_DELAY_NS, FCD_TCF_SINGLE_FULL_WAIT)
 };
 
 template <int CIN, int COUT>
@@ -54,7 +57,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
     static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;
     static constexpr int CTAS_PER_SM = (COUT == 16 && 2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
-    static_assert(NST >= 4 && TCOLS <= 512, "resources");
+    static_assert(NST >= 4 && TCOLS <= 512, "resources");   // NST >= 4: the FULL double wait needs 7 < 2 NST
 };
 
 struct Item { int n, h0, w0, d0, d1, p_lo, p_hi, chunk; };
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 const int s = seq % NST;
                 if (lane == 0) { prog_set(ctx, warp == 0 ? 0 : 26, (int)seq); prog_set(ctx, warp == 0 ? 1 : 27, item); }
                 mbar_wait(EMPTY(s), ((seq / NST) & 1u) ^ 1u, ctx, 1, (int)seq);
+                if (p.dbg_delay_ns > 0) __nanosleep((unsigned)p.dbg_delay_ns);
                 const bf16* plane = p.A + ((long long)it.n * p.D + pl) * plane_elems;
                 const uint32_t dst0 = ring_u + s * K::PLANE_BYTES + c8 * K::LBO_A + v0 * 16;
 #pragma unroll
@@ -223,7 +227,19 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 if (valid) {
                     sq = seq_base + (pl - it.p_lo);
                     if (lane == 0) prog_set(ctx, 8 + me, (2 << 24) | (int)(sq & 0xffffff));
-                    mbar_wait(FULL(sq % NST), (sq / NST) & 1u, ctx, 2, item);
+                    // A parity wait is only meaningful while the waiter is at most ONE phase ahead of the barrier.  A
+                    // warp's consecutive planes are 3 apart in the plane counter g, but when the plane in between is a
+                    // zero-padding plane it owns (an item boundary) the next LOADED plane it waits for can be up to 7
+                    // ring positions after the last one it consumed -- more than the NST = 4 stages of the 64 -> 32
+                    // configuration.  Slot sq % NST may then still be waiting for plane sq - NST, and "phase sq / NST
+                    // done" would be answered from plane sq - 2 NST, which has the same parity: the warp would multiply
+                    // a stale plane and its early EMPTY arrival would leave the producer one phase out of step (the
+                    // time-outs and bad tiles of round 1: segments AND several items per CTA give boundaries with
+                    // exactly one padding plane).  Waiting for plane sq - NST first keeps every wait in step: at that
+                    // point plane sq - 2 NST is certainly loaded (7 < 2 NST).
+                    const uint32_t ph = sq / NST;
+                    if (ph > 0 && !p.dbg_single_full_wait) mbar_wait(FULL(sq % NST), (ph - 1u) & 1u, ctx, 5, item);
+                    mbar_wait(FULL(sq % NST), ph & 1u, ctx, 2, item);
                 }
                 // every output this plane touches must have been handed back (zeroed) by the epilogue; this also
                 // keeps a warp from running more than R outputs ahead, i.e. from lapping the PDONE phases
@@ -383,6 +399,9 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     if (p.nseg != nseg) return -1;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
     p.status = fcd_status_dev();
+    static const int dbg_delay = getenv("FCD_TCF_PRODUCER_DELAY_NS") ? atoi(getenv("FCD_TCF_PRODUCER_DELAY_NS")) : 0;
+    static const int dbg_single = getenv("FCD_TCF_SINGLE_FULL_WAIT") != nullptr;
+    p.dbg_delay_ns = dbg_delay; p.dbg_single_full_wait = dbg_single;
 #define FCD_TCF_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, flip, stream)
     FCD_TCF_CASE(16, 16); FCD_TCF_CASE(32, 16); FCD_TCF_CASE(64, 16);
     FCD_TCF_CASE(16, 32); FCD_TCF_CASE(32, 32); FCD_TCF_CASE(64, 32);

@@ -390,23 +390,20 @@ def test_wgrad_gemm_tc(ops, B, Ci, Co, D, H, W):
     close(w2.grad, gw, rel=6e-3, what="wgrad gemm_tc")
 
 
-def test_depth_segments_only_with_one_item_per_cta(ops):
-    """`fcd_conv3_tc_nseg` never combines several d-segments per column with several work items per CTA (the open
-    defect of DESIGN.md section 9, item 0): nseg > 1 only while columns x nseg <= SM count.  The 4-5 window batches of
-    sharded sliding-window inference (640 columns at 128^3) must therefore run full-depth columns; the small training
-    levels keep their segments."""
+def test_segment_chooser_minimises_rounds(ops):
+    """`fcd_conv3_tc_nseg` minimises rounds x (planes per item + 1) over power-of-two segment counts with >= 4 planes
+    per segment.  Round 1 additionally forbade several segments together with several work items per CTA (the open
+    defect of that round); with the FULL-barrier double wait in conv_tcf.cu the restriction is gone: the 4-5 window
+    batches of sharded inference get their segments back (tests/test_gpu_conv_stress.py runs exactly those shapes)."""
     from fcd_b200 import _lib
     L = _lib.lib()
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for B in (1, 2, 3, 4, 5, 9, 18):
-        for S in (16, 32, 64, 128):
-            for K, N in ((16, 16), (32, 16), (32, 32), (64, 32)):
+    for B in (1, 2, 4, 5, 9, 18):
+        for S in (32, 64, 128):
+            for K, N in ((16, 16), (32, 16), (32, 32), (64, 32), (32, 64)):
                 nseg = L.fcd_conv3_tc_nseg(B, S, S, S, K, N)
-                cols = B * (S // 16) * (S // 8)
-                assert nseg >= 1
-                assert nseg == 1 or cols * nseg <= sms, (B, S, K, N, nseg)
-                assert S // nseg >= 4
-    assert L.fcd_conv3_tc_nseg(5, 128, 128, 128, 16, 16) == 1
-    assert L.fcd_conv3_tc_nseg(4, 128, 128, 128, 32, 16) == 1
-    assert L.fcd_conv3_tc_nseg(2, 64, 64, 64, 32, 32) == 2          # training level 2: 64 columns x 2 segments
-    assert L.fcd_conv3_tc_nseg(2, 32, 32, 32, 64, 32) > 1           # training level 3 keeps its segments
+                assert nseg >= 1 and S % nseg == 0
+                assert nseg == 1 or S // nseg >= 4
+    assert L.fcd_conv3_tc_nseg(5, 128, 128, 128, 16, 16) == 2      # 640 columns: 5 rounds of 65 planes beat 3 of 129
+    assert L.fcd_conv3_tc_nseg(18, 128, 128, 128, 16, 16) == 1
+    assert L.fcd_conv3_tc_nseg(2, 64, 64, 64, 32, 32) >= 2
+    assert L.fcd_conv3_tc_nseg(2, 32, 32, 32, 64, 32) > 1
