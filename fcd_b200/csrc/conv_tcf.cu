@@ -27,10 +27,10 @@ constexpr int TH = 16, TW = 8, HH = TH + 2, HW = TW + 2, HV = HH * HW;
 constexpr int NPROD = 2, NMMA = 3;
 constexpr int NTHREADS = 32 * (NPROD + NMMA + 4);
 constexpr int R = 5;                      // accumulator ring slots (3 accumulating + slack for the epilogue)
-// Plane-done barriers: a multiple of NMMA (one warp owns every phase of a barrier) and more than the furthest the MMA
-// warps can run ahead of the epilogue's wait pointer -- TEMPTY keeps them within R = 5 outputs, i.e. within
-// 5 + 2 planes per item boundary crossed (<= 4 boundaries with 1-plane items) + 2 = 15 planes -- so a barrier can never
-// complete two phases before the epilogue has looked at the first.
+// Plane-done barriers: more than the furthest the MMA warps can run ahead of the epilogue's wait pointer -- every plane
+// (loaded or padding) first waits for TEMPTY of the outputs it touches, which keeps the warps within R = 5 outputs,
+// i.e. within 5 + 2 planes per item boundary crossed (<= 4 boundaries with 1-plane items) + 2 = 15 planes -- so a
+// barrier can never complete two phases before the epilogue has looked at the first.
 constexpr int NPB = 18;
 
 struct ConvTcfParams {
@@ -41,7 +41,7 @@ struct ConvTcfParams {
     float* part;
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
     int* status;
-    int dbg_delay_ns, dbg_single_full_wait;   // reproducer switches (FCD_TCF_PRODUCER_DELAY_NS, FCD_TCF_SINGLE_FULL_WAIT)
+    int dbg_delay_ns;                         // reproducer switch FCD_TCF_PRODUCER_DELAY_NS: slow the producers down
 };
 
 template <int CIN, int COUT>
@@ -57,7 +57,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
     static constexpr int SMEM = W_BYTES + NST * PLANE_BYTES + 2560;
     static constexpr int CTAS_PER_SM = (COUT == 16 && 2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
-    static_assert(NST >= 4 && TCOLS <= 512, "resources");   // NST >= 4: the FULL double wait needs 7 < 2 NST
+    static_assert(NST >= 4 && TCOLS <= 512, "resources");   // NST > NMMA: see the FULL wait of the MMA warps
 };
 
 struct Item { int n, h0, w0, d0, d1, p_lo, p_hi, chunk; };
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
         flush_to(seq);
     } else if (warp < NPROD + NMMA) {
         // ===================================================================== MMA issuers: the three warps take turns on
-        // PLANES (plane g -> warp g % 3): one warp pays a plane's waits / commits / bookkeeping once and issues all
+        // PLANES: one warp pays a plane's waits / commits / bookkeeping once and issues all
         // 9*CIN/16 instructions of it, while the other two work on the neighbouring planes.  Each warp accumulates
         // into its own set of R slots (concurrent warps never share an accumulator); the epilogue adds the three sets.
         const int me = warp - NPROD;
@@ -218,28 +218,25 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             const int nload = it.p_hi - it.p_lo + 1, DLi = it.d1 - it.d0;
             for (int i = 0; i <= DLi + 1; ++i) {               // input plane z = d0 - 1 + i feeds outputs i-2, i-1, i
                 const uint32_t g = pc0 + i;
-                if ((int)(g % NMMA) != me) continue;
                 const int pl = it.d0 - 1 + i;
                 const bool valid = pl >= 0 && pl < p.D;
+                // LOADED planes take turns by their position in the halo ring (sq % 3), zero-padding planes by the plane
+                // counter.  A parity wait is only meaningful while the waiter is at most one phase behind the barrier:
+                // waiting for plane sq on slot sq % NST presumes plane sq - NST has been loaded.  With turns by sq a
+                // warp's consecutive FULL waits are exactly 3 ring positions apart, so the plane it consumed last
+                // (sq - 3) vouches for plane sq - NST (NST >= 4 > 3, planes are handed over in order).  Round 1 took
+                // turns by the plane COUNTER g: at an item boundary with exactly one padding plane (several d-segments
+                // AND several items per CTA) the warp owning the padding plane then jumped 5 ring positions, one more
+                // than the 4 stages of the 64 -> 32 configuration; "phase sq / NST done" was answered by plane
+                // sq - 2 NST (same parity), the warp multiplied a stale plane and its early EMPTY arrival left the
+                // producer one phase out of step -- the rare bad tiles and 0.2 s time-outs of sharded inference.
+                const uint32_t sq = valid ? seq_base + (uint32_t)(pl - it.p_lo) : 0u;
+                if ((int)((valid ? sq : g) % NMMA) != me) continue;
                 const int j_lo = max(i - 2, 0), j_hi = min(i, DLi - 1);
-                uint32_t sq = 0;
                 if (lane == 0) { prog_set(ctx, 2 + me, (int)g); prog_set(ctx, 5 + me, item); }
                 if (valid) {
-                    sq = seq_base + (pl - it.p_lo);
                     if (lane == 0) prog_set(ctx, 8 + me, (2 << 24) | (int)(sq & 0xffffff));
-                    // A parity wait is only meaningful while the waiter is at most ONE phase ahead of the barrier.  A
-                    // warp's consecutive planes are 3 apart in the plane counter g, but when the plane in between is a
-                    // zero-padding plane it owns (an item boundary) the next LOADED plane it waits for can be up to 7
-                    // ring positions after the last one it consumed -- more than the NST = 4 stages of the 64 -> 32
-                    // configuration.  Slot sq % NST may then still be waiting for plane sq - NST, and "phase sq / NST
-                    // done" would be answered from plane sq - 2 NST, which has the same parity: the warp would multiply
-                    // a stale plane and its early EMPTY arrival would leave the producer one phase out of step (the
-                    // time-outs and bad tiles of round 1: segments AND several items per CTA give boundaries with
-                    // exactly one padding plane).  Waiting for plane sq - NST first keeps every wait in step: at that
-                    // point plane sq - 2 NST is certainly loaded (7 < 2 NST).
-                    const uint32_t ph = sq / NST;
-                    if (ph > 0 && !p.dbg_single_full_wait) mbar_wait(FULL(sq % NST), (ph - 1u) & 1u, ctx, 5, item);
-                    mbar_wait(FULL(sq % NST), ph & 1u, ctx, 2, item);
+                    mbar_wait(FULL(sq % NST), (sq / NST) & 1u, ctx, 2, item);
                 }
                 // every output this plane touches must have been handed back (zeroed) by the epilogue; this also
                 // keeps a warp from running more than R outputs ahead, i.e. from lapping the PDONE phases
@@ -400,8 +397,7 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
     p.status = fcd_status_dev();
     static const int dbg_delay = getenv("FCD_TCF_PRODUCER_DELAY_NS") ? atoi(getenv("FCD_TCF_PRODUCER_DELAY_NS")) : 0;
-    static const int dbg_single = getenv("FCD_TCF_SINGLE_FULL_WAIT") != nullptr;
-    p.dbg_delay_ns = dbg_delay; p.dbg_single_full_wait = dbg_single;
+    p.dbg_delay_ns = dbg_delay;
 #define FCD_TCF_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, flip, stream)
     FCD_TCF_CASE(16, 16); FCD_TCF_CASE(32, 16); FCD_TCF_CASE(64, 16);
     FCD_TCF_CASE(16, 32); FCD_TCF_CASE(32, 32); FCD_TCF_CASE(64, 32);

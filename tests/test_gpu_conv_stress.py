@@ -131,12 +131,26 @@ def test_plain_tc_many_items_and_segments(ops, B, Ci, Co, S, nseg):
     _lib.check_errors()
 
 
+def test_slow_producers_cannot_make_the_mma_warps_read_a_stale_plane():
+    """Regression test of round 1's defect (root-caused in round 2, see the FULL wait in csrc/conv_tcf.cu): with the
+    producers slowed down (FCD_TCF_PRODUCER_DELAY_NS) the MMA warps are always waiting for the next halo plane, which is
+    when a warp that jumped 5 ring positions over an item boundary with one padding plane used to see the parity of
+    plane sq - 2 NST and multiply a stale plane (4 of 4 runs failed with time-outs: profiles/r02_defect_ab.txt).  The
+    4-stage-ring shapes run in a subprocess because the switch is read once per process."""
+    env = dict(os.environ, FCD_TCF_PRODUCER_DELAY_NS="3000")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_conv_stress.py"), "-q", "-m",
+                        "gpu", "-p", "no:cacheprovider", "-k", "test_tcf_many and (64-32-64-8 or 64-32-32-8)"],
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=1200)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "4 passed" in r.stdout
+
+
 def test_window_forward_graph_replays_with_unrestricted_segments():
-    """The reproducer of round 1's open defect: CUDA-graph replays of the whole MS_DSA_NET forward on a 5-window batch
-    with the segment chooser unrestricted (128^3 levels get 2 segments, 64^3 / 32^3 levels 8 short ones; branch streams
-    active).  Runs in a subprocess because the chooser reads FCD_NSEG_UNRESTRICTED once per process."""
-    env = dict(os.environ, FCD_NSEG_UNRESTRICTED="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_window_forward.py"), "150", "5"],
+    """The regime round 1's defect was seen in: CUDA-graph replays of the whole MS_DSA_NET forward on a 5-window batch
+    (128^3 levels get 2 segments, 64^3 / 32^3 levels 8 short ones; branch streams active); every replay must reproduce
+    the first bit for bit with a clean status word.  Subprocess: a fresh CUDA context and graph pool."""
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_window_forward.py"), "300", "5"],
                        capture_output=True, text=True, env=env, cwd=ROOT, timeout=1500)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, "window-forward stress failed (see output)"
