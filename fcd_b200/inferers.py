@@ -143,6 +143,14 @@ def slab_bounds(planes: int, rank: int, world: int):
     return rank * slab, (rank + 1) * slab, slab
 
 
+def assemble_label_slabs(full: torch.Tensor, pad_lo_z: int, depth: int) -> torch.Tensor:
+    """All-gathered label slabs [world][B][slab][nch][H][W] (rank r holds padded planes [r*slab, (r+1)*slab)) ->
+    [B][nch][depth][H][W]: concatenate along D and crop the symmetric z padding of images smaller than the roi."""
+    world, B, slab, nch, H, W = full.shape
+    lab = full.permute(1, 3, 0, 2, 4, 5).reshape(B, nch, world * slab, H, W)
+    return lab[:, :, pad_lo_z:pad_lo_z + depth].contiguous()
+
+
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,
                              overlap: float = 0.25, mode: str = "constant", *, label_mode: str | None = None,
                              shard: bool = False, group=None, return_logits: bool = True, **unused):
@@ -270,12 +278,13 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
                 call("fcd_sw_finalize", acc=mine[b], dst=None, label_f=tmp[b] if lm == 1 else None,
                      label_u8=tmp[b] if lm == 2 else None, z_lo=z_lo, z_hi=z_hi, acc_z0=lo, out_z0=lo - pad_lo[0],
                      out_planes=slab, **common)
-        lab_slab.copy_(tmp.transpose(1, 2))
+        if nch == 1:
+            lab_slab = tmp.view(B, slab, 1, orig[1], orig[2])      # [1][slab] and [slab][1] are the same memory
+        else:
+            lab_slab.copy_(tmp.transpose(1, 2))
         full = torch.empty((world, B, slab, nch, orig[1], orig[2]), dtype=ldt, device=dev)
         dist.all_gather_into_tensor(full, lab_slab, group=group)
-        # [world][B][slab] -> [B][nch][world*slab] planes in the padded frame; crop to the image
-        lab = full.permute(1, 3, 0, 2, 4, 5).reshape(B, nch, world * slab, orig[1], orig[2])
-        lab = lab[:, :, pad_lo[0]:pad_lo[0] + orig[0]].contiguous()
+        lab = assemble_label_slabs(full, pad_lo[0], orig[0])
         return None, lab
 
     if world > 1:

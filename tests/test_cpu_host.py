@@ -192,3 +192,22 @@ def test_window_shard_partitions_windows():
             parts = [window_shard(total, r, world) for r in range(world)]
             assert sorted(i for p in parts for i in p) == list(range(total))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_slab_bounds_and_label_assembly():
+    """Sharded labels-only inference: the padded accumulation volume is cut into `world` equal D-slabs for the
+    reduce-scatter; the all-gathered label slabs are put back together and the z padding is cropped."""
+    from fcd_b200.inferers import assemble_label_slabs, slab_bounds
+    for planes in (1, 7, 32, 182, 192, 256):
+        for world in (1, 2, 3, 4, 8):
+            b = [slab_bounds(planes, r, world) for r in range(world)]
+            slab = b[0][2]
+            assert all(x[2] == slab for x in b) and slab * world >= planes and (slab - 1) * world < planes
+            assert b[0][0] == 0 and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    g = torch.Generator().manual_seed(0)
+    for (B, nch, Dp, H, W, pz, D, world) in [(1, 1, 32, 5, 6, 4, 24, 4), (2, 2, 37, 3, 4, 0, 37, 8), (1, 1, 16, 2, 2, 3, 9, 3)]:
+        slab = slab_bounds(Dp, 0, world)[2]
+        vol = torch.randint(0, 255, (B, nch, world * slab, H, W), generator=g, dtype=torch.uint8)
+        full = torch.stack([vol[:, :, r * slab:(r + 1) * slab].permute(0, 2, 1, 3, 4) for r in range(world)])
+        out = assemble_label_slabs(full, pz, D)
+        assert torch.equal(out, vol[:, :, pz:pz + D])
