@@ -51,7 +51,17 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches timed for the CPU baseline")
+    ap.add_argument("--loss", default=None, help="DiceCELoss (default) | DiceFocalLoss | DiceLoss")
+    ap.add_argument("--tv", type=float, default=0.0, help="tv_loss_weight (configs[3] uses 0.1)")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing the stock PyTorch (cuDNN/cuBLAS) bf16/fp16-autocast step on the same GPU")
     return ap.parse_args()
+
+
+def loss_name(args):
+    if args.loss:
+        return args.loss
+    return "DiceFocalLoss" if args.model.startswith("segresnet") and "dsa" not in args.model else "DiceCELoss"
 
 
 def peaks():
@@ -118,15 +128,73 @@ class ClockSampler:
 
 
 def _kernel_errors():
-    """Error words of the bounded mbarrier waits in the tcgen05 kernels (0 = no wait ever timed out)."""
+    """Status word of the bounded mbarrier waits in the tcgen05 kernels (0 = no wait ever timed out) + its record."""
     from fcd_b200 import _lib
-    L = _lib.lib()
-    return {n: int(getattr(L, n)()) for n in ("fcd_tc_error", "fcd_tcf_error", "fcd_gemm_tc_error", "fcd_wgrad_tc_error",
-                                               "fcd_wgrad_gemm_tc_error")}
+    st = _lib.status()
+    return {"word": st["word"]} if st["word"] == 0 else st
+
+
+def gpu_reference(model_type, patch, batch, loss_over, dev, steps=4, warm=2):
+    """The existing Blackwell implementation of the path (SURVEY 2.1 / 8d "the kernel to beat"): the SAME network
+    arithmetic through stock PyTorch -- cuDNN / cuBLAS eager kernels -- on this GPU, under bf16 autocast and under fp16
+    autocast (+ GradScaler) as the reference trains (train.py:328,373): forward + loss + backward + fused AdamW, batch
+    `batch`.  The network is the functional restatement of the reference modules (oracle/nets.py; the reference's own
+    files need MONAI, which cannot be installed here) and runs WITHOUT dropout, which favours it slightly."""
+    from oracle import losses as olosses
+    from oracle import nets as onets
+    from oracle import synth
+    import fcd_b200
+    params = fcd_b200.get_default_params()
+    params.update(model_type=model_type, patch_size=(patch,) * 3)
+    params.update(loss_over)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    spec = synth.spec_of(model.state_dict())
+    del model
+    sd = synth.synthetic_state_dict(spec, seed=1)
+    fk = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    x = synth.image(batch, 2, patch, seed=3).to(dev)
+    y = synth.label(batch, patch, seed=5).to(dev)
+    noise = torch.randn((batch, 256), device=dev)
+    out = {}
+    for name, dtype in (("bf16_autocast", torch.bfloat16), ("fp16_autocast", torch.float16)):
+        try:
+            leaf = {k: (v.to(dev).clone().requires_grad_(True) if k in fk else v.to(dev).clone()) for k, v in sd.items()}
+            opt = torch.optim.AdamW([leaf[k] for k in fk], lr=1e-4, weight_decay=1e-5, fused=True)
+            scaler = torch.amp.GradScaler("cuda", enabled=dtype == torch.float16)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(warm + steps):
+                if i == warm:
+                    torch.cuda.synchronize()
+                    e0.record()
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=dtype):
+                    o = onets.forward(model_type, leaf, x, True, {}, noise)
+                    vae = None
+                    if isinstance(o, tuple):
+                        o, vae = o
+                    loss = olosses.combined_loss(params, o, y)
+                    if vae is not None:
+                        loss = loss + params["loss_vae_weight"] * vae
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms}
+            del leaf, opt
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = (f"oracle/nets.py functional {model_type} through stock torch {torch.__version__} eager (cuDNN "
+                   f"{torch.backends.cudnn.version()}), fwd + loss + bwd + fused AdamW, batch {batch}, {steps} steps after "
+                   f"{warm} warm-up, no dropout, no CUDA graph")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference(model_type, patch, n_patches, warm=1):
+def cpu_reference(model_type, patch, n_patches, warm=1, loss_over=None):
     """The reference's CPU implementation of the path: the oracle port (reference network files cannot travel, and
     their MONAI dependency is not installable here) -- fp32, all host threads, batch 1, fwd + DiceCE + bwd."""
     from oracle import losses as olosses
@@ -136,6 +204,7 @@ def cpu_reference(model_type, patch, n_patches, warm=1):
     torch.set_num_threads(os.cpu_count() or 1)
     params = fcd_b200.get_default_params()
     params.update(model_type=model_type, patch_size=(patch,) * 3, loss="DiceCELoss")
+    params.update(loss_over or {})
     # parameter names / shapes come from the product's module tree (identical to the reference's); values synthetic
     with contextlib.redirect_stdout(io.StringIO()):
         model, params = fcd_b200.get_model(params)
@@ -159,17 +228,50 @@ def cpu_reference(model_type, patch, n_patches, warm=1):
     return len(t) / sum(t), sum(t) / len(t)
 
 
+def cpu_sliding_window(model_type, patch, cores):
+    """CPU baseline of configs[4] on a bounded sample: ONE predictor call of 2 windows (the reference's sw_batch_size,
+    train.py:159) of the 18 through the oracle network in eval mode, scaled to 9 calls, plus the reference's scipy
+    post-processing (utils_common.py:10-33) measured on a 128^3 crop and scaled by volume."""
+    from oracle import inferer as oinf
+    from oracle import nets as onets
+    from oracle import synth
+    import fcd_b200
+    torch.set_num_threads(cores)
+    params = fcd_b200.get_default_params()
+    params.update(model_type=model_type, patch_size=(patch,) * 3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=1)
+    del model
+    x = synth.image(2, 2, patch, seed=3)
+    with torch.no_grad():
+        onets.forward(model_type, sd, x[:1], False, {})
+        t0 = time.perf_counter()
+        out = onets.forward(model_type, sd, x, False, {})
+        t_call = time.perf_counter() - t0
+    mask = (synth.label(1, 128, seed=31, n_blobs=4)[0, 0] > 0).numpy().astype("float32")
+    t0 = time.perf_counter()
+    oinf.post_process_segment(mask, 50)
+    t_pp = (time.perf_counter() - t0) * (256 * 256 * 192) / 128 ** 3
+    sec = 9 * t_call
+    return {"value": 1.0 / sec, "unit": "vols/s", "cores": cores, "kind": "port",
+            "sample": f"1 of 9 predictor calls (2 windows of {patch}^3, eval, fp32, {cores} threads: {t_call:.1f} s) scaled to "
+                      f"the 18 windows; blend/finalize excluded",
+            "post_process_s_per_vol": t_pp, "post_process_sample": "scipy post_process_segment on a 128^3 crop, scaled by volume"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     k = max(1, min(args.steps, 3))
-    pps, sec = cpu_reference(args.model, args.patch, k, warm=1 if args.warmup > 0 else 0)
+    pps, sec = cpu_reference(args.model, args.patch, k, warm=1 if args.warmup > 0 else 0,
+                             loss_over=dict(loss=loss_name(args), tv_loss_weight=args.tv))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
         "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} train step (fwd + DiceCE + bwd), 2ch {args.patch}^3, batch 1, CPU"},
+        "config": {"workload": f"{args.model} train step (fwd + {loss_name(args)} + bwd), 2ch {args.patch}^3, batch 1, CPU"},
         "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{k} patches of batch 1 after 1 warm-up, torch {torch.__version__} CPU fp32"},
         "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -192,7 +294,8 @@ def main():
     pk = peaks()
 
     params = fcd_b200.get_default_params()
-    params.update(model_type=args.model, patch_size=(args.patch,) * 3, loss="DiceCELoss")
+    loss_over = dict(loss=loss_name(args), tv_loss_weight=args.tv)
+    params.update(model_type=args.model, patch_size=(args.patch,) * 3, **loss_over)
     torch.manual_seed(42)
     with contextlib.redirect_stdout(io.StringIO()):
         model, params = fcd_b200.get_model(params)
@@ -357,142 +460,210 @@ def main():
     e2e_value = patches / (ms_e2e / 1e3)
     final_loss = float(loss_host)
     errs = _kernel_errors()
-    if any(errs.values()):
-        raise RuntimeError(f"tcgen05 pipeline time-outs during the training steps: {errs}")
+    if errs["word"]:
+        raise RuntimeError(f"tcgen05 pipeline time-out during the training steps: {errs}")
 
-    # ---- roofline from the profiled eager step (CUDA events around every C-ABI call on the launching stream).
-    # Dominant kernel = the tcgen05/TMEM implicit-GEMM conv (forward + data gradient launches); the whole conv family
-    # (tcgen05 conv + tcgen05 wgrad + the mma.sync kernels of the deep levels, with their reduce kernels) beside it.
-    def fam(names):
-        sel = [v for k, v in agg.items() if k.split(":")[0] in names]
-        return sum(v["ms"] for v in sel), sum(v["flops"] for v in sel), sum(v["calls"] for v in sel)
-    tc_ms, tc_fl, tc_calls = fam(("fcd_conv3_tcf", "fcd_conv3_tc"))
-    conv_ms, conv_fl, conv_calls = fam(("fcd_conv3_tcf", "fcd_conv3_tc", "fcd_wgrad3_tc", "fcd_conv_gemm_tc",
-                                        "fcd_splitk_reduce", "fcd_igemm", "fcd_igemm_splitk", "fcd_wgrad",
-                                        "fcd_wgrad_reduce", "fcd_pack_weight", "fcd_pack_weight_batched"))
+    # ---- roofline from the profiled eager step (CUDA events around every C-ABI call on the launching stream, stream
+    # overlap off so that every launch is timed alone).  Per-family table; the DOMINANT family is the one with the largest
+    # share of the serialized step, and the `roofline` object describes it (bound, achieved, peak, frac).
+    FAMILIES = [
+        ("tcgen05 conv3x3x3 fwd/dgrad", "tensor", ("fcd_conv3_tcf", "fcd_conv3_tc")),
+        ("tcgen05 deep-level GEMM conv (+split-K reduce)", "tensor", ("fcd_conv_gemm_tc", "fcd_splitk_reduce")),
+        ("tcgen05 weight gradients (+reduce)", "tensor", ("fcd_wgrad3_tc", "fcd_wgrad_gemm_tc", "fcd_wgrad_reduce")),
+        ("mma.sync conv / linear / deconv / pointwise", "tensor", ("fcd_igemm", "fcd_igemm_splitk", "fcd_pw_conv",
+                                                                   "fcd_wgrad", "fcd_pack_weight", "fcd_pack_weight_batched")),
+        ("norm + activation + residual (IN/BN/GN)", "hbm", ("fcd_norm_apply", "fcd_norm_stats", "fcd_norm_finalize",
+                                                            "fcd_norm_bwd")),
+        ("DSA attention + LayerNorm", "hbm", ("fcd_dsa_fwd", "fcd_dsa_bwd", "fcd_dsa_bwd_ef", "fcd_ln_fwd", "fcd_ln_bwd")),
+        ("loss + output conv", "hbm", ("fcd_loss_fwd", "fcd_loss_bwd", "fcd_outconv_fwd", "fcd_outconv_bwd",
+                                       "fcd_mse_fwd", "fcd_mse_bwd")),
+    ]
     step_ms_eager = sum(v["ms"] for v in agg.values())
-    top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:10]
     tf = (lambda fl, ms: fl / (ms * 1e-3) / 1e12 if ms > 0 else None)
-    roof = {"bound": "tensor", "kernel": "fcd_conv3_tcf (+fcd_conv3_tc for Cout 64): tcgen05/TMEM implicit-GEMM conv3x3x3, forward + data-gradient launches",
-            "achieved": tf(tc_fl, tc_ms), "peak": pk["tf_sust"], "unit": "TFLOP/s",
-            "frac": (tf(tc_fl, tc_ms) / pk["tf_sust"]) if tc_ms > 0 else None,
-            "traffic": None,
-            "traffic_sample": {"launch": "16->16 @128^3 batch 2 (profiles/r01_ncu_conv3_tcf_16x16.txt)",
-                               "dram_bytes": 223.3e6, "algorithmic_bytes": 268.4e6,
-                               "note": "ncu's hmma cycles-active counter is a work counter on this part (DESIGN.md "
-                                       "3.1): utilisation is quoted from FLOPs / CUDA-event time only"},
-            "peak_source": pk["source"] + " (sustained bf16)",
-            "timing": "CUDA events around each launch in one serialized eager step (stream overlap off)",
-            "share_of_step": tc_ms / step_ms_eager if step_ms_eager > 0 else None, "launches": tc_calls,
-            "conv_family": {"kernels": "fcd_conv3_tc + fcd_wgrad3_tc + fcd_igemm(_splitk) + fcd_wgrad(+reduce, pack)",
-                            "achieved": tf(conv_fl, conv_ms), "frac": (tf(conv_fl, conv_ms) / pk["tf_sust"]) if conv_ms > 0 else None,
-                            "share_of_step": conv_ms / step_ms_eager if step_ms_eager > 0 else None,
-                            "launches": conv_calls},
-            "top_calls_ms": {k: round(v["ms"], 3) for k, v in top}}
-    hbm_names = ("fcd_norm_apply", "fcd_norm_stats", "fcd_norm_bwd")
-    hbm = [v for k, v in agg.items() if k.split(":")[0] in hbm_names]
-    hbm_ms = sum(v["ms"] for v in hbm)
-    hbm_b = sum(v["bytes"] for v in hbm)
-    # the family's aggregate is dominated by the ~150 launch-latency-bound calls on the tiny deep-level tensors; the
-    # roofline figure that says something about the kernels is the largest call (level-1 tensors, 134 MB each)
+    gbs = (lambda nb, ms: nb / (ms * 1e-3) / 1e9 if ms > 0 else None)
+    seen = set()
+    table = []
+    for label, bound, names in FAMILIES:
+        sel = {k: v for k, v in agg.items() if k.split(":")[0] in names}
+        seen.update(sel)
+        ms_, fl_, nb_, calls_ = (sum(v[f] for v in sel.values()) for f in ("ms", "flops", "bytes", "calls"))
+        row = {"family": label, "bound": bound, "ms": round(ms_, 3), "share_of_step": ms_ / step_ms_eager if step_ms_eager else None,
+               "calls": calls_}
+        if bound == "tensor" and fl_ > 0 and ms_ > 0:
+            row.update(achieved=tf(fl_, ms_), unit="TFLOP/s", frac=tf(fl_, ms_) / pk["tf_sust"])
+        elif bound == "hbm" and nb_ > 0 and ms_ > 0:
+            row.update(achieved=gbs(nb_, ms_), unit="GB/s", frac=gbs(nb_, ms_) / pk["hbm"])
+        table.append(row)
+    rest = {k: v for k, v in agg.items() if k not in seen}
+    rest_ms = sum(v["ms"] for v in rest.values())
+    table.append({"family": "other (pool, upsample, copies, adds, dropout masks, layout)", "bound": "hbm", "ms": round(rest_ms, 3),
+                  "share_of_step": rest_ms / step_ms_eager if step_ms_eager else None,
+                  "calls": sum(v["calls"] for v in rest.values())})
+    dom = max(table[:-1], key=lambda r: r["ms"])
+    dom_names = next(n for l, _, n in FAMILIES if l == dom["family"])
+    # the dominant family's largest single launch (by algorithmic work) is the kernel the roofline object is quoted on
     big = None
     for name, tag, ev0, ev1, fl, nb in prof.records:
-        if name in hbm_names and nb > 0 and (big is None or nb > big[1]):
-            big = (name, nb, ev0.elapsed_time(ev1))
-    roof["hbm_family"] = {"kernel": "fcd_norm_stats/apply/bwd", "achieved_gbs": hbm_b / (hbm_ms * 1e-3) / 1e9
-                          if hbm_ms > 0 else None, "peak_gbs": pk["hbm"],
-                          "frac": hbm_b / (hbm_ms * 1e-3) / 1e9 / pk["hbm"] if hbm_ms > 0 else None,
-                          "share_of_step": hbm_ms / step_ms_eager if step_ms_eager > 0 else None,
-                          "largest_call": None if big is None else {
-                              "kernel": big[0], "algorithmic_bytes": big[1], "ms": round(big[2], 4),
-                              "achieved_gbs": big[1] / (big[2] * 1e-3) / 1e9,
-                              "frac": big[1] / (big[2] * 1e-3) / 1e9 / pk["hbm"]},
-                          "ncu": "profiles/r01_ncu_norm_kernels.txt (DRAM bytes / duration: 0.65-0.83 of the measured copy peak)"}
+        w = fl if dom["bound"] == "tensor" else nb
+        if name in dom_names and w > 0 and (big is None or w > big[1]):
+            big = (name + (":" + tag if tag else ""), w, ev0.elapsed_time(ev1))
+    # measured DRAM traffic of that kind of launch, from the committed ncu capture (per launch), if there is one
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and big is not None:
+        with open(tpath) as f:
+            tj = json.load(f)
+        hit = tj.get(big[0].split(":")[0])
+        if hit:
+            traffic, traffic_src = hit.get("dram_bytes"), hit
+    roof = {"bound": dom["bound"], "kernel": dom["family"], "achieved": dom.get("achieved"),
+            "peak": pk["tf_sust"] if dom["bound"] == "tensor" else pk["hbm"], "unit": dom.get("unit"),
+            "frac": dom.get("frac"), "traffic": traffic, "traffic_source": traffic_src,
+            "share_of_step": dom["share_of_step"], "launches": dom["calls"],
+            "largest_launch": None if big is None else {
+                "call": big[0], ("algorithmic_flops" if dom["bound"] == "tensor" else "algorithmic_bytes"): big[1],
+                "ms": round(big[2], 4),
+                "achieved": (tf(big[1], big[2]) if dom["bound"] == "tensor" else gbs(big[1], big[2])),
+                "frac": (tf(big[1], big[2]) / pk["tf_sust"] if dom["bound"] == "tensor" else gbs(big[1], big[2]) / pk["hbm"])},
+            "peak_source": pk["source"] + (" (sustained bf16)" if dom["bound"] == "tensor" else " (copy bandwidth)"),
+            "timing": "CUDA events around each launch in one serialized eager step (stream overlap off); the kernels' "
+                      "share of the step agrees with the ncu launch list under profiles/",
+            "serialized_step_ms": round(step_ms_eager, 3),
+            "families": table,
+            "top_calls_ms": {k: round(v["ms"], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
+    whole_flops = sum(v["flops"] for v in agg.values())
+    roof["whole_step"] = {"algorithmic_tflop": whole_flops / 1e12, "achieved": tf(whole_flops, ms_dev / args.steps),
+                          "frac_of_tensor_peak": tf(whole_flops, ms_dev / args.steps) / pk["tf_sust"]}
 
-    # ---- sliding-window inference (configs[4]) : 256x256x192, roi 128, overlap 0.5 -> 18 windows
+    # ---- sliding-window whole-volume inference (configs[4]): 256x256x192, roi 128, overlap 0.5 -> 18 windows.
+    # value : volume resident in HBM -> uint8 label map in HBM (all ranks hold it);  e2e : pinned HOST volume -> HOST label
+    # map (rank 0 copies the volume once and broadcasts it over NVLink at N > 1; D2H of the label map on every rank).
+    # N > 1: windows dealt round-robin, fp32 partial volumes reduce-scattered along D, slab finalize, label all-gather.
     aux = {}
-    if not args.no_infer and args.model in ("ms_dsa_net", "baseunet", "segresnet"):
+    if not args.no_infer and args.model in ("ms_dsa_net", "ms_dsa_net_ps", "baseunet", "segresnet"):
         try:
+            from fcd_b200.inferers import post_process_segment
             del graph
             static.clear()
             opt.zero_grad(set_to_none=True)
             torch.cuda.empty_cache()
             model.eval()
-            vol = torch.randn((1, 2, 256, 256, 192), generator=torch.Generator().manual_seed(7)).pin_memory()
+            vshape = (1, 2, 256, 256, 192)
+            vol = torch.randn(vshape, generator=torch.Generator().manual_seed(7)).pin_memory()
             vol_d = torch.empty_like(vol, device=dev)
-            lab_h = torch.empty((1, 1, 256, 256, 192), dtype=torch.uint8).pin_memory()
+            vol_d.copy_(vol)
+            lab_h = torch.empty((1, 1) + vshape[2:], dtype=torch.uint8).pin_memory()
             # sw_batch_size is free in configs[4]: every rank pushes all of its windows through ONE
             # forward (18 at N=1, 3 at N=8) -- the deep levels are latency-bound, so they amortise over the batch
             sw_bs = 18
-            with torch.no_grad():
-                for _ in range(4):            # warm-up runs the timed body (incl. the pinned D2H and the sync)
-                    vol_d.copy_(vol, non_blocking=True)
-                    _, lab = sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5,
-                                                      label_mode="argmax")
-                    lab_h.copy_(lab, non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
-                barrier()
-                n_vol = 8
+
+            def infer_dev():
+                _, lab = sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5, label_mode="argmax",
+                                                  shard=world > 1, return_logits=False)
+                return lab
+
+            def infer_e2e():
+                if rank == 0:
+                    vol_d.copy_(vol, non_blocking=True)                        # H2D of the volume (pinned), once per job
+                if world > 1:
+                    torch.distributed.broadcast(vol_d, 0)                      # NVLink, not 8 PCIe copies
+                lab = infer_dev()
+                lab_h.copy_(lab, non_blocking=True)                            # D2H of the label map (pinned)
+                torch.cuda.current_stream().synchronize()
+                return lab
+
+            def timed_vols(fn, n_vol):
                 import gc
-                import time as _time
+                for _ in range(3):
+                    fn()
+                barrier()
                 gc.collect()
-                gc.disable()          # a generational collection inside the loop showed up as a 7-80 ms stall on one volume
+                gc.disable()      # a generational collection inside the loop showed up as a 7-80 ms stall on one volume
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                per_vol = []
                 e0.record()
                 for _ in range(n_vol):
-                    t0 = _time.perf_counter()
-                    vol_d.copy_(vol, non_blocking=True)                        # H2D of the volume (pinned)
-                    _, lab = sliding_window_inference(vol_d, args.patch, sw_bs, model, overlap=0.5,
-                                                      label_mode="argmax")
-                    lab_h.copy_(lab, non_blocking=True)                        # D2H of the label map (pinned)
-                    torch.cuda.current_stream().synchronize()
-                    per_vol.append(round((_time.perf_counter() - t0) * 1e3, 2))
+                    lab = fn()
                 e1.record()
                 gc.enable()
                 barrier()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms], device=dev)
-                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-                ms = float(t)
+                ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                    ms = float(t)
+                return ms / n_vol, lab
+
+            n_vol = 8
+            with torch.no_grad():
+                ms_vol, lab = timed_vols(infer_dev, n_vol)
+                ms_vol_e2e, lab = timed_vols(infer_e2e, n_vol)
+                # post-processing of the label map on the device (train.py:167-182; the reference: D2H + scipy + H2D)
+                pp_ms = None
+                for _ in range(2):
+                    post_process_segment(lab[0, 0], 50)
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(5):
+                    pp_mask, _ = post_process_segment(lab[0, 0], 50)
+                p1.record()
+                torch.cuda.synchronize()
+                pp_ms = p0.elapsed_time(p1) / 5
             errs = _kernel_errors()
-            bad = torch.tensor([float(any(errs.values()))], device=dev)
+            bad = torch.tensor([float(errs["word"] != 0)], device=dev)
             if world > 1:                      # a time-out on ANY rank voids the volume every rank contributed to
                 torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
             if float(bad) > 0:
-                raise RuntimeError(f"tcgen05 pipeline time-outs during inference (this rank: {errs})")
-            aux = {"metric": "ms_dsa_net_sliding_window_vols_per_s", "value": n_vol / (ms / 1e3), "unit": "vols/s",
-                   "workload": "2ch 256x256x192, roi 128^3, overlap 0.5, 18 windows sharded over ranks (all windows "
-                               "of a rank in one forward), H2D volume + D2H uint8 label map inside the timed region",
-                   "ms_per_vol_rank0": per_vol, "fg_fraction": float(lab_h.float().mean())}
+                raise RuntimeError(f"tcgen05 pipeline time-out during inference (this rank: {errs})")
+            fwd_flops = sum(v["flops"] for k, v in agg.items() if k.endswith((":fwd", ":deconv_fwd"))) / B   # per window
+            aux = {"metric": "sliding_window_vols_per_s", "value": 1e3 / ms_vol, "unit": "vols/s", "n_gpus": world,
+                   "ms_per_vol": ms_vol, "scaling": "strong", "dtype": "bf16",
+                   "config": {"workload": f"{args.model} eval, 2ch 256x256x192 volume, roi {args.patch}^3, overlap 0.5, 18 windows"
+                                          + (f" dealt over {world} ranks, reduce-scatter + slab finalize + label all-gather"
+                                             if world > 1 else " in one forward") + ", argmax uint8 label map"},
+                   "e2e": {"value": 1e3 / ms_vol_e2e, "unit": "vols/s", "ms_per_vol": ms_vol_e2e,
+                           "h2d_bytes_per_step": vol.numel() * 4, "d2h_bytes_per_step": lab_h.numel() * world},
+                   "roofline": {"bound": "tensor", "algorithmic_tflop_per_vol": 18 * fwd_flops / 1e12,
+                                "achieved": 18 * fwd_flops / (ms_vol * 1e-3) / 1e12 / world, "unit": "TFLOP/s per GPU",
+                                "peak": pk["tf_sust"], "frac": 18 * fwd_flops / (ms_vol * 1e-3) / 1e12 / world / pk["tf_sust"]},
+                   "post_process_ms": pp_ms, "post_process": "fcd_post_process on the device (opening, 5^3 fill-holes, "
+                                                             "26-connected components, size filter 50), not in value/e2e",
+                   "fg_fraction": float(lab_h.float().mean()), "kept_voxels": int(pp_mask.sum().item())}
         except Exception as e:
             aux = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         return
     cpu = None
+    gpu_ref = None
+    ar_desc = ("2 buckets, early bucket overlapped with backward" if (reducer.overlap and reducer.early_launches)
+               else "1 bucket after backward")
+    if world == 1 and not args.no_gpu_reference:
+        del model, opt, reducer
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference(args.model, args.patch, B, loss_over, dev)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        pps, sec = cpu_reference(args.model, args.patch, args.cpu_sample, warm=1)
+        pps, sec = cpu_reference(args.model, args.patch, args.cpu_sample, warm=1, loss_over=loss_over)
         cpu = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} patches of batch 1 (fwd + DiceCE + bwd) after 1 warm-up, fp32, "
+               "sample": f"{args.cpu_sample} patches of batch 1 (fwd + {loss_over['loss']} + bwd) after 1 warm-up, fp32, "
                          f"{cores} host threads; ~{sec:.1f} s per patch"}
+        if aux and "error" not in aux:
+            aux["cpu_baseline"] = cpu_sliding_window(args.model, args.patch, cores)
     nbytes_in = sx.numel() * 4 + sy.numel() * 4
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} train step: fwd + DiceCELoss + bwd + AdamW, 2ch {args.patch}^3 patches, "
+        "config": {"workload": f"{args.model} train step: fwd + {loss_over['loss']}"
+                               f"{' + TV ' + str(args.tv) if args.tv > 0 else ''} + bwd + AdamW, 2ch {args.patch}^3 patches, "
                                f"batch {B}/GPU, dropout p=0.1 active", "global_batch": B * world,
                    "parallelism": f"dp{world}", "cuda_graph": graph_ok, "l2": "inputs_exceed_l2",
-                   **({"grad_allreduce": ("2 buckets, early bucket overlapped with backward"
-                                          if (reducer.overlap and reducer.early_launches) else "1 bucket after backward")}
-                      if world > 1 else {})},
+                   **({"grad_allreduce": ar_desc} if world > 1 else {})},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": gpu_launches * args.steps, "gpu_launches_per_step": gpu_launches,
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "aux": aux, "final_loss": final_loss,
+        "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "clocks": clocks, "aux": aux,
+        "final_loss": final_loss,
     }
     if graph_err:
         line["config"]["graph_error"] = graph_err

@@ -924,6 +924,7 @@ class LossFn(Function):
         pbuf = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if tv else None
         keep = torch.empty((B, D, H, W), dtype=torch.uint8, device=dev) if (tv and cfg["tv_exclude"]) else None
         res = torch.zeros((16,), dtype=torch.float32, device=dev)
+        _lib.note_work(None, 0.0, 12.0 * B * D * H * W)       # 2 fp32 logits + fp32 label per voxel
         call("fcd_loss_fwd", pred=pred, target=target, B=B, D=D, H=H, W=W, keep=keep, pbuf=pbuf, part=part,
              tvpart=tvpart, res=res, **cfg)
         ctx.save_for_backward(pred, target, keep, pbuf, res)
@@ -936,6 +937,7 @@ class LossFn(Function):
         B, C, D, H, W = pred.shape
         dpred = torch.empty_like(pred)
         gout = gout.detach().float().reshape(1).contiguous()
+        _lib.note_work(None, 0.0, 20.0 * B * D * H * W)       # forward's reads + 2 fp32 gradients written
         call("fcd_loss_bwd", pred=pred, target=target, B=B, D=D, H=H, W=W, keep=keep, pbuf=pbuf, res=res, gout=gout,
              dpred=dpred, **ctx.cfg)
         return dpred, None, None
@@ -960,6 +962,7 @@ class LNPosFn(Function):
         rstd = torch.empty((B * N,), dtype=torch.float32, device=x.device)
         posc = None if pos is None else pos.detach().float().contiguous()
         wc, bc = w.detach().float().contiguous(), b.detach().float().contiguous()
+        _lib.note_work(None, 0.0, 6.0 * B * N * Cp + (4.0 * N * C if pos is not None else 0.0))
         call("fcd_ln_fwd", x=x, ldx=ld(x), pos=posc, w=wc, b=bc, t=t, ldt=Cp, ln=ln, ldl=Cp, mean=mean, rstd=rstd,
              rows=B * N, N=N, C=C, Cp=Cp, eps=eps)
         ctx.save_for_backward(t, mean, rstd, wc)
@@ -980,6 +983,7 @@ class LNPosFn(Function):
         part = torch.empty((nblk, 2, Cp), dtype=torch.float32, device=t.device)
         dw = torch.empty((C,), dtype=torch.float32, device=t.device)
         db = torch.empty((C,), dtype=torch.float32, device=t.device)
+        _lib.note_work(None, 0.0, 8.0 * B * N * Cp + (4.0 * N * C if has_pos else 0.0))
         call("fcd_ln_bwd", dln=dln, lddl=ld(dln), dtd=dt, lddt=ld(dt), t=t, ldt=Cp, mean=mean, rstd=rstd, w=wc, dx=dx,
              lddx=Cp, dpos=dpos, part=part, dw=dw, db=db, B=B, N=N, C=C, Cp=Cp)
         return dx, (dpos.view(pshape) if has_pos else None), dw, db, None, None
@@ -1047,6 +1051,8 @@ class DSAFn(Function):
         t2 = temperature2.detach().float().contiguous()
         g = gamma.detach().float().contiguous()
         snap = step_snapshot(dev) if sa_drop > 0 else None      # the backward regenerates the mask from the SAME value
+        # qkvv (4C bf16 per token) read once for the reductions and once for the apply, t read, y written, EF
+        _lib.note_work(None, 0.0, B * N * (2 * 8.0 * C + 4.0 * Cp) + 4.0 * N * P)
         call("fcd_dsa_fwd", qkvv=qkvv, ldq=ld(qkvv), EF=EFc, temperature=t1, temperature2=t2, gamma=g, t=t, ldt=ld(t),
              y=y, ldy=Cp, ca_scale=ca_scale, sa_drop=float(sa_drop), seed=int(seed),
              seed_dev=snap, part=part, inv_n=inv_n, Ghat=Ghat,
@@ -1082,6 +1088,7 @@ class DSAFn(Function):
         ef_side = (EFp is not None and EFp.is_leaf and EFp.grad is None
                    and not getattr(EFp, "_backward_hooks", None))
         dEF = None if ef_side else torch.empty((N, P), **f32)
+        _lib.note_work(None, 0.0, B * N * (2 * 8.0 * C + 2 * 2.0 * Cp + 8.0 * C) + 4.0 * N * P)   # + dy read, dqkvv written
         call("fcd_dsa_bwd", qkvv=qkvv, ldq=ld(qkvv), dy=dy, lddy=ld(dy), EF=EFc, temperature=t1, temperature2=t2,
              gamma=g, ca_scale=ca_scale, sa_drop=sa_drop, seed=seed,
              seed_dev=snap, inv_n=inv_n, Ghat=Ghat, A=A, Ad=Ad, KV=KV,
