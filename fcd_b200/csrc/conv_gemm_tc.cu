@@ -13,6 +13,7 @@
 //
 // Warps: 0-3 producers (cp.async 16 B: A rows gathered with zero-fill, B rows from the packed bf16 weights, both into
 // the UMMA no-swizzle K-major layout [k/8][row][8]), 4 MMA issuer, then warps 0-3 drain TMEM.
+#include "last_block.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -31,6 +32,7 @@ struct GemmTcParams {
     float* ws;                            // ksplit > 1: [ksplit][M][N] fp32
     int Bn, D, H, W, K, N, M, mode, ksplit;
     int* status;
+    unsigned* tickets;                    // ksplit > 1: one slot per output tile (in-kernel reduction by the last CTA)
 };
 
 template <int BN>
@@ -183,6 +185,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_gemm_tc_kernel(const GemmTcP
     tc_fence_before();
     __syncthreads();
     if (warp == NPRODW) tmem_dealloc<K::TMEM_COLS>(tmem_base);
+    // split-K: the CTA that wrote the LAST partial of this output tile sums the ksplit partials in the fixed order
+    // z = 0, 1, ... (deterministic) and writes the bf16 rows -- no fcd_splitk_reduce launch
+    if (p.ksplit > 1 && p.tickets != nullptr &&
+        lastblk::arrive(p.tickets + (blockIdx.y * gridDim.x + blockIdx.x), (unsigned)p.ksplit)) {
+        constexpr int CH = BM * (BN / 8);
+        for (int idx = tid; idx < CH; idx += NTHREADS) {
+            const int row = idx / (BN / 8), c8 = idx % (BN / 8);
+            const int m = m0 + row, n = n0 + c8 * 8;
+            if (m >= p.M) continue;
+            float a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = 0.f;
+            for (int z = 0; z < p.ksplit; ++z) {
+                const float4* src = reinterpret_cast<const float4*>(p.ws + ((long long)z * p.M + m) * p.N + n);
+                const float4 u = __ldcg(src), v = __ldcg(src + 1);
+                a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w; a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+            }
+            st8(p.C + (long long)m * p.ldc + n, pack8(a));
+        }
+    }
 }
 
 template <int BN>
@@ -221,7 +243,7 @@ FCD_API int fcd_conv_gemm_tc_ksplit(long long M, int K, int N) {
 
 // A: NDHWC bf16 rows (pitch lda >= K); Wp: packed bf16 [27][N][K]; mode 0 forward / 1 data gradient (Wp then holds the
 // transposed weights, as for fcd_igemm mode 1).  ksplit == 1: bf16 rows into C (pitch ldc); ksplit > 1: fp32 partials
-// into ws[ksplit][M][N], to be finished by fcd_splitk_reduce.
+// into ws[ksplit][M][N], summed (fixed order) into the bf16 rows of C by the CTA that finishes an output tile last.
 FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void* C, long long ldc, float* ws, int Bn,
                              int D, int H, int W, int K, int N, int mode, int ksplit, cudaStream_t stream) {
     const int bn = pick_bn(N);
@@ -233,6 +255,7 @@ FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void*
     const long long M = (long long)Bn * D * H * W;
     if (M > 0x7fffffffLL) return -1;
     p.M = (int)M; p.status = fcd_status_dev();
+    p.tickets = ksplit > 1 ? lastblk::next_tickets((unsigned)(((M + BM - 1) / BM) * (N / bn))) : nullptr;
     if (bn == 256) return launch<256>(p, stream);
     if (bn == 128) return launch<128>(p, stream);
     return launch<64>(p, stream);

@@ -25,6 +25,8 @@
 //           so the separate statistics pass over the tensor disappears.
 #include <cstdlib>
 
+#include "last_block.cuh"
+#include "norm_fin.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -54,6 +56,8 @@ struct ConvTcParams {
     int nht, nwt, nseg, DL, nitems;
     int flip;           // 1: use tap 26-t (data gradient of a stride-1 conv = correlation with the mirrored kernel)
     int* status;
+    NormFin fin;        // fin.mean != nullptr: the last CTA turns the fused partials into mean / rstd
+    unsigned* ticket;
 };
 
 template <int CIN, int COUT>
@@ -360,6 +364,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     tc_fence_before();
     __syncthreads();
     if (warp == NPROD) tmem_dealloc<K::TMEM_COLS>(tmem_base);
+    if (STATS && p.fin.mean != nullptr && lastblk::arrive(p.ticket, gridDim.x))
+        norm_finalize_body(p.part, p.fin, tid >> 5, NTHREADS >> 5);
 }
 
 template <int CIN, int COUT, bool STATS, bool FLIP>
@@ -425,7 +431,9 @@ FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
 // part: optional [Bn][nchunk][2][N] fp32 partial (sum, sum of squares) of the rounded outputs.
 FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                         int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream) {
+                         int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                          int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
+                          cudaStream_t stream) {
     if (!shape_ok(D, H, W, K, N) || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
     if (((uintptr_t)A & 15) || ((uintptr_t)C & 15) || kseg < 1 || ksegpad < 1 || nsg < 1 || nsgpad < 1) return -1;
     ConvTcParams p;
@@ -438,6 +446,10 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
     p.nseg = (D + p.DL - 1) / p.DL;
     if (p.nseg != nseg) return -1;              // caller sizes `part` with nseg: must be exact
     p.nitems = Bn * p.nht * p.nwt * p.nseg; p.status = fcd_status_dev();
+    // optional: the last CTA finishes the fused statistics (mean / rstd of the norm that follows the conv)
+    p.fin = NormFin{part != nullptr ? mean : nullptr, rstd, running_mean, running_var, Bn, N, p.nht * p.nwt * p.nseg,
+                    norm_mode, crun, (long long)D * H * W, eps, momentum};
+    p.ticket = p.fin.mean != nullptr ? lastblk::next_ticket() : nullptr;
     p.flip = flip;
 #define FCD_TC_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, stream)
     FCD_TC_CASE(16, 16); FCD_TC_CASE(16, 32); FCD_TC_CASE(32, 16); FCD_TC_CASE(32, 32);

@@ -17,6 +17,8 @@
 // Producers, halo-plane ring, weight staging from the fp32 parameter, fused statistics: as in conv_tc.cu.
 #include <cstdlib>
 
+#include "last_block.cuh"
+#include "norm_fin.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -41,6 +43,8 @@ struct ConvTcfParams {
     float* part;
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
     int* status;
+    NormFin fin;        // fin.mean != nullptr: the last CTA turns the fused partials into mean / rstd
+    unsigned* ticket;
     int dbg_delay_ns;                         // reproducer switch FCD_TCF_PRODUCER_DELAY_NS: slow the producers down
 };
 
@@ -354,6 +358,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     tc_fence_before();
     __syncthreads();
     if (warp == NPROD) tmem_dealloc<K::TMEM_COLS>(tmem_base);
+    if (STATS && p.fin.mean != nullptr && lastblk::arrive(p.ticket, gridDim.x))
+        norm_finalize_body(p.part, p.fin, tid >> 5, NTHREADS >> 5);
 }
 
 template <int CIN, int COUT, bool STATS, bool FLIP>
@@ -382,7 +388,9 @@ int launch(const ConvTcfParams& p, int flip, cudaStream_t stream) {
 // anything else so the caller can fall back to fcd_conv3_tc.
 FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                           long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, cudaStream_t stream) {
+                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                          int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
+                          cudaStream_t stream) {
     if (H % TH || W % TW || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
     if (!(K == 16 || K == 32 || K == 64) || !(N == 16 || N == 32)) return -1;
     if (((uintptr_t)A & 15) || ((uintptr_t)C & 15) || kseg < 1 || ksegpad < 1 || nsg < 1 || nsgpad < 1) return -1;
@@ -396,6 +404,10 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     if (p.nseg != nseg) return -1;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
     p.status = fcd_status_dev();
+    // optional: the last CTA finishes the fused statistics (mean / rstd of the norm that follows the conv)
+    p.fin = NormFin{part != nullptr ? mean : nullptr, rstd, running_mean, running_var, Bn, N, p.nht * p.nwt * p.nseg,
+                    norm_mode, crun, (long long)D * H * W, eps, momentum};
+    p.ticket = p.fin.mean != nullptr ? lastblk::next_ticket() : nullptr;
     static const int dbg_delay = getenv("FCD_TCF_PRODUCER_DELAY_NS") ? atoi(getenv("FCD_TCF_PRODUCER_DELAY_NS")) : 0;
     p.dbg_delay_ns = dbg_delay;
 #define FCD_TCF_CASE(CI, CO) if (K == CI && N == CO) return launch<CI, CO>(p, flip, stream)

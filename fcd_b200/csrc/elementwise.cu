@@ -2,6 +2,8 @@
 // with LeakyReLU/ReLU and the residual add), LayerNorm(+pos_embed), pixel-shuffle blur, dropout, small utilities.
 // All activations are channels-last bf16 [B][D][H][W][C] (C % 8 == 0), moved with 128-bit loads/stores.
 #include "common.cuh"
+#include "last_block.cuh"
+#include "norm_fin.cuh"
 
 namespace {
 
@@ -111,8 +113,9 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 // ----------------------------------------------------------------------------------------------- norm stats
 // Per-(b, c) partial sums over a slab of rows: part[b][chunk][0..C) = sum x, part[b][chunk][C..2C) = sum x^2.
 // blockDim = 256; thread t owns channel chunk t % C8 and rows t / C8 + k * (256 / C8).
+// fin.mean != nullptr: the block that finishes last turns the partials into mean / rstd (no second launch).
 __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ part, long long S,
-                                  int C8, int nchunk) {
+                                  int C8, int nchunk, NormFin fin, unsigned* ticket) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int c8 = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
     const long long rows_per = (S + nchunk - 1) / nchunk;
@@ -154,49 +157,13 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, floa
 #pragma unroll
         for (int k = 0; k < 8; ++k) { o[c8 * 8 + k] = sum[k]; o[C + c8 * 8 + k] = sq[k]; }
     }
+    if (fin.mean != nullptr && lastblk::arrive(ticket, gridDim.x * gridDim.y) &&
+        (int)(threadIdx.x >> 5) < (int)(blockDim.x >> 5))            // full warps only (the block may end in a partial one)
+        norm_finalize_body(part, fin, threadIdx.x >> 5, blockDim.x >> 5);
 }
 
-// mode 0 instance (per b,c), 1 batch (per c over b), 2 group-of-2-channels (per b, c/2).
-// Writes mean[b][c], rstd[b][c]; for batch mode also updates running stats (momentum, unbiased var) if given.
-__global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean,
-                                                            float* __restrict__ rstd, int B, int C, int nchunk,
-                                                            long long S, int mode, float eps,
-                                                            float* __restrict__ running_mean,
-                                                            float* __restrict__ running_var, int crun, float momentum) {
-    // one WARP per (b, c): the lanes stride over the chunk partials (fixed order => deterministic), fp64 accumulation
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= B * C) return;
-    const int b = i / C, c = i % C;
-    double s = 0.0, q = 0.0, n = 0.0;
-    auto add = [&](int bb, int cc) {
-        const float* o = part + (long long)bb * nchunk * 2 * C;
-        for (int k = lane; k < nchunk; k += 32) { s += o[(long long)k * 2 * C + cc]; q += o[(long long)k * 2 * C + C + cc]; }
-        n += (double)S;
-    };
-    if (mode == 0) {
-        add(b, c);
-    } else if (mode == 1) {
-        for (int bb = 0; bb < B; ++bb) add(bb, c);
-    } else {
-        add(b, c & ~1);
-        add(b, c | 1);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane != 0) return;
-    const double m = s / n;
-    double var = q / n - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[i] = (float)m;
-    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
-    if (mode == 1 && b == 0 && running_mean != nullptr && c < crun) {
-        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
-    }
+__global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restrict__ part, NormFin f) {
+    norm_finalize_body(part, f, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
 }
 
 // y = act( g1*(x1-mean1)*rstd1 + b1  [+ g2*(x2-mean2)*rstd2 + b2]  [+ r] ),  act(v) = v > 0 ? v : slope*v
@@ -273,12 +240,90 @@ __global__ void __launch_bounds__(256, 2) norm_apply_kernel(const bf16* __restri
 
 // Backward statistics.  ds = dy * act'(y) (y = saved forward output; nullptr => no activation).
 // part[b][chunk][0..C) = sum ds, [C..2C) = sum ds*xhat1, [2C..3C) = sum ds*xhat2 (if x2).
+struct NormBwdFin {
+    const float* rstd1; const float* rstd2; const float* gamma1;
+    float* coef; float* dgamma; float* dbeta;
+    int B, C, nchunk, mode, has2;
+    long long S;
+};
+// one WARP per (b, c), warps w0, w0 + nw, ...: lanes stride over the chunk partials, xor-shuffle totals (every lane ends
+// with the sums)
+__device__ __forceinline__ void norm_bwd_finalize_one(const float* __restrict__ part, const NormBwdFin& f, int i) {
+    const float* rstd1 = f.rstd1; const float* rstd2 = f.rstd2; const float* gamma1 = f.gamma1;
+    float* coef = f.coef; float* dgamma = f.dgamma; float* dbeta = f.dbeta;
+    const int B = f.B, C = f.C, nchunk = f.nchunk, mode = f.mode, has2 = f.has2;
+    const long long S = f.S;
+    const int lane = threadIdx.x & 31;
+    const int b = i / C, c = i % C;
+    auto sum3 = [&](int bb, int cc, double& s0, double& s1, double& s2) {
+        const float* o = part + (long long)bb * nchunk * 3 * C;
+        s0 = s1 = s2 = 0.0;
+        for (int k = lane; k < nchunk; k += 32) {
+            s0 += __ldcg(o + (long long)k * 3 * C + cc);
+            s1 += __ldcg(o + (long long)k * 3 * C + C + cc);
+            s2 += __ldcg(o + (long long)k * 3 * C + 2 * C + cc);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        }
+    };
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, n = 0.0;   // group sums of gamma*ds, gamma*ds*xhat1, ds*xhat2
+    auto addgrp = [&](int bb, int cc) {
+        double s0, s1, s2;
+        sum3(bb, cc, s0, s1, s2);
+        const double g = gamma1 ? (double)gamma1[cc] : 1.0;
+        g0 += g * s0; g1 += g * s1; g2 += s2;
+        n += (double)S;
+    };
+    if (mode == 0) addgrp(b, c);
+    else if (mode == 1) { for (int bb = 0; bb < B; ++bb) addgrp(bb, c); }
+    else { addgrp(b, c & ~1); addgrp(b, c | 1); }
+    const double g = gamma1 ? (double)gamma1[c] : 1.0;
+    float* o = coef + (long long)i * 6;
+    const bool writer = lane == 0;
+    if (writer) o[0] = (float)(g * rstd1[i]);
+    if (writer) {
+        o[1] = (float)(rstd1[i] * (g0 / n));
+        o[2] = (float)(rstd1[i] * (g1 / n));
+    }
+    if (has2) {
+        // second input never has affine parameters; its ds sum is the un-weighted one
+        double u0 = 0.0, u2 = 0.0, nn = 0.0;
+        auto add2 = [&](int bb, int cc) { double s0, s1, s2; sum3(bb, cc, s0, s1, s2); u0 += s0; u2 += s2; nn += (double)S; };
+        if (mode == 0) add2(b, c);
+        else if (mode == 1) { for (int bb = 0; bb < B; ++bb) add2(bb, c); }
+        else { add2(b, c & ~1); add2(b, c | 1); }
+        if (writer) {
+            o[3] = rstd2[i];
+            o[4] = (float)(rstd2[i] * (u0 / nn));
+            o[5] = (float)(rstd2[i] * (u2 / nn));
+        }
+    } else if (writer) {
+        o[3] = o[4] = o[5] = 0.f;
+    }
+    (void)g2;
+    if (dgamma != nullptr && b == 0) {
+        double dg = 0.0, db = 0.0;
+        for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
+        if (writer) {
+            dgamma[c] = (float)dg;
+            dbeta[c] = (float)db;
+        }
+    }
+}
+__device__ __forceinline__ void norm_bwd_finalize_body(const float* __restrict__ part, const NormBwdFin& f, int w0, int nw) {
+    for (int i = w0; i < f.B * f.C; i += nw) norm_bwd_finalize_one(part, f, i);
+}
+
 __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
                                       const float* __restrict__ mean1, const float* __restrict__ rstd1,
                                       const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
                                       const float* __restrict__ rstd2, float* __restrict__ part, long long S, int C8,
-                                      int nchunk, float slope) {
+                                      int nchunk, float slope, NormBwdFin fin, unsigned* ticket) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int C = C8 * 8;
     const int c8 = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
@@ -371,81 +416,15 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
             o[2 * C + c8 * 8 + k] = a2[k];
         }
     }
+    // the block that finishes last turns the partials into the per-(b,c) coefficients (no separate finalize launch)
+    if (lastblk::arrive(ticket, gridDim.x * gridDim.y) && (int)(threadIdx.x >> 5) < (int)(blockDim.x >> 5))
+        norm_bwd_finalize_body(part, fin, threadIdx.x >> 5, blockDim.x >> 5);
 }
 
 // Turn the backward partial sums into per-(b,c) coefficients:
 //   dx_j = k1_j * ds - k2_j - k3_j * xhat_j     (j = 1, 2)
 // with k1 = gamma*rstd, k2 = rstd*mean_grp(gamma*ds), k3 = rstd*mean_grp(gamma*ds*xhat); also dgamma/dbeta (written, not accumulated).
 // coef[b][c][0..2] for input 1, coef[b][c][3..5] for input 2.
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ rstd1,
-                                         const float* __restrict__ rstd2, const float* __restrict__ gamma1,
-                                         float* __restrict__ coef, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, int B, int C, int nchunk, long long S, int mode,
-                                         int has2) {
-    // one WARP per (b, c): lanes stride over the chunk partials, xor-shuffle totals (every lane ends with the sums)
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= B * C) return;
-    const int b = i / C, c = i % C;
-    auto sum3 = [&](int bb, int cc, double& s0, double& s1, double& s2) {
-        const float* o = part + (long long)bb * nchunk * 3 * C;
-        s0 = s1 = s2 = 0.0;
-        for (int k = lane; k < nchunk; k += 32) {
-            s0 += o[(long long)k * 3 * C + cc];
-            s1 += o[(long long)k * 3 * C + C + cc];
-            s2 += o[(long long)k * 3 * C + 2 * C + cc];
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, d);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-        }
-    };
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, n = 0.0;   // group sums of gamma*ds, gamma*ds*xhat1, ds*xhat2
-    auto addgrp = [&](int bb, int cc) {
-        double s0, s1, s2;
-        sum3(bb, cc, s0, s1, s2);
-        const double g = gamma1 ? (double)gamma1[cc] : 1.0;
-        g0 += g * s0; g1 += g * s1; g2 += s2;
-        n += (double)S;
-    };
-    if (mode == 0) addgrp(b, c);
-    else if (mode == 1) { for (int bb = 0; bb < B; ++bb) addgrp(bb, c); }
-    else { addgrp(b, c & ~1); addgrp(b, c | 1); }
-    const double g = gamma1 ? (double)gamma1[c] : 1.0;
-    float* o = coef + (long long)i * 6;
-    const bool writer = lane == 0;
-    if (writer) o[0] = (float)(g * rstd1[i]);
-    if (writer) {
-        o[1] = (float)(rstd1[i] * (g0 / n));
-        o[2] = (float)(rstd1[i] * (g1 / n));
-    }
-    if (has2) {
-        // second input never has affine parameters; its ds sum is the un-weighted one
-        double u0 = 0.0, u2 = 0.0, nn = 0.0;
-        auto add2 = [&](int bb, int cc) { double s0, s1, s2; sum3(bb, cc, s0, s1, s2); u0 += s0; u2 += s2; nn += (double)S; };
-        if (mode == 0) add2(b, c);
-        else if (mode == 1) { for (int bb = 0; bb < B; ++bb) add2(bb, c); }
-        else { add2(b, c & ~1); add2(b, c | 1); }
-        if (writer) {
-            o[3] = rstd2[i];
-            o[4] = (float)(rstd2[i] * (u0 / nn));
-            o[5] = (float)(rstd2[i] * (u2 / nn));
-        }
-    } else if (writer) {
-        o[3] = o[4] = o[5] = 0.f;
-    }
-    (void)g2;
-    if (dgamma != nullptr && b == 0) {
-        double dg = 0.0, db = 0.0;
-        for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
-        if (writer) {
-            dgamma[c] = (float)dg;
-            dbeta[c] = (float)db;
-        }
-    }
-}
-
 // dx1 = k1*ds - k2 - k3*xhat1 ; dx2 likewise (optional) ; dres = ds (optional).  ds = dy*act'(y).
 __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
@@ -648,9 +627,8 @@ FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean
     if (C % 8 || C / 8 > 256) return -1;
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, B);
-    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk);
-    norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
-                                                             running_mean, running_var, crun, momentum);
+    const NormFin fin{mean, rstd, running_mean, running_var, B, C, nchunk, mode, crun, S, eps, momentum};
+    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk, fin, lastblk::next_ticket());
     FCD_LAUNCH_CHECK();
 }
 
@@ -678,10 +656,10 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
     if (x1 == nullptr && (y == nullptr || !(slope > 0.f) || gamma1 != nullptr || dres != nullptr)) return -1;
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 g1(nchunk, B);
+    const NormBwdFin fin{rstd1, rstd2, gamma1, coef, dgamma, dbeta, B, C, nchunk, mode, x2 != nullptr, S};
     norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
-                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope);
-    norm_bwd_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, rstd1, rstd2, gamma1, coef, dgamma, dbeta, B,
-                                                                 C, nchunk, S, mode, x2 != nullptr);
+                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope,
+                                              fin, lastblk::next_ticket());
     dim3 g2(grid_for(S * (C / 8), nt, 8), B);
     norm_bwd_apply_kernel<<<g2, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, coef, (bf16*)dx1, ldd1,
@@ -694,8 +672,8 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
 FCD_API int fcd_norm_finalize(const float* part, float* mean, float* rstd, int B, long long S, int C, int nchunk,
                               int mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                               cudaStream_t st) {
-    norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, mean, rstd, B, C, nchunk, S, mode, eps,
-                                                             running_mean, running_var, crun, momentum);
+    const NormFin fin{mean, rstd, running_mean, running_var, B, C, nchunk, mode, crun, S, eps, momentum};
+    norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, fin);
     FCD_LAUNCH_CHECK();
 }
 
@@ -709,7 +687,7 @@ FCD_API int fcd_colsum(const void* x, long long ld, float* part, float* out, lon
     }
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, 1);
-    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk);
+    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, rows, C / 8, nchunk, NormFin{}, nullptr);
     colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, out, C, nchunk);
     FCD_LAUNCH_CHECK();
 }

@@ -12,6 +12,7 @@
 //   mode 1 (data gradient):      q = m + pad - tap, valid iff q % stride == 0, s = q / stride
 // out_mode 1 scatters N = 8*Cq columns to the 2x2x2 sub-lattice of a (2Dm,2Hm,2Wm) grid (ConvTranspose3d k2 s2).
 #include "common.cuh"
+#include "last_block.cuh"
 
 struct IGemmParams {
     const bf16* A;
@@ -26,6 +27,7 @@ struct IGemmParams {
     int M, Cq;
     int ksplit;        // > 1: blockIdx.z takes a slice of the (tap, k-chunk) loop and writes fp32 partials to ws
     float* ws;         // [ksplit][M][N] fp32
+    unsigned* tickets; // ksplit > 1: one slot per output tile; the CTA that finishes a tile last sums its partials
 };
 
 namespace {
@@ -191,6 +193,32 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
                 if (row + 8 < p.M) *reinterpret_cast<float2*>(&w[(long long)(row + 8) * p.N + col]) = make_float2(acc[mi][nj][2], acc[mi][nj][3]);
             }
         }
+        if (p.tickets == nullptr) return;          // partials only: fcd_splitk_reduce finishes
+        // The CTA that writes the LAST partial of this output tile sums the ksplit partials (fixed order z = 0, 1, ...:
+        // deterministic whatever the arrival order), adds the bias and writes the bf16 rows -- no reduce launch.
+        if (!lastblk::arrive(p.tickets + (blockIdx.y * gridDim.x + blockIdx.x), (unsigned)p.ksplit)) return;
+        constexpr int T_CHUNKS = BM * (BN / 8);
+        for (int idx = tid; idx < T_CHUNKS; idx += NT) {
+            const int row = idx / (BN / 8), c8 = idx % (BN / 8);
+            const int m = m0 + row, n = n0 + c8 * 8;
+            if (m >= p.M || n >= p.N) continue;
+            float a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = p.bias ? p.bias[n + k] : 0.f;
+            for (int z = 0; z < p.ksplit; ++z) {
+                const float4* src = reinterpret_cast<const float4*>(p.ws + ((long long)z * p.M + m) * p.N + n);
+                const float4 u = __ldcg(src), v = __ldcg(src + 1);
+                a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w; a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+            }
+            bf16* dst = p.C + (long long)m * p.ldc + n;
+            if (p.accumulate) {
+                float b[8];
+                unpack8(ld8(dst), b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += b[k];
+            }
+            st8(dst, pack8(a));
+        }
         return;
     }
     // ---- epilogue: (+bias) -> bf16 tile in smem -> 16B coalesced rows (plain / accumulate / k2s2 scatter)
@@ -306,7 +334,7 @@ FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long
     p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
     p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
     p.mode = mode; p.out_mode = out_mode; p.accumulate = accumulate; p.Cq = Cq > 0 ? Cq : 1;
-    p.ksplit = 1; p.ws = nullptr;
+    p.ksplit = 1; p.ws = nullptr; p.tickets = nullptr;
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
@@ -343,13 +371,17 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
     p.A = (const bf16*)A; p.lda = lda; p.W = (const bf16*)W; p.C = (bf16*)C; p.ldc = ldc; p.bias = nullptr;
     p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
     p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
-    p.mode = mode; p.out_mode = 0; p.accumulate = 0; p.Cq = 1;
+    p.mode = mode; p.out_mode = 0; p.accumulate = accumulate; p.Cq = 1;
     p.ksplit = ksplit; p.ws = ws;
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
+    // in-kernel reduction: one ticket per 64 x 64 output tile (falls back to the reduce launch if the ring is too small)
+    const unsigned ntiles = (unsigned)(((M + BM - 1) / BM) * ((N + 63) / 64));
+    p.tickets = lastblk::next_tickets(ntiles);
+    p.bias = p.tickets != nullptr ? bias : nullptr;
     int rc = (K % 32 == 0) ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
-    if (rc != 0) return rc;
+    if (rc != 0 || p.tickets != nullptr) return rc;
     const long long total = M * (N / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 8 * fcd_num_sms()) blocks = 8 * fcd_num_sms();

@@ -60,6 +60,20 @@ def _act_slope(act_name):
     raise ValueError(f"unsupported activation {act_name!r}")
 
 
+def stats_for(norm_mod):
+    """What ops.conv3d needs to finish the statistics of the norm that consumes its output inside the conv kernel
+    (None: statistics are not taken from the batch, or the norm type is not one the fused epilogue serves)."""
+    if isinstance(norm_mod, nn.InstanceNorm3d):
+        return ("instance", norm_mod.eps, None, 0.0)
+    if isinstance(norm_mod, nn.BatchNorm3d):
+        training = norm_mod.training or not norm_mod.track_running_stats
+        if not training:
+            return None
+        bufs = (norm_mod.running_mean, norm_mod.running_var) if norm_mod.track_running_stats else None
+        return ("batch", norm_mod.eps, bufs, norm_mod.momentum)
+    return None
+
+
 def apply_norm(norm_mod, x, x2=None, res=None, slope=1.0):
     """Run InstanceNorm3d / BatchNorm3d / GroupNorm(2 ch per group) fused with the activation and residual."""
     if isinstance(norm_mod, nn.InstanceNorm3d):
@@ -111,9 +125,10 @@ class UnetResBlock(nn.Module):
             with branch:
                 c3 = ops.conv3d(inp, self.conv3.conv.weight, self.conv3.conv.bias, 1, cin_seg=cin_seg)
                 ops.attach_stats(c3, "instance", self.norm2.eps)
-        c1 = ops.conv3d(inp, self.conv1.conv.weight, self.conv1.conv.bias, 3, cin_seg=cin_seg)
+        c1 = ops.conv3d(inp, self.conv1.conv.weight, self.conv1.conv.bias, 3, cin_seg=cin_seg,
+                        stats_for=stats_for(self.norm1))
         a1 = apply_norm(self.norm1, c1, slope=self.slope)
-        c2 = ops.conv3d(a1, self.conv2.conv.weight, self.conv2.conv.bias, 3)
+        c2 = ops.conv3d(a1, self.conv2.conv.weight, self.conv2.conv.bias, 3, stats_for=stats_for(self.norm2))
         if self.downsample:
             branch.join()
             return ops.norm_act(c2, c3, None, None, None, "instance", self.slope, self.norm2.eps)

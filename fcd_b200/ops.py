@@ -72,6 +72,7 @@ def to_channels_last(x: torch.Tensor, cp: int | None = None) -> torch.Tensor:
 
 
 def to_ncdhw(x: torch.Tensor, C: int) -> torch.Tensor:
+    finish_forward(x.device)
     x = rows(x)
     B, D, H, W, _ = x.shape
     y = _empty((B, C, D, H, W), x, torch.float32)
@@ -113,6 +114,7 @@ class _PackCache:
 
     def get(self, w, args):
         import weakref
+        _wait_pack(w.device)
         src = w.detach()
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.float().contiguous()
@@ -238,10 +240,51 @@ def pack_table_epoch(device):
     return _PACKS.epoch.get(device.index, 0)
 
 
+PACK_OVERLAP = os.environ.get("FCD_PACK_OVERLAP", "1") != "0"
+_PACK_STREAM = {}
+_PACK_PENDING = {}      # device index -> [event recorded after the batched pack, set of stream ids that waited on it]
+
+
 def prepack_weights(device):
-    """Called by the networks at the top of forward(): refresh all cached packed weights in one launch."""
+    """Called by the networks at the top of forward(): refresh all cached packed weights in one launch.
+
+    The launch (0.12-0.19 ms for MS_DSA_NET) runs on its own stream, forked from the current one: the first consumers of
+    packed weights are the mma.sync kernels of level 3 and below, 0.7 ms into the forward, so the pack hides behind the
+    level-1/2 encoder (which reads the fp32 parameters directly).  Every stream waits for it the first time it asks for
+    a packed weight (`_wait_pack`); `finish_forward` joins it if nobody asked."""
     _FWD_STREAMS.pop(device.index, None)
-    _PACKS.refresh(device)
+    if not (PACK_OVERLAP and device.type == "cuda"):
+        _PACKS.refresh(device)
+        return
+    main = torch.cuda.current_stream(device)
+    side = _PACK_STREAM.get(device.index)
+    if side is None:
+        side = _PACK_STREAM[device.index] = torch.cuda.Stream(device=device)
+    side.wait_stream(main)                   # parameters were last written (optimizer) / read (backward) before here
+    with torch.cuda.stream(side):
+        _PACKS.refresh(device)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    _PACK_PENDING[device.index] = [ev, set()]
+
+
+def _wait_pack(device):
+    pend = _PACK_PENDING.get(device.index)
+    if pend is None:
+        return
+    cur = torch.cuda.current_stream(device)
+    if cur.cuda_stream not in pend[1]:
+        cur.wait_event(pend[0])
+        pend[1].add(cur.cuda_stream)
+
+
+def finish_forward(device):
+    """Called at the end of a forward (the heads every network ends with, `out_conv` / `to_ncdhw`, call it): the stream
+    that returns the logits joins the weight-pack stream.  A CUDA-graph capture must not end with unjoined work, and the
+    backward pass is ordered after this stream."""
+    if device.index in _PACK_PENDING:
+        _wait_pack(device)
+        del _PACK_PENDING[device.index]
 
 
 def pack_weight(w, T, N, K, Np, Kp, sn, sk, st, kseg=None, ksegpad=None, nseg=None, nsegpad=None):
@@ -418,6 +461,8 @@ def _off_critical_path(fn, *keep):
         return _SIDE.run(fn, *keep)
     return fn()
 _LAST_PART = [None]                               # fused InstanceNorm partials of the most recent ConvFn.forward
+_LAST_MEANRSTD = [None]                           # ... or the finished (mean, rstd) when the conv's last CTA made them
+_NOFIN = dict(mean=None, rstd=None, norm_mode=0, eps=0.0, running_mean=None, running_var=None, crun=0, momentum=0.0)
 
 
 def _tc_nseg(B, D, H, W, K, N, k, stride, pad, bias):
@@ -461,10 +506,9 @@ def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
         ks = _lib.lib().fcd_conv_gemm_tc_ksplit(M, K, N)
         if ks > 0:          # deep levels: tcgen05 split-K GEMM with streamed weights
             ws = torch.empty((ks, M, N), dtype=torch.float32, device=a.device) if ks > 1 else None
+            # split-K partials are summed inside the kernel by the CTA that finishes an output tile last
             call("fcd_conv_gemm_tc", A=a, lda=ld(a), Wp=wp, C=c, ldc=ld(c), ws=ws, Bn=B, D=dst[0], H=dst[1], W=dst[2],
                  K=K, N=N, mode=mode, ksplit=ks)
-            if ks > 1:
-                call("fcd_splitk_reduce", ws=ws, C=c, ldc=ld(c), bias=None, M=M, N=N, ksplit=ks, accumulate=0)
             return
     ks = _lib.lib().fcd_igemm_ksplit(M, N, K, k ** 3)
     common = dict(A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), bias=bias, Bn=B, Ds=src[0], Hs=src[1], Ws=src[2], Dm=dst[0],
@@ -483,7 +527,7 @@ class ConvFn(Function):
     each padded to `segpad` in x (torch.cat elimination, conv_blocks.py:685)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, stride, pad, cin_seg):
+    def forward(ctx, x, weight, bias, k, stride, pad, cin_seg, stats_for=None):
         x = rows(x)
         B, D, H, W, Kp = x.shape
         Co, Ci = weight.shape[0], weight.shape[1]
@@ -495,22 +539,33 @@ class ConvFn(Function):
         _lib.note_work("fwd", 2.0 * B * Do * Ho * Wo * Co * Ci * T, 2.0 * B * (D * H * W * Ci + Do * Ho * Wo * Co))
         nseg = _tc_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias)
         _LAST_PART[0] = None
+        _LAST_MEANRSTD[0] = None
         if nseg > 0:
             part = None
+            fin = _NOFIN
             if Np <= 32:
                 nchunk = (H // 16) * (W // 8) * nseg
                 part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
                 _LAST_PART[0] = (part, nchunk)
+                if stats_for is not None:
+                    # the norm that follows is known: the conv's last CTA finishes its statistics (no finalize launch)
+                    mode, eps, bufs, momentum = stats_for
+                    mean = torch.empty((B, Np), dtype=torch.float32, device=x.device)
+                    rstd = torch.empty((B, Np), dtype=torch.float32, device=x.device)
+                    rm, rv = bufs if bufs is not None else (None, None)
+                    fin = dict(mean=mean, rstd=rstd, norm_mode=MODE[mode], eps=float(eps), running_mean=rm,
+                               running_var=rv, crun=0 if rm is None else rm.numel(), momentum=float(momentum or 0.0))
+                    _LAST_MEANRSTD[0] = (mean, rstd)
             call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
-                 nseg=nseg)
+                 nseg=nseg, **fin)
         elif _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci) > 0:
             ns2 = _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci)
             w32 = _w32(weight)
             for i in range(2):
                 call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                      ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp,
-                     N=32, flip=0, nseg=ns2)
+                     N=32, flip=0, nseg=ns2, **_NOFIN)
         elif _pw_ok(B * D * H * W, Kp, Np, k, stride, pad, bias):
             call("fcd_pw_conv", A=x, lda=ld(x), Wf=_w32(weight), sn=Ci, sk=1, Nr=Co, Kr=Ci, kseg=seg, ksegpad=segpad,
                  nsg=Co, nsgpad=Np, C=y, ldc=Np, M=B * D * H * W, K=Kp, N=Np)
@@ -539,14 +594,14 @@ class ConvFn(Function):
                 # dX = correlation of dY with the mirrored kernel: output channels = Cin (in concat segments)
                 call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
                      ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
-                     flip=1, nseg=nseg)
+                     flip=1, nseg=nseg, **_NOFIN)
             elif _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None if seg == Ci else 1, Co, Ci) > 0:
                 ns2 = _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None, Co, Ci)
                 w32 = _w32(weight).view(-1)
                 for i in range(2):
                     call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
                          kseg=Co, ksegpad=Np, nsg=32, nsgpad=32, C=dx[..., 32 * i:], ldc=Kp, part=None, Bn=B, D=D, H=H,
-                         W=W, K=Np, N=32, flip=1, nseg=ns2)
+                         W=W, K=Np, N=32, flip=1, nseg=ns2, **_NOFIN)
             elif _pw_ok(B * D * H * W, Np, Kp, k, stride, pad, None):
                 # dX rows = dY rows x W: the same pointwise kernel with the weight read transposed
                 call("fcd_pw_conv", A=dy, lda=ld(dy), Wf=_w32(weight), sn=1, sk=Ci, Nr=Ci, Kr=Co, kseg=Co, ksegpad=Np,
@@ -590,14 +645,21 @@ class ConvFn(Function):
                 dw = wgrad_work()
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy, Co)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv3d(x, weight, bias=None, k=3, stride=1, pad=None, cin_seg=None):
+def conv3d(x, weight, bias=None, k=3, stride=1, pad=None, cin_seg=None, stats_for=None):
+    """stats_for = (mode, eps, (running_mean, running_var) | None, momentum) of the norm that consumes the result, when
+    known: a tcgen05 conv with the fused statistics epilogue then also finishes mean / rstd (see ConvFn.forward)."""
     if pad is None:
         pad = (k - 1) // 2
-    y = ConvFn.apply(x, weight, bias, k, stride, pad, cin_seg)
-    if _LAST_PART[0] is not None:      # statistics of y came out of the conv epilogue: the next norm skips its pass
+    y = ConvFn.apply(x, weight, bias, k, stride, pad, cin_seg, stats_for)
+    if _LAST_MEANRSTD[0] is not None:  # ... and mean / rstd as well: the next norm launches nothing for its statistics
+        y._fcd_meanrstd = _LAST_MEANRSTD[0]
+        y._fcd_stats_mode = MODE[stats_for[0]]
+        _LAST_MEANRSTD[0] = None
+        _LAST_PART[0] = None
+    elif _LAST_PART[0] is not None:    # statistics of y came out of the conv epilogue: the next norm skips its pass
         y._fcd_part = _LAST_PART[0]
         _LAST_PART[0] = None
     return y
@@ -785,10 +847,13 @@ class NormActFn(Function):
         res = rows(res) if res is not None else None
         g = _vpad(gamma, C, 1.0)
         b = _vpad(beta, C, 0.0)
+        pre1 = getattr(x1, "_fcd_meanrstd", None)
         if mode == 1 and not training:
             rm, rv = bn_buffers
             mean1 = _vpad(rm, C).unsqueeze(0).expand(B, C).contiguous()
             rstd1 = torch.rsqrt(_vpad(rv, C, 1.0) + eps).unsqueeze(0).expand(B, C).contiguous()
+        elif pre1 is not None and getattr(x1, "_fcd_stats_mode", mode) == mode and pre1[0].shape == (B, C):
+            mean1, rstd1 = pre1             # finished by the producing conv (incl. the BatchNorm running statistics)
         elif mode == 1:
             rm, rv = bn_buffers
             mean1, rstd1 = _stats(x1, 1, eps, rm, rv, rm.numel(), momentum)
@@ -901,6 +966,7 @@ class OutConvFn(Function):
 
 
 def out_conv(x, weight, bias):
+    finish_forward(x.device)
     return OutConvFn.apply(x, weight, bias)
 
 
