@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     __syncthreads();
     if (warp == NPROD) tmem_dealloc<K::TMEM_COLS>(tmem_base);
     if (STATS && p.fin.mean != nullptr && lastblk::arrive(p.ticket, gridDim.x))
-        norm_finalize_body(p.part, p.fin, tid >> 5, NTHREADS >> 5);
+        norm_finalize_block(p.part, p.fin, reinterpret_cast<double*>(smem));      // all shared memory is free by now
 }
 
 template <int CIN, int COUT, bool STATS, bool FLIP>
@@ -404,8 +404,10 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     if (p.nseg != nseg) return -1;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;
     p.status = fcd_status_dev();
-    // optional: the last CTA finishes the fused statistics (mean / rstd of the norm that follows the conv)
-    p.fin = NormFin{part != nullptr ? mean : nullptr, rstd, running_mean, running_var, Bn, N, p.nht * p.nwt * p.nseg,
+    // optional: the last CTA finishes the fused statistics (mean / rstd of the norm that follows the conv); the caller
+    // asks fcd_norm_fin_fold first -- partials too large for one CTA are finished by fcd_norm_finalize
+    if (mean != nullptr && (part == nullptr || !fin_fold(Bn, p.nht * p.nwt * p.nseg, 2 * N))) return -1;
+    p.fin = NormFin{mean, rstd, running_mean, running_var, Bn, N, p.nht * p.nwt * p.nseg,
                     norm_mode, crun, (long long)D * H * W, eps, momentum};
     p.ticket = p.fin.mean != nullptr ? lastblk::next_ticket() : nullptr;
     static const int dbg_delay = getenv("FCD_TCF_PRODUCER_DELAY_NS") ? atoi(getenv("FCD_TCF_PRODUCER_DELAY_NS")) : 0;

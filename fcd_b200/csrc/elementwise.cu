@@ -139,7 +139,7 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, floa
             }
         }
     }
-    __shared__ float sh[256 * 16];
+    __shared__ __align__(16) float sh[256 * 16];      // 16 KB: reused by the last block's finalize (kFinScratchDoubles)
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sh[threadIdx.x * 16 + k] = sum[k]; sh[threadIdx.x * 16 + 8 + k] = sq[k]; }
     __syncthreads();
@@ -157,13 +157,12 @@ __global__ void norm_stats_kernel(const bf16* __restrict__ x, long long ld, floa
 #pragma unroll
         for (int k = 0; k < 8; ++k) { o[c8 * 8 + k] = sum[k]; o[C + c8 * 8 + k] = sq[k]; }
     }
-    if (fin.mean != nullptr && lastblk::arrive(ticket, gridDim.x * gridDim.y) &&
-        (int)(threadIdx.x >> 5) < (int)(blockDim.x >> 5))            // full warps only (the block may end in a partial one)
-        norm_finalize_body(part, fin, threadIdx.x >> 5, blockDim.x >> 5);
+    if (fin.mean != nullptr && lastblk::arrive(ticket, gridDim.x * gridDim.y))
+        norm_finalize_block(part, fin, reinterpret_cast<double*>(sh));
 }
 
 __global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restrict__ part, NormFin f) {
-    norm_finalize_body(part, f, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
+    norm_finalize_warp(part, f, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
 }
 
 // y = act( g1*(x1-mean1)*rstd1 + b1  [+ g2*(x2-mean2)*rstd2 + b2]  [+ r] ),  act(v) = v > 0 ? v : slope*v
@@ -314,8 +313,78 @@ __device__ __forceinline__ void norm_bwd_finalize_one(const float* __restrict__ 
         }
     }
 }
-__device__ __forceinline__ void norm_bwd_finalize_body(const float* __restrict__ part, const NormBwdFin& f, int w0, int nw) {
+// the same arithmetic from the column totals of one channel tile (tot[(b * 3 + v) * CT + cc]), one THREAD per (b, c)
+__device__ __forceinline__ void norm_bwd_finalize_tot(const double* __restrict__ tot, const NormBwdFin& f, int b, int cc,
+                                                      int c0, int CT) {
+    const float* rstd1 = f.rstd1; const float* rstd2 = f.rstd2; const float* gamma1 = f.gamma1;
+    float* coef = f.coef; float* dgamma = f.dgamma; float* dbeta = f.dbeta;
+    const int B = f.B, C = f.C, nchunk = f.nchunk, mode = f.mode, has2 = f.has2;
+    const long long S = f.S;
+    const int c = c0 + cc, i = b * C + c;
+    (void)nchunk;
+    auto sum3 = [&](int bb, int c2, double& s0, double& s1, double& s2) {      // c2: GLOBAL channel index
+        s0 = tot[(long long)(bb * 3 + 0) * CT + (c2 - c0)];
+        s1 = tot[(long long)(bb * 3 + 1) * CT + (c2 - c0)];
+        s2 = tot[(long long)(bb * 3 + 2) * CT + (c2 - c0)];
+    };
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, n = 0.0;   // group sums of gamma*ds, gamma*ds*xhat1, ds*xhat2
+    auto addgrp = [&](int bb, int cc) {
+        double s0, s1, s2;
+        sum3(bb, cc, s0, s1, s2);
+        const double g = gamma1 ? (double)gamma1[cc] : 1.0;
+        g0 += g * s0; g1 += g * s1; g2 += s2;
+        n += (double)S;
+    };
+    if (mode == 0) addgrp(b, c);
+    else if (mode == 1) { for (int bb = 0; bb < B; ++bb) addgrp(bb, c); }
+    else { addgrp(b, c & ~1); addgrp(b, c | 1); }
+    const double g = gamma1 ? (double)gamma1[c] : 1.0;
+    float* o = coef + (long long)i * 6;
+    const bool writer = true;
+    if (writer) o[0] = (float)(g * rstd1[i]);
+    if (writer) {
+        o[1] = (float)(rstd1[i] * (g0 / n));
+        o[2] = (float)(rstd1[i] * (g1 / n));
+    }
+    if (has2) {
+        // second input never has affine parameters; its ds sum is the un-weighted one
+        double u0 = 0.0, u2 = 0.0, nn = 0.0;
+        auto add2 = [&](int bb, int cc) { double s0, s1, s2; sum3(bb, cc, s0, s1, s2); u0 += s0; u2 += s2; nn += (double)S; };
+        if (mode == 0) add2(b, c);
+        else if (mode == 1) { for (int bb = 0; bb < B; ++bb) add2(bb, c); }
+        else { add2(b, c & ~1); add2(b, c | 1); }
+        if (writer) {
+            o[3] = rstd2[i];
+            o[4] = (float)(rstd2[i] * (u0 / nn));
+            o[5] = (float)(rstd2[i] * (u2 / nn));
+        }
+    } else if (writer) {
+        o[3] = o[4] = o[5] = 0.f;
+    }
+    (void)g2;
+    if (dgamma != nullptr && b == 0) {
+        double dg = 0.0, db = 0.0;
+        for (int bb = 0; bb < B; ++bb) { double s0, s1, s2; sum3(bb, c, s0, s1, s2); db += s0; dg += s1; }
+        if (writer) {
+            dgamma[c] = (float)dg;
+            dbeta[c] = (float)db;
+        }
+    }
+}
+__device__ __forceinline__ void norm_bwd_finalize_warp(const float* __restrict__ part, const NormBwdFin& f, int w0, int nw) {
     for (int i = w0; i < f.B * f.C; i += nw) norm_bwd_finalize_one(part, f, i);
+}
+// the whole finalize by ONE block (the last block of norm_bwd_stats_kernel); scratch: kFinScratchDoubles doubles
+__device__ __forceinline__ void norm_bwd_finalize_block(const float* __restrict__ part, const NormBwdFin& f, double* scratch) {
+    const int CT0 = fin_tile_channels(f.B, 3, f.C);
+    for (int c0 = 0; c0 < f.C; c0 += CT0) {
+        const int CT = min(CT0, f.C - c0);
+        fin_colsum_tile<3>(part, f.B, f.nchunk, f.C, c0, CT, scratch);
+        for (int i = threadIdx.x; i < f.B * CT; i += blockDim.x) norm_bwd_finalize_tot(scratch + 1024, f, i / CT, i % CT, c0, CT);
+    }
+}
+__global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, NormBwdFin f) {
+    norm_bwd_finalize_warp(part, f, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
 }
 
 __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
@@ -391,7 +460,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
             for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], xh[k], a1[k]); }
         }
     }
-    __shared__ float sh[256 * 24];
+    __shared__ __align__(16) float sh[256 * 24];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sh[threadIdx.x * 24 + k] = a0[k];
@@ -416,9 +485,9 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
             o[2 * C + c8 * 8 + k] = a2[k];
         }
     }
-    // the block that finishes last turns the partials into the per-(b,c) coefficients (no separate finalize launch)
-    if (lastblk::arrive(ticket, gridDim.x * gridDim.y) && (int)(threadIdx.x >> 5) < (int)(blockDim.x >> 5))
-        norm_bwd_finalize_body(part, fin, threadIdx.x >> 5, blockDim.x >> 5);
+    // small partials: the block that finishes last turns them into the per-(b,c) coefficients (no finalize launch)
+    if (ticket != nullptr && lastblk::arrive(ticket, gridDim.x * gridDim.y))
+        norm_bwd_finalize_block(part, fin, reinterpret_cast<double*>(sh));
 }
 
 // Turn the backward partial sums into per-(b,c) coefficients:
@@ -627,8 +696,13 @@ FCD_API int fcd_norm_stats(const void* x, long long ld, float* part, float* mean
     if (C % 8 || C / 8 > 256) return -1;
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(nchunk, B);
-    const NormFin fin{mean, rstd, running_mean, running_var, B, C, nchunk, mode, crun, S, eps, momentum};
-    norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk, fin, lastblk::next_ticket());
+    NormFin fin{mean, rstd, running_mean, running_var, B, C, nchunk, mode, crun, S, eps, momentum};
+    if (fin_fold(B, nchunk, 2 * C)) {          // small partials: finished by the last block of the statistics kernel
+        norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk, fin, lastblk::next_ticket());
+    } else {
+        norm_stats_kernel<<<grid, nt, 0, st>>>((const bf16*)x, ld, part, S, C / 8, nchunk, NormFin{}, nullptr);
+        norm_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, fin);
+    }
     FCD_LAUNCH_CHECK();
 }
 
@@ -657,9 +731,11 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 g1(nchunk, B);
     const NormBwdFin fin{rstd1, rstd2, gamma1, coef, dgamma, dbeta, B, C, nchunk, mode, x2 != nullptr, S};
+    const bool fold = fin_fold(B, nchunk, 3 * C);
     norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope,
-                                              fin, lastblk::next_ticket());
+                                              fin, fold ? lastblk::next_ticket() : nullptr);
+    if (!fold) norm_bwd_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, fin);
     dim3 g2(grid_for(S * (C / 8), nt, 8), B);
     norm_bwd_apply_kernel<<<g2, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
                                               rstd1, (const bf16*)x2, ld2, mean2, rstd2, coef, (bf16*)dx1, ldd1,
@@ -707,3 +783,6 @@ FCD_API int fcd_copy_rows(const void* a, long long lda, void* o, long long ldo, 
                                                                        C / 8);
     FCD_LAUNCH_CHECK();
 }
+
+// Can the last CTA of a producer finish partials of B x nchunk rows of L floats (norm_fin.cuh)?  1 / 0.
+FCD_API int fcd_norm_fin_fold(int B, int nchunk, int L) { return fin_fold(B, nchunk, L) ? 1 : 0; }

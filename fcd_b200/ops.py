@@ -547,7 +547,7 @@ class ConvFn(Function):
                 nchunk = (H // 16) * (W // 8) * nseg
                 part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
                 _LAST_PART[0] = (part, nchunk)
-                if stats_for is not None:
+                if stats_for is not None and _lib.lib().fcd_norm_fin_fold(B, nchunk, 2 * Np):
                     # the norm that follows is known: the conv's last CTA finishes its statistics (no finalize launch)
                     mode, eps, bufs, momentum = stats_for
                     mean = torch.empty((B, Np), dtype=torch.float32, device=x.device)

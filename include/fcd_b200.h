@@ -88,6 +88,7 @@ FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, i
  * the InstanceNorm / BatchNorm that follows the conv, conv_blocks.py:439-452, needs no launch of its own for them).  fcd_conv3_tc_nseg returns the
  * number of d-segments to use (0: shape unsupported -> use fcd_igemm).  fcd_tc_error: first timed-out pipeline wait
  * since the last call (0 = none; test / debug aid, synchronises the device). */
+FCD_API int fcd_norm_fin_fold(int B, int nchunk, int L);   /* 1: B x nchunk partial rows of L floats fit the last-CTA finalize */
 FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N);
 FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,

@@ -136,7 +136,8 @@ def test_whole_model_gradient_directional_derivatives():
     """Layer by layer: the analytic gradient of every parameter tensor against a central finite difference of OUR OWN
     forward + fused loss along that gradient's direction (a 2 % perturbation of the layer).  This is independent of how
     ill-conditioned the gradient is with respect to bf16 rounding upstream (the oracle comparison below cannot have a
-    fixed bound for that reason), and a mis-scaled or mis-routed gradient in ANY layer fails it: fixed tolerance 6 %."""
+    fixed bound for that reason), and a mis-scaled or mis-routed gradient in ANY layer fails it: fixed tolerance 5 % + 1e-4 / |dL| at the 0.5 % step
+    (measured on B200: <= 6.5 %, and the 2 % step's 9-16 % on the encoder layers is truncation error: it shrinks 4-30x)."""
     import fcd_b200
     model, sd = _shallow_unet()
     x = synth.image(2, 2, 32, seed=3).to(DEV)
@@ -171,13 +172,14 @@ def test_whole_model_gradient_directional_derivatives():
                 skipped += 1
                 continue
             checked += 1
-            if err > worst[1]:
-                worst = (k, err)
+            tol = 0.05 + 1e-4 / pred      # 5 % + the resolution of a bf16 forward pass (~1e-4 in the loss difference)
+            if err / tol > worst[1]:
+                worst = (k, err / tol)
             print(f"  {k:45s} step 0.5 %: predicted dL {pred:.4e} measured {meas:.4e} rel err {err:.3f}   "
                   f"(step 2 %: rel err {errs[0][2]:.3f})")
     print(f"directional derivatives: {checked} parameter tensors checked, {skipped} below resolution, worst {worst}")
     assert checked >= 15
-    assert worst[1] <= 6e-2, worst
+    assert worst[1] <= 1.0, f"gradient of {worst[0]} disagrees with the finite difference ({worst[1]:.2f} x tolerance)"
 
 
 def test_well_conditioned_whole_model_gradients():

@@ -35,9 +35,11 @@ def _conv(ops, entry, x, w32, Ci, Co, nseg, flip=0, stats=True):
     fin = dict(ops._NOFIN)
     if stats and Np <= 32:
         part = torch.empty((B, (H // 16) * (W // 8) * nseg, 2, Np), dtype=torch.float32, device=x.device)
-        # InstanceNorm statistics finished by the conv's last CTA (returned in place of the raw partials' consumer)
-        fin.update(mean=torch.empty((B, Np), dtype=torch.float32, device=x.device),
-                   rstd=torch.empty((B, Np), dtype=torch.float32, device=x.device), norm_mode=0, eps=1e-5)
+        from fcd_b200 import _lib
+        if _lib.lib().fcd_norm_fin_fold(B, part.shape[1], 2 * Np):
+            # InstanceNorm statistics finished by the conv's last CTA
+            fin.update(mean=torch.empty((B, Np), dtype=torch.float32, device=x.device),
+                       rstd=torch.empty((B, Np), dtype=torch.float32, device=x.device), norm_mode=0, eps=1e-5)
     if flip:    # data gradient: x plays dY (Ci = conv's Cout), the weight is read transposed and mirrored
         ops.call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=27, sk=Co * 27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
                  nsgpad=Np, C=y, ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=1, nseg=nseg, **ops._NOFIN)
@@ -45,7 +47,7 @@ def _conv(ops, entry, x, w32, Ci, Co, nseg, flip=0, stats=True):
     else:
         ops.call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=Ci * 27, sk=27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
                  nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0, nseg=nseg, **fin)
-        if part is not None:
+        if part is not None and fin["mean"] is not None:
             part = torch.cat([part.reshape(B, -1), fin["mean"], fin["rstd"]], 1)    # compared bit for bit across launches
             y._mean_rstd = (fin["mean"], fin["rstd"])
     return y, part
@@ -94,9 +96,12 @@ def test_tcf_many_items_and_segments(ops, B, Ci, Co, S, nseg, flip, iters):
     del ref, got
     if p0 is not None:
         yf = y0.float().reshape(B, -1, y0.shape[-1])
-        mean, rstd = y0._mean_rstd
-        assert torch.allclose(mean, yf.mean(1), rtol=1e-4, atol=1e-5), "fused mean (finished by the last CTA)"
-        assert torch.allclose(rstd[:, :Co], torch.rsqrt(yf.var(1, unbiased=False) + 1e-5)[:, :Co], rtol=2e-4), "fused rstd"
+        if hasattr(y0, "_mean_rstd"):
+            mean, rstd = y0._mean_rstd
+            assert torch.allclose(mean, yf.mean(1), rtol=1e-4, atol=1e-5), "fused mean (finished by the last CTA)"
+            assert torch.allclose(rstd[:, :Co], torch.rsqrt(yf.var(1, unbiased=False) + 1e-5)[:, :Co], rtol=2e-4)
+        else:
+            assert torch.allclose(p0.sum(1)[:, 0], yf.sum(1), rtol=1e-4, atol=1e-2)
         del yf
     # other tcgen05 convs resident on the same SMs (what the branch streams of a window forward do)
     side = torch.cuda.Stream()
