@@ -243,7 +243,8 @@ FCD_API int fcd_conv_gemm_tc_ksplit(long long M, int K, int N) {
 
 // A: NDHWC bf16 rows (pitch lda >= K); Wp: packed bf16 [27][N][K]; mode 0 forward / 1 data gradient (Wp then holds the
 // transposed weights, as for fcd_igemm mode 1).  ksplit == 1: bf16 rows into C (pitch ldc); ksplit > 1: fp32 partials
-// into ws[ksplit][M][N], summed (fixed order) into the bf16 rows of C by the CTA that finishes an output tile last.
+// into ws[ksplit][M][N]: for ksplit == 2 summed into the bf16 rows of C by the CTA that finishes an output tile last,
+// for ksplit > 2 to be finished by fcd_splitk_reduce.
 FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void* C, long long ldc, float* ws, int Bn,
                              int D, int H, int W, int K, int N, int mode, int ksplit, cudaStream_t stream) {
     const int bn = pick_bn(N);
@@ -255,7 +256,9 @@ FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void*
     const long long M = (long long)Bn * D * H * W;
     if (M > 0x7fffffffLL) return -1;
     p.M = (int)M; p.status = fcd_status_dev();
-    p.tickets = ksplit > 1 ? lastblk::next_tickets((unsigned)(((M + BM - 1) / BM) * (N / bn))) : nullptr;
+    // in-kernel reduction only for ksplit == 2 (a single CTA summing many partial tiles is a serial tail: measured
+    // 1.8x slower kernels at ksplit 8-27); otherwise the caller launches fcd_splitk_reduce
+    p.tickets = ksplit == 2 ? lastblk::next_tickets((unsigned)(((M + BM - 1) / BM) * (N / bn))) : nullptr;
     if (bn == 256) return launch<256>(p, stream);
     if (bn == 128) return launch<128>(p, stream);
     return launch<64>(p, stream);

@@ -405,20 +405,31 @@ bool shape_ok(int D, int H, int W, int K, int N) {
 // The fused statistics buffer has nchunk = (H/16)*(W/8)*nseg entries per sample.
 FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
     if (!shape_ok(D, H, W, K, N)) return 0;
-    // minimise rounds x (planes per item + 1) over power-of-two segment counts with >= 4 planes per segment
+    // Minimise  rounds x (planes per item + 3)  over power-of-two segment counts with >= 4 planes per segment, where
+    // rounds = ceil(items / resident CTAs) and "+ 3" = the two halo planes an item loads beyond its outputs plus its
+    // pipeline fill.  Resident CTAs: two per SM for the kd-folded Cout = 16 configurations whose shared memory allows it
+    // (conv_tcf.cu Cfg), else one.  (Measured, batch 2 @128^3 16 -> 16: 1 segment 109 us, 4 segments 127 us -- the
+    // first model, rounds over the SM count x (planes + 1), preferred 4.)
+    // Round 1 additionally forbade several segments together with several items per CTA because that regime hit rare
+    // time-outs; the cause (an aliased FULL-barrier parity wait, conv_tcf.cu) is fixed and tests/test_gpu_conv_stress.py
+    // covers the regime.  FCD_NSEG_RESTRICTED=1 restores the old rule for A/B runs.
+    static const bool restricted = getenv("FCD_NSEG_RESTRICTED") != nullptr;
     const int cols = Bn * (H / TH) * (W / TW), sms = fcd_num_sms();
+    int per_sm = 1;
+    if (N == 16 && K <= 64) {
+        const int w_bytes = 27 * K * N * 2, plane = 180 * K * 2;
+        int nst = (220 * 1024 - w_bytes) / plane;
+        if (nst > 6) nst = 6;
+        if (2 * (w_bytes + nst * plane + 2560) <= 226 * 1024) per_sm = 2;
+    }
+    const long long ctas = (long long)sms * per_sm;
     int nseg = 1;
     long long best = -1;
     for (int c = 1; c == 1 || D / c >= 4; c *= 2) {
         const int dl = (D + c - 1) / c;
         if ((D + dl - 1) / dl != c) continue;
-        // (Round 1 restricted c > 1 to one work item per CTA because segments AND several items per CTA hit rare
-        // time-outs; the cause -- an aliased FULL-barrier parity wait at item boundaries with one padding plane,
-        // conv_tcf.cu -- is fixed, tests/test_gpu_conv_stress.py covers the regime.  FCD_NSEG_RESTRICTED=1 restores
-        // the old choice for A/B timing.)
-        static const bool restricted = getenv("FCD_NSEG_RESTRICTED") != nullptr;
         if (restricted && c > 1 && (long long)cols * c > sms) continue;
-        const long long cost = (long long)((cols * c + sms - 1) / sms) * (dl + 1);
+        const long long cost = (((long long)cols * c + ctas - 1) / ctas) * (dl + 3);
         if (best < 0 || cost < best) { best = cost; nseg = c; }
     }
     return nseg;

@@ -377,8 +377,10 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
     // in-kernel reduction: one ticket per 64 x 64 output tile (falls back to the reduce launch if the ring is too small)
+    // (only for ksplit <= 2: one CTA summing many partial tiles is a serial tail -- measured 1.4x slower kernels at the
+    // deep levels' ksplit of 8-27 -- while the reduce launch spreads the same reads over all SMs)
     const unsigned ntiles = (unsigned)(((M + BM - 1) / BM) * ((N + 63) / 64));
-    p.tickets = lastblk::next_tickets(ntiles);
+    p.tickets = ksplit <= 2 ? lastblk::next_tickets(ntiles) : nullptr;
     p.bias = p.tickets != nullptr ? bias : nullptr;
     int rc = (K % 32 == 0) ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
     if (rc != 0 || p.tickets != nullptr) return rc;

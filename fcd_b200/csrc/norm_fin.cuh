@@ -7,13 +7,16 @@
 // loop in a single block is a chain of dependent L2 latencies: measured 2x slower than the separate launch), in a fixed
 // order (deterministic), in fp64, staged through 16 KB of shared memory, one channel tile at a time.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 constexpr int kFinScratchDoubles = 2048;           // 16 KB: k-split exchange [0, 1024) + tile totals [1024, 2048)
 constexpr long long kFinFoldBytes = 128 << 10;     // partials up to this size are finished by the last block
 
 static inline bool fin_fold(int B, int nchunk, int L) {
-    return (long long)B * nchunk * L * 4 <= kFinFoldBytes && B * 3 * 4 <= 1024;
+    static const long long limit = getenv("FCD_FIN_FOLD_BYTES") ? atoll(getenv("FCD_FIN_FOLD_BYTES")) : kFinFoldBytes;
+    return (long long)B * nchunk * L * 4 <= limit && B * 3 * 4 <= 1024;
 }
 
 // mode 0 instance (per b,c), 1 batch (per c over b), 2 group-of-2-channels (per b, c/2).

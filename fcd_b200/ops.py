@@ -506,9 +506,10 @@ def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
         ks = _lib.lib().fcd_conv_gemm_tc_ksplit(M, K, N)
         if ks > 0:          # deep levels: tcgen05 split-K GEMM with streamed weights
             ws = torch.empty((ks, M, N), dtype=torch.float32, device=a.device) if ks > 1 else None
-            # split-K partials are summed inside the kernel by the CTA that finishes an output tile last
             call("fcd_conv_gemm_tc", A=a, lda=ld(a), Wp=wp, C=c, ldc=ld(c), ws=ws, Bn=B, D=dst[0], H=dst[1], W=dst[2],
                  K=K, N=N, mode=mode, ksplit=ks)
+            if ks > 2:      # ks == 2 is summed inside the kernel by the CTA that finishes an output tile last
+                call("fcd_splitk_reduce", ws=ws, C=c, ldc=ld(c), bias=None, M=M, N=N, ksplit=ks, accumulate=0)
             return
     ks = _lib.lib().fcd_igemm_ksplit(M, N, K, k ** 3)
     common = dict(A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), bias=bias, Bn=B, Ds=src[0], Hs=src[1], Ws=src[2], Dm=dst[0],
