@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches timed for the CPU baseline")
     ap.add_argument("--loss", default=None, help="DiceCELoss (default) | DiceFocalLoss | DiceLoss")
     ap.add_argument("--tv", type=float, default=0.0, help="tv_loss_weight (configs[3] uses 0.1)")
+    ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip timing the stock PyTorch (cuDNN/cuBLAS) bf16/fp16-autocast step on the same GPU")
     return ap.parse_args()
@@ -302,7 +303,11 @@ def main():
     model.apply(synthetic.initialize_weights)
     model = model.to(dev).train()
     loss_fn = fcd_b200.CombinedLoss(params, dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=params["lr"], weight_decay=params["weight_decay"], fused=True)
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(model.parameters(), lr=params["lr"], weight_decay=params["weight_decay"], fused=True)
+    else:       # one fcd_adamw_multi launch for all parameter tensors (torch's fused AdamW: ~10 launches)
+        from fcd_b200.optim import FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=params["lr"], weight_decay=params["weight_decay"])
     reducer = parallel.GradAllReducer(model.parameters(), overlap=not args.no_overlap)
     reducer.sync_params()
     B = args.batch
@@ -346,7 +351,7 @@ def main():
     fwd_bwd()
     _lib.set_profiler(None)
     agg = prof.summary()
-    gpu_launches = prof.launches
+    gpu_launches = prof.launches + (0 if args.torch_adamw else 1)      # + the one-launch optimizer step
     _ops.WGRAD_OVERLAP, _ops.BRANCH_OVERLAP = saved_overlap
     reducer.enabled = True
     reducer.allreduce()
@@ -597,17 +602,23 @@ def main():
             with torch.no_grad():
                 ms_vol, lab = timed_vols(infer_dev, n_vol)
                 ms_vol_e2e, lab = timed_vols(infer_e2e, n_vol)
-                # post-processing of the label map on the device (train.py:167-182; the reference: D2H + scipy + H2D)
-                pp_ms = None
-                for _ in range(2):
-                    post_process_segment(lab[0, 0], 50)
-                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                p0.record()
-                for _ in range(5):
-                    pp_mask, _ = post_process_segment(lab[0, 0], 50)
-                p1.record()
-                torch.cuda.synchronize()
-                pp_ms = p0.elapsed_time(p1) / 5
+                # post-processing on the device (train.py:167-182; the reference: D2H + scipy on one core + H2D), timed on
+                # the label map this (untrained) model predicts -- usually one huge component, the worst case for
+                # connected components -- and on a realistic one (three lesions, ~1 % foreground)
+                def time_pp(m):
+                    for _ in range(2):
+                        post_process_segment(m, 50)
+                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    p0.record()
+                    for _ in range(5):
+                        out_m, _ = post_process_segment(m, 50)
+                    p1.record()
+                    torch.cuda.synchronize()
+                    return p0.elapsed_time(p1) / 5, out_m
+                pp_ms, pp_mask = time_pp(lab[0, 0])
+                _, lesions = synthetic.make_batch(1, 2, tuple(vshape[2:]), seed=5)
+                lesions = lesions[0, 0].to(dev)
+                pp_ms_real, pp_mask_real = time_pp(lesions)
             errs = _kernel_errors()
             bad = torch.tensor([float(errs["word"] != 0)], device=dev)
             if world > 1:                      # a time-out on ANY rank voids the volume every rank contributed to
@@ -625,9 +636,12 @@ def main():
                    "roofline": {"bound": "tensor", "algorithmic_tflop_per_vol": 18 * fwd_flops / 1e12,
                                 "achieved": 18 * fwd_flops / (ms_vol * 1e-3) / 1e12 / world, "unit": "TFLOP/s per GPU",
                                 "peak": pk["tf_sust"], "frac": 18 * fwd_flops / (ms_vol * 1e-3) / 1e12 / world / pk["tf_sust"]},
-                   "post_process_ms": pp_ms, "post_process": "fcd_post_process on the device (opening, 5^3 fill-holes, "
-                                                             "26-connected components, size filter 50), not in value/e2e",
-                   "fg_fraction": float(lab_h.float().mean()), "kept_voxels": int(pp_mask.sum().item())}
+                   "post_process": {"what": "fcd_post_process on the device (opening, 5^3 fill-holes, 26-connected components, "
+                                            "size filter 50); not part of value / e2e",
+                                    "ms_synthetic_lesions": pp_ms_real, "fg_fraction_synthetic": float(lesions.mean()),
+                                    "kept_voxels_synthetic": int(pp_mask_real.sum().item()),
+                                    "ms_model_label_map": pp_ms, "fg_fraction_model": float(lab_h.float().mean()),
+                                    "kept_voxels_model": int(pp_mask.sum().item())}}
         except Exception as e:
             aux = {"error": f"{type(e).__name__}: {e}"[:300]}
 
@@ -657,6 +671,7 @@ def main():
         "config": {"workload": f"{args.model} train step: fwd + {loss_over['loss']}"
                                f"{' + TV ' + str(args.tv) if args.tv > 0 else ''} + bwd + AdamW, 2ch {args.patch}^3 patches, "
                                f"batch {B}/GPU, dropout p=0.1 active", "global_batch": B * world,
+                   "optimizer": "torch.optim.AdamW(fused=True)" if args.torch_adamw else "fcd_b200.optim.FusedAdamW (1 launch)",
                    "parallelism": f"dp{world}", "cuda_graph": graph_ok, "l2": "inputs_exceed_l2",
                    **({"grad_allreduce": ar_desc} if world > 1 else {})},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 4,

@@ -258,4 +258,13 @@ FCD_API long long fcd_post_process_ws_bytes(int D, int H, int W);
 FCD_API int fcd_post_process(const float* pred_f, const void* pred_u8, float threshold, int l_min, float* out_mask,
                              float* out_lab, int D, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream);
 
+/* ---- optimizer step: torch.optim.AdamW as built by train_utils.py:63-71 and stepped at train.py:382, for ALL parameter
+ *      tensors in one launch.  jobs: device array of njobs records {float* p; const float* g; float* m; float* v;
+ *      long long n; long long blk0;} (48 bytes, blk0 = running sum of ceil(n / fcd_adamw_chunk()), ascending from 0);
+ *      nblocks = the total; step: device fp32 scalar with the 1-based count of this update.  Decoupled weight decay,
+ *      bias correction, eps after the square root -- the arithmetic of torch's implementation, fp32. ---- */
+FCD_API int fcd_adamw_chunk(void);
+FCD_API int fcd_adamw_multi(const void* jobs, int njobs, int nblocks, const float* step, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, cudaStream_t stream);
+
 #endif /* FCD_B200_H */
