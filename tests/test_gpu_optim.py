@@ -36,8 +36,8 @@ def test_fused_adamw_matches_torch(cfg):
         for p, q in zip(a, b):
             assert torch.allclose(p, q, rtol=2e-6, atol=1e-7), (step, p.shape, float((p - q).abs().max()))
     for p, q in zip(a, b):
-        assert torch.allclose(ours.state[p]["exp_avg"], ref.state[q]["exp_avg"], rtol=2e-6, atol=1e-8)
-        assert torch.allclose(ours.state[p]["exp_avg_sq"], ref.state[q]["exp_avg_sq"], rtol=2e-6, atol=1e-10)
+        assert torch.allclose(ours.state[p]["exp_avg"], ref.state[q]["exp_avg"], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(ours.state[p]["exp_avg_sq"], ref.state[q]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
         assert float(ours.state[p]["step"]) == float(ref.state[q]["step"]) == 6.0
 
 
