@@ -584,14 +584,15 @@ def main():
                 barrier()
                 gc.collect()
                 gc.disable()      # a generational collection inside the loop showed up as a 7-80 ms stall on one volume
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(n_vol):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_vol + 1)]
+                evs[0].record()
+                for k in range(n_vol):
                     lab = fn()
-                e1.record()
+                    evs[k + 1].record()
                 gc.enable()
                 barrier()
-                ms = e0.elapsed_time(e1)
+                ms = evs[0].elapsed_time(evs[-1])
+                per_vol.append([round(evs[k].elapsed_time(evs[k + 1]), 2) for k in range(n_vol)])
                 if world > 1:
                     t = torch.tensor([ms], device=dev)
                     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -599,6 +600,7 @@ def main():
                 return ms / n_vol, lab
 
             n_vol = 8
+            per_vol = []
             with torch.no_grad():
                 ms_vol, lab = timed_vols(infer_dev, n_vol)
                 ms_vol_e2e, lab = timed_vols(infer_e2e, n_vol)
@@ -627,7 +629,7 @@ def main():
                 raise RuntimeError(f"tcgen05 pipeline time-out during inference (this rank: {errs})")
             fwd_flops = sum(v["flops"] for k, v in agg.items() if k.endswith((":fwd", ":deconv_fwd"))) / B   # per window
             aux = {"metric": "sliding_window_vols_per_s", "value": 1e3 / ms_vol, "unit": "vols/s", "n_gpus": world,
-                   "ms_per_vol": ms_vol, "scaling": "strong", "dtype": "bf16",
+                   "ms_per_vol": ms_vol, "ms_each_vol_rank0": per_vol, "scaling": "strong", "dtype": "bf16",
                    "config": {"workload": f"{args.model} eval, 2ch 256x256x192 volume, roi {args.patch}^3, overlap 0.5, 18 windows"
                                           + (f" dealt over {world} ranks, reduce-scatter + slab finalize + label all-gather"
                                              if world > 1 else " in one forward") + ", argmax uint8 label map"},
