@@ -608,8 +608,9 @@ def main():
                 # the label map this (untrained) model predicts -- usually one huge component, the worst case for
                 # connected components -- and on a realistic one (three lesions, ~1 % foreground)
                 def time_pp(m):
-                    for _ in range(2):
+                    for _ in range(4):
                         post_process_segment(m, 50)
+                    torch.cuda.synchronize()
                     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     p0.record()
                     for _ in range(5):

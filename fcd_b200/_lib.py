@@ -19,6 +19,7 @@ LIBPATH = os.environ.get("FCD_B200_LIB") or os.path.join(_HERE, "libfcd_b200.so"
 _CT = {
     "int": ctypes.c_int,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "long long": ctypes.c_longlong,
     "cudaStream_t": ctypes.c_void_p,
 }

@@ -17,8 +17,8 @@ constexpr int ADAM_THREADS = 256;
 constexpr int ADAM_CHUNK = ADAM_THREADS * 16;      // elements per block
 
 __global__ void __launch_bounds__(ADAM_THREADS) adamw_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
-                                                                   const float* __restrict__ step, float lr, float beta1,
-                                                                   float beta2, float eps, float wd) {
+                                                                   const float* __restrict__ step, double lr, double beta1,
+                                                                   double beta2, float eps, double wd) {
     __shared__ AdamJob job;
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
@@ -29,18 +29,20 @@ __global__ void __launch_bounds__(ADAM_THREADS) adamw_multi_kernel(const AdamJob
         }
         job = jobs[lo];
         const double t = (double)step[0];
-        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
-        s_step_size = (float)((double)lr / bc1);
+        const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
+        s_step_size = (float)(lr / bc1);
         s_bc2_sqrt = (float)sqrt(bc2);
     }
     __syncthreads();
     const long long base = ((long long)blockIdx.x - job.blk0) * ADAM_CHUNK;
-    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, decay = 1.f - lr * wd;
+    // scalar factors formed in double and rounded once, as torch does with its Python-float hyper-parameters
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, decay = (float)(1.0 - lr * wd);
+    const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), b2 = (float)beta2;
     const bool vec = ((((uintptr_t)job.p | (uintptr_t)job.g | (uintptr_t)job.m | (uintptr_t)job.v) & 15) == 0);
     auto upd = [&](float& p, float g, float& m, float& v) {
         p *= decay;
-        m = m + (g - m) * (1.f - beta1);                      // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * beta2 + (1.f - beta2) * g * g;                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m = m + (g - m) * omb1;                               // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * b2 + omb2 * (g * g);                          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
         p -= step_size * (m / denom);
     };
@@ -69,10 +71,10 @@ FCD_API int fcd_adamw_chunk(void) { return ADAM_CHUNK; }
 
 // jobs: device array of njobs {p, g, m, v, n, blk0} records (48 bytes each, blk0 ascending from 0), nblocks = total
 // blocks; step: device fp32 scalar holding the 1-based step count of THIS update (the host increments it first).
-FCD_API int fcd_adamw_multi(const void* jobs, int njobs, int nblocks, const float* step, float lr, float beta1,
-                            float beta2, float eps, float weight_decay, cudaStream_t stream) {
+FCD_API int fcd_adamw_multi(const void* jobs, int njobs, int nblocks, const float* step, double lr, double beta1,
+                            double beta2, double eps, double weight_decay, cudaStream_t stream) {
     if (njobs < 1 || nblocks < 1 || jobs == nullptr || step == nullptr) return -1;
     adamw_multi_kernel<<<nblocks, ADAM_THREADS, 0, stream>>>(static_cast<const AdamJob*>(jobs), njobs, step, lr, beta1,
-                                                             beta2, eps, weight_decay);
+                                                             beta2, (float)eps, weight_decay);
     FCD_LAUNCH_CHECK();
 }

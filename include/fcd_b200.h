@@ -264,7 +264,7 @@ FCD_API int fcd_post_process(const float* pred_f, const void* pred_u8, float thr
  *      nblocks = the total; step: device fp32 scalar with the 1-based count of this update.  Decoupled weight decay,
  *      bias correction, eps after the square root -- the arithmetic of torch's implementation, fp32. ---- */
 FCD_API int fcd_adamw_chunk(void);
-FCD_API int fcd_adamw_multi(const void* jobs, int njobs, int nblocks, const float* step, float lr, float beta1,
-                            float beta2, float eps, float weight_decay, cudaStream_t stream);
+FCD_API int fcd_adamw_multi(const void* jobs, int njobs, int nblocks, const float* step, double lr, double beta1,
+                            double beta2, double eps, double weight_decay, cudaStream_t stream);
 
 #endif /* FCD_B200_H */
