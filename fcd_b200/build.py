@@ -28,14 +28,26 @@ def _digest():
     h = hashlib.sha256()
     for f in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
             sorted(glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h"))):
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # names, not absolute paths: the tree is copied to the GPU box
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(a for a in NVCC_FLAGS if not os.path.isabs(a)).encode())
     return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    # one builder at a time: the ranks of a multi-process job may all find a stale library at import
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
@@ -58,7 +70,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    tmp = LIB + ".tmp"
+    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    os.replace(tmp, LIB)        # atomic: a concurrent loader sees the old or the new file, never half of one
     with open(STAMP, "w") as f:
         f.write(dig)
     return LIB

@@ -171,13 +171,19 @@ class UnetrUpBlock(nn.Module):
 
 
 class DSA(nn.Module):
-    """conv_blocks.py:211-359, sa_type='parallel' (the reference default, config.py:7)."""
+    """conv_blocks.py:211-359: sa_type 'parallel' (the reference default, config.py:7), 'spatial' (236-258) and 'channel'
+    (260-279).  The two single-branch types have three projections (q, k, v); they run on the SAME fused kernels as
+    'parallel' by giving the missing value projection zero weights: x_CA = attn_CA @ 0 (spatial) or
+    x_SA = attn_SA @ (0 . EF)^T (channel) vanish exactly, forward and backward, and the parameters the reference branch
+    never touches (temperature / temperature2, EF) are passed detached so that their .grad stays None as there.
+    'serial' (281-314) feeds the spatial output through the channel attention -- a different data flow, not built."""
 
     def __init__(self, input_size, hidden_size, proj_size, num_heads=4, qkv_bias=False, channel_attn_drop=0.1,
                  spatial_attn_drop=0.1, sa_type="parallel"):
         super().__init__()
-        if sa_type != "parallel":
-            raise NotImplementedError("fcd_b200 DSA implements sa_type='parallel' (SURVEY 8f rank 4 lists the others)")
+        if sa_type not in ("parallel", "spatial", "channel"):
+            raise NotImplementedError("fcd_b200 DSA implements sa_type 'parallel', 'spatial' and 'channel'; 'serial' "
+                                      "(conv_blocks.py:281-314) is listed as next in SURVEY 8f rank 4")
         if qkv_bias:
             raise NotImplementedError("qkv_bias=True is never used by get_model")
         self.num_heads = num_heads
@@ -186,7 +192,7 @@ class DSA(nn.Module):
         self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
         self.temperature2 = nn.Parameter(torch.ones(num_heads, 1, 1))
         self.sa_type = sa_type
-        self.num = 4
+        self.num = 4 if sa_type == "parallel" else 3
         self.qkvv = nn.Linear(hidden_size, hidden_size * self.num, bias=qkv_bias)
         ef = torch.zeros(int(input_size), proj_size)
         std = 1.0 / (proj_size ** 0.5)
@@ -199,19 +205,29 @@ class DSA(nn.Module):
 
     def forward(self, ln, t, gamma):
         """ln = LayerNorm(t); returns t + gamma * DSA(ln) (the residual of TransformerBlock line 77 is fused)."""
-        qkvv = ops.linear(ln, self.qkvv.weight)
+        w = self.qkvv.weight
+        EF, temp, temp2 = self.EF, self.temperature, self.temperature2
+        if self.sa_type != "parallel":
+            C = self.hidden_size
+            zero = w.new_zeros((C, C))
+            if self.sa_type == "spatial":       # rows: q | k | v_CA = 0 | v_SA
+                w = torch.cat([w[:2 * C], zero, w[2 * C:]], 0)
+                temp = temp.detach()
+            else:                               # rows: q | k | v_CA | v_SA = 0
+                w = torch.cat([w, zero], 0)
+                EF, temp2 = EF.detach(), temp2.detach()
+        qkvv = ops.linear(ln, w)
         B = t.shape[0]
         c, H = self.head_dim, self.num_heads
         ca_scale, sa_p, seed = None, 0.0, 0
         if self.training:
-            if self.attn_drop.p > 0:
+            if self.attn_drop.p > 0 and self.sa_type != "spatial":
                 pk = self.attn_drop.p
                 ca_scale = ops.keep_scale((B, H, c, c), pk, t.device)
-            if self.attn_drop_2.p > 0:
+            if self.attn_drop_2.p > 0 and self.sa_type != "channel":
                 sa_p = float(self.attn_drop_2.p)
                 seed = _host_rng.getrandbits(62)     # host-side counter RNG: no device sync
-        return ops.dsa_attention(qkvv, t, self.EF, self.temperature, self.temperature2, gamma, self.hidden_size, H,
-                                 self.proj_size, ca_scale, sa_p, seed)
+        return ops.dsa_attention(qkvv, t, EF, temp, temp2, gamma, self.hidden_size, H, self.proj_size, ca_scale, sa_p, seed)
 
 
 class TransformerBlock(nn.Module):
@@ -268,22 +284,45 @@ class SubpixelUpsample(nn.Module):
 
 
 class UpSample(nn.Sequential):
-    """MONAI UpSample(mode='pixelshuffle') container: single child `pixelshuffle` (conv_blocks.py:727-735)."""
+    """MONAI UpSample container (conv_blocks.py:727-735; segresnet_dsa.py:133-141) with MONAI's child names:
+    'pixelshuffle' -> `pixelshuffle` (SubpixelUpsample); 'deconv' -> `deconv` (ConvTranspose3d k2 s2, bias);
+    'nontrainable' -> `preconv` (1x1 conv with bias, only when the channel count changes) + `upsample_non_trainable`
+    (nn.Upsample trilinear, no parameters)."""
 
     def __init__(self, spatial_dims, in_channels, out_channels, scale_factor=2, mode="pixelshuffle",
                  interp_mode="linear", align_corners=False, bias=True):
         super().__init__()
-        if str(mode).lower().split(".")[-1] != "pixelshuffle" or int(scale_factor) != 2 or spatial_dims != 3:
-            raise NotImplementedError("fcd_b200 UpSample implements mode='pixelshuffle', scale 2 (config.py:57); "
-                                      "'deconv' / 'nontrainable' are listed as next in SURVEY 8f rank 4")
-        self.add_module("pixelshuffle", SubpixelUpsample(in_channels, out_channels or in_channels, bias))
+        self.mode = str(mode).lower().split(".")[-1]
+        out_channels = out_channels or in_channels
+        self.out_channels = out_channels
+        if int(scale_factor) != 2 or spatial_dims != 3:
+            raise NotImplementedError("fcd_b200 UpSample: spatial_dims=3, scale_factor=2 (as get_model)")
+        if self.mode == "pixelshuffle":
+            self.add_module("pixelshuffle", SubpixelUpsample(in_channels, out_channels, bias))
+        elif self.mode == "deconv":
+            self.add_module("deconv", nn.ConvTranspose3d(in_channels, out_channels, 2, 2, bias=bias))
+        elif self.mode == "nontrainable":
+            if str(interp_mode).lower().split(".")[-1] not in ("linear", "trilinear") or align_corners:
+                raise NotImplementedError("fcd_b200 UpSample(nontrainable): trilinear, align_corners=False (as get_model)")
+            if out_channels != in_channels:
+                self.add_module("preconv", nn.Conv3d(in_channels, out_channels, kernel_size=1, bias=bias))
+            self.add_module("upsample_non_trainable", nn.Upsample(scale_factor=2, mode="trilinear", align_corners=False))
+        else:
+            raise NotImplementedError(f"Unsupported upsampling mode {mode!r}")
 
     def forward(self, x, skip=None, mode="plain"):
-        return self.pixelshuffle(x, skip, mode)
+        if self.mode == "pixelshuffle":
+            return self.pixelshuffle(x, skip, mode)
+        if self.mode == "deconv":
+            return ops.deconv_upsample(x, self.deconv.weight, self.deconv.bias, skip, mode)
+        if hasattr(self, "preconv"):
+            x = ops.conv3d(x, self.preconv.weight, self.preconv.bias, k=1)
+        return ops.trilinear_upsample(x, skip, mode)
 
 
 class GeneralUnetrUpBlock(nn.Module):
-    """conv_blocks.py:692-775 with upsample_mode='pixelshuffle' (MS_DSA_NET_PS, get_model.py:32-49)."""
+    """conv_blocks.py:692-775 (MS_DSA_NET_PS, get_model.py:32-49): upsample_mode 'pixelshuffle' (the configured one),
+    'deconv' or 'nontrainable'."""
 
     def __init__(self, spatial_dims, in_channels, out_channels, kernel_size, norm_name,
                  act_name=("leakyrelu", {"inplace": True, "negative_slope": 0.01}), res_block=False, bias=False,

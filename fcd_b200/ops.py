@@ -671,37 +671,45 @@ def linear(x, weight):
     return ConvFn.apply(x, weight.view(weight.shape[0], weight.shape[1], 1, 1, 1), None, 1, 1, 0, None)
 
 
-class UpConcatFn(Function):
-    """ConvTranspose3d(k2, s2, no bias) scattered straight into the left half of the concat buffer, skip copied
-    into the right half: replaces transp_conv + torch.cat (conv_blocks.py:683-685)."""
+class DeconvFn(Function):
+    """ConvTranspose3d(k2, s2) with the pixel scatter fused into the GEMM epilogue.  mode 'concat': the result goes
+    straight into the left half of the concat buffer and `skip` is copied into the right half -- replaces transp_conv +
+    torch.cat (conv_blocks.py:683-685); 'plain' / 'add': a buffer of its own (+ skip), MONAI UpSample(mode="deconv")
+    in SegResNet.decode (segresnet_dsa.py:217).  bias: UnetrUpBlock has none, UpSample's deconv has one."""
 
     @staticmethod
-    def forward(ctx, x, skip, weight):
-        x, skip = rows(x), rows(skip)
+    def forward(ctx, x, skip, weight, bias, mode):
+        x = rows(x)
+        skip = rows(skip) if skip is not None else None
         B, D, H, W, Kp = x.shape
         Ci, Co = weight.shape[0], weight.shape[1]
         Cq = pad16(Co)
-        Cs = skip.shape[4]
+        Cs = skip.shape[4] if mode == "concat" else 0
         wp = pack_weight(weight, 8, Co, Ci, Cq, Kp, sn=8, sk=Co * 8, st=1)
         buf = _empty((B, 2 * D, 2 * H, 2 * W, Cq + Cs), x)
         _lib.note_work("deconv_fwd", 2.0 * B * D * H * W * 8 * Co * Ci, 2.0 * B * D * H * W * (Ci + 8 * Co))
-        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=None, Bn=B, Ds=D, Hs=H, Ws=W, Dm=D, Hm=H,
-             Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0, Cq=Cq)
-        right = buf[..., Cq:]
-        call("fcd_copy_rows", a=skip, lda=ld(skip), o=right, ldo=Cq + Cs, rows=B * 8 * D * H * W, C=Cs)
+        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=_vpad(bias, Cq), Bn=B, Ds=D, Hs=H, Ws=W, Dm=D,
+             Hm=H, Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0, Cq=Cq)
+        if mode == "concat":
+            right = buf[..., Cq:]
+            call("fcd_copy_rows", a=skip, lda=ld(skip), o=right, ldo=Cq + Cs, rows=B * 8 * D * H * W, C=Cs)
+        elif mode == "add":
+            out = _empty((B, 2 * D, 2 * H, 2 * W, Cq), x)
+            call("fcd_add", a=buf, lda=Cq, b=skip, ldb=ld(skip), o=out, ldo=Cq, rows=B * 8 * D * H * W, C=Cq)
+            buf = out
         ctx.save_for_backward(x, weight)
-        ctx.cq = Cq
+        ctx.cfg = (Cq, mode, bias is not None)
         return buf
 
     @staticmethod
     def backward(ctx, dbuf):
         x, weight = ctx.saved_tensors
-        Cq = ctx.cq
+        Cq, mode, has_bias = ctx.cfg
         dbuf = rows(dbuf)
         B, D, H, W, Kp = x.shape
         Ci, Co = weight.shape[0], weight.shape[1]
         dleft = dbuf[..., :Cq]
-        dx = dw = dskip = None
+        dx = dw = db = dskip = None
         if ctx.needs_input_grad[0]:
             wt = pack_weight(weight, 8, Ci, Co, Kp, Cq, sn=Co * 8, sk=8, st=1)
             dx = _empty((B, D, H, W, Kp), x)
@@ -721,13 +729,61 @@ class UpConcatFn(Function):
             call("fcd_wgrad_reduce", part=part, out=dw, nsplit=ns, T=8, N=Ci, K=Co, Np=Kp, Kp=Cq, sn=Co * 8, sk=8,
                  st=1, kseg=Co, ksegpad=Cq, accumulate=0)
             dw = dw.to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[3]:
+            db = _colsum(dleft, Co)
         if ctx.needs_input_grad[1]:
-            dskip = dbuf[..., Cq:]
-        return dx, dskip, dw
+            dskip = dbuf[..., Cq:] if mode == "concat" else dbuf
+        return dx, dskip, dw, db, None
 
 
 def up_concat(x, skip, weight):
-    return UpConcatFn.apply(x, skip, weight)
+    return DeconvFn.apply(x, skip, weight, None, "concat")
+
+
+def deconv_upsample(x, weight, bias, skip=None, mode="plain"):
+    """MONAI UpSample(mode="deconv"): ConvTranspose3d(cin, cout, k=2, s=2, bias) (+ skip / into a concat buffer)."""
+    return DeconvFn.apply(x, skip, weight, bias, mode)
+
+
+class TrilinearUpFn(Function):
+    """nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False) (MONAI UpSample(mode="nontrainable")); modes as
+    PSBlurFn: 'plain' | 'add' (+ skip) | 'concat' (left half of a [.., C + Cs] buffer, skip copied into the right half)."""
+
+    @staticmethod
+    def forward(ctx, src, skip, mode):
+        src = rows(src)
+        B, D, H, W, C = src.shape
+        skip = rows(skip) if skip is not None else None
+        if mode == "concat":
+            cs = skip.shape[4]
+            out = _empty((B, 2 * D, 2 * H, 2 * W, C + cs), src)
+            call("fcd_trilinear_up_fwd", src=src, lds=ld(src), skip=None, ldk=0, out=out, ldo=C + cs, B=B, D=D, H=H, W=W,
+                 C=C)
+            call("fcd_copy_rows", a=skip, lda=ld(skip), o=out[..., C:], ldo=C + cs, rows=B * 8 * D * H * W, C=cs)
+        else:
+            out = _empty((B, 2 * D, 2 * H, 2 * W, C), src)
+            sk = skip if mode == "add" else None
+            call("fcd_trilinear_up_fwd", src=src, lds=ld(src), skip=sk, ldk=ld(sk) if sk is not None else 0, out=out,
+                 ldo=C, B=B, D=D, H=H, W=W, C=C)
+        ctx.cfg = (mode, (B, D, H, W, C))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mode, (B, D, H, W, C) = ctx.cfg
+        dout = rows(dout)
+        dsrc = torch.empty((B, D, H, W, C), dtype=BF16, device=dout.device)
+        call("fcd_trilinear_up_bwd", dout=dout, lddo=ld(dout), dsrc=dsrc, ldds=C, B=B, D=D, H=H, W=W, C=C)
+        dskip = None
+        if mode == "add":
+            dskip = dout
+        elif mode == "concat":
+            dskip = dout[..., C:]
+        return dsrc, dskip, None
+
+
+def trilinear_upsample(x, skip=None, mode="plain"):
+    return TrilinearUpFn.apply(x, skip, mode)
 
 
 # ------------------------------------------------------------------------------------------------ pooling

@@ -223,6 +223,12 @@ FCD_API int fcd_ps_blur_fwd(const void* src, long long lds, const void* skip, lo
                             int B, int D, int H, int W, int Cq, cudaStream_t stream);
 FCD_API int fcd_ps_blur_bwd(const void* dout, long long lddo, void* dsrc, long long ldds, int B, int D, int H, int W,
                             int Cq, cudaStream_t stream);
+/* UpSample(mode="nontrainable") = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=False) (same call sites
+ * with upsample_mode="nontrainable"); optional skip add / concat-buffer output as above. */
+FCD_API int fcd_trilinear_up_fwd(const void* src, long long lds, const void* skip, long long ldk, void* out,
+                                 long long ldo, int B, int D, int H, int W, int C, cudaStream_t stream);
+FCD_API int fcd_trilinear_up_bwd(const void* dout, long long lddo, void* dsrc, long long ldds, int B, int D, int H,
+                                 int W, int C, cudaStream_t stream);
 
 /* ---- F.mse_loss of the VAE reconstruction (segresnet_dsa.py:357); part: fcd_loss_blocks() floats ---- */
 FCD_API int fcd_mse_fwd(const float* a, const float* b, long long n, float* part, float* out, cudaStream_t stream);

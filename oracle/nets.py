@@ -65,17 +65,46 @@ def subpixel_upsample(sd, pre, x):
     return F.avg_pool3d(x, 2, 1)
 
 
+def upsample(sd, pre, x):
+    """MONAI UpSample, mode read off the children present in the state dict: pixelshuffle | deconv
+    (ConvTranspose3d k2 s2, bias) | nontrainable (optional 1x1 preconv + trilinear x2, align_corners=False)."""
+    if (pre + ".pixelshuffle.conv_block.weight") in sd:
+        return subpixel_upsample(sd, pre + ".pixelshuffle", x)
+    if (pre + ".deconv.weight") in sd:
+        return F.conv_transpose3d(x, sd[pre + ".deconv.weight"], sd.get(pre + ".deconv.bias"), stride=2)
+    if (pre + ".preconv.weight") in sd:
+        x = F.conv3d(x, sd[pre + ".preconv.weight"], sd.get(pre + ".preconv.bias"))
+    return F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+
+
 def general_up_block(sd, pre, inp, skip):
-    """GeneralUnetrUpBlock.forward, pixelshuffle mode (conv_blocks.py:766-775)."""
-    out = subpixel_upsample(sd, pre + ".upsample.pixelshuffle", inp)
+    """GeneralUnetrUpBlock.forward (conv_blocks.py:766-775)."""
+    out = upsample(sd, pre + ".upsample", inp)
     return unet_res_block(sd, pre + ".conv_block", torch.cat((out, skip), 1))
 
 
 def dsa(sd, pre, x, heads=4):
-    """DSA.forward, sa_type='parallel' (conv_blocks.py:328-355), dropout p=0.  x: [B,N,C]."""
+    """DSA.forward (conv_blocks.py:316-355), dropout p=0.  x: [B,N,C].  The sa_type is read off the projection count of
+    qkvv.weight: 4C rows = 'parallel' (328-355); 3C rows = 'spatial' (forward_spatial, 236-258) or 'channel'
+    (forward_channel, 260-279), told apart by the key `<pre>.__sa_type__` the tests put into the state dict ('spatial'
+    if absent)."""
     B, N, C = x.shape
     c = C // heads
-    qkvv = F.linear(x, sd[pre + ".qkvv.weight"]).reshape(B, N, 4, heads, c).permute(2, 0, 3, 1, 4)
+    W = sd[pre + ".qkvv.weight"]
+    if W.shape[0] == 3 * C:
+        qkv = F.linear(x, W).reshape(B, N, 3, heads, c).permute(2, 0, 3, 1, 4)
+        q, k, v = (t.transpose(-2, -1) for t in (qkv[0], qkv[1], qkv[2]))                  # [B,h,c,N]
+        if sd.get(pre + ".__sa_type__", "spatial") == "channel":
+            q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+            attn = ((q @ k.transpose(-2, -1)) * sd[pre + ".temperature"]).softmax(dim=-1)
+            return (attn @ v).permute(0, 3, 1, 2).reshape(B, N, C)
+        EF = sd[pre + ".EF"]
+        k_proj = torch.einsum("bhdn,nk->bhdk", k, EF)
+        v_proj = torch.einsum("bhdn,nk->bhdk", v, EF)
+        q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+        attn = ((q.permute(0, 1, 3, 2) @ k_proj) * sd[pre + ".temperature2"]).softmax(dim=-1)
+        return (attn @ v_proj.transpose(-2, -1)).permute(0, 3, 1, 2).reshape(B, N, C)
+    qkvv = F.linear(x, W).reshape(B, N, 4, heads, c).permute(2, 0, 3, 1, 4)
     q, k, v_ca, v_sa = (t.transpose(-2, -1) for t in (qkvv[0], qkvv[1], qkvv[2], qkvv[3]))  # [B,h,c,N]
     EF = sd[pre + ".EF"]
     k_proj = torch.einsum("bhdn,nk->bhdk", k, EF)
@@ -88,6 +117,15 @@ def dsa(sd, pre, x, heads=4):
     # line 353: [B,h,N,c] -> permute(0,3,1,2) = [B,c,h,N] -> reshape(B,N,C): a memory scramble, kept as is
     x_sa = (attn_sa @ v_proj.transpose(-2, -1)).permute(0, 3, 1, 2).reshape(B, N, C)
     return x_ca + x_sa
+
+
+def with_sa_type(sd, sa_type):
+    """Copy of the state dict carrying the `<prefix>.dsa.__sa_type__` markers `dsa` reads (3-projection types only)."""
+    out = dict(sd)
+    for k in sd:
+        if k.endswith(".dsa.qkvv.weight"):
+            out[k[:-len("qkvv.weight")] + "__sa_type__"] = sa_type
+    return out
 
 
 def transformer_block(sd, pre, x, training=True, bn_out=None):
@@ -157,7 +195,7 @@ def _seg_resblock(sd, pre, x):
 def _seg_up(sd, pre, x):
     """up_samples[i] = 1x1 conv C->C/2 + UpSample(pixelshuffle) (segresnet_dsa.py:130-141)."""
     x = F.conv3d(x, sd[pre + ".0.conv.weight"])
-    return subpixel_upsample(sd, pre + ".1.pixelshuffle", x)
+    return upsample(sd, pre + ".1", x)
 
 
 def _seg_final(sd, pre, x):
@@ -231,7 +269,7 @@ def segresnet(sd, x, training=True, bn_out=None, vae_noise=None, vae=False):
     v = F.relu(F.linear(v, sd["vae_fc3.weight"], sd["vae_fc3.bias"]))
     v = v.reshape(-1, *fc_shape)
     v = F.conv3d(v, sd["vae_fc_up_sample.0.conv.weight"])
-    v = subpixel_upsample(sd, "vae_fc_up_sample.1.pixelshuffle", v)
+    v = upsample(sd, "vae_fc_up_sample.1", v)
     v = F.relu(F.instance_norm(v, eps=EPS))
     v = _seg_final(sd, "vae_conv_final", run_up(v, None))
     return logits, reg + F.mse_loss(net_input, v)

@@ -296,3 +296,99 @@ def test_training_steps_eager_equal_cuda_graph(fused):
     assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
     err = float((pe - pg).norm() / pe.norm())
     assert err <= 1e-6, f"parameters after 4 steps differ between eager and graph execution: rel {err:.3e}"
+
+
+@pytest.mark.parametrize("sa_type", ["spatial", "channel"])
+def test_single_branch_attention_types(sa_type):
+    """MS_DSA_NET with sa_type 'spatial' / 'channel' (conv_blocks.py:236-279; three projections, one attention branch)
+    against the CPU oracle (itself bit-exact against the reference's classes, tests/test_oracle_vs_reference.py): logits
+    and loss within the bf16 bounds of the other model tests; the parameters the reference branch never touches keep
+    .grad None (AdamW must not decay them), the three-projection weight gets a full gradient."""
+    import fcd_b200
+    from oracle import losses as olosses
+    from oracle import nets as onets
+    from oracle import synth
+    params = fcd_b200.get_default_params()
+    params.update(model_type="ms_dsa_net", patch_size=(64,) * 3, feature_size=4, sa_type=sa_type, loss="DiceCELoss")
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=1)
+    assert sd["trans3.0.dsa.qkvv.weight"].shape[0] == 3 * sd["trans3.0.dsa.qkvv.weight"].shape[1]
+    model.load_state_dict(sd)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+            m.p = 0.0
+    model = model.to(DEV).train()
+    x, y = synth.image(1, 2, 64, seed=3), synth.label(1, 64, seed=5)
+    leaves = {k: (v.clone().requires_grad_(True)
+                  if not isinstance(v, str) and v.is_floating_point() and "running" not in k else v)
+              for k, v in onets.with_sa_type(sd, sa_type).items()}
+    ref = onets.forward("ms_dsa_net", leaves, x, True, {})
+    ref_loss = olosses.combined_loss(H.loss_params(dict(loss_params=dict(loss="DiceCELoss"))), ref, y)
+    ref_loss.backward()
+    out = model(x.to(DEV))
+    loss = fcd_b200.CombinedLoss(params, DEV)(out, y.to(DEV))
+    loss.backward()
+    r = rel(out.detach().cpu(), ref.detach())
+    print(f"[ms_dsa_net sa_type={sa_type}] logits rel L2 {r:.3e}, loss {float(loss):.5f} (oracle {float(ref_loss):.5f})")
+    assert r <= 6e-2
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * max(1.0, abs(float(ref_loss)))
+    dsa = model.trans3[0].dsa
+    g = dsa.qkvv.weight.grad
+    assert g is not None and g.shape == dsa.qkvv.weight.shape and bool(torch.isfinite(g).all()) and float(g.norm()) > 0
+    og = leaves["trans3.0.dsa.qkvv.weight"].grad
+    cos = float((g.cpu().double() * og.double()).sum() / (g.cpu().double().norm() * og.double().norm()))
+    assert cos > 0.7, f"qkv weight gradient points elsewhere than the oracle's (cosine {cos:.3f})"
+    if sa_type == "spatial":
+        assert dsa.temperature.grad is None and dsa.temperature2.grad is not None and dsa.EF.grad is not None
+        assert leaves["trans3.0.dsa.temperature"].grad is None
+    else:
+        assert dsa.temperature2.grad is None and dsa.EF.grad is None and dsa.temperature.grad is not None
+        assert leaves["trans3.0.dsa.EF"].grad is None
+
+
+@pytest.mark.parametrize("mode", ["deconv", "nontrainable"])
+def test_segresnet_other_upsample_modes(mode):
+    """segresnet_upsample_mode 'deconv' (ConvTranspose3d k2 s2 + bias) and 'nontrainable' (trilinear x2,
+    align_corners=False) -- config.py:57, MONAI UpSample -- against the CPU oracle (bit-exact against the
+    reference's classes, tests/test_oracle_vs_reference.py): logits, loss, and the gradients of the upsampling
+    parameters / of the layers below it (which flow through the upsampling backward)."""
+    import fcd_b200
+    from oracle import losses as olosses
+    from oracle import nets as onets
+    from oracle import synth
+    params = fcd_b200.get_default_params()
+    params.update(model_type="segresnet", patch_size=(32,) * 3, feature_size=8, segresnet_upsample_mode=mode,
+                  loss="DiceFocalLoss")
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, params = fcd_b200.get_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=1)
+    model.load_state_dict(sd)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+            m.p = 0.0
+    model = model.to(DEV).train()
+    x, y = synth.image(2, 2, 32, seed=3), synth.label(2, 32, seed=5)
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    ref = onets.forward("segresnet", leaves, x, True, {})
+    ref_loss = olosses.combined_loss(H.loss_params(dict(loss_params=dict(loss="DiceFocalLoss"))), ref, y)
+    ref_loss.backward()
+    out = model(x.to(DEV))
+    loss = fcd_b200.CombinedLoss(params, DEV)(out, y.to(DEV))
+    loss.backward()
+    r = rel(out.detach().cpu(), ref.detach())
+    print(f"[segresnet upsample {mode}] logits rel L2 {r:.3e}, loss {float(loss):.5f} (oracle {float(ref_loss):.5f})")
+    assert r <= 6e-2
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * max(1.0, abs(float(ref_loss)))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        og = leaves[k].grad
+        if og is None or float(og.norm()) < 1e-6:
+            continue
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+        e = rel(p.grad.cpu(), og)
+        worst = max(worst, e)
+        if "deconv" in k or k.startswith(("up_samples.0.0", "down_layers.3")):
+            print(f"   {k:45s} grad rel err {e:.3e}")
+            assert e <= 0.25, (k, e)          # (SegResNet golden cases: stock bf16 autocast 0.07 parameter-weighted)
+    print(f"   worst parameter gradient error {worst:.3e}")

@@ -44,6 +44,72 @@ def test_forward_bit_exact(mt, patch, fs, batch):
         assert torch.allclose(msd[k].float(), v.float(), rtol=0, atol=0), k
 
 
+@pytest.mark.parametrize("sa_type", ["spatial", "channel"])
+def test_forward_bit_exact_single_branch_attention(sa_type):
+    """sa_type 'spatial' / 'channel' (conv_blocks.py:236-279): three projections, one attention branch."""
+    params = ref_loader.default_params()
+    params.update(model_type="ms_dsa_net", patch_size=(64,) * 3, feature_size=4, sa_type=sa_type)
+    model, params = ref_loader.build_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=2)
+    model.load_state_dict(sd)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+            m.p = 0.0
+    model.train()
+    x = synth.image(1, 2, 64, seed=4)
+    with torch.no_grad():
+        ref = model(x)
+        ora = onets.forward("ms_dsa_net", onets.with_sa_type(sd, sa_type), x, True, {})
+    assert torch.equal(ref, ora)
+
+
+@pytest.mark.parametrize("mt,mode", [("segresnet", "deconv"), ("segresnet", "nontrainable"), ("segresnetvae", "deconv")])
+def test_forward_bit_exact_other_upsample_modes(mt, mode):
+    """segresnet_upsample_mode 'deconv' / 'nontrainable' (config.py:57; MONAI UpSample)."""
+    params = ref_loader.default_params()
+    params.update(model_type=mt, patch_size=(32,) * 3, feature_size=8, segresnet_upsample_mode=mode)
+    model, params = ref_loader.build_model(params)
+    sd = synth.synthetic_state_dict(synth.spec_of(model.state_dict()), seed=2)
+    model.load_state_dict(sd)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout3d)):
+            m.p = 0.0
+    model.train()
+    x = synth.image(1, 2, 32, seed=4)
+    noise = synth.tensor((1, 256), "vae_noise", 9, 1.0, dist="normal")
+    with mock.patch.object(torch, "randn_like", lambda t, **k: noise.to(t)), torch.no_grad():
+        ref = model(x)
+        ora = onets.forward(mt, sd, x, True, {}, noise)
+    if isinstance(ref, tuple):
+        assert torch.equal(ref[0], ora[0])
+        assert abs(float(ref[1]) - float(ora[1])) <= 1e-6 * abs(float(ref[1]))
+    else:
+        assert torch.equal(ref, ora)
+
+
+@pytest.mark.parametrize("over", [dict(model_type="segresnet", segresnet_upsample_mode="deconv"),
+                                  dict(model_type="segresnet", segresnet_upsample_mode="nontrainable"),
+                                  dict(model_type="segresnetvae", segresnet_upsample_mode="nontrainable"),
+                                  dict(model_type="ms_dsa_net", sa_type="spatial"),
+                                  dict(model_type="ms_dsa_net", sa_type="channel"),
+                                  dict(model_type="segresnet", segresnet_deeper=True)])
+def test_product_state_dict_equals_reference_for_the_other_branches(over):
+    """The non-default get_model branches fcd_b200 builds have the reference's state-dict keys, order and shapes."""
+    import contextlib
+    import io
+    import fcd_b200
+    params = ref_loader.default_params()
+    params.update(patch_size=(64,) * 3, feature_size=8, **over)
+    ref, _ = ref_loader.build_model(dict(params), init_weights=False)
+    mine_params = fcd_b200.get_default_params()
+    mine_params.update(patch_size=(64,) * 3, feature_size=8, **over)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mine, _ = fcd_b200.get_model(mine_params)
+    a = [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    b = [(k, tuple(v.shape)) for k, v in mine.state_dict().items()]
+    assert a == b
+
+
 def test_default_init_param_counts():
     """MS_DSA_NET 43,524,802 and BaseUNet 22,966,690 trainable parameters at the default config."""
     params = ref_loader.default_params()
