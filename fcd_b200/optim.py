@@ -17,7 +17,11 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameters")
-        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        # the remaining keys of torch.optim.AdamW's param groups, so that a state dict saved here loads into torch's
+        # class with the same meaning (without `decoupled_weight_decay` torch falls back to coupled L2 decay)
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False,
+                                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                                      decoupled_weight_decay=True))
         self._tables = {}          # group index -> dict(ptrs, dev, host, nblocks, step)
 
     def _table(self, gi, group, plist):
@@ -49,6 +53,8 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
+            if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay") is False:
+                raise NotImplementedError("FusedAdamW: amsgrad / maximize / coupled weight decay are not implemented")
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
                 continue
