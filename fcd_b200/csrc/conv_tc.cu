@@ -52,6 +52,7 @@ struct ConvTcParams {
     bf16* C;
     long long ldc;
     float* part;        // nullptr or [B][nchunk][2][COUT] fp32, nchunk = nht*nwt*nseg
+    const float* bias;  // nullptr or [COUT] fp32, added before the bf16 rounding
     int Bn, D, H, W;
     int nht, nwt, nseg, DL, nitems;
     int flip;           // 1: use tap 26-t (data gradient of a stride-1 conv = correlation with the mirrored kernel)
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
     WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
     float* red = reinterpret_cast<float*>(ctx + 1);              // [4 warps][2][COUT] (STATS)  <= 2 KB for COUT 64
+    float* sbias = red + 8 * (COUT <= 32 ? COUT : 0);            // (no statistics for COUT 64: red is unused there)
 
     const int tid = threadIdx.x, lane = tid & 31;
     // shfl from a fixed lane: provably warp-uniform, so the role branches and everything inside the MMA role stay on
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             *reinterpret_cast<bf16x8*>(wsm + t * K::TAP_BYTES + c8 * K::LBO_B + np_ * 16) = pack8(f);
         }
     }
+    if (tid < COUT) sbias[tid] = p.bias != nullptr ? p.bias[tid] : 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 for (int c0 = 0; c0 < COUT; c0 += 8) {
                     float f[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = v[c0 + k];
+                    for (int k = 0; k < 8; ++k) f[k] = v[c0 + k] + sbias[c0 + k];
                     const bf16x8 pk = pack8(f);
                     st8(dst + c0, pk);
                     if (STATS) {
@@ -442,7 +445,8 @@ FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
 // part: optional [Bn][nchunk][2][N] fp32 partial (sum, sum of squares) of the rounded outputs.
 FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                         int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                         const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
+                         float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream) {
     if (!shape_ok(D, H, W, K, N) || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
@@ -451,7 +455,7 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
     p.A = (const bf16*)A; p.lda = lda;
     p.Wf = Wf; p.sn = sn; p.sk = sk; p.st = st; p.Nr = Nr; p.Kr = Kr;
     p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
-    p.C = (bf16*)C; p.ldc = ldc; p.part = part;
+    p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W;
     p.nht = H / TH; p.nwt = W / TW; p.nseg = nseg; p.DL = (D + nseg - 1) / nseg;
     p.nseg = (D + p.DL - 1) / p.DL;

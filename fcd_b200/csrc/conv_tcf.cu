@@ -41,6 +41,7 @@ struct ConvTcfParams {
     int Nr, Kr, kseg, ksegpad, nsg, nsgpad;
     bf16* C; long long ldc;
     float* part;
+    const float* bias;   // nullptr or [COUT] fp32, added before the bf16 rounding (sub-pixel convs, conv_blocks.py:727-735)
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
     int* status;
     NormFin fin;        // fin.mean != nullptr: the last CTA turns the fused partials into mean / rstd
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + NPB + R);
     WaitCtx* ctx = reinterpret_cast<WaitCtx*>(tmem_slot + 4);
     float* red = reinterpret_cast<float*>(ctx + 1);
+    float* sbias = red + 8 * COUT;
     // ctx->prog (debug record of a timed-out wait): [0] / [26] producer warp 0 / 1 plane seq, [1] / [27] its item;
     // [2+me] MMA warp's plane counter g, [5+me] its item, [8+me] (wait site << 24 | sq or zc; site 7 = issued g);
     // [11+q] epilogue outputs done, [15+q] plane it waits for (| 0x40000000: past the waits), [19+q] its item;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
             *reinterpret_cast<bf16x8*>(wsm + khw * K::KHW_BYTES + c8 * K::LBO_B + ((2 - kd) * COUT + np_) * 16) = pack8(f);
         }
     }
+    if (tid < COUT) sbias[tid] = p.bias != nullptr ? p.bias[tid] : 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -326,7 +329,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                     float f[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        f[k] = (__uint_as_float(t[0][c0 + k]) + __uint_as_float(t[1][c0 + k])) + __uint_as_float(t[2][c0 + k]);
+                        f[k] = ((__uint_as_float(t[0][c0 + k]) + __uint_as_float(t[1][c0 + k])) + __uint_as_float(t[2][c0 + k])) +
+                               sbias[c0 + k];
                     const bf16x8 pk = pack8(f);
                     st8(dst + c0, pk);
                     if (STATS) {
@@ -388,7 +392,8 @@ int launch(const ConvTcfParams& p, int flip, cudaStream_t stream) {
 // anything else so the caller can fall back to fcd_conv3_tc.
 FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                           long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                          const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
+                          float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream) {
     if (H % TH || W % TW || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
@@ -397,7 +402,7 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     ConvTcfParams p;
     p.A = (const bf16*)A; p.lda = lda; p.Wf = Wf; p.sn = sn; p.sk = sk; p.st = st; p.Nr = Nr; p.Kr = Kr;
     p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
-    p.C = (bf16*)C; p.ldc = ldc; p.part = part;
+    p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W;
     p.nht = H / TH; p.nwt = W / TW; p.DL = (D + nseg - 1) / nseg;
     p.nseg = (D + p.DL - 1) / p.DL;

@@ -462,14 +462,27 @@ def _off_critical_path(fn, *keep):
     return fn()
 _LAST_PART = [None]                               # fused InstanceNorm partials of the most recent ConvFn.forward
 _LAST_MEANRSTD = [None]                           # ... or the finished (mean, rstd) when the conv's last CTA made them
-_NOFIN = dict(mean=None, rstd=None, norm_mode=0, eps=0.0, running_mean=None, running_var=None, crun=0, momentum=0.0)
+_NOFIN = dict(bias=None, mean=None, rstd=None, norm_mode=0, eps=0.0, running_mean=None, running_var=None, crun=0,
+              momentum=0.0)
 
 
 def _tc_nseg(B, D, H, W, K, N, k, stride, pad, bias):
     """d-segment count if the tcgen05 kernel takes this conv, else 0."""
-    if not USE_TC or k != 3 or stride != 1 or pad != 1 or bias is not None:
+    if not USE_TC or k != 3 or stride != 1 or pad != 1:
         return 0
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, N)
+
+
+def _tc_wide_nseg(B, D, H, W, K, N, k, stride, pad, cin_seg):
+    """3x3x3 conv with MORE than 64 output channels from <= 64 input channels on a volume the tcgen05 kernels tile --
+    MONAI SubpixelUpsample's conv Cin -> 8*Cout (conv_blocks.py:727-735; segresnet_dsa.py:133-141): it runs as N / 32
+    kd-folded launches, each writing a 32-channel slice of the output rows.  Returns the d-segment count of one slice,
+    0 if not applicable."""
+    if not (USE_TC and USE_TCF and k == 3 and stride == 1 and pad == 1 and cin_seg is None):
+        return 0
+    if not (K in (16, 32, 64) and N > 64 and N % 32 == 0):
+        return 0
+    return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, 32)
 
 
 def _tc_nslice_nseg(B, D, H, W, K, N, k, stride, pad, bias, cin_seg, Co, Ci):
@@ -543,7 +556,7 @@ class ConvFn(Function):
         _LAST_MEANRSTD[0] = None
         if nseg > 0:
             part = None
-            fin = _NOFIN
+            fin = dict(_NOFIN, bias=_vpad(bias, Np))
             if Np <= 32:
                 nchunk = (H // 16) * (W // 8) * nseg
                 part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
@@ -554,12 +567,23 @@ class ConvFn(Function):
                     mean = torch.empty((B, Np), dtype=torch.float32, device=x.device)
                     rstd = torch.empty((B, Np), dtype=torch.float32, device=x.device)
                     rm, rv = bufs if bufs is not None else (None, None)
-                    fin = dict(mean=mean, rstd=rstd, norm_mode=MODE[mode], eps=float(eps), running_mean=rm,
-                               running_var=rv, crun=0 if rm is None else rm.numel(), momentum=float(momentum or 0.0))
+                    fin = dict(bias=_vpad(bias, Np), mean=mean, rstd=rstd, norm_mode=MODE[mode], eps=float(eps),
+                               running_mean=rm, running_var=rv, crun=0 if rm is None else rm.numel(),
+                               momentum=float(momentum or 0.0))
                     _LAST_MEANRSTD[0] = (mean, rstd)
             call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
                  nseg=nseg, **fin)
+        elif _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg) > 0:
+            nsw = _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg)
+            w32 = _w32(weight)
+            bp = _vpad(bias, Np)
+            for i in range(Np // 32):
+                nr = max(0, min(32, Co - 32 * i))
+                call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:] if nr > 0 else w32, Nr=nr, Kr=Ci, sn=Ci * T, sk=T, st=1,
+                     kseg=seg, ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None,
+                     Bn=B, D=D, H=H, W=W, K=Kp, N=32, flip=0, nseg=nsw,
+                     **dict(_NOFIN, bias=None if bp is None else bp[32 * i:32 * i + 32]))
         elif _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci) > 0:
             ns2 = _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci)
             w32 = _w32(weight)

@@ -82,7 +82,8 @@ FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, i
 
 /* tcgen05/TMEM implicit-GEMM path of the 3x3x3 stride-1 pad-1 convs (conv_blocks.py:393-416 conv1/conv2 of
  * UnetResBlock; MONAI ResBlock segresnet_dsa.py:102) and, with flip=1, their data gradients.  TMA halo planes in,
- * NDHWC bf16 out, weights read straight from the fp32 parameter (no pack kernel), optional fused InstanceNorm partial statistics part[Bn][nchunk][2][N] (sum, sum of squares of the
+ * NDHWC bf16 out, weights read straight from the fp32 parameter (no pack kernel), optional fp32 bias[N] added before
+ * the bf16 rounding (MONAI SubpixelUpsample's conv, conv_blocks.py:727-735), optional fused InstanceNorm partial statistics part[Bn][nchunk][2][N] (sum, sum of squares of the
  * rounded outputs; nchunk = (H/16)*(W/8)*nseg), finished either by fcd_norm_finalize or -- when mean / rstd
  * ([Bn][N] fp32) are given -- by the LAST CTA of the conv itself (norm_mode / eps / running statistics as fcd_norm_stats:
  * the InstanceNorm / BatchNorm that follows the conv, conv_blocks.py:439-452, needs no launch of its own for them).  fcd_conv3_tc_nseg returns the
@@ -92,7 +93,8 @@ FCD_API int fcd_norm_fin_fold(int B, int nchunk, int L);   /* 1: B x nchunk part
 FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N);
 FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                          long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                         int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                         const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
+                         float* rstd,
                          int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                          cudaStream_t stream);
 FCD_API int fcd_tc_error(void);
@@ -100,7 +102,8 @@ FCD_API int fcd_tc_error(void);
  * tile (csrc/conv_tcf.cu).  Same arguments and results as fcd_conv3_tc; -1 when the shape is not taken. */
 FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                           long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                          int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean, float* rstd,
+                          const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
+                          float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream);
 FCD_API int fcd_tcf_error(void);

@@ -408,3 +408,44 @@ def test_segment_chooser_minimises_rounds(ops):
     assert L.fcd_conv3_tc_nseg(18, 128, 128, 128, 16, 16) == 1
     assert L.fcd_conv3_tc_nseg(2, 64, 64, 64, 32, 32) >= 2
     assert L.fcd_conv3_tc_nseg(2, 32, 32, 32, 64, 32) > 1
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", [(2, 16, 128, 8, 16, 16), (1, 24, 100, 5, 32, 8), (1, 64, 256, 4, 16, 16),
+                                            (2, 16, 32, 6, 16, 8), (1, 32, 64, 4, 16, 16)])
+def test_biased_and_wide_convs_on_tcgen05(ops, B, Ci, Co, D, H, W):
+    """3x3x3 convs WITH bias, and with more than 64 output channels (MONAI SubpixelUpsample's Cin -> 8*Cout conv,
+    conv_blocks.py:727-735): bias added in the tcgen05 epilogue, wide outputs as 32-channel slices of kd-folded launches
+    -- no mma.sync launch in the forward pass.  Forward, data gradient, weight and bias gradients vs fp32 PyTorch."""
+    from fcd_b200 import _lib
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
+    b = rnd(Co, seed=2).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, w, b, padding=1)
+    dy = rnd(*ref.shape, seed=3)
+    gx, gw, gb = torch.autograd.grad(ref, [xr, w, b], dy)
+    xc = cl(ops, x, True)
+    w2 = w.detach().clone().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True)
+    seen = []
+    orig = _lib.call
+
+    def spy(name, **kw):
+        seen.append(name)
+        return orig(name, **kw)
+    ops.call = spy
+    try:
+        y = ops.conv3d(xc, w2, b2, k=3)
+    finally:
+        ops.call = orig
+    assert seen and all(n in ("fcd_conv3_tcf", "fcd_conv3_tc") for n in seen), seen
+    _lib.check_errors()
+    Np = ops.pad16(Co)
+    close(ops.to_ncdhw(y, Co), ref, what="biased / wide conv fwd")
+    if Np > Co:
+        assert float(y[..., Co:].abs().max()) == 0.0
+    y.backward(ops.to_channels_last(dy, Np))
+    _lib.check_errors()
+    close(ops.to_ncdhw(xc.grad, Ci), gx, what="dgrad")
+    close(w2.grad, gw, rel=6e-3, what="wgrad")
+    close(b2.grad, gb, rel=6e-3, what="bias grad")
