@@ -44,6 +44,7 @@ struct ConvTcfParams {
     const float* bias;   // nullptr or [COUT] fp32, added before the bf16 rounding (sub-pixel convs, conv_blocks.py:727-735)
     int Bn, D, H, W, nht, nwt, nseg, DL, nitems;
     int* status;
+    int accumulate;      // 1: C += result (bf16 read-modify-write): K-sliced data gradients of convs with > 64 output channels
     NormFin fin;        // fin.mean != nullptr: the last CTA turns the fused partials into mean / rstd
     unsigned* ticket;
     int dbg_delay_ns;                         // reproducer switch FCD_TCF_PRODUCER_DELAY_NS: slow the producers down
@@ -331,6 +332,12 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                     for (int k = 0; k < 8; ++k)
                         f[k] = ((__uint_as_float(t[0][c0 + k]) + __uint_as_float(t[1][c0 + k])) + __uint_as_float(t[2][c0 + k])) +
                                sbias[c0 + k];
+                    if (p.accumulate) {
+                        float o[8];
+                        unpack8(ld8(dst + c0), o);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] += o[k];
+                    }
                     const bf16x8 pk = pack8(f);
                     st8(dst + c0, pk);
                     if (STATS) {
@@ -392,8 +399,8 @@ int launch(const ConvTcfParams& p, int flip, cudaStream_t stream) {
 // anything else so the caller can fall back to fcd_conv3_tc.
 FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                           long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                          const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
-                          float* rstd,
+                          const float* bias, int accumulate, int Bn, int D, int H, int W, int K, int N, int flip, int nseg,
+                          float* mean, float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream) {
     if (H % TH || W % TW || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
@@ -402,7 +409,7 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     ConvTcfParams p;
     p.A = (const bf16*)A; p.lda = lda; p.Wf = Wf; p.sn = sn; p.sk = sk; p.st = st; p.Nr = Nr; p.Kr = Kr;
     p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
-    p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias;
+    p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias; p.accumulate = accumulate;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W;
     p.nht = H / TH; p.nwt = W / TW; p.DL = (D + nseg - 1) / nseg;
     p.nseg = (D + p.DL - 1) / p.DL;

@@ -334,6 +334,15 @@ def _conv3_entry(K, N):
     return "fcd_conv3_tcf" if (USE_TCF and N in (16, 32) and K in (16, 32, 64)) else "fcd_conv3_tc"
 
 
+def _conv3_call(entry, **kw):
+    """fcd_conv3_tcf additionally takes `accumulate` (default 0); the plain kernel does not."""
+    if entry == "fcd_conv3_tcf":
+        kw.setdefault("accumulate", 0)
+    else:
+        assert not kw.pop("accumulate", 0), "fcd_conv3_tc has no accumulate mode"
+    return call(entry, **kw)
+
+
 class _SideWork:
     """Weight gradients are not on the backward critical path (only the optimizer reads them), and on the deep
     levels they are many small kernels that cannot fill 148 SMs.  They are launched on one side stream per device,
@@ -485,6 +494,16 @@ def _tc_wide_nseg(B, D, H, W, K, N, k, stride, pad, cin_seg):
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, 32)
 
 
+def _tc_wide_dgrad_nseg(B, D, H, W, Kdy, Ndx, k, stride, pad, seg, Ci):
+    """Data gradient of a 3x3x3 conv with more than 64 (padded) output channels into <= 32 input channels: d-segment count
+    of one 64 -> Ndx kd-folded slice launch, 0 if not applicable."""
+    if not (USE_TC and USE_TCF and k == 3 and stride == 1 and pad == 1 and seg == Ci):
+        return 0
+    if not (Kdy > 64 and Kdy % 64 == 0 and Ndx in (16, 32)):
+        return 0
+    return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, 64, Ndx)
+
+
 def _tc_nslice_nseg(B, D, H, W, K, N, k, stride, pad, bias, cin_seg, Co, Ci):
     """64 -> 64 channels on a large volume (encoder3.conv2 at 32^3): the 27 x 64 x 64 weights do not fit beside the halo
     planes, so the conv runs as TWO kd-folded 64 -> 32 convs writing the two halves of the output rows (measured
@@ -571,7 +590,7 @@ class ConvFn(Function):
                                running_mean=rm, running_var=rv, crun=0 if rm is None else rm.numel(),
                                momentum=float(momentum or 0.0))
                     _LAST_MEANRSTD[0] = (mean, rstd)
-            call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
+            _conv3_call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
                  nseg=nseg, **fin)
         elif _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg) > 0:
@@ -580,7 +599,7 @@ class ConvFn(Function):
             bp = _vpad(bias, Np)
             for i in range(Np // 32):
                 nr = max(0, min(32, Co - 32 * i))
-                call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:] if nr > 0 else w32, Nr=nr, Kr=Ci, sn=Ci * T, sk=T, st=1,
+                _conv3_call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:] if nr > 0 else w32, Nr=nr, Kr=Ci, sn=Ci * T, sk=T, st=1,
                      kseg=seg, ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None,
                      Bn=B, D=D, H=H, W=W, K=Kp, N=32, flip=0, nseg=nsw,
                      **dict(_NOFIN, bias=None if bp is None else bp[32 * i:32 * i + 32]))
@@ -588,7 +607,7 @@ class ConvFn(Function):
             ns2 = _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci)
             w32 = _w32(weight)
             for i in range(2):
-                call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
+                _conv3_call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                      ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp,
                      N=32, flip=0, nseg=ns2, **_NOFIN)
         elif _pw_ok(B * D * H * W, Kp, Np, k, stride, pad, bias):
@@ -617,14 +636,25 @@ class ConvFn(Function):
             nseg = _tc_nseg(B, D, H, W, Np, Kp, k, stride, pad, None)
             if nseg > 0:
                 # dX = correlation of dY with the mirrored kernel: output channels = Cin (in concat segments)
-                call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
+                _conv3_call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
                      ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
                      flip=1, nseg=nseg, **_NOFIN)
+            elif _tc_wide_dgrad_nseg(B, D, H, W, Np, Kp, k, stride, pad, seg, Ci) > 0:
+                # conv with more than 64 output channels (sub-pixel upsampling): dX = sum over 64-channel slices of dY of
+                # a kd-folded data-gradient launch each, the later ones accumulating into dX (bf16 read-modify-write)
+                nsw = _tc_wide_dgrad_nseg(B, D, H, W, Np, Kp, k, stride, pad, seg, Ci)
+                w32 = _w32(weight).view(-1)
+                for i in range(Np // 64):
+                    kr = max(0, min(64, Co - 64 * i))
+                    _conv3_call("fcd_conv3_tcf", A=dy[..., 64 * i:], lda=ld(dy), Wf=w32[64 * i * Ci * T:] if kr > 0 else w32,
+                                Nr=Ci, Kr=kr, sn=T, sk=Ci * T, st=1, kseg=64, ksegpad=64, nsg=seg, nsgpad=segpad, C=dx,
+                                ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=64, N=Kp, flip=1, nseg=nsw,
+                                **dict(_NOFIN, accumulate=int(i > 0)))
             elif _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None if seg == Ci else 1, Co, Ci) > 0:
                 ns2 = _tc_nslice_nseg(B, D, H, W, Np, Kp, k, stride, pad, None, None, Co, Ci)
                 w32 = _w32(weight).view(-1)
                 for i in range(2):
-                    call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
+                    _conv3_call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
                          kseg=Co, ksegpad=Np, nsg=32, nsgpad=32, C=dx[..., 32 * i:], ldc=Kp, part=None, Bn=B, D=D, H=H,
                          W=W, K=Np, N=32, flip=1, nseg=ns2, **_NOFIN)
             elif _pw_ok(B * D * H * W, Np, Kp, k, stride, pad, None):

@@ -99,11 +99,12 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
                          cudaStream_t stream);
 FCD_API int fcd_tc_error(void);
 /* kd-folded variant for N in {16, 32}: one instruction of N = 3*Cout feeds three consecutive output planes from one A
- * tile (csrc/conv_tcf.cu).  Same arguments and results as fcd_conv3_tc; -1 when the shape is not taken. */
+ * tile (csrc/conv_tcf.cu).  Same arguments and results as fcd_conv3_tc; -1 when the shape is not taken.  accumulate = 1:
+ * C += result (K-sliced data gradients of convs with more than 64 output channels: one launch per 64 channels of dY). */
 FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr, int Kr, long long sn, long long sk,
                           long long st, int kseg, int ksegpad, int nsg, int nsgpad, void* C, long long ldc, float* part,
-                          const float* bias, int Bn, int D, int H, int W, int K, int N, int flip, int nseg, float* mean,
-                          float* rstd,
+                          const float* bias, int accumulate, int Bn, int D, int H, int W, int K, int N, int flip, int nseg,
+                          float* mean, float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream);
 FCD_API int fcd_tcf_error(void);

@@ -41,12 +41,12 @@ def _conv(ops, entry, x, w32, Ci, Co, nseg, flip=0, stats=True):
             fin.update(mean=torch.empty((B, Np), dtype=torch.float32, device=x.device),
                        rstd=torch.empty((B, Np), dtype=torch.float32, device=x.device), norm_mode=0, eps=1e-5)
     if flip:    # data gradient: x plays dY (Ci = conv's Cout), the weight is read transposed and mirrored
-        ops.call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=27, sk=Co * 27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
-                 nsgpad=Np, C=y, ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=1, nseg=nseg, **ops._NOFIN)
+        ops._conv3_call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=27, sk=Co * 27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
+                        nsgpad=Np, C=y, ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=1, nseg=nseg, **ops._NOFIN)
         part = None
     else:
-        ops.call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=Ci * 27, sk=27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
-                 nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0, nseg=nseg, **fin)
+        ops._conv3_call(entry, A=x, lda=Kp, Wf=w32, Nr=Co, Kr=Ci, sn=Ci * 27, sk=27, st=1, kseg=Ci, ksegpad=Kp, nsg=Co,
+                        nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0, nseg=nseg, **fin)
         if part is not None and fin["mean"] is not None:
             part = torch.cat([part.reshape(B, -1), fin["mean"], fin["rstd"]], 1)    # compared bit for bit across launches
             y._mean_rstd = (fin["mean"], fin["rstd"])

@@ -440,6 +440,7 @@ def test_biased_and_wide_convs_on_tcgen05(ops, B, Ci, Co, D, H, W):
         ops.call = orig
     assert seen and all(n in ("fcd_conv3_tcf", "fcd_conv3_tc") for n in seen), seen
     _lib.check_errors()
+    seen.clear()
     Np = ops.pad16(Co)
     close(ops.to_ncdhw(y, Co), ref, what="biased / wide conv fwd")
     if Np > Co:

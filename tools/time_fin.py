@@ -29,7 +29,7 @@ def run(B, Ci, Co, S, fin, iters=30):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.call(ops._conv3_entry(Kp, Np), A=x, lda=Kp, Wf=w, Nr=Co, Kr=Ci, sn=Ci * 27, sk=27, st=1, kseg=Ci, ksegpad=Kp,
+        ops._conv3_call(ops._conv3_entry(Kp, Np), A=x, lda=Kp, Wf=w, Nr=Co, Kr=Ci, sn=Ci * 27, sk=27, st=1, kseg=Ci, ksegpad=Kp,
                  nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=S, H=S, W=S, K=Kp, N=Np, flip=0, nseg=nseg, **kw)
         if fin == "launch":
             ops.call("fcd_norm_finalize", part=part, mean=mean, rstd=rstd, B=B, S=S ** 3, C=Np, nchunk=nchunk, mode=0,
