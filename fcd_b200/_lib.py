@@ -27,7 +27,7 @@ _CT = {
 # CUDA kernels launched by one call of each entry point (for bench.py's gpu_launches count)
 KERNELS_PER_CALL = {
     "fcd_norm_stats": 1, "fcd_colsum": 2, "fcd_norm_bwd": 2, "fcd_outconv_bwd": 2, "fcd_loss_fwd": 2,
-    "fcd_ln_bwd": 2, "fcd_dsa_fwd": 5, "fcd_dsa_bwd": 7, "fcd_mse_fwd": 2, "fcd_igemm_splitk": 2,
+    "fcd_ln_bwd": 2, "fcd_dsa_fwd": 5, "fcd_dsa_bwd": 7, "fcd_mse_fwd": 2, "fcd_igemm_splitk": 2, "fcd_igemm_dgrad_s2": 8,
 }
 
 

@@ -28,6 +28,11 @@ struct IGemmParams {
     int ksplit;        // > 1: blockIdx.z takes a slice of the (tap, k-chunk) loop and writes fp32 partials to ws
     float* ws;         // [ksplit][M][N] fp32
     unsigned* tickets; // ksplit > 1: one slot per output tile; the CTA that finishes a tile last sums its partials
+    // Parity-class mode (data gradient of a stride-2 conv): the GEMM rows are the voxels of ONE parity class of the
+    // (Dm, Hm, Wm) grid, (z%2, y%2, x%2) = (par>>2&1, par>>1&1, par&1) for par_on, and only the ntaps taps that can reach
+    // that class are multiplied (1, 2, 4 or 8 of the 27) -- walking all 27 taps over mixed-parity rows multiplies 7/8
+    // zero rows (measured: 4.4 of SegResNet's 18.6 ms step).
+    int par_on, par, ntaps, taps[8];
 };
 
 namespace {
@@ -76,15 +81,23 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
         int m = m0 + row;
         r_ok[i] = m < p.M;
         int mm = r_ok[i] ? m : 0;
-        int x = mm % p.Wm; mm /= p.Wm;
-        int y = mm % p.Hm; mm /= p.Hm;
-        int z = mm % p.Dm; mm /= p.Dm;
+        int x, y, z;
+        if (p.par_on) {
+            const int W2 = p.Wm >> 1, H2 = p.Hm >> 1, D2 = p.Dm >> 1;
+            x = 2 * (mm % W2) + (p.par & 1); mm /= W2;
+            y = 2 * (mm % H2) + ((p.par >> 1) & 1); mm /= H2;
+            z = 2 * (mm % D2) + ((p.par >> 2) & 1); mm /= D2;
+        } else {
+            x = mm % p.Wm; mm /= p.Wm;
+            y = mm % p.Hm; mm /= p.Hm;
+            z = mm % p.Dm; mm /= p.Dm;
+        }
         r_x[i] = x; r_y[i] = y; r_z[i] = z;
         r_base[i] = (long long)mm * p.Ds * p.Hs * p.Ws;
     }
 
     const int kchunks = p.K / BK;
-    const int T = p.kd * p.kh * p.kw;
+    const int T = p.par_on ? p.ntaps : p.kd * p.kh * p.kw;
     const int nk_all = T * kchunks;
     // split-K: this CTA runs iterations [it0, it0 + nk) of the flattened (tap, k-chunk) loop
     const int it0 = (int)((long long)nk_all * blockIdx.z / p.ksplit);
@@ -92,7 +105,8 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
 
     auto load_stage = [&](int it_local, int slot) {
         const int it = it0 + it_local;
-        const int t = it / kchunks, kc = it - t * kchunks;
+        const int tl = it / kchunks, kc = it - tl * kchunks;
+        const int t = p.par_on ? p.taps[tl] : tl;
         const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
         const uint32_t sa = smem_base + slot * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
@@ -251,7 +265,14 @@ __global__ void __launch_bounds__(128 * (BN / WN)) igemm_kernel(const IGemmParam
         if (m >= p.M || n >= p.N) continue;
         bf16x8 v = *reinterpret_cast<const bf16x8*>(&ctile[row * CLD + c8 * 8]);
         bf16* dst;
-        if (p.out_mode == 0) {
+        if (p.out_mode == 0 && p.par_on) {
+            int mm = m;
+            const int W2 = p.Wm >> 1, H2 = p.Hm >> 1, D2 = p.Dm >> 1;
+            const int x = 2 * (mm % W2) + (p.par & 1); mm /= W2;
+            const int y = 2 * (mm % H2) + ((p.par >> 1) & 1); mm /= H2;
+            const int z = 2 * (mm % D2) + ((p.par >> 2) & 1); mm /= D2;
+            dst = p.C + ((((long long)mm * p.Dm + z) * p.Hm + y) * p.Wm + x) * p.ldc + n;
+        } else if (p.out_mode == 0) {
             dst = p.C + (long long)m * p.ldc + n;
         } else {
             int tap = n / p.Cq, co = n - tap * p.Cq;
@@ -334,7 +355,7 @@ FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long
     p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
     p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
     p.mode = mode; p.out_mode = out_mode; p.accumulate = accumulate; p.Cq = Cq > 0 ? Cq : 1;
-    p.ksplit = 1; p.ws = nullptr; p.tickets = nullptr;
+    p.ksplit = 1; p.ws = nullptr; p.tickets = nullptr; p.par_on = 0; p.par = 0; p.ntaps = 0;
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
@@ -372,7 +393,7 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
     p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
     p.K = K; p.N = N; p.kd = kd; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
     p.mode = mode; p.out_mode = 0; p.accumulate = accumulate; p.Cq = 1;
-    p.ksplit = ksplit; p.ws = ws;
+    p.ksplit = ksplit; p.ws = ws; p.par_on = 0; p.par = 0; p.ntaps = 0;
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
@@ -401,4 +422,42 @@ FCD_API int fcd_splitk_reduce(const float* ws, void* C, long long ldc, const flo
     if (blocks > 8 * fcd_num_sms()) blocks = 8 * fcd_num_sms();
     igemm_splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, (bf16*)C, ldc, bias, (int)M, N, ksplit, accumulate);
     return (int)cudaGetLastError();
+}
+
+// Data gradient of a 3x3x3 stride-2 pad-1 conv (MONAI SegResNet down-sampling, segresnet_dsa.py:97): dX[Bn][Dm][Hm][Wm][N]
+// from dY[Bn][Ds][Hs][Ws][K] (Ds = Dm / 2 ...) and the packed transposed weights W[27][N][K] (as fcd_igemm mode 1), as
+// EIGHT launches, one per parity class of the dX grid, each multiplying only the taps that reach its class.
+FCD_API int fcd_igemm_dgrad_s2(const void* A, long long lda, const void* W, void* C, long long ldc, int Bn, int Ds, int Hs,
+                               int Ws, int Dm, int Hm, int Wm, int K, int N, cudaStream_t stream) {
+    if (K % 16 != 0 || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0) return -1;
+    if ((Dm | Hm | Wm) & 1 || Ds * 2 != Dm || Hs * 2 != Hm || Ws * 2 != Wm) return -1;
+    IGemmParams p;
+    p.A = (const bf16*)A; p.lda = lda; p.W = (const bf16*)W; p.C = (bf16*)C; p.ldc = ldc; p.bias = nullptr;
+    p.Bn = Bn; p.Ds = Ds; p.Hs = Hs; p.Ws = Ws; p.Dm = Dm; p.Hm = Hm; p.Wm = Wm;
+    p.K = K; p.N = N; p.kd = 3; p.kh = 3; p.kw = 3; p.stride = 2; p.pad = 1;
+    p.mode = 1; p.out_mode = 0; p.accumulate = 0; p.Cq = 1;
+    p.ksplit = 1; p.ws = nullptr; p.tickets = nullptr; p.par_on = 1;
+    const long long M = (long long)Bn * (Dm / 2) * (Hm / 2) * (Wm / 2);
+    if (M <= 0 || M > 0x7fffffffLL) return -1;
+    p.M = (int)M;
+    for (int cls = 0; cls < 8; ++cls) {
+        p.par = cls;
+        // voxel index i, tap t, source q = (i + 1 - t) / 2: t must have the parity of i + 1 -> even i: t = 1; odd i: t in {0, 2}
+        int tz[2], ty[2], tx[2];
+        const int nz = ((cls >> 2) & 1) ? 2 : 1, ny = ((cls >> 1) & 1) ? 2 : 1, nx = (cls & 1) ? 2 : 1;
+        tz[0] = nz == 2 ? 0 : 1; tz[1] = 2;
+        ty[0] = ny == 2 ? 0 : 1; ty[1] = 2;
+        tx[0] = nx == 2 ? 0 : 1; tx[1] = 2;
+        p.ntaps = 0;
+        for (int a = 0; a < nz; ++a)
+            for (int b = 0; b < ny; ++b)
+                for (int c = 0; c < nx; ++c) p.taps[p.ntaps++] = (tz[a] * 3 + ty[b]) * 3 + tx[c];
+        int rc;
+        const bool k32 = (K % 32 == 0);
+        if (N <= 16) rc = k32 ? launch_igemm<16, 16, 32>(p, stream) : launch_igemm<16, 16, 16>(p, stream);
+        else if (N <= 32) rc = k32 ? launch_igemm<32, 32, 32>(p, stream) : launch_igemm<32, 32, 16>(p, stream);
+        else rc = k32 ? launch_igemm<64, 32, 32>(p, stream) : launch_igemm<64, 32, 16>(p, stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
 }

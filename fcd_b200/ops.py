@@ -489,7 +489,7 @@ def _tc_wide_nseg(B, D, H, W, K, N, k, stride, pad, cin_seg):
     0 if not applicable."""
     if not (USE_TC and USE_TCF and k == 3 and stride == 1 and pad == 1 and cin_seg is None):
         return 0
-    if not (K in (16, 32, 64) and N > 64 and N % 32 == 0):
+    if not (K in (16, 32, 64) and N > 64 and N % 16 == 0):
         return 0
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, K, 32)
 
@@ -543,6 +543,12 @@ def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
             if ks > 2:      # ks == 2 is summed inside the kernel by the CTA that finishes an output tile last
                 call("fcd_splitk_reduce", ws=ws, C=c, ldc=ld(c), bias=None, M=M, N=N, ksplit=ks, accumulate=0)
             return
+    if mode == 1 and k == 3 and stride == 2 and pad == 1 and bias is None and not any(v & 1 for v in dst) \
+            and tuple(2 * v for v in src) == tuple(dst) and B * dst[0] * dst[1] * dst[2] >= 8 * 4096:
+        # data gradient of a stride-2 conv: one launch per parity class of dX, each with only the taps that reach it
+        call("fcd_igemm_dgrad_s2", A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), Bn=B, Ds=src[0], Hs=src[1], Ws=src[2],
+             Dm=dst[0], Hm=dst[1], Wm=dst[2], K=K, N=N)
+        return
     ks = _lib.lib().fcd_igemm_ksplit(M, N, K, k ** 3)
     common = dict(A=a, lda=ld(a), W=wp, C=c, ldc=ld(c), bias=bias, Bn=B, Ds=src[0], Hs=src[1], Ws=src[2], Dm=dst[0],
                   Hm=dst[1], Wm=dst[2], K=K, N=N, kd=k, kh=k, kw=k, stride=stride, pad=pad, mode=mode, accumulate=0)
@@ -597,12 +603,13 @@ class ConvFn(Function):
             nsw = _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg)
             w32 = _w32(weight)
             bp = _vpad(bias, Np)
-            for i in range(Np // 32):
-                nr = max(0, min(32, Co - 32 * i))
-                _conv3_call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:] if nr > 0 else w32, Nr=nr, Kr=Ci, sn=Ci * T, sk=T, st=1,
-                     kseg=seg, ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None,
-                     Bn=B, D=D, H=H, W=W, K=Kp, N=32, flip=0, nseg=nsw,
-                     **dict(_NOFIN, bias=None if bp is None else bp[32 * i:32 * i + 32]))
+            for n0 in range(0, Np, 32):
+                wd = min(32, Np - n0)               # 32-channel slices, a trailing 16-channel one if Np % 32 == 16
+                nr = max(0, min(wd, Co - n0))
+                _conv3_call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[n0:] if nr > 0 else w32, Nr=nr, Kr=Ci, sn=Ci * T, sk=T,
+                            st=1, kseg=seg, ksegpad=segpad, nsg=wd, nsgpad=wd, C=y[..., n0:], ldc=Np, part=None,
+                            Bn=B, D=D, H=H, W=W, K=Kp, N=wd, flip=0, nseg=nsw,
+                            **dict(_NOFIN, bias=None if bp is None else bp[n0:n0 + wd]))
         elif _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci) > 0:
             ns2 = _tc_nslice_nseg(B, D, H, W, Kp, Np, k, stride, pad, bias, cin_seg, Co, Ci)
             w32 = _w32(weight)

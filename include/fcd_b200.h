@@ -53,6 +53,10 @@ FCD_API int fcd_pack_weight_batched(const void* jobs, int njobs, int nblocks, cu
 FCD_API int fcd_igemm(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias, int Bn,
                       int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh, int kw, int stride,
                       int pad, int mode, int out_mode, int accumulate, int Cq, cudaStream_t stream);
+/* data gradient of a 3x3x3 stride-2 pad-1 conv (segresnet_dsa.py:97) as eight parity-class launches that multiply only
+ * the taps reaching each class (W: packed transposed weights [27][N][K] as for fcd_igemm mode 1; even Dm, Hm, Wm) */
+FCD_API int fcd_igemm_dgrad_s2(const void* A, long long lda, const void* W, void* C, long long ldc, int Bn, int Ds, int Hs,
+                               int Ws, int Dm, int Hm, int Wm, int K, int N, cudaStream_t stream);
 FCD_API int fcd_igemm_ksplit(long long M, int N, int K, int T);
 FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
                              int Bn, int Ds, int Hs, int Ws, int Dm, int Hm, int Wm, int K, int N, int kd, int kh,

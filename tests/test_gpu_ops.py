@@ -59,6 +59,9 @@ CONV_CASES = [
     (1, 128, 256, 4, 4, 4, 3, 1, False),
     (2, 32, 16, 10, 12, 8, 1, 1, True),
     (2, 16, 32, 12, 8, 10, 3, 2, False),
+    (1, 16, 32, 32, 32, 32, 3, 2, False),      # stride-2 data gradient as eight parity-class launches (fcd_igemm_dgrad_s2)
+    (2, 32, 64, 16, 32, 48, 3, 2, False),
+    (1, 24, 40, 32, 16, 64, 3, 2, True),
     (1, 24, 40, 7, 9, 11, 3, 1, True),
 ]
 
