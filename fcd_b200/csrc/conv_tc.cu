@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 __syncwarp();
                 if (lane == 0) mbar_arrive(TEMPTY(buf));
                 bf16* dst = p.C + ((((long long)it.n * p.D + od) * p.H + it.h0 + hh) * p.W + it.w0 + ww) * p.ldc;
+                if (!(it.h0 + hh < p.H && it.w0 + ww < p.W)) continue;     // ragged edge tile: H % 16 or W % 8 != 0
 #pragma unroll
                 for (int c0 = 0; c0 < COUT; c0 += 8) {
                     float f[8];
@@ -396,7 +397,7 @@ int launch(const ConvTcParams& p, cudaStream_t stream) {
 }
 
 bool shape_ok(int D, int H, int W, int K, int N) {
-    if (H % TH || W % TW || D < 1) return false;
+    if (H < 1 || W < 1 || D < 1) return false;   // H, W need not be multiples of the 16 x 8 tile: edge tiles are masked
     if (!(K == 16 || K == 32 || K == 64) || !(N == 16 || N == 32 || N == 64)) return false;
     if (K == 64 && N == 64) return false;       // 27 taps of 64x64 weights do not fit next to the halo ring
     return true;
@@ -417,7 +418,7 @@ FCD_API int fcd_conv3_tc_nseg(int Bn, int D, int H, int W, int K, int N) {
     // time-outs; the cause (an aliased FULL-barrier parity wait, conv_tcf.cu) is fixed and tests/test_gpu_conv_stress.py
     // covers the regime.  FCD_NSEG_RESTRICTED=1 restores the old rule for A/B runs.
     static const bool restricted = getenv("FCD_NSEG_RESTRICTED") != nullptr;
-    const int cols = Bn * (H / TH) * (W / TW), sms = fcd_num_sms();
+    const int cols = Bn * ((H + TH - 1) / TH) * ((W + TW - 1) / TW), sms = fcd_num_sms();
     int per_sm = 1;
     if (N == 16 && K <= 64) {
         const int w_bytes = 27 * K * N * 2, plane = 180 * K * 2;
@@ -457,7 +458,7 @@ FCD_API int fcd_conv3_tc(const void* A, long long lda, const float* Wf, int Nr, 
     p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
     p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W;
-    p.nht = H / TH; p.nwt = W / TW; p.nseg = nseg; p.DL = (D + nseg - 1) / nseg;
+    p.nht = (H + TH - 1) / TH; p.nwt = (W + TW - 1) / TW; p.nseg = nseg; p.DL = (D + nseg - 1) / nseg;
     p.nseg = (D + p.DL - 1) / p.DL;
     if (p.nseg != nseg) return -1;              // caller sizes `part` with nseg: must be exact
     p.nitems = Bn * p.nht * p.nwt * p.nseg; p.status = fcd_status_dev();

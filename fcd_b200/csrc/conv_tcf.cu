@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CIN, COUT>::CTAS_PER_SM) conv3_t
                 __syncwarp();
                 if (lane == 0) mbar_arrive(TEMPTY(slot));
                 bf16* dst = p.C + ((((long long)it.n * p.D + od) * p.H + it.h0 + hh) * p.W + it.w0 + ww) * p.ldc;
+                if (!(it.h0 + hh < p.H && it.w0 + ww < p.W)) continue;     // ragged edge tile: H % 16 or W % 8 != 0
 #pragma unroll
                 for (int c0 = 0; c0 < COUT; c0 += 8) {
                     float f[8];
@@ -403,7 +404,7 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
                           float* mean, float* rstd,
                           int norm_mode, float eps, float* running_mean, float* running_var, int crun, float momentum,
                           cudaStream_t stream) {
-    if (H % TH || W % TW || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
+    if (H < 1 || W < 1 || D < 1 || nseg < 1 || lda % 8 || ldc % 8 || lda < K || ldc < N) return -1;
     if (!(K == 16 || K == 32 || K == 64) || !(N == 16 || N == 32)) return -1;
     if (((uintptr_t)A & 15) || ((uintptr_t)C & 15) || kseg < 1 || ksegpad < 1 || nsg < 1 || nsgpad < 1) return -1;
     ConvTcfParams p;
@@ -411,7 +412,7 @@ FCD_API int fcd_conv3_tcf(const void* A, long long lda, const float* Wf, int Nr,
     p.kseg = kseg; p.ksegpad = ksegpad; p.nsg = nsg; p.nsgpad = nsgpad;
     p.C = (bf16*)C; p.ldc = ldc; p.part = part; p.bias = bias; p.accumulate = accumulate;
     p.Bn = Bn; p.D = D; p.H = H; p.W = W;
-    p.nht = H / TH; p.nwt = W / TW; p.DL = (D + nseg - 1) / nseg;
+    p.nht = (H + TH - 1) / TH; p.nwt = (W + TW - 1) / TW; p.DL = (D + nseg - 1) / nseg;
     p.nseg = (D + p.DL - 1) / p.DL;
     if (p.nseg != nseg) return -1;
     p.nitems = Bn * p.nht * p.nwt * p.nseg;

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
 #pragma unroll
                 for (int q = 0; q < NJ; ++q) {
                     const int v = v0 + q * VS;               // tile voxel: hh = v / 8, ww = v % 8
-                    cp_async16(dst0 + q * VS * 16, plane + ((long long)(v >> 3) * p.W + (v & 7)) * p.ldu, true);
+                    const bool ok = it.h0 + (v >> 3) < p.H && it.w0 + (v & 7) < p.W;      // ragged edge tile: zero rows
+                    cp_async16(dst0 + q * VS * 16, ok ? plane + ((long long)(v >> 3) * p.W + (v & 7)) * p.ldu : Up, ok);
                 }
                 cp_async_commit();
                 if (seq + 1 >= 2) {                         // NU = 4: hand over with a lag of one plane
@@ -276,8 +277,8 @@ int launch(const WgradTcParams& p, int grid, int nslices, cudaStream_t stream) {
 }
 
 int pick_dl(int Bn, int D, int H, int W) {
-    if (H % TH || W % TW) return 0;
-    const long long cols = (long long)Bn * (H / TH) * (W / TW);
+    if (H < 1 || W < 1) return 0;
+    const long long cols = (long long)Bn * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
     if (D % 8 == 0 && cols * (D / 8) >= 2 * fcd_num_sms()) return 8;
     if (D % 4 == 0) return 4;
     return 0;
@@ -289,7 +290,7 @@ int pick_dl(int Bn, int D, int H, int W) {
 FCD_API int fcd_wgrad3_tc_nsplit(int Bn, int D, int H, int W) {
     const int dl = pick_dl(Bn, D, H, W);
     if (dl == 0) return 0;
-    const long long items = (long long)Bn * (H / TH) * (W / TW) * (D / dl);
+    const long long items = (long long)Bn * ((H + TH - 1) / TH) * ((W + TW - 1) / TW) * (D / dl);
     return (int)(items < 2LL * fcd_num_sms() ? items : 2LL * fcd_num_sms());   // two CTAs per SM when they fit
 }
 
@@ -308,7 +309,7 @@ FCD_API int fcd_wgrad3_tc(const void* S, long long lds, const void* U, long long
     WgradTcParams p;
     p.S = (const bf16*)S; p.lds = lds; p.U = (const bf16*)U; p.ldu = ldu; p.part = part;
     p.ldn = ldn; p.ldk = ldk; p.n_off = n_off; p.k_off = k_off; p.nks = nks;
-    p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.nht = H / TH; p.nwt = W / TW; p.nseg = D / dl;
+    p.Bn = Bn; p.D = D; p.H = H; p.W = W; p.nht = (H + TH - 1) / TH; p.nwt = (W + TW - 1) / TW; p.nseg = D / dl;
     p.nitems = Bn * p.nht * p.nwt * p.nseg; p.status = fcd_status_dev();
     const int grid = p.nitems < 2 * fcd_num_sms() ? p.nitems : 2 * fcd_num_sms();   // == fcd_wgrad3_tc_nsplit
 #define FCD_WG_CASE(A, B, L) if (CS == A && CU == B && dl == L) return launch<A, B, L>(p, grid, nns * nks, stream)

@@ -583,7 +583,7 @@ class ConvFn(Function):
             part = None
             fin = dict(_NOFIN, bias=_vpad(bias, Np))
             if Np <= 32:
-                nchunk = (H // 16) * (W // 8) * nseg
+                nchunk = ((H + 15) // 16) * ((W + 7) // 8) * nseg
                 part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=x.device)
                 _LAST_PART[0] = (part, nchunk)
                 if stats_for is not None and _lib.lib().fcd_norm_fin_fold(B, nchunk, 2 * Np):

@@ -34,7 +34,7 @@ def _conv(ops, entry, x, w32, Ci, Co, nseg, flip=0, stats=True):
     part = None
     fin = dict(ops._NOFIN)
     if stats and Np <= 32:
-        part = torch.empty((B, (H // 16) * (W // 8) * nseg, 2, Np), dtype=torch.float32, device=x.device)
+        part = torch.empty((B, ((H + 15) // 16) * ((W + 7) // 8) * nseg, 2, Np), dtype=torch.float32, device=x.device)
         from fcd_b200 import _lib
         if _lib.lib().fcd_norm_fin_fold(B, part.shape[1], 2 * Np):
             # InstanceNorm statistics finished by the conv's last CTA
@@ -86,7 +86,7 @@ def test_tcf_many_items_and_segments(ops, B, Ci, Co, S, nseg, flip, iters):
         w = (torch.randn((Co, Ci, 3, 3, 3), generator=g) * 0.05)
         ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.to(dev), padding=1)
     w32 = w.to(dev).contiguous()
-    nitems = B * (S // 16) * (S // 8) * nseg
+    nitems = B * ((S + 15) // 16) * ((S + 7) // 8) * nseg
     _lib.status()       # clear
     y0, p0 = _conv(ops, "fcd_conv3_tcf", x, w32, Ci, Co, nseg, flip)
     _lib.check_errors()

@@ -37,6 +37,9 @@ TC_CASES = [
     (1, 32, 64, 5, 16, 8),
     (1, 24, 12, 1, 16, 8),        # single plane, ragged real channel counts
     (1, 16, 16, 40, 16, 8),       # several d-segments per column
+    (1, 64, 32, 8, 40, 40),       # ragged edge tiles: H % 16 = 8 (the 40^3 level of a 160^3 patch)
+    (2, 32, 32, 8, 20, 20),       # H % 16 = 4, W % 8 = 4 (the 20^3 level)
+    (1, 16, 64, 4, 24, 12),       # plain kernel, ragged in both directions
 ]
 
 

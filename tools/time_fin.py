@@ -15,7 +15,7 @@ def run(B, Ci, Co, S, fin, iters=30):
     x = (torch.randn((B, S, S, S, Kp), generator=g) * 0.5).to(torch.bfloat16).to(dev)
     w = (torch.randn((Co, Ci, 3, 3, 3), generator=g) * 0.05).to(dev)
     nseg = L.fcd_conv3_tc_nseg(B, S, S, S, Kp, Np)
-    nchunk = (S // 16) * (S // 8) * nseg
+    nchunk = ((S + 15) // 16) * ((S + 7) // 8) * nseg
     y = torch.empty((B, S, S, S, Np), dtype=torch.bfloat16, device=dev)
     part = torch.empty((B, nchunk, 2, Np), dtype=torch.float32, device=dev)
     mean = torch.empty((B, Np), dtype=torch.float32, device=dev)
