@@ -1,17 +1,19 @@
-// Fused segmentation loss: Dice (+ CE | + sigmoid-focal) (+ total variation), forward and backward.
+// Fused segmentation loss: Dice | generalized Dice (+ CE | + sigmoid-focal) (+ total variation), forward and backward.
 //
 // Replaces, for a 2-class prediction, the ~15 ATen kernels of the reference's CombinedLoss.forward
 // (get_loss.py:24-39): MONAI DiceLoss / DiceCELoss / DiceFocalLoss built at get_loss.py:46-78
-// (include_background=False, to_onehot_y=True, softmax=True, batch=True, smooth 1e-5) and
-// compute_total_variation_loss / dilate_mask (get_loss.py:100-165).
+// (include_background=False, to_onehot_y=True, softmax=True, batch=True, smooth 1e-5), GeneralizedDiceLoss /
+// GeneralizedDiceFocalLoss built at get_loss.py:79-93 (include_background=True: both channels, class weights
+// 1/G_c^2 | 1/G_c | 1 from the label counts) and compute_total_variation_loss / dilate_mask (get_loss.py:100-165).
 // pred: fp32 NCDHW [B,2,D,H,W] logits; target: fp32 [B,1,D,H,W] in {0,1}.  All reductions are fp32 per thread,
 // combined in double by a single finalize block; nothing is read back to the host.
 #include "common.cuh"
 
 struct LossCfg {
-    int kind;        // 0 Dice, 1 DiceCE, 2 DiceFocal
+    int kind;        // 0 Dice, 1 DiceCE, 2 DiceFocal, 3 GeneralizedDice, 4 GeneralizedDiceFocal
     float lambda_dice, lambda_2, w_bg, w_fg, gamma;
     int squared, jaccard;
+    int w_type;      // kinds 3, 4: class weight 0 = 1/G^2 ("square"), 1 = 1/G ("simple"), 2 = 1 ("uniform")
     float smooth_nr, smooth_dr;
     float tv_w;
     int tv_norm, tv_exclude;
@@ -24,6 +26,20 @@ constexpr int LOSS_THREADS = 256;
 
 __device__ __forceinline__ float softplusf(float x) { return x > 0.f ? x + log1pf(__expf(-x)) : log1pf(__expf(x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// MONAI sigmoid focal term of one logit x with label t in {0,1}: exp(gamma * logsigmoid(-x (2t-1))) * bce(x, t)
+__device__ __forceinline__ float focal_term(float x, float t, float gamma) {
+    const float bce = x - x * t + softplusf(-x);                // x - x t - logsigmoid(x)
+    const float invp = -softplusf(x * (2.f * t - 1.f));         // logsigmoid(-x (2t-1))
+    return __expf(gamma * invp) * bce;
+}
+__device__ __forceinline__ float focal_grad(float x, float t, float gamma) {    // d focal_term / dx
+    const float sgn = 2.f * t - 1.f;
+    const float u = -x * sgn;
+    const float bce = x - x * t + softplusf(-x);
+    const float e = __expf(gamma * -softplusf(-u));
+    return e * (gamma * (-sgn) * sigmoidf_(-u) * bce + (sigmoidf_(x) - t));
+}
 
 // border mask of get_loss.py:141-150: 1 where the clipped 5^3 window holds both a 0 and a 1 of gt.
 __global__ void tv_mask_kernel(const float* __restrict__ gt, unsigned char* __restrict__ keep, int B, int D, int H,
@@ -64,17 +80,16 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_fwd_kernel(const float* __r
         const float d = l1 - l0;
         const float p = sigmoidf_(d);
         a[0] += p * y;
-        a[1] += cfg.squared ? p * p : p;
+        a[1] += (cfg.squared && cfg.kind < 3) ? p * p : p;
         a[2] += y;
         if (cfg.kind == 1) {
             const float w = y > 0.f ? cfg.w_fg : cfg.w_bg;
             a[3] += w * softplusf(y > 0.f ? -d : d);
             a[4] += w;
         } else if (cfg.kind == 2) {
-            const float sgn = 2.f * y - 1.f;
-            const float bce = l1 - l1 * y + softplusf(-l1);          // x - x t - logsigmoid(x)
-            const float invp = -softplusf(l1 * sgn);                 // logsigmoid(-x (2t-1))
-            a[5] += __expf(cfg.gamma * invp) * bce;
+            a[5] += focal_term(l1, y, cfg.gamma);
+        } else if (cfg.kind == 4) {                                  // include_background: both one-hot channels
+            a[5] += focal_term(l1, y, cfg.gamma) + focal_term(l0, 1.f - y, cfg.gamma);
         }
         if (pbuf) pbuf[i] = keep ? (keep[i] ? p : 0.f) : p;
     };
@@ -129,7 +144,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) tv_fwd_kernel(const float* __res
     }
 }
 
-// res[0]=total, [1]=dice N, [2]=dice Dn, [3]=CE weight sum, [4..6]=tv_z,tv_y,tv_x, [7]=dice, [8]=ce|focal, [9]=tv
+// res[0]=total, [1]=dice N, [2]=dice Dn, [3]=CE weight sum, [4..6]=tv_z,tv_y,tv_x, [7]=dice, [8]=ce|focal, [9]=tv,
+// [10],[11] = generalized-Dice class weights w_bg, w_fg
 __global__ void loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ tvpart, int nblk,
                                      LossCfg cfg, int B, int D, int H, int W, float* __restrict__ res,
                                      const int* __restrict__ status) {
@@ -146,15 +162,36 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, const float
     __syncthreads();
     if (threadIdx.x == 0) {
         const double I = sh[0], P = sh[1], G = sh[2];
-        const double N = 2.0 * I + cfg.smooth_nr;
-        double base = G + P;
-        if (cfg.jaccard) base = 2.0 * (base - I);
-        const double Dn = base + cfg.smooth_dr;
+        const double vox = (double)B * D * H * W;
+        double N, Dn, gw[2] = {0.0, 0.0};
+        if (cfg.kind >= 3) {
+            // MONAI GeneralizedDiceLoss.forward with batch=True over the channels (1-p, p) / (1-y, y): the background
+            // sums follow from the foreground ones.  w = 1/G^2 | 1/G | 1; an infinite weight (empty class) is replaced
+            // by the largest finite one.
+            const double Ic[2] = {vox - P - G + I, I}, Gc[2] = {vox - G, G}, Pc[2] = {vox - P, P};
+            bool inf[2];
+            double wmax = 0.0;
+            for (int c = 0; c < 2; ++c) {
+                inf[c] = cfg.w_type != 2 && Gc[c] == 0.0;
+                if (!inf[c]) gw[c] = cfg.w_type == 0 ? 1.0 / (Gc[c] * Gc[c]) : (cfg.w_type == 1 ? 1.0 / Gc[c] : 1.0);
+                // the reference computes w in fp32 (ground_o.float()): round the same way
+                gw[c] = (double)(float)gw[c];
+                if (!inf[c]) wmax = fmax(wmax, gw[c]);
+            }
+            for (int c = 0; c < 2; ++c) if (inf[c]) gw[c] = wmax;
+            N = 2.0 * (Ic[0] * gw[0] + Ic[1] * gw[1]) + cfg.smooth_nr;
+            Dn = (Gc[0] + Pc[0]) * gw[0] + (Gc[1] + Pc[1]) * gw[1] + cfg.smooth_dr;
+        } else {
+            N = 2.0 * I + cfg.smooth_nr;
+            double base = G + P;
+            if (cfg.jaccard) base = 2.0 * (base - I);
+            Dn = base + cfg.smooth_dr;
+        }
         const double dice = 1.0 - N / Dn;
         double second = 0.0;
-        const double vox = (double)B * D * H * W;
         if (cfg.kind == 1) second = sh[3] / sh[4];
         else if (cfg.kind == 2) second = sh[5] / vox;
+        else if (cfg.kind == 4) second = sh[5] / (2.0 * vox);
         double tv[3] = {0.0, 0.0, 0.0}, tvsum = 0.0;
         if (tvpart != nullptr) {
             const double cnt[3] = {(double)B * (D - 1) * H * W, (double)B * D * (H - 1) * W, (double)B * D * H * (W - 1)};
@@ -163,13 +200,15 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, const float
                 tvsum += tv[k];
             }
         }
-        double total = (cfg.kind == 0 ? dice : cfg.lambda_dice * dice + cfg.lambda_2 * second) + cfg.tv_w * tvsum;
+        double total = ((cfg.kind == 0 || cfg.kind == 3) ? dice : cfg.lambda_dice * dice + cfg.lambda_2 * second) +
+                       cfg.tv_w * tvsum;
         // a tcgen05 pipeline wait timed out somewhere upstream (status word, csrc/status.cu): the activations this loss
         // was computed from may contain a bad tile -- report NaN instead of a plausible number
         if (status != nullptr && *reinterpret_cast<const volatile int*>(status) != 0) total = nan("");
         res[0] = (float)total; res[1] = (float)N; res[2] = (float)Dn; res[3] = (float)sh[4];
         res[4] = (float)tv[0]; res[5] = (float)tv[1]; res[6] = (float)tv[2];
         res[7] = (float)dice; res[8] = (float)second; res[9] = (float)tvsum;
+        res[10] = (float)gw[0]; res[11] = (float)gw[1];
     }
 }
 
@@ -186,7 +225,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(const float* __r
     const long long total = (long long)B * S;
     const float go = gout[0];
     const float N = res[1], Dn = res[2], cew = res[3];
-    const float ldice = cfg.kind == 0 ? 1.f : cfg.lambda_dice;
+    const float ldice = (cfg.kind == 0 || cfg.kind == 3) ? 1.f : cfg.lambda_dice;
+    const float gw0 = res[10], gw1 = res[11];
     const float cntz = (float)((double)B * (D - 1) * H * W), cnty = (float)((double)B * D * (H - 1) * W),
                 cntx = (float)((double)B * D * H * (W - 1));
     // gradient pair (d/dl0, d/dl1) of one voxel
@@ -195,9 +235,16 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(const float* __r
         const float d = l1 - l0;
         const float p = sigmoidf_(d);
         // dice: f = 1 - N/Dn
-        const float dP = cfg.squared ? 2.f * p : 1.f;
-        const float dDn = cfg.jaccard ? 2.f * (dP - y) : dP;
-        float gp = ldice * (-(2.f * y * Dn - N * dDn) / (Dn * Dn));     // dL/dp
+        float dN, dDn;                                                   // d numerator / dp, d denominator / dp
+        if (cfg.kind >= 3) {
+            dN = 2.f * (gw1 * y - gw0 * (1.f - y));
+            dDn = gw1 - gw0;
+        } else {
+            const float dP = cfg.squared ? 2.f * p : 1.f;
+            dN = 2.f * y;
+            dDn = cfg.jaccard ? 2.f * (dP - y) : dP;
+        }
+        float gp = ldice * (-(dN * Dn - N * dDn) / (Dn * Dn));           // dL/dp
         if (pbuf != nullptr) {                                           // total variation on p' = p * keep
             long long r = s;
             const int x = (int)(r % W); r /= W;
@@ -220,20 +267,17 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(const float* __r
             gp += cfg.tv_w * gt;
         }
         float gd = gp * p * (1.f - p);                                   // through p = sigmoid(l1 - l0)
-        float g1_extra = 0.f;
+        float g1_extra = 0.f, g0_extra = 0.f;
         if (cfg.kind == 1) {
             const float w = y > 0.f ? cfg.w_fg : cfg.w_bg;
             gd += cfg.lambda_2 * w * (p - y) / cew;
         } else if (cfg.kind == 2) {
-            const float sgn = 2.f * y - 1.f;
-            const float u = -l1 * sgn;
-            const float bce = l1 - l1 * y + softplusf(-l1);
-            const float invp = -softplusf(-u);
-            const float e = __expf(cfg.gamma * invp);
-            const float dfl = e * (cfg.gamma * (-sgn) * sigmoidf_(-u) * bce + (sigmoidf_(l1) - y));
-            g1_extra = cfg.lambda_2 * dfl / (float)total;
+            g1_extra = cfg.lambda_2 * focal_grad(l1, y, cfg.gamma) / (float)total;
+        } else if (cfg.kind == 4) {
+            g1_extra = cfg.lambda_2 * focal_grad(l1, y, cfg.gamma) / (2.f * (float)total);
+            g0_extra = cfg.lambda_2 * focal_grad(l0, 1.f - y, cfg.gamma) / (2.f * (float)total);
         }
-        g0 = -go * gd;
+        g0 = go * (g0_extra - gd);
         g1 = go * (gd + g1_extra);
     };
     const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gn = (long long)gridDim.x * blockDim.x;
@@ -309,9 +353,9 @@ FCD_API int fcd_loss_blocks() { return LOSS_BLOCKS; }
 // when tv_w == 0), keep B*S bytes (only when tv_exclude), res >= 16 floats.
 FCD_API int fcd_loss_fwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
                          float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
-                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
+                         int jaccard, int w_type, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
                          unsigned char* keep, float* pbuf, float* part, float* tvpart, float* res, cudaStream_t st) {
-    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, smooth_nr, smooth_dr, tv_w, tv_norm,
+    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, w_type, smooth_nr, smooth_dr, tv_w, tv_norm,
                 tv_exclude};
     const long long S = (long long)D * H * W;
     const bool tv = tv_w > 0.f;
@@ -330,10 +374,10 @@ FCD_API int fcd_loss_fwd(const float* pred, const float* target, int B, int D, i
 
 FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
                          float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
-                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
+                         int jaccard, int w_type, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
                          const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
                          float* dpred, cudaStream_t st) {
-    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, smooth_nr, smooth_dr, tv_w, tv_norm,
+    LossCfg cfg{kind, lambda_dice, lambda_2, w_bg, w_fg, gamma, squared, jaccard, w_type, smooth_nr, smooth_dr, tv_w, tv_norm,
                 tv_exclude};
     const bool tv = tv_w > 0.f;
     loss_bwd_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, st>>>(pred, target, B, D, H, W, cfg,

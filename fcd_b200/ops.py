@@ -1089,7 +1089,8 @@ def out_conv(x, weight, bias):
 
 
 # ------------------------------------------------------------------------------------------------ loss
-LOSS_KIND = {"DiceLoss": 0, "DiceCELoss": 1, "DiceFocalLoss": 2}
+LOSS_KIND = {"DiceLoss": 0, "DiceCELoss": 1, "DiceFocalLoss": 2, "GeneralizedDiceLoss": 3, "GeneralizedDiceFocalLoss": 4}
+GDICE_WTYPE = {"square": 0, "simple": 1, "uniform": 2}
 
 
 class LossFn(Function):

@@ -178,13 +178,13 @@ FCD_API int fcd_outconv_bwd(const void* x, long long ld, const float* w, const f
 FCD_API int fcd_loss_blocks(void);
 FCD_API int fcd_loss_fwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
                          float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
-                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
-                         unsigned char* keep, float* pbuf, float* part, float* tvpart, float* res,
+                         int jaccard, int w_type, float smooth_nr, float smooth_dr, float tv_w, int tv_norm,
+                         int tv_exclude, unsigned char* keep, float* pbuf, float* part, float* tvpart, float* res,
                          cudaStream_t stream);
 FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, int H, int W, int kind,
                          float lambda_dice, float lambda_2, float w_bg, float w_fg, float gamma, int squared,
-                         int jaccard, float smooth_nr, float smooth_dr, float tv_w, int tv_norm, int tv_exclude,
-                         const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
+                         int jaccard, int w_type, float smooth_nr, float smooth_dr, float tv_w, int tv_norm,
+                         int tv_exclude, const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
                          float* dpred, cudaStream_t stream);
 
 /* ---- TransformerBlock token path: pos_embed add + LayerNorm (conv_blocks.py:72-77) ---- */

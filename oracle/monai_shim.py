@@ -693,6 +693,88 @@ class DiceFocalLoss(nn.Module):
         return self.lambda_dice * self.dice(input, target) + self.lambda_focal * self.focal(input, target)
 
 
+class GeneralizedDiceLoss(nn.Module):
+    """MONAI 1.5.1 monai/losses/dice.py GeneralizedDiceLoss (Sudre et al. 2017), restated from its published
+    algorithm: per-class weights 1/G^2 | 1/G | 1 of the label volumes, infinite weights (absent class) replaced by
+    the largest finite one, ONE ratio over the weighted class sums."""
+
+    def __init__(self, include_background=True, to_onehot_y=False, sigmoid=False, softmax=False, other_act=None,
+                 w_type="square", reduction="mean", smooth_nr=1e-5, smooth_dr=1e-5, batch=False, soft_label=False):
+        super().__init__()
+        if str(w_type) not in ("square", "simple", "uniform"):
+            raise ValueError(f"w_type {w_type!r}")
+        self.include_background, self.to_onehot_y = include_background, to_onehot_y
+        self.sigmoid, self.softmax, self.w_type, self.reduction = sigmoid, softmax, str(w_type), reduction
+        self.smooth_nr, self.smooth_dr, self.batch = float(smooth_nr), float(smooth_dr), batch
+
+    def w_func(self, grnd):
+        if self.w_type == "simple":
+            return torch.reciprocal(grnd)
+        if self.w_type == "square":
+            return torch.reciprocal(grnd * grnd)
+        return torch.ones_like(grnd)
+
+    def forward(self, input, target):
+        if self.sigmoid:
+            input = torch.sigmoid(input)
+        n_pred_ch = input.shape[1]
+        if self.softmax and n_pred_ch != 1:
+            input = torch.softmax(input, 1)
+        if self.to_onehot_y and n_pred_ch != 1:
+            target = one_hot(target, num_classes=n_pred_ch)
+        if not self.include_background and n_pred_ch != 1:
+            target = target[:, 1:]
+            input = input[:, 1:]
+        if target.shape != input.shape:
+            raise AssertionError(f"ground truth has differing shape ({target.shape}) from input ({input.shape})")
+        reduce_axis = torch.arange(2, len(input.shape)).tolist()
+        if self.batch:
+            reduce_axis = [0] + reduce_axis
+        intersection = torch.sum(target * input, reduce_axis)
+        ground_o = torch.sum(target, reduce_axis)
+        pred_o = torch.sum(input, reduce_axis)
+        denominator = ground_o + pred_o
+        w = self.w_func(ground_o.float())
+        infs = torch.isinf(w)
+        if self.batch:
+            w[infs] = 0.0
+            w = w + infs * torch.max(w)
+        else:
+            w[infs] = 0.0
+            max_values = torch.max(w, dim=1)[0].unsqueeze(dim=1)
+            w = w + infs * max_values
+        final_reduce_dim = 0 if self.batch else 1
+        numer = 2.0 * (intersection * w).sum(final_reduce_dim, keepdim=True) + self.smooth_nr
+        denom = (denominator * w).sum(final_reduce_dim, keepdim=True) + self.smooth_dr
+        f = 1.0 - (numer / denom)
+        if self.reduction == "mean":
+            f = torch.mean(f)
+        elif self.reduction == "sum":
+            f = torch.sum(f)
+        return f
+
+
+class GeneralizedDiceFocalLoss(nn.Module):
+    """MONAI 1.5.1 GeneralizedDiceFocalLoss: lambda_gdl * GeneralizedDiceLoss + lambda_focal * FocalLoss, both with the
+    caller's include_background / to_onehot_y."""
+
+    def __init__(self, include_background=True, to_onehot_y=False, sigmoid=False, softmax=False, other_act=None,
+                 w_type="square", reduction="mean", smooth_nr=1e-5, smooth_dr=1e-5, batch=False, gamma=2.0,
+                 focal_weight=None, weight=None, lambda_gdl=1.0, lambda_focal=1.0):
+        super().__init__()
+        self.generalized_dice = GeneralizedDiceLoss(include_background=include_background, to_onehot_y=to_onehot_y,
+                                                    sigmoid=sigmoid, softmax=softmax, w_type=w_type,
+                                                    reduction=reduction, smooth_nr=smooth_nr, smooth_dr=smooth_dr,
+                                                    batch=batch)
+        weight = focal_weight if focal_weight is not None else weight
+        self.focal = FocalLoss(include_background=include_background, to_onehot_y=to_onehot_y, gamma=gamma,
+                               weight=weight, reduction=reduction)
+        self.lambda_gdl, self.lambda_focal = lambda_gdl, lambda_focal
+
+    def forward(self, input, target):
+        return self.lambda_gdl * self.generalized_dice(input, target) + self.lambda_focal * self.focal(input, target)
+
+
 class _Unavailable(nn.Module):
     def __init__(self, *a, **k):
         raise NotImplementedError("out of scope (SURVEY.md section 2): not restated by the shim")
@@ -816,7 +898,7 @@ def install():
     _mod("monai.networks.nets", SegResNet=SegResNet, SegResNetVAE=SegResNetVAE, UNETR=_Unavailable,
          SwinUNETR=_Unavailable, VNet=_Unavailable, UNet=_Unavailable)
     _mod("monai.losses", DiceLoss=DiceLoss, DiceCELoss=DiceCELoss, DiceFocalLoss=DiceFocalLoss, FocalLoss=FocalLoss,
-         GeneralizedDiceLoss=_Unavailable, GeneralizedDiceFocalLoss=_Unavailable)
+         GeneralizedDiceLoss=GeneralizedDiceLoss, GeneralizedDiceFocalLoss=GeneralizedDiceFocalLoss)
     _mod("monai.inferers", sliding_window_inference=sliding_window_inference)
     if "thop" not in sys.modules:
         _mod("thop", profile=lambda *a, **k: (0, 0), clever_format=lambda x, *a, **k: x)

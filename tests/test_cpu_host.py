@@ -99,7 +99,12 @@ def test_loss_config_mapping():
                                             tv_loss_weight=0.1, tv_loss_norm="l2", tvloss_exclude_borders=True)))
     c = loss_config(p)
     assert c["kind"] == 2 and c["gamma"] == 3.0 and c["lambda_2"] == 2.0 and c["tv_norm"] == 2 and c["tv_exclude"] == 1
-    for bad in (dict(loss="GeneralizedDiceLoss"), dict(sigmoid=True), dict(chans_out=3)):
+    g = loss_config(dict(p, loss="GeneralizedDiceFocalLoss", gdice_wtype="simple", lambda_dice=0.7))
+    assert g["kind"] == 4 and g["w_type"] == 1 and g["lambda_dice"] == 0.7 and g["lambda_2"] == 2.0
+    assert loss_config(dict(p, loss="GeneralizedDiceLoss"))["w_type"] == 0          # config.py default 'square'
+    with pytest.raises(ValueError):
+        loss_config(dict(p, loss="GeneralizedDiceLoss", gdice_wtype="cubic"))
+    for bad in (dict(loss="TverskyLoss"), dict(sigmoid=True), dict(chans_out=3)):
         q = dict(p)
         q.update(bad)
         with pytest.raises(NotImplementedError):

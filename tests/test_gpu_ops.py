@@ -316,6 +316,10 @@ LOSS_CASES = [
     dict(loss="DiceCELoss", tv_loss_weight=0.1), dict(loss="DiceCELoss", tv_loss_weight=0.1, tv_loss_norm="l2"),
     dict(loss="DiceCELoss", tv_loss_weight=0.1, tvloss_exclude_borders=True),
     dict(loss="DiceFocalLoss", tv_loss_weight=0.2, tv_loss_norm="l2", tvloss_exclude_borders=True),
+    dict(loss="GeneralizedDiceLoss"), dict(loss="GeneralizedDiceLoss", gdice_wtype="simple"),
+    dict(loss="GeneralizedDiceLoss", gdice_wtype="uniform"),
+    dict(loss="GeneralizedDiceFocalLoss", lambda_dice=0.7, lambda_focal=2.0, gamma_focal=3.0),
+    dict(loss="GeneralizedDiceFocalLoss", gdice_wtype="simple", tv_loss_weight=0.1),
 ]
 
 

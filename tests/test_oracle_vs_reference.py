@@ -126,7 +126,10 @@ def test_combined_loss_matches_reference():
     pred = synth.tensor((1, 2, 12, 14, 16), "lp", 1, 2.0, dist="normal")
     tgt = synth.label(1, (12, 14, 16), seed=2)
     for over in (dict(loss="DiceCELoss"), dict(loss="DiceFocalLoss", tv_loss_weight=0.1, tv_loss_norm="l2"),
-                 dict(loss="DiceLoss", tv_loss_weight=0.3, tvloss_exclude_borders=True)):
+                 dict(loss="DiceLoss", tv_loss_weight=0.3, tvloss_exclude_borders=True),
+                 dict(loss="GeneralizedDiceLoss"), dict(loss="GeneralizedDiceLoss", gdice_wtype="simple"),
+                 dict(loss="GeneralizedDiceFocalLoss", gdice_wtype="uniform", lambda_dice=0.7, gamma_focal=3.0),
+                 dict(loss="GeneralizedDiceFocalLoss", tv_loss_weight=0.1)):
         p = dict(base)
         p.update(over)
         ref = gl.CombinedLoss(p, torch.device("cpu"))(pred, tgt)

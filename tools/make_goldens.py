@@ -103,6 +103,11 @@ def run_loss_cases():
         "dicece_tv_l1_xb": dict(loss="DiceCELoss", tv_loss_weight=0.1, tvloss_exclude_borders=True),
         "dicefocal_tv_l2_xb": dict(loss="DiceFocalLoss", tv_loss_weight=0.2, tv_loss_norm="l2",
                                    tvloss_exclude_borders=True),
+        "gdice": dict(loss="GeneralizedDiceLoss"),
+        "gdice_simple": dict(loss="GeneralizedDiceLoss", gdice_wtype="simple"),
+        "gdice_uniform": dict(loss="GeneralizedDiceLoss", gdice_wtype="uniform"),
+        "gdicefocal": dict(loss="GeneralizedDiceFocalLoss", lambda_dice=0.7, lambda_focal=2.0, gamma_focal=3.0),
+        "gdicefocal_simple_tv": dict(loss="GeneralizedDiceFocalLoss", gdice_wtype="simple", tv_loss_weight=0.1),
     }
     pred = synth.tensor((2, 2, 20, 24, 28), "loss_pred", 11, 2.0, dist="normal")
     tgt = synth.label(2, (20, 24, 28), seed=13)
