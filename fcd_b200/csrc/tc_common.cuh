@@ -1,5 +1,5 @@
-// Blackwell (sm_100a) building blocks shared by the tcgen05 kernels: mbarrier, TMEM allocation / loads / stores,
-// UMMA shared-memory + instruction descriptors, tcgen05.mma / commit.
+// Blackwell (sm_100a) building blocks shared by the tcgen05 kernels: mbarrier, TMA tensor-map loads, TMEM allocation /
+// loads / stores, UMMA shared-memory + instruction descriptors, tcgen05.mma / commit.
 //
 // Every wait is BOUNDED: a pipeline bug must not hang the GPU.  A wait that exceeds kWaitCycles sets the CTA-wide
 // `dead` flag (all later waits fall through at once) and the library-wide status block (csrc/status.cu): the sticky
@@ -87,6 +87,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, WaitCtx
     }
 }
 
+// ---------------------------------------------------------------------------------------------- TMA (tensor maps)
+// cp.async.bulk.tensor: ONE thread moves a whole box of a tiled tensor map into shared memory; out-of-bounds elements
+// (negative or too-large coordinates: the halo of a conv tile) arrive as zeros and still count towards the transaction
+// bytes the mbarrier expects.
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {   // one full warp
@@ -130,6 +160,14 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
     const uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+// K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+// (SBO), 16-byte chunks XOR-swizzled by the row index inside a group; the tile base must be 1024-byte aligned.  LBO is
+// not used by swizzled K-major layouts (1 by convention); a 16-element K step advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (1u << 16);
+    const uint32_t hi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
 // advance the start address of a descriptor by `bytes` (multiple of 16; no carry out of the 14-bit field allowed)

@@ -515,6 +515,21 @@ def _tc_nslice_nseg(B, D, H, W, K, N, k, stride, pad, bias, cin_seg, Co, Ci):
     return _lib.lib().fcd_conv3_tc_nseg(B, D, H, W, 64, 32)
 
 
+# 3x3x3 convs with 64-multiple channel counts on both sides that the sliced kd-folded launches would take (64 -> 128 as
+# four 32-channel slices, 64 -> 64 as two halves) go to the TMA-fed split-K GEMM instead when the volume has at most this
+# many voxels (batch included): there the slices are short columns on a few CTAs, the GEMM fills the GPU by splitting K
+GEMM_FIRST_M = int(os.environ.get("FCD_GEMM_FIRST_M", "65536"))
+
+
+def _gemm_preferred(B, D, H, W, K, N, k, stride, pad, bias):
+    if not (USE_TC and USE_GEMM_TC and k == 3 and stride == 1 and pad == 1 and bias is None):
+        return False
+    if K % 64 or N % 64 or B * D * H * W > GEMM_FIRST_M:
+        return False
+    L = _lib.lib()
+    return bool(L.fcd_conv_gemm_tc_tma_ok(B, D, H, W)) and L.fcd_conv_gemm_tc_ksplit_vol(B, D, H, W, K, N) > 0
+
+
 USE_PW = os.environ.get("FCD_USE_PW", "1") != "0"
 
 
@@ -535,8 +550,8 @@ def _igemm(a, wp, c, bias, B, src, dst, K, N, k, stride, pad, mode):
     """Legacy (mma.sync) implicit GEMM into contiguous rows of c; split-K when the output grid cannot fill the SMs."""
     M = B * dst[0] * dst[1] * dst[2]
     if USE_TC and USE_GEMM_TC and k == 3 and stride == 1 and pad == 1 and bias is None and tuple(src) == tuple(dst):
-        ks = _lib.lib().fcd_conv_gemm_tc_ksplit(M, K, N)
-        if ks > 0:          # deep levels: tcgen05 split-K GEMM with streamed weights
+        ks = _lib.lib().fcd_conv_gemm_tc_ksplit_vol(B, dst[0], dst[1], dst[2], K, N)
+        if ks > 0:          # deep levels: tcgen05 split-K GEMM with streamed weights (TMA halo tiles where they apply)
             ws = torch.empty((ks, M, N), dtype=torch.float32, device=a.device) if ks > 1 else None
             call("fcd_conv_gemm_tc", A=a, lda=ld(a), Wp=wp, C=c, ldc=ld(c), ws=ws, Bn=B, D=dst[0], H=dst[1], W=dst[2],
                  K=K, N=N, mode=mode, ksplit=ks)
@@ -599,6 +614,9 @@ class ConvFn(Function):
             _conv3_call(_conv3_entry(Kp, Np), A=x, lda=ld(x), Wf=_w32(weight), Nr=Co, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                  ksegpad=segpad, nsg=Co, nsgpad=Np, C=y, ldc=Np, part=part, Bn=B, D=D, H=H, W=W, K=Kp, N=Np, flip=0,
                  nseg=nseg, **fin)
+        elif _gemm_preferred(B, D, H, W, Kp, Np, k, stride, pad, bias):
+            wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
+            _igemm(x, wp, y, None, B, (D, H, W), (Do, Ho, Wo), Kp, Np, k, stride, pad, 0)
         elif _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg) > 0:
             nsw = _tc_wide_nseg(B, D, H, W, Kp, Np, k, stride, pad, cin_seg)
             w32 = _w32(weight)
@@ -646,6 +664,9 @@ class ConvFn(Function):
                 _conv3_call(_conv3_entry(Np, Kp), A=dy, lda=ld(dy), Wf=_w32(weight), Nr=Ci, Kr=Co, sn=T, sk=Ci * T, st=1, kseg=Co,
                      ksegpad=Np, nsg=seg, nsgpad=segpad, C=dx, ldc=Kp, part=None, Bn=B, D=D, H=H, W=W, K=Np, N=Kp,
                      flip=1, nseg=nseg, **_NOFIN)
+            elif _gemm_preferred(B, D, H, W, Np, Kp, k, stride, pad, None):
+                wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
+                _igemm(dy, wt, dx, None, B, (Do, Ho, Wo), (D, H, W), Np, Kp, k, stride, pad, 1)
             elif _tc_wide_dgrad_nseg(B, D, H, W, Np, Kp, k, stride, pad, seg, Ci) > 0:
                 # conv with more than 64 output channels (sub-pixel upsampling): dX = sum over 64-channel slices of dY of
                 # a kd-folded data-gradient launch each, the later ones accumulating into dX (bf16 read-modify-write)

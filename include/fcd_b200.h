@@ -68,8 +68,14 @@ FCD_API int fcd_splitk_reduce(const float* ws, void* C, long long ldc, const flo
  * 393-416 at encoder levels 3-6 / decoder / TransformerBlock.conv51): streamed packed weights, 128-voxel x up-to-256-
  * channel tiles, (tap, k-chunk) loop split over gridDim.z.  mode 0 forward, 1 data gradient. */
 FCD_API int fcd_conv_gemm_tc_ksplit(long long M, int K, int N);
+FCD_API int fcd_conv_gemm_tc_ksplit_vol(int Bn, int D, int H, int W, int K, int N);
 FCD_API int fcd_conv_gemm_tc(const void* A, long long lda, const void* Wp, void* C, long long ldc, float* ws, int Bn,
                              int D, int H, int W, int K, int N, int mode, int ksplit, cudaStream_t stream);
+/* feed selection: volumes whose 128-voxel row tiles are boxes (W, H, D powers of two) are fed by TMA halo tiles
+ * (cp.async.bulk.tensor, out-of-volume coordinates = the zero padding); use_tma(0) forces the cp.async feed, (-1) only
+ * queries; both return the previous setting. */
+FCD_API int fcd_conv_gemm_tc_use_tma(int on);
+FCD_API int fcd_conv_gemm_tc_tma_ok(int Bn, int D, int H, int W);
 FCD_API int fcd_gemm_tc_error(void);
 /* weight gradient of the same deep-level convs: voxels as the GEMM K dimension, 128 input channels x up to 256 output
  * channels per CTA, one CTA per (tap, tile, voxel slice); part[nsplit][27][Np][Kp] is finished by fcd_wgrad_reduce. */

@@ -349,15 +349,50 @@ GEMM_TC_CASES = [
     (2, 512, 512, 8, 8, 8),
     (2, 128, 128, 16, 16, 16),
     (1, 128, 64, 32, 32, 32),  # enough row tiles for ksplit 1: direct bf16 output
-    (1, 192, 64, 11, 10, 13),  # ragged volume: the last row tile is partial
+    (1, 192, 64, 11, 10, 13),  # ragged volume: the last row tile is partial (never a TMA box)
+    (16, 128, 64, 4, 4, 4),    # a 128-voxel tile spans two samples: the TMA box has a batch extent of 2
+    (4, 128, 64, 4, 8, 8),     # tiles of 8 x 8 x 2 voxels, D = 4: halo planes above / below every tile
+    (1, 128, 128, 2, 4, 128),  # W = 128: one row per tile
+]
+GEMM_TMA_ONLY_CASES = [
+    (2, 64, 64, 16, 16, 16),   # 64 input channels: taken only with the TMA feed (TransformerBlock.conv51 at level 4)
+    (2, 64, 128, 16, 16, 16),  # encoder4.conv1
+    (2, 256, 512, 4, 4, 4),    # the 4^3 level: ONE 128-voxel tile spanning both samples, 64-channel N tiles x 27 splits
+    (2, 512, 512, 4, 4, 4),
+    (4, 256, 256, 4, 4, 4),
 ]
 
 
+@pytest.mark.parametrize("tma", [1, 0])
 @pytest.mark.parametrize("B,Ci,Co,D,H,W", GEMM_TC_CASES)
-def test_conv_gemm_tc_fwd_bwd(ops, B, Ci, Co, D, H, W):
-    """Deep-level convs through the tcgen05 split-K GEMM kernel (forward + data gradient) vs torch fp32."""
+def test_conv_gemm_tc_fwd_bwd(ops, B, Ci, Co, D, H, W, tma):
+    """Deep-level convs through the tcgen05 split-K GEMM kernel (forward + data gradient) vs torch fp32, with both
+    operand feeds: TMA halo tiles (cp.async.bulk.tensor, zero padding = out-of-volume coordinates) where 128 consecutive
+    voxels form a box, and the cp.async gather."""
     from fcd_b200 import _lib
     assert _lib.lib().fcd_conv_gemm_tc_ksplit(B * D * H * W, Ci, Co) > 0
+    prev = _lib.lib().fcd_conv_gemm_tc_use_tma(tma)
+    try:
+        ragged = (D, H, W) == (11, 10, 13)
+        assert _lib.lib().fcd_conv_gemm_tc_tma_ok(B, D, H, W) == (1 if (tma and not ragged) else 0)
+        _conv_gemm_tc_case(ops, B, Ci, Co, D, H, W)
+    finally:
+        _lib.lib().fcd_conv_gemm_tc_use_tma(prev)
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W", GEMM_TMA_ONLY_CASES)
+def test_conv_gemm_tc_tma_only_shapes(ops, B, Ci, Co, D, H, W):
+    """Shapes the GEMM kernel takes only because the TMA feed removed the producer limit."""
+    from fcd_b200 import _lib
+    L = _lib.lib()
+    assert L.fcd_conv_gemm_tc_ksplit(B * D * H * W, Ci, Co) == 0 or Ci >= 128
+    assert L.fcd_conv_gemm_tc_tma_ok(B, D, H, W) == 1 and L.fcd_conv_gemm_tc_ksplit_vol(B, D, H, W, Ci, Co) > 0
+    assert ops._gemm_preferred(B, D, H, W, Ci, Co, 3, 1, 1, None)
+    _conv_gemm_tc_case(ops, B, Ci, Co, D, H, W)
+
+
+def _conv_gemm_tc_case(ops, B, Ci, Co, D, H, W):
+    from fcd_b200 import _lib
     x = rnd(B, Ci, D, H, W)
     w = rnd(Co, Ci, 3, 3, 3, scale=(2.0 / (Ci * 27)) ** 0.5, seed=1).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
