@@ -530,6 +530,13 @@ def _gemm_preferred(B, D, H, W, K, N, k, stride, pad, bias):
     return bool(L.fcd_conv_gemm_tc_tma_ok(B, D, H, W)) and L.fcd_conv_gemm_tc_ksplit_vol(B, D, H, W, K, N) > 0
 
 
+USE_ROWGEMM = os.environ.get("FCD_ROWGEMM", "1") != "0"   # persistent TMA + tcgen05 kernel for 1x1x1 convs / k2s2 deconvs
+
+
+def _rowgemm_ok(mode, B, D, H, W, M, K, N):
+    return bool(USE_TC and USE_ROWGEMM and _lib.lib().fcd_rowgemm_ok(mode, B, D, H, W, M, K, N))
+
+
 USE_PW = os.environ.get("FCD_USE_PW", "1") != "0"
 
 
@@ -635,6 +642,11 @@ class ConvFn(Function):
                 _conv3_call("fcd_conv3_tcf", A=x, lda=ld(x), Wf=w32[32 * i:], Nr=32, Kr=Ci, sn=Ci * T, sk=T, st=1, kseg=seg,
                      ksegpad=segpad, nsg=32, nsgpad=32, C=y[..., 32 * i:], ldc=Np, part=None, Bn=B, D=D, H=H, W=W, K=Kp,
                      N=32, flip=0, nseg=ns2, **_NOFIN)
+        elif k == 1 and stride == 1 and pad == 0 and _rowgemm_ok(0, B, D, H, W, B * D * H * W, Kp, Np):
+            # 1x1x1 conv / linear rows on a big volume: persistent TMA + tcgen05 kernel, weights resident in shared memory
+            wp = pack_weight(weight, T, Co, Ci, Np, Kp, sn=Ci * T, sk=T, st=1, kseg=seg, ksegpad=segpad)
+            call("fcd_rowgemm", mode=0, A=x, lda=ld(x), Wp=wp, C=y, ldc=Np, bias=_vpad(bias, Np), Bn=B, D=D, H=H, W=W,
+                 M=B * D * H * W, K=Kp, N=Np, Cq=0)
         elif _pw_ok(B * D * H * W, Kp, Np, k, stride, pad, bias):
             call("fcd_pw_conv", A=x, lda=ld(x), Wf=_w32(weight), sn=Ci, sk=1, Nr=Co, Kr=Ci, kseg=seg, ksegpad=segpad,
                  nsg=Co, nsgpad=Np, C=y, ldc=Np, M=B * D * H * W, K=Kp, N=Np)
@@ -685,6 +697,10 @@ class ConvFn(Function):
                     _conv3_call("fcd_conv3_tcf", A=dy, lda=ld(dy), Wf=w32[32 * i * T:], Nr=32, Kr=Co, sn=T, sk=Ci * T, st=1,
                          kseg=Co, ksegpad=Np, nsg=32, nsgpad=32, C=dx[..., 32 * i:], ldc=Kp, part=None, Bn=B, D=D, H=H,
                          W=W, K=Np, N=32, flip=1, nseg=ns2, **_NOFIN)
+            elif k == 1 and stride == 1 and pad == 0 and _rowgemm_ok(0, B, D, H, W, B * D * H * W, Np, Kp):
+                wt = pack_weight(weight, T, Ci, Co, Kp, Np, sn=T, sk=Ci * T, st=1, nseg=seg, nsegpad=segpad)
+                call("fcd_rowgemm", mode=0, A=dy, lda=ld(dy), Wp=wt, C=dx, ldc=Kp, bias=None, Bn=B, D=D, H=H, W=W,
+                     M=B * D * H * W, K=Np, N=Kp, Cq=0)
             elif _pw_ok(B * D * H * W, Np, Kp, k, stride, pad, None):
                 # dX rows = dY rows x W: the same pointwise kernel with the weight read transposed
                 call("fcd_pw_conv", A=dy, lda=ld(dy), Wf=_w32(weight), sn=1, sk=Ci, Nr=Ci, Kr=Co, kseg=Co, ksegpad=Np,
@@ -770,8 +786,14 @@ class DeconvFn(Function):
         wp = pack_weight(weight, 8, Co, Ci, Cq, Kp, sn=8, sk=Co * 8, st=1)
         buf = _empty((B, 2 * D, 2 * H, 2 * W, Cq + Cs), x)
         _lib.note_work("deconv_fwd", 2.0 * B * D * H * W * 8 * Co * Ci, 2.0 * B * D * H * W * (Ci + 8 * Co))
-        call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=_vpad(bias, Cq), Bn=B, Ds=D, Hs=H, Ws=W, Dm=D,
-             Hm=H, Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0, Cq=Cq)
+        if _rowgemm_ok(1, B, D, H, W, B * D * H * W, Kp, 8 * Cq):
+            # one GEMM row per coarse voxel, N = 8 * Cq columns scattered to the 2x2x2 fine voxels by the epilogue
+            call("fcd_rowgemm", mode=1, A=x, lda=ld(x), Wp=wp, C=buf, ldc=Cq + Cs, bias=_vpad(bias, Cq), Bn=B, D=D, H=H,
+                 W=W, M=B * D * H * W, K=Kp, N=8 * Cq, Cq=Cq)
+        else:
+            call("fcd_igemm", A=x, lda=ld(x), W=wp, C=buf, ldc=Cq + Cs, bias=_vpad(bias, Cq), Bn=B, Ds=D, Hs=H, Ws=W,
+                 Dm=D, Hm=H, Wm=W, K=Kp, N=8 * Cq, kd=1, kh=1, kw=1, stride=1, pad=0, mode=0, out_mode=1, accumulate=0,
+                 Cq=Cq)
         if mode == "concat":
             right = buf[..., Cq:]
             call("fcd_copy_rows", a=skip, lda=ld(skip), o=right, ldo=Cq + Cs, rows=B * 8 * D * H * W, C=Cs)
@@ -796,9 +818,14 @@ class DeconvFn(Function):
             wt = pack_weight(weight, 8, Ci, Co, Kp, Cq, sn=Co * 8, sk=8, st=1)
             dx = _empty((B, D, H, W, Kp), x)
             _lib.note_work("deconv_dgrad", 2.0 * B * D * H * W * 8 * Co * Ci, 2.0 * B * D * H * W * (Ci + 8 * Co))
-            call("fcd_igemm", A=dleft, lda=ld(dbuf), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=2 * D, Hs=2 * H,
-                 Ws=2 * W, Dm=D, Hm=H, Wm=W, K=Cq, N=Kp, kd=2, kh=2, kw=2, stride=2, pad=0, mode=0, out_mode=0,
-                 accumulate=0, Cq=0)
+            if _rowgemm_ok(2, B, D, H, W, B * D * H * W, Cq, Kp):
+                # eight taps, each a strided TMA box of the fine grid, accumulated in TMEM
+                call("fcd_rowgemm", mode=2, A=dleft, lda=ld(dbuf), Wp=wt, C=dx, ldc=Kp, bias=None, Bn=B, D=D, H=H, W=W,
+                     M=B * D * H * W, K=Cq, N=Kp, Cq=0)
+            else:
+                call("fcd_igemm", A=dleft, lda=ld(dbuf), W=wt, C=dx, ldc=Kp, bias=None, Bn=B, Ds=2 * D, Hs=2 * H,
+                     Ws=2 * W, Dm=D, Hm=H, Wm=W, K=Cq, N=Kp, kd=2, kh=2, kw=2, stride=2, pad=0, mode=0, out_mode=0,
+                     accumulate=0, Cq=0)
         if ctx.needs_input_grad[2]:
             B_ = x.shape[0]
             M = B_ * D * H * W

@@ -26,7 +26,7 @@
 #endif
 
 /* ---- status block: every pipeline wait of the tcgen05 kernels is bounded; the first wait that times out writes the
- * sticky error word (kernel id << 24 | wait site << 16 | CTA; kernel ids: 1 fcd_conv3_tc, 2 fcd_conv3_tcf,
+ * sticky error word (kernel id << 24 | wait site << 16 | CTA; kernel ids: 1 fcd_conv3_tc, 2 fcd_conv3_tcf, 6 fcd_rowgemm,
  * 3 fcd_conv_gemm_tc, 4 fcd_wgrad3_tc, 5 fcd_wgrad_gemm_tc) and a debug record into a device-resident block of
  * FCD_STATUS_INTS ints: [0] error word, [1] kernel id, [2] wait site, [3] CTA, [4] thread, [5] mbarrier shared
  * address, [6] parity waited for, [7] work item, [8] grid size, [9] blockIdx.y, [16..48) the CTA's per-role progress
@@ -64,6 +64,15 @@ FCD_API int fcd_igemm_splitk(const void* A, long long lda, const void* W, void* 
                              cudaStream_t stream);
 FCD_API int fcd_splitk_reduce(const float* ws, void* C, long long ldc, const float* bias, long long M, int N, int ksplit,
                               int accumulate, cudaStream_t stream);
+/* Pointwise contractions on large volumes -- 1x1x1 Conv3d / nn.Linear rows (conv_blocks.py:420-437, 57, 225;
+ * ms_dsa_net.py:215) and ConvTranspose3d k2 s2 (conv_blocks.py:640-649) forward / data gradient -- as ONE persistent
+ * TMA + tcgen05 kernel (csrc/rowgemm_tma.cu): 128-row tiles streamed by cp.async.bulk.tensor, weights resident in shared
+ * memory, two TMEM accumulators.  mode 0: C[m][n] = sum_k A[m][k] Wp[n][k] + bias[n]; mode 1: N = 8*Cq columns scattered
+ * to the 2x2x2 fine voxels of the coarse voxel m (C = the fine, possibly concat, buffer); mode 2: data gradient of the
+ * transposed conv (A = the fine grid, 8 strided taps).  K in {16,32,64}, N in {16,...,256}; _ok() = 1 if taken. */
+FCD_API int fcd_rowgemm_ok(int mode, int Bn, int D, int H, int W, long long M, int K, int N);
+FCD_API int fcd_rowgemm(int mode, const void* A, long long lda, const void* Wp, void* C, long long ldc, const float* bias,
+                        int Bn, int D, int H, int W, long long M, int K, int N, int Cq, cudaStream_t stream);
 /* tcgen05 split-K GEMM form of the 3x3x3 stride-1 pad-1 convs of the DEEP levels (K, N multiples of 64; conv_blocks.py:
  * 393-416 at encoder levels 3-6 / decoder / TransformerBlock.conv51): streamed packed weights, 128-voxel x up-to-256-
  * channel tiles, (tap, k-chunk) loop split over gridDim.z.  mode 0 forward, 1 data gradient. */
