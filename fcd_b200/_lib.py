@@ -21,6 +21,7 @@ _CT = {
     "float": ctypes.c_float,
     "double": ctypes.c_double,
     "long long": ctypes.c_longlong,
+    "unsigned long long": ctypes.c_ulonglong,
     "cudaStream_t": ctypes.c_void_p,
 }
 

@@ -24,6 +24,14 @@ namespace {
 constexpr int LOSS_BLOCKS = 592;   // 4 x 148
 constexpr int LOSS_THREADS = 256;
 
+// streaming (read-once) 16-byte fp32 load that does not allocate in L1
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float softplusf(float x) { return x > 0.f ? x + log1pf(__expf(-x)) : log1pf(__expf(x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
@@ -97,14 +105,27 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_fwd_kernel(const float* __r
     if ((S & 3) == 0 && (((uintptr_t)pred | (uintptr_t)target) & 15) == 0) {
         // four consecutive voxels per thread: 16-byte loads of both logit planes and of the label (3 independent 16 B
         // loads in flight per thread instead of 3 scalar ones; one 64-bit division per 4 voxels)
-        const long long S4 = S >> 2;
-        for (long long j = gtid; j < (long long)B * S4; j += gn) {
+        // two such groups per iteration: six independent 16 B loads in flight per thread before the first
+        // transcendental (the kernel moves 100 MB in ~15 us at the HBM roofline: latency, not arithmetic, is what it hides)
+        const long long S4 = S >> 2, n4 = (long long)B * S4;
+        for (long long j = gtid; j < n4; j += 2 * gn) {
+            const long long j2 = j + gn;
+            const bool two = j2 < n4;
             const long long b = j / S4, s = (j - b * S4) << 2;
-            const float4 l0 = *reinterpret_cast<const float4*>(pred + (b * 2) * S + s);
-            const float4 l1 = *reinterpret_cast<const float4*>(pred + (b * 2 + 1) * S + s);
-            const float4 t = *reinterpret_cast<const float4*>(target + b * S + s);
+            const long long b2 = two ? j2 / S4 : b, s2 = two ? (j2 - b2 * S4) << 2 : s;
+            const float4 l0 = ldg_stream4(pred + (b * 2) * S + s);
+            const float4 l1 = ldg_stream4(pred + (b * 2 + 1) * S + s);
+            const float4 t = ldg_stream4(target + b * S + s);
+            const float4 m0 = ldg_stream4(pred + (b2 * 2) * S + s2);
+            const float4 m1 = ldg_stream4(pred + (b2 * 2 + 1) * S + s2);
+            const float4 u = ldg_stream4(target + b2 * S + s2);
             const long long i = b * S + s;
             voxel(l0.x, l1.x, t.x, i); voxel(l0.y, l1.y, t.y, i + 1); voxel(l0.z, l1.z, t.z, i + 2); voxel(l0.w, l1.w, t.w, i + 3);
+            if (two) {
+                const long long i2 = b2 * S + s2;
+                voxel(m0.x, m1.x, u.x, i2); voxel(m0.y, m1.y, u.y, i2 + 1); voxel(m0.z, m1.z, u.z, i2 + 2);
+                voxel(m0.w, m1.w, u.w, i2 + 3);
+            }
         }
     } else {
         for (long long i = gtid; i < total; i += gn) {

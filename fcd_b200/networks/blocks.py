@@ -176,14 +176,15 @@ class DSA(nn.Module):
     'parallel' by giving the missing value projection zero weights: x_CA = attn_CA @ 0 (spatial) or
     x_SA = attn_SA @ (0 . EF)^T (channel) vanish exactly, forward and backward, and the parameters the reference branch
     never touches (temperature / temperature2, EF) are passed detached so that their .grad stays None as there.
-    'serial' (281-314) feeds the spatial output through the channel attention -- a different data flow, not built."""
+    'serial' (281-314) feeds the spatial output -- head-merged, not scrambled -- through the channel attention as its
+    value: two passes of the same kernels (spatial with t = 0, gamma = 1; its output un-scrambled by an index permutation
+    and placed in the v_CA slot of the second pass, which runs the channel branch with the residual and gamma)."""
 
     def __init__(self, input_size, hidden_size, proj_size, num_heads=4, qkv_bias=False, channel_attn_drop=0.1,
                  spatial_attn_drop=0.1, sa_type="parallel"):
         super().__init__()
-        if sa_type not in ("parallel", "spatial", "channel"):
-            raise NotImplementedError("fcd_b200 DSA implements sa_type 'parallel', 'spatial' and 'channel'; 'serial' "
-                                      "(conv_blocks.py:281-314) is listed as next in SURVEY 8f rank 4")
+        if sa_type not in ("parallel", "spatial", "channel", "serial"):
+            raise ValueError(f"sa_type {sa_type!r}: expected parallel, serial, spatial or channel (conv_blocks.py:213)")
         if qkv_bias:
             raise NotImplementedError("qkv_bias=True is never used by get_model")
         self.num_heads = num_heads
@@ -207,6 +208,8 @@ class DSA(nn.Module):
         """ln = LayerNorm(t); returns t + gamma * DSA(ln) (the residual of TransformerBlock line 77 is fused)."""
         w = self.qkvv.weight
         EF, temp, temp2 = self.EF, self.temperature, self.temperature2
+        if self.sa_type == "serial":
+            return self._forward_serial(ln, t, gamma)
         if self.sa_type != "parallel":
             C = self.hidden_size
             zero = w.new_zeros((C, C))
@@ -228,6 +231,32 @@ class DSA(nn.Module):
                 sa_p = float(self.attn_drop_2.p)
                 seed = _host_rng.getrandbits(62)     # host-side counter RNG: no device sync
         return ops.dsa_attention(qkvv, t, EF, temp, temp2, gamma, self.hidden_size, H, self.proj_size, ca_scale, sa_p, seed)
+
+
+    def _forward_serial(self, ln, t, gamma):
+        """forward_serial (conv_blocks.py:281-314): x = attn_CA @ (attn_SA @ v_proj^T)^T, head-merged."""
+        C, H, c, P = self.hidden_size, self.num_heads, self.head_dim, self.proj_size
+        w = self.qkvv.weight
+        w1 = torch.cat([w[:2 * C], w.new_zeros((C, C)), w[2 * C:]], 0)          # rows: q | k | v_CA = 0 | v_SA
+        qkvv = ops.linear(ln, w1)
+        ca_scale, sa_p, seed = None, 0.0, 0
+        if self.training:
+            if self.attn_drop.p > 0:
+                ca_scale = ops.keep_scale((t.shape[0], H, c, c), self.attn_drop.p, t.device)
+            if self.attn_drop_2.p > 0:
+                sa_p = float(self.attn_drop_2.p)
+                seed = _host_rng.getrandbits(62)
+        # pass 1: the spatial branch alone (t = 0, gamma = 1): scramble(x_SA) = x_SA[b,h,n,c] stored as [b][c][h][n]
+        sa = ops.dsa_attention(qkvv, torch.zeros_like(t), self.EF, self.temperature.detach(), self.temperature2,
+                               torch.ones_like(gamma).detach(), C, H, P, None, sa_p, seed)
+        B = t.shape[0]
+        sa = sa[..., :C]                                     # rows may carry channel padding (hidden_size % 16 != 0)
+        N = sa.numel() // (B * C)
+        xsa = sa.reshape(B, c, H, N).permute(0, 3, 2, 1).reshape(qkvv.shape[:-1] + (C,))     # token rows, (h, c) channels
+        # pass 2: the channel branch with v_CA = x_SA (v_SA = 0 makes the spatial term vanish), residual and gamma fused
+        qkvv2 = torch.cat([qkvv[..., :2 * C], xsa, xsa.new_zeros(xsa.shape[:-1] + (qkvv.shape[-1] - 3 * C,))], -1)
+        return ops.dsa_attention(qkvv2, t, self.EF.detach(), self.temperature, self.temperature2.detach(), gamma, C, H, P,
+                                 ca_scale, 0.0, 0)
 
 
 class TransformerBlock(nn.Module):

@@ -202,6 +202,19 @@ FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, i
                          int tv_exclude, const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
                          float* dpred, cudaStream_t stream);
 
+/* ---- on-device patch sampling + augmentation (get_transforms.py:63-84: RandCropByPosNegLabeld, RandFlipd x 3,
+ * RandShiftIntensityd, RandGaussianNoised) on a volume resident in HBM; decisions = counter hash of (seed, sample),
+ * recorded in meta[S][fcd_sampling_meta_floats()] = z0, y0, x0, flip bits, shift, noise std, class, rank, cz, cy, cx, 0 ---- */
+FCD_API int fcd_sampling_block_voxels(void);
+FCD_API int fcd_sampling_meta_floats(void);
+FCD_API int fcd_fg_block_counts(const float* label, long long V, int* counts, cudaStream_t stream);
+FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H, int W, int rd, int rh, int rw, int S,
+                             unsigned long long seed, float pos_ratio, float flip_p, float shift_max, float shift_p,
+                             float noise_std, float noise_p, float* meta, cudaStream_t stream);
+FCD_API int fcd_crop_augment(const float* img, const float* label, int C, int D, int H, int W, int rd, int rh, int rw,
+                             int S, const float* meta, unsigned long long seed, float* out_img, float* out_lab,
+                             cudaStream_t stream);
+
 /* ---- TransformerBlock token path: pos_embed add + LayerNorm (conv_blocks.py:72-77) ---- */
 FCD_API int fcd_ln_fwd(const void* x, long long ldx, const float* pos, const float* w, const float* b, void* t,
                        long long ldt, void* ln, long long ldl, float* mean, float* rstd, long long rows, int N, int C,

@@ -85,9 +85,10 @@ def general_up_block(sd, pre, inp, skip):
 
 def dsa(sd, pre, x, heads=4):
     """DSA.forward (conv_blocks.py:316-355), dropout p=0.  x: [B,N,C].  The sa_type is read off the projection count of
-    qkvv.weight: 4C rows = 'parallel' (328-355); 3C rows = 'spatial' (forward_spatial, 236-258) or 'channel'
-    (forward_channel, 260-279), told apart by the key `<pre>.__sa_type__` the tests put into the state dict ('spatial'
-    if absent)."""
+    qkvv.weight: 4C rows = 'parallel' (328-355); 3C rows = 'spatial' (forward_spatial, 236-258), 'channel'
+    (forward_channel, 260-279) or 'serial' (forward_serial, 281-314: the spatial output, NOT scrambled, is the value of
+    the channel attention), told apart by the key `<pre>.__sa_type__` the tests put into the state dict ('spatial' if
+    absent)."""
     B, N, C = x.shape
     c = C // heads
     W = sd[pre + ".qkvv.weight"]
@@ -103,6 +104,10 @@ def dsa(sd, pre, x, heads=4):
         v_proj = torch.einsum("bhdn,nk->bhdk", v, EF)
         q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
         attn = ((q.permute(0, 1, 3, 2) @ k_proj) * sd[pre + ".temperature2"]).softmax(dim=-1)
+        if sd.get(pre + ".__sa_type__", "spatial") == "serial":
+            x_sa = attn @ v_proj.transpose(-2, -1)                                          # [B,h,N,c]
+            attn_ca = ((q @ k.transpose(-2, -1)) * sd[pre + ".temperature"]).softmax(dim=-1)
+            return (attn_ca @ x_sa.transpose(-2, -1)).permute(0, 3, 1, 2).reshape(B, N, C)
         return (attn @ v_proj.transpose(-2, -1)).permute(0, 3, 1, 2).reshape(B, N, C)
     qkvv = F.linear(x, W).reshape(B, N, 4, heads, c).permute(2, 0, 3, 1, 4)
     q, k, v_ca, v_sa = (t.transpose(-2, -1) for t in (qkvv[0], qkvv[1], qkvv[2], qkvv[3]))  # [B,h,c,N]

@@ -298,7 +298,7 @@ def test_training_steps_eager_equal_cuda_graph(fused):
     assert err <= 1e-6, f"parameters after 4 steps differ between eager and graph execution: rel {err:.3e}"
 
 
-@pytest.mark.parametrize("sa_type", ["spatial", "channel"])
+@pytest.mark.parametrize("sa_type", ["spatial", "channel", "serial"])
 def test_single_branch_attention_types(sa_type):
     """MS_DSA_NET with sa_type 'spatial' / 'channel' (conv_blocks.py:236-279; three projections, one attention branch)
     against the CPU oracle (itself bit-exact against the reference's classes, tests/test_oracle_vs_reference.py): logits
@@ -339,7 +339,9 @@ def test_single_branch_attention_types(sa_type):
     og = leaves["trans3.0.dsa.qkvv.weight"].grad
     cos = float((g.cpu().double() * og.double()).sum() / (g.cpu().double().norm() * og.double().norm()))
     assert cos > 0.7, f"qkv weight gradient points elsewhere than the oracle's (cosine {cos:.3f})"
-    if sa_type == "spatial":
+    if sa_type == "serial":
+        assert dsa.temperature.grad is not None and dsa.temperature2.grad is not None and dsa.EF.grad is not None
+    elif sa_type == "spatial":
         assert dsa.temperature.grad is None and dsa.temperature2.grad is not None and dsa.EF.grad is not None
         assert leaves["trans3.0.dsa.temperature"].grad is None
     else:

@@ -438,6 +438,52 @@ def test_dsa_token_path_tight(ops):
             close(mine[k[2:]].grad, g, rel=1.5e-2, mx=6e-2, what=f"dsa grad {k} C={C}")
 
 
+@pytest.mark.parametrize("sa_type", ["serial", "spatial", "channel"])
+def test_dsa_three_projection_types_tight(ops, sa_type):
+    """sa_type 'serial' (conv_blocks.py:281-314: the head-merged spatial output is the value of the channel attention;
+    two passes of the fused kernels), 'spatial' and 'channel': the token path alone against the fp32 oracle, forward and
+    every gradient the reference branch produces, <= 1.5e-2 (serial: <= 4e-2 -- x_SA crosses HBM as bf16 between the
+    two passes, as it does under the reference's autocast; measured 3.2e-2 on the 8-element norm.bias of C = 8)."""
+    from fcd_b200.networks.blocks import TransformerBlock
+    from oracle import nets as onets
+    from oracle import synth
+    for C, dims, P in [(32, (4, 4, 4), 64), (8, (4, 6, 4), 64), (64, (2, 4, 4), 32)]:
+        N = dims[0] * dims[1] * dims[2]
+        blk = TransformerBlock(input_size=N, hidden_size=C, proj_size=P, num_heads=4, dropout_rate=0.0, pos_embed=True,
+                               sa_type=sa_type)
+        sd = synth.synthetic_state_dict(synth.spec_of(blk.state_dict()), seed=7)
+        assert sd["dsa.qkvv.weight"].shape[0] == 3 * C
+        blk.load_state_dict(sd)
+        blk = blk.to(_dev()).train()
+        B = 2
+        x = rnd(B, C, *dims)
+        sdg = {("b." + k): v.to(_dev()).clone().requires_grad_(v.is_floating_point() and "running" not in k)
+               for k, v in sd.items()}
+        sdg["b.dsa.__sa_type__"] = sa_type
+        xr = x.clone().requires_grad_(True)
+        t = xr.reshape(B, C, N).permute(0, 2, 1) + sdg["b.pos_embed"]
+        ln = F.layer_norm(t, (C,), sdg["b.norm.weight"], sdg["b.norm.bias"], 1e-5)
+        ref = t + sdg["b.gamma"] * onets.dsa(sdg, "b.dsa", ln)
+        dy = rnd(B, N, C, seed=3)
+        names = ["b.pos_embed", "b.norm.weight", "b.norm.bias", "b.gamma", "b.dsa.qkvv.weight"]
+        names += {"serial": ["b.dsa.EF", "b.dsa.temperature", "b.dsa.temperature2"],
+                  "spatial": ["b.dsa.EF", "b.dsa.temperature2"], "channel": ["b.dsa.temperature"]}[sa_type]
+        grads = torch.autograd.grad(ref, [xr] + [sdg[k] for k in names], dy)
+        xc = cl(ops, x, True)
+        tt, lnn = ops.ln_pos(xc, blk.pos_embed, blk.norm.weight, blk.norm.bias, C, 1e-5)
+        y = blk.dsa(lnn, tt, blk.gamma)
+        close(y[..., :C].reshape(B, N, C), ref, rel=5e-3, mx=2e-2, what=f"{sa_type} fwd C={C}")
+        dyc = torch.zeros_like(y)
+        dyc[..., :C] = dy.reshape(B, *dims, C).to(torch.bfloat16)
+        y.backward(dyc)
+        close(xc.grad[..., :C].reshape(B, N, C), grads[0].reshape(B, C, N).permute(0, 2, 1), rel=1e-2, mx=4e-2,
+              what=f"{sa_type} dx C={C}")
+        mine = dict(blk.named_parameters())
+        for k, g in zip(names, grads[1:]):
+            close(mine[k[2:]].grad, g, rel=4e-2 if sa_type == "serial" else 1.5e-2, mx=8e-2 if sa_type == "serial" else 6e-2,
+                  what=f"{sa_type} grad {k} C={C}")
+
+
 def test_dsa_dropout_is_reproducible_and_unbiased(ops):
     """attn_drop / attn_drop_2 (p=0.1 in train mode, get_model.py:29): backward regenerates the forward's
     counter-based mask (finite-difference consistency through the same seed) and E[out] matches p=0."""

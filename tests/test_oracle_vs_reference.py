@@ -44,7 +44,7 @@ def test_forward_bit_exact(mt, patch, fs, batch):
         assert torch.allclose(msd[k].float(), v.float(), rtol=0, atol=0), k
 
 
-@pytest.mark.parametrize("sa_type", ["spatial", "channel"])
+@pytest.mark.parametrize("sa_type", ["spatial", "channel", "serial"])
 def test_forward_bit_exact_single_branch_attention(sa_type):
     """sa_type 'spatial' / 'channel' (conv_blocks.py:236-279): three projections, one attention branch."""
     params = ref_loader.default_params()
@@ -92,6 +92,7 @@ def test_forward_bit_exact_other_upsample_modes(mt, mode):
                                   dict(model_type="segresnetvae", segresnet_upsample_mode="nontrainable"),
                                   dict(model_type="ms_dsa_net", sa_type="spatial"),
                                   dict(model_type="ms_dsa_net", sa_type="channel"),
+                                  dict(model_type="ms_dsa_net", sa_type="serial"),
                                   dict(model_type="segresnet", segresnet_deeper=True)])
 def test_product_state_dict_equals_reference_for_the_other_branches(over):
     """The non-default get_model branches fcd_b200 builds have the reference's state-dict keys, order and shapes."""
