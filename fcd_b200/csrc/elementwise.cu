@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(256) norm_finalize_kernel(const float* __restr
 
 // y = act( g1*(x1-mean1)*rstd1 + b1  [+ g2*(x2-mean2)*rstd2 + b2]  [+ r] ),  act(v) = v > 0 ? v : slope*v
 // mean/rstd are per (b,c); gamma/beta per c (nullptr => 1/0).  grid.y = B.
+// HAS2 / HASR: second normalised input / residual given (compile-time, as for the backward kernels); U rows in flight.
+template <bool HAS2, bool HASR, int U>
 __global__ void __launch_bounds__(256, 2) norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, const float* __restrict__ mean1,
                                   const float* __restrict__ rstd1, const float* __restrict__ gamma1,
                                   const float* __restrict__ beta1, const bf16* __restrict__ x2, long long ld2,
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) norm_apply_kernel(const bf16* __restri
         float r = rstd1[b * C + c];
         a1[k] = g * r;
         o1[k] = be - mean1[b * C + c] * g * r;
-        if (x2) {
+        if (HAS2) {
             float r2 = rstd2[b * C + c];
             a2[k] = r2;
             o2[k] = -mean2[b * C + c] * r2;
@@ -195,37 +197,37 @@ __global__ void __launch_bounds__(256, 2) norm_apply_kernel(const bf16* __restri
         }
     }
     // rows r0, r0 + rstep, ... (gstride is a multiple of C8, so c8 is fixed per thread and no division is needed);
-    // 4 rows per iteration: all loads first (up to 12 independent 16 B loads in flight), then the math.
+    // U rows per iteration: all loads first (U independent 16 B loads per stream in flight), then the math.
     const long long r0 = gtid / C8, rstep = gstride / C8;
     const bf16* p1 = x1 + (long long)b * S * ld1 + c8 * 8;
-    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
-    const bf16* pr = res ? res + (long long)b * S * ldr + c8 * 8 : nullptr;
+    const bf16* p2 = HAS2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    const bf16* pr = HASR ? res + (long long)b * S * ldr + c8 * 8 : nullptr;
     bf16* py = y + (long long)b * S * ldy + c8 * 8;
-    for (long long r = r0; r < S; r += 4 * rstep) {
-        bf16x8 u1[4], u2[4], ur[4];
+    for (long long r = r0; r < S; r += (long long)U * rstep) {
+        bf16x8 u1[U], u2[U], ur[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long rr = r + u * rstep;
             if (rr < S) {
                 u1[u] = ld8_stream(p1 + rr * ld1);
-                if (p2) u2[u] = ld8_stream(p2 + rr * ld2);
-                if (pr) ur[u] = ld8_stream(pr + rr * ldr);
+                if (HAS2) u2[u] = ld8_stream(p2 + rr * ld2);
+                if (HASR) ur[u] = ld8_stream(pr + rr * ldr);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long rr = r + u * rstep;
             if (rr >= S) break;
             float f[8], v[8];
             unpack8(u1[u], f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = fmaf(f[k], a1[k], o1[k]);
-            if (p2) {
+            if (HAS2) {
                 unpack8(u2[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] += fmaf(f[k], a2[k], o2[k]);
             }
-            if (pr) {
+            if (HASR) {
                 unpack8(ur[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] += f[k];
@@ -387,7 +389,10 @@ __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __r
     norm_bwd_finalize_warp(part, f, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5);
 }
 
-__global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
+// HASY / HAS1 / HAS2: y, x1, x2 given (compile-time: the generic kernel carried every stream's registers -- 120 of them, two
+// CTAs per SM, 2 rows in flight -- for the common level-1 case that reads only dy and y); U rows in flight per thread.
+template <bool HASY, bool HAS1, bool HAS2, int U>
+__global__ void __launch_bounds__(256, (HAS1 && HAS2) ? 2 : 3) norm_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
                                       const float* __restrict__ mean1, const float* __restrict__ rstd1,
                                       const bf16* __restrict__ x2, long long ld2, const float* __restrict__ mean2,
@@ -402,39 +407,38 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = c8 * 8 + k;
-        m1[k] = mean1[b * C + c]; i1[k] = rstd1[b * C + c];
-        m2[k] = x2 ? mean2[b * C + c] : 0.f; i2[k] = x2 ? rstd2[b * C + c] : 0.f;
+        m1[k] = HAS1 ? mean1[b * C + c] : 0.f; i1[k] = HAS1 ? rstd1[b * C + c] : 0.f;
+        m2[k] = HAS2 ? mean2[b * C + c] : 0.f; i2[k] = HAS2 ? rstd2[b * C + c] : 0.f;
         a0[k] = a1[k] = a2[k] = 0.f;
     }
     const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
-    const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
-    // x1 == nullptr: xhat1 is RECONSTRUCTED from the saved output, xhat1 = act^-1(y) - xhat2 (no affine, no residual,
+    const bf16* py = HASY ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
+    // !HAS1: xhat1 is RECONSTRUCTED from the saved output, xhat1 = act^-1(y) - xhat2 (no affine, no residual,
     // slope > 0: the host checks), so the backward never reads (and the forward never keeps) the conv output x1:
     // one 2E-byte stream less in each of the two passes of this HBM-bound pair
-    const bool recon = (x1 == nullptr);
     const float inv_slope = 1.f / slope;
-    const bf16* p1 = recon ? nullptr : x1 + (long long)b * S * ld1 + c8 * 8;
-    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
-    for (long long s = s0 + r0; s < s1; s += 2LL * rstep) {      // 2 rows x up to 4 streams of 16 B loads in flight
-        bf16x8 vg[2], vy[2], v1[2], v2[2];
+    const bf16* p1 = HAS1 ? x1 + (long long)b * S * ld1 + c8 * 8 : nullptr;
+    const bf16* p2 = HAS2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    for (long long s = s0 + r0; s < s1; s += (long long)U * rstep) {      // U rows x up to 4 streams of 16 B loads in flight
+        bf16x8 vg[U], vy[U], v1[U], v2[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long rr = s + u * rstep;
             if (rr < s1) {
                 vg[u] = ld8_stream(pdy + rr * lddy);
-                if (py) vy[u] = ld8_stream(py + rr * ldy);
-                if (p1) v1[u] = ld8_stream(p1 + rr * ld1);
-                if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
+                if (HASY) vy[u] = ld8_stream(py + rr * ldy);
+                if (HAS1) v1[u] = ld8_stream(p1 + rr * ld1);
+                if (HAS2) v2[u] = ld8_stream(p2 + rr * ld2);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (s + u * rstep >= s1) break;
             float g[8], f[8], xh[8];
             unpack8(vg[u], g);
 #pragma unroll
             for (int k = 0; k < 8; ++k) xh[k] = 0.f;
-            if (py) {
+            if (HASY) {
                 unpack8(vy[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
                     xh[k] = f[k] > 0.f ? f[k] : f[k] * inv_slope;          // pre-activation sum (used when recon)
                 }
             }
-            if (p2) {
+            if (HAS2) {
                 unpack8(v2[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
                     xh[k] -= x2h;
                 }
             }
-            if (p1) {
+            if (HAS1) {
                 unpack8(v1[u], f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) xh[k] = (f[k] - m1[k]) * i1[k];
@@ -495,6 +499,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const bf16* __re
 // with k1 = gamma*rstd, k2 = rstd*mean_grp(gamma*ds), k3 = rstd*mean_grp(gamma*ds*xhat); also dgamma/dbeta (written, not accumulated).
 // coef[b][c][0..2] for input 1, coef[b][c][3..5] for input 2.
 // dx1 = k1*ds - k2 - k3*xhat1 ; dx2 likewise (optional) ; dres = ds (optional).  ds = dy*act'(y).
+template <bool HASY, bool HAS1, bool HAS2, bool HASR, int U>
 __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y,
                                       long long ldy, const bf16* __restrict__ x1, long long ld1,
                                       const float* __restrict__ mean1, const float* __restrict__ rstd1,
@@ -514,10 +519,11 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
     for (int q = 0; q < 8; ++q) {
         const int c = c8 * 8 + q;
         const float* kk = coef + ((long long)b * C + c) * 6;
-        const float m1 = mean1[b * C + c], i1 = rstd1[b * C + c];
-        if (x1) { kA1[q] = kk[0]; cX1[q] = kk[2] * i1; cB1[q] = kk[1] - kk[2] * i1 * m1; }
-        else { kA1[q] = kk[0]; cX1[q] = kk[2]; cB1[q] = kk[1]; }      // reconstructed xhat1 is used directly
-        if (x2) {
+        if (HAS1) {
+            const float m1 = mean1[b * C + c], i1 = rstd1[b * C + c];
+            kA1[q] = kk[0]; cX1[q] = kk[2] * i1; cB1[q] = kk[1] - kk[2] * i1 * m1;
+        } else { kA1[q] = kk[0]; cX1[q] = kk[2]; cB1[q] = kk[1]; }      // reconstructed xhat1 is used directly
+        if (HAS2) {
             const float m2 = mean2[b * C + c], i2 = rstd2[b * C + c];
             kA2[q] = kk[3]; cX2[q] = kk[5] * i2; cB2[q] = kk[4] - kk[5] * i2 * m2;
         } else {
@@ -526,41 +532,41 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
     }
     const long long r0 = gtid / C8, rstep = gstride / C8;     // gstride is a multiple of C8: c8 fixed per thread
     const bf16* pdy = dy + (long long)b * S * lddy + c8 * 8;
-    const bf16* py = y ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
-    const bf16* p1 = x1 ? x1 + (long long)b * S * ld1 + c8 * 8 : nullptr;      // nullptr: reconstruct xhat1 from y
+    const bf16* py = HASY ? y + (long long)b * S * ldy + c8 * 8 : nullptr;
+    const bf16* p1 = HAS1 ? x1 + (long long)b * S * ld1 + c8 * 8 : nullptr;      // !HAS1: reconstruct xhat1 from y
     const float inv_slope = 1.f / slope;
     float m2v[8], i2v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        m2v[q] = x2 ? mean2[b * C + c8 * 8 + q] : 0.f;
-        i2v[q] = x2 ? rstd2[b * C + c8 * 8 + q] : 0.f;
+        m2v[q] = (HAS2 && !HAS1) ? mean2[b * C + c8 * 8 + q] : 0.f;
+        i2v[q] = (HAS2 && !HAS1) ? rstd2[b * C + c8 * 8 + q] : 0.f;
     }
-    const bf16* p2 = x2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
+    const bf16* p2 = HAS2 ? x2 + (long long)b * S * ld2 + c8 * 8 : nullptr;
     bf16* q1 = dx1 + (long long)b * S * ldd1 + c8 * 8;
-    bf16* q2 = x2 ? dx2 + (long long)b * S * ldd2 + c8 * 8 : nullptr;
-    bf16* qr = dres ? dres + (long long)b * S * lddr + c8 * 8 : nullptr;
-    for (long long r = r0; r < S; r += 2 * rstep) {           // 2 rows x up to 5 streams of 16 B loads in flight
-        bf16x8 vg[2], vy[2], v1[2], v2[2], vr[2];
+    bf16* q2 = HAS2 ? dx2 + (long long)b * S * ldd2 + c8 * 8 : nullptr;
+    bf16* qr = HASR ? dres + (long long)b * S * lddr + c8 * 8 : nullptr;
+    for (long long r = r0; r < S; r += (long long)U * rstep) {           // U rows x up to 5 streams of 16 B loads in flight
+        bf16x8 vg[U], vy[U], v1[U], v2[U], vr[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long rr = r + u * rstep;
             if (rr < S) {
                 vg[u] = ld8_stream(pdy + rr * lddy);
-                if (py) vy[u] = ld8_stream(py + rr * ldy);
-                if (p1) v1[u] = ld8_stream(p1 + rr * ld1);
-                if (p2) v2[u] = ld8_stream(p2 + rr * ld2);
-                if (qr && acc_res) vr[u] = ld8(qr + rr * lddr);
+                if (HASY) vy[u] = ld8_stream(py + rr * ldy);
+                if (HAS1) v1[u] = ld8_stream(p1 + rr * ld1);
+                if (HAS2) v2[u] = ld8_stream(p2 + rr * ld2);
+                if (HASR && acc_res) vr[u] = ld8(qr + rr * lddr);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long rr = r + u * rstep;
             if (rr >= S) break;
             float g[8], f[8], o[8], xh[8];
             unpack8(vg[u], g);
 #pragma unroll
             for (int q = 0; q < 8; ++q) xh[q] = 0.f;
-            if (py) {
+            if (HASY) {
                 unpack8(vy[u], f);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -568,20 +574,20 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const bf16* __re
                     xh[q] = f[q] > 0.f ? f[q] : f[q] * inv_slope;
                 }
             }
-            if (p2) {
+            if (HAS2) {
                 unpack8(v2[u], f);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     o[q] = fmaf(kA2[q], g[q], -fmaf(cX2[q], f[q], cB2[q]));
-                    xh[q] -= (f[q] - m2v[q]) * i2v[q];
+                    if (!HAS1) xh[q] -= (f[q] - m2v[q]) * i2v[q];
                 }
                 st8(q2 + rr * ldd2, pack8(o));
             }
-            if (p1) unpack8(v1[u], xh);                               // the real x1 (cX1/cB1 fold mean and rstd in)
+            if (HAS1) unpack8(v1[u], xh);                             // the real x1 (cX1/cB1 fold mean and rstd in)
 #pragma unroll
             for (int q = 0; q < 8; ++q) o[q] = fmaf(kA1[q], g[q], -fmaf(cX1[q], xh[q], cB1[q]));
             st8(q1 + rr * ldd1, pack8(o));
-            if (qr) {
+            if (HASR) {
                 if (acc_res) {
                     unpack8(vr[u], f);
 #pragma unroll
@@ -713,8 +719,16 @@ FCD_API int fcd_norm_apply(const void* x1, long long ld1, const float* mean1, co
     if (C % 8 || C / 8 > 256) return -1;
     const int nt = (256 / (C / 8)) * (C / 8);   // block size: a multiple of the chunk count
     dim3 grid(grid_for(S * (C / 8), nt, 8), B);
-    norm_apply_kernel<<<grid, nt, 0, st>>>((const bf16*)x1, ld1, mean1, rstd1, gamma1, beta1, (const bf16*)x2, ld2,
-                                            mean2, rstd2, (const bf16*)res, ldr, (bf16*)y, ldy, S, C / 8, slope);
+#define FCD_NAPPLY(H2, HR, UU)                                                                                          \
+    norm_apply_kernel<H2, HR, UU><<<grid, nt, 0, st>>>((const bf16*)x1, ld1, mean1, rstd1, gamma1, beta1, (const bf16*)x2, \
+                                                       ld2, mean2, rstd2, (const bf16*)res, ldr, (bf16*)y, ldy, S, C / 8, \
+                                                       slope)
+    const bool h2 = x2 != nullptr, hr = res != nullptr;
+    if (!h2 && !hr) FCD_NAPPLY(false, false, 8);
+    else if (h2 && !hr) FCD_NAPPLY(true, false, 4);
+    else if (!h2 && hr) FCD_NAPPLY(false, true, 4);
+    else FCD_NAPPLY(true, true, 3);
+#undef FCD_NAPPLY
     FCD_LAUNCH_CHECK();
 }
 
@@ -732,14 +746,39 @@ FCD_API int fcd_norm_bwd(const void* dy, long long lddy, const void* y, long lon
     dim3 g1(nchunk, B);
     const NormBwdFin fin{rstd1, rstd2, gamma1, coef, dgamma, dbeta, B, C, nchunk, mode, x2 != nullptr, S};
     const bool fold = fin_fold(B, nchunk, 3 * C);
-    norm_bwd_stats_kernel<<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
-                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, S, C / 8, nchunk, slope,
-                                              fin, fold ? lastblk::next_ticket() : nullptr);
-    if (!fold) norm_bwd_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, fin);
+    unsigned* ticket = fold ? lastblk::next_ticket() : nullptr;
+    const bool hy = y != nullptr, h1 = x1 != nullptr, h2 = x2 != nullptr, hr = dres != nullptr;
     dim3 g2(grid_for(S * (C / 8), nt, 8), B);
-    norm_bwd_apply_kernel<<<g2, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1,
-                                              rstd1, (const bf16*)x2, ld2, mean2, rstd2, coef, (bf16*)dx1, ldd1,
-                                              (bf16*)dx2, ldd2, (bf16*)dres, lddr, S, C / 8, slope, acc_res);
+#define FCD_NB_STATS(HY, H1, H2, UU)                                                                                    \
+    norm_bwd_stats_kernel<HY, H1, H2, UU><<<g1, nt, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, \
+                                                             ld1, mean1, rstd1, (const bf16*)x2, ld2, mean2, rstd2, part, \
+                                                             S, C / 8, nchunk, slope, fin, ticket)
+#define FCD_NB_APPLY(HY, H1, H2, HR, UU)                                                                                \
+    norm_bwd_apply_kernel<HY, H1, H2, HR, UU><<<g2, nt, 0, st>>>(                                                       \
+        (const bf16*)dy, lddy, (const bf16*)y, ldy, (const bf16*)x1, ld1, mean1, rstd1, (const bf16*)x2, ld2, mean2,      \
+        rstd2, coef, (bf16*)dx1, ldd1, (bf16*)dx2, ldd2, (bf16*)dres, lddr, S, C / 8, slope, acc_res)
+    // rows in flight: 4 while a thread streams <= 2 tensors, else 2
+    if (hy && !h1 && !h2) FCD_NB_STATS(true, false, false, 4);
+    else if (hy && !h1 && h2) FCD_NB_STATS(true, false, true, 2);
+    else if (hy && h1 && !h2) FCD_NB_STATS(true, true, false, 2);
+    else if (hy && h1 && h2) FCD_NB_STATS(true, true, true, 2);
+    else if (!hy && h1 && !h2) FCD_NB_STATS(false, true, false, 4);
+    else if (!hy && h1 && h2) FCD_NB_STATS(false, true, true, 2);
+    else return -1;                                   // no activation output AND no x1: nothing to take xhat1 from
+    if (!fold) norm_bwd_finalize_kernel<<<(B * C + 7) / 8, 256, 0, st>>>(part, fin);
+    if (hy && !h1 && !h2 && !hr) FCD_NB_APPLY(true, false, false, false, 4);
+    else if (hy && !h1 && h2 && !hr) FCD_NB_APPLY(true, false, true, false, 2);
+    else if (hy && h1 && !h2 && !hr) FCD_NB_APPLY(true, true, false, false, 2);
+    else if (hy && h1 && h2 && !hr) FCD_NB_APPLY(true, true, true, false, 2);
+    else if (hy && h1 && !h2 && hr) FCD_NB_APPLY(true, true, false, true, 2);
+    else if (hy && h1 && h2 && hr) FCD_NB_APPLY(true, true, true, true, 2);
+    else if (!hy && h1 && !h2 && !hr) FCD_NB_APPLY(false, true, false, false, 4);
+    else if (!hy && h1 && h2 && !hr) FCD_NB_APPLY(false, true, true, false, 2);
+    else if (!hy && h1 && !h2 && hr) FCD_NB_APPLY(false, true, false, true, 2);
+    else if (!hy && h1 && h2 && hr) FCD_NB_APPLY(false, true, true, true, 2);
+    else return -1;
+#undef FCD_NB_STATS
+#undef FCD_NB_APPLY
     FCD_LAUNCH_CHECK();
 }
 

@@ -442,7 +442,7 @@ def test_dsa_token_path_tight(ops):
 def test_dsa_three_projection_types_tight(ops, sa_type):
     """sa_type 'serial' (conv_blocks.py:281-314: the head-merged spatial output is the value of the channel attention;
     two passes of the fused kernels), 'spatial' and 'channel': the token path alone against the fp32 oracle, forward and
-    every gradient the reference branch produces, <= 1.5e-2 (serial: <= 4e-2 -- x_SA crosses HBM as bf16 between the
+    every gradient the reference branch produces, <= 2e-2 (serial: <= 4e-2 -- x_SA crosses HBM as bf16 between the
     two passes, as it does under the reference's autocast; measured 3.2e-2 on the 8-element norm.bias of C = 8)."""
     from fcd_b200.networks.blocks import TransformerBlock
     from oracle import nets as onets
@@ -480,7 +480,7 @@ def test_dsa_three_projection_types_tight(ops, sa_type):
               what=f"{sa_type} dx C={C}")
         mine = dict(blk.named_parameters())
         for k, g in zip(names, grads[1:]):
-            close(mine[k[2:]].grad, g, rel=4e-2 if sa_type == "serial" else 1.5e-2, mx=8e-2 if sa_type == "serial" else 6e-2,
+            close(mine[k[2:]].grad, g, rel=4e-2 if sa_type == "serial" else 2e-2, mx=8e-2 if sa_type == "serial" else 6e-2,
                   what=f"{sa_type} grad {k} C={C}")
 
 
