@@ -372,7 +372,7 @@ def main():
             torch.cuda.synchronize()
             opt.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=_ops.compute_stream(dev)):
                 static["loss"] = fwd_bwd()
             torch.cuda.synchronize()
         except Exception as e:  # keep the bench alive; the JSON line records that the step ran eagerly

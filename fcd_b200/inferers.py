@@ -100,7 +100,7 @@ class _GraphedWindowForward:
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=ops.compute_stream(device)):   # same priority as the branch streams
             self.y = self._fwd(predictor)
         self.pack_epoch = ops.pack_table_epoch(device)
 

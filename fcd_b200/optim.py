@@ -41,8 +41,16 @@ class FusedAdamW(torch.optim.Optimizer):
             for i, (p, g, m, v, n) in enumerate(ptrs):
                 rec[i] = (p, g, m, v, n, blk)
                 blk += (n + chunk - 1) // chunk
+            # the previous step's asynchronous copy may not have run yet (the host runs ahead of the GPU): the pinned
+            # staging buffer must not be rewritten under it, or that step would update through THIS step's pointers
+            ev = tab.get("copied")
+            if ev is not None and not torch.cuda.is_current_stream_capturing():
+                ev.synchronize()
             tab["host"].copy_(torch.from_numpy(rec.view(np.uint8).copy()))
             tab["dev"].copy_(tab["host"], non_blocking=True)
+            if not torch.cuda.is_current_stream_capturing():
+                tab["copied"] = torch.cuda.Event()
+                tab["copied"].record()
             tab["ptrs"], tab["nblocks"] = ptrs, blk
         return tab
 
