@@ -475,6 +475,7 @@ def main():
         ("tcgen05 conv3x3x3 fwd/dgrad", "tensor", ("fcd_conv3_tcf", "fcd_conv3_tc")),
         ("tcgen05 deep-level GEMM conv (+split-K reduce)", "tensor", ("fcd_conv_gemm_tc", "fcd_splitk_reduce")),
         ("tcgen05 weight gradients (+reduce)", "tensor", ("fcd_wgrad3_tc", "fcd_wgrad_gemm_tc", "fcd_wgrad_reduce")),
+        ("TMA + tcgen05 row GEMM (1x1x1 conv / linear / deconv k2s2)", "hbm", ("fcd_rowgemm",)),
         ("mma.sync conv / linear / deconv / pointwise", "tensor", ("fcd_igemm", "fcd_igemm_splitk", "fcd_pw_conv",
                                                                    "fcd_wgrad", "fcd_pack_weight", "fcd_pack_weight_batched")),
         ("norm + activation + residual (IN/BN/GN)", "hbm", ("fcd_norm_apply", "fcd_norm_stats", "fcd_norm_finalize",

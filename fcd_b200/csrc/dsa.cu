@@ -587,30 +587,22 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
     stage_f4(sKP, KV + ((long long)b * 2 * C + hd * CH) * P, CH * P);
     stage_f4(sVP, KV + ((long long)b * 2 * C + C + hd * CH) * P, CH * P);
     __syncthreads();
-    // phase 1: FOUR adjacent lanes per token, each owning P/4 of the projection axis (lg / da live in P/4 registers
-    // each instead of P: the one-thread-per-token version ran at 168 registers and 11 % occupancy, 120 us for 21 MB at
-    // level 3).  Softmax max / sum, s = <a, da> and the P-long dot products are completed by two xor-shuffles.  All NT =
-    // 4 * TN threads then take part in the phase-2 reduction.
-    constexpr int LPT = 4, PL = P / LPT;
-    static_assert(NT == LPT * TN && PL % 4 == 0, "four lanes per token");
-    const int tq = threadIdx.x / LPT, sub = threadIdx.x % LPT;
-    const int n = tile * TN + tq;
-    float* my = sT + tq * ROW;
-    // the four lanes of a token always branch together; the tokens of a warp may not (last tile): quad masks
-    const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
-    auto quad_sum = [qmask](float v) {
-        v += __shfl_xor_sync(qmask, v, 1);
-        v += __shfl_xor_sync(qmask, v, 2);
-        return v;
-    };
-    if (n < N) {
+    // phase 1 runs on the first TN threads (one token each); all NT threads take part in the phase-2 reduction
+    // (NT = 64 when there are enough token tiles to fill the GPU, 256 on the deep levels with a handful of blocks)
+    const bool tok = threadIdx.x < TN;
+    const int n = tile * TN + threadIdx.x;
+    float* my = sT + (tok ? threadIdx.x : 0) * ROW;
+    if (tok && n < N) {
         const bf16* row = qkvv + ((long long)b * N + n) * ldq;
         const float tau2 = temperature2[hd];
-        // the token's row segments arrive as 16-byte loads (the four lanes take turns on the segments) and are parked in
-        // its shared-memory row; the channel loops below stay rolled (unrolling them lets the compiler hoist every KP/VP
-        // row)
+        // live per-thread arrays: lg[P] and da[P] only
+        float lg[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] = 0.f;
+        // the token's row segments arrive as 16-byte loads and are parked in its shared-memory row; the channel loops
+        // below stay rolled (unrolling them lets the compiler hoist every KP/VP row: 255 registers + KBs of spills)
         constexpr int CK = CH % 8 == 0 ? 8 : CH;          // channels per 16-byte row segment
-        for (int j0 = sub * CK; j0 < CH; j0 += LPT * CK) {
+        for (int j0 = 0; j0 < CH; j0 += CK) {
             float q8[CK], g8[CK], v8[CK];
             ld_seg_bf16<CK>(row + hd * CH + j0, q8);
             ld_seg_bf16<CK>(dy + ((long long)b * N + n) * lddy + hd * CH + j0, g8);
@@ -623,40 +615,34 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
                 my[2 * P + 3 * CH + j] = v8[jj];
             }
         }
-        // gradient of the scrambled x_SA elements: flat index f -> (n', ch'); lane `sub` gathers j = sub, sub + 4, ...
-        for (int j = sub; j < CH; j += LPT) {
+#pragma unroll 1
+        for (int j = 0; j < CH; ++j) fma_row<P>(lg, my[2 * P + CH + j], sKP + j * P);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
+        float den = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { lg[p] = __expf(lg[p] - mx); den += lg[p]; }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int p = 0; p < P; ++p) lg[p] *= inv;                       // a[p]
+        float da[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) da[p] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < CH; ++j) {
+            // gradient of the scrambled x_SA element: flat index f -> (n', ch')
             const long long f = ((long long)j * H + hd) * N + n;
             const long long n2 = f / C;
             const int ch2 = (int)(f % C);
-            my[2 * P + j] = gamma[ch2] * __bfloat162float(dy[((long long)b * N + n2) * lddy + ch2]);
+            const float dxs = gamma[ch2] * __bfloat162float(dy[((long long)b * N + n2) * lddy + ch2]);
+            my[2 * P + j] = dxs;
+            fma_row<P>(da, dxs, sVP + j * P);
         }
-        __syncwarp(qmask);
-        const int p0 = sub * PL;
-        float lg[PL];
-#pragma unroll
-        for (int p = 0; p < PL; ++p) lg[p] = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < CH; ++j) fma_row<PL>(lg, my[2 * P + CH + j], sKP + j * P + p0);
-        float mx = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < PL; ++p) { lg[p] *= tau2; mx = fmaxf(mx, lg[p]); }
-        mx = fmaxf(mx, __shfl_xor_sync(qmask, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(qmask, mx, 2));
-        float den = 0.f;
-#pragma unroll
-        for (int p = 0; p < PL; ++p) { lg[p] = __expf(lg[p] - mx); den += lg[p]; }
-        const float inv = 1.f / quad_sum(den);
-#pragma unroll
-        for (int p = 0; p < PL; ++p) lg[p] *= inv;                      // a[p]
-        float da[PL];
-#pragma unroll
-        for (int p = 0; p < PL; ++p) da[p] = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < CH; ++j) fma_row<PL>(da, my[2 * P + j], sVP + j * P + p0);
         float s = 0.f;
-        const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P + p0;
+        const unsigned long long e0 = (((unsigned long long)b * H + hd) * N + n) * P;
 #pragma unroll
-        for (int p = 0; p < PL; p += 4) {
+        for (int p = 0; p < P; p += 4) {
             float4 kept;
             float* kv = reinterpret_cast<float*>(&kept);
 #pragma unroll
@@ -666,11 +652,10 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
                 s = fmaf(lg[p + u], da[p + u], s);
                 kv[u] = lg[p + u] * kf;                                   // dropped-out attention row (for dVP)
             }
-            *reinterpret_cast<float4*>(my + p0 + p) = kept;
+            *reinterpret_cast<float4*>(my + p) = kept;
         }
-        s = quad_sum(s);
 #pragma unroll
-        for (int p = 0; p < PL; p += 4) {
+        for (int p = 0; p < P; p += 4) {
             float4 d4;
             float* dv = reinterpret_cast<float*>(&d4);
 #pragma unroll
@@ -678,7 +663,7 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
                 dv[u] = lg[p + u] * (da[p + u] - s);
                 da[p + u] = dv[u];                                        // reuse as dlog
             }
-            *reinterpret_cast<float4*>(my + P + p0 + p) = d4;
+            *reinterpret_cast<float4*>(my + P + p) = d4;
         }
         // dt2 = sum_p dlog[p] * raw[p] with raw[p] = sum_j qh[j] KP[j][p]  ==  sum_j qh[j] * (sum_p dlog[p] KP[j][p])
         float dt2 = 0.f;
@@ -689,19 +674,18 @@ __global__ void __launch_bounds__(NT) dsa_bwd_reduce_kernel(const bf16* __restri
 #pragma unroll
             for (int jj = 0; jj < C4; ++jj) {
                 const int j = j0 + jj;
-                float a = quad_sum(dot_row<PL>(da, sKP + j * P + p0));
+                float a = dot_row<P>(da, sKP + j * P);
                 const float qh = my[2 * P + CH + j];
                 dt2 = fmaf(qh, a, dt2);
                 a *= tau2;
                 o[jj] = a;
-                if (sub == 0) my[2 * P + 4 * CH + j] = a * qh;
+                my[2 * P + 4 * CH + j] = a * qh;
             }
-            if (((j0 / C4) & (LPT - 1)) == sub)           // every lane holds the full sums: they take turns storing
-                st_seg_f32<C4>(dqh + ((long long)b * N + n) * C + hd * CH + j0, o);
+            st_seg_f32<C4>(dqh + ((long long)b * N + n) * C + hd * CH + j0, o);
         }
-        if (sub == 0) my[2 * P + 5 * CH] = dt2;
-    } else {
-        for (int i = sub; i < ROW; i += LPT) my[i] = 0.f;
+        my[2 * P + 5 * CH] = dt2;
+    } else if (tok) {
+        for (int i = 0; i < ROW; ++i) my[i] = 0.f;
     }
     __syncthreads();
     float* out = part + (((long long)b * H + hd) * ntiles + tile) * dsa_bsize(CH, P);
@@ -1075,12 +1059,17 @@ int launch_bwd_reduce(const bf16* qkvv, long long ldq, const bf16* dy, long long
     const int smem = (2 * CH * P + 64 * ((2 * P + 5 * CH + 1 + 3) & ~3)) * 4;
     static bool conf = false;
     if (!conf) {
+        cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(dsa_bwd_reduce_kernel<CH, P, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         conf = true;
     }
     dim3 grid((N + 63) / 64, H, B);
-    dsa_bwd_reduce_kernel<CH, P, 256><<<grid, 256, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N, C,
-                                                              ds, dth, seed, seed_dev);
+    if ((long long)grid.x * H * B >= 2LL * fcd_num_sms())
+        dsa_bwd_reduce_kernel<CH, P, 64><<<grid, 64, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part, N,
+                                                                C, ds, dth, seed, seed_dev);
+    else
+        dsa_bwd_reduce_kernel<CH, P, 256><<<grid, 256, smem, st>>>(qkvv, ldq, dy, lddy, gamma, inv_n, KV, t2, dqh, part,
+                                                                  N, C, ds, dth, seed, seed_dev);
     return (int)cudaGetLastError();
 }
 

@@ -986,10 +986,13 @@ def pool_and_skip(x):
 MODE = {"instance": 0, "batch": 1, "group2": 2}
 
 
+_NORM_CTAS = int(os.environ.get("FCD_NORM_CTAS", "444"))      # 3 CTAs per SM: one full wave (592 = 1.33 waves: measured 140 vs 126 us)
+
+
 def _nchunk(B, S):
     # slabs of >= 64 rows: the deep levels (512 or 64 rows per sample) are latency chains, a one-block reduction of 512
-    # rows cost 16 us there; the big tensors still get 2 x SMs blocks
-    return int(max(1, min(592 // max(B, 1), S // 64)))
+    # rows cost 16 us there; the big tensors still get _NORM_CTAS blocks
+    return int(max(1, min(_NORM_CTAS // max(B, 1), S // 64)))
 
 
 def _stats(x, mode, eps, running_mean=None, running_var=None, crun=0, momentum=0.1):

@@ -13,4 +13,12 @@ for _ in range(3):
     y.backward(dy)
     x.grad = x2.grad = None
 torch.cuda.synchronize()
+torch.cuda.profiler.start()                 # ncu --profile-from-start off: one two-input and one single-input pass
+y = ops.norm_act(x, x2, None, None, None, "instance", 0.01)
+y.backward(dy)
+x.grad = x2.grad = None
+y = ops.norm_act(x, None, None, None, None, "instance", 0.01)
+y.backward(dy)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(y.float().abs().mean()))
