@@ -54,6 +54,21 @@ class FusedAdamW(torch.optim.Optimizer):
             tab["ptrs"], tab["nblocks"] = ptrs, blk
         return tab
 
+    def state_dict(self):
+        """torch.optim.AdamW's layout exactly: ONE 0-dim fp32 CPU `step` tensor PER parameter.  The live state shares a
+        single device counter between the parameters of a group; handing that shared tensor out would make
+        torch.optim.AdamW.load_state_dict adopt it as is (it does not copy `step`) and then increment it once per
+        parameter per step."""
+        sd = super().state_dict()
+        state = {}
+        for k, st in sd["state"].items():
+            st = dict(st)
+            if isinstance(st.get("step"), torch.Tensor):
+                st["step"] = st["step"].detach().to("cpu", torch.float32).clone()
+            state[k] = st
+        sd["state"] = state
+        return sd
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

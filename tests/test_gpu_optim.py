@@ -54,6 +54,11 @@ def test_fused_adamw_state_dict_round_trips_with_torch():
         ref.step()
     # swap the states: ours continues from torch's state, torch from ours
     sd_ours, sd_ref = ours.state_dict(), ref.state_dict()
+    # torch.optim.AdamW.load_state_dict adopts `step` tensors without copying and then increments each one once per
+    # parameter: the state dict must hold one tensor per parameter (the live state shares one device counter)
+    steps = [st["step"] for st in sd_ours["state"].values()]
+    assert len({id(t) for t in steps}) == len(steps) and all(float(t) == 3.0 and not t.is_cuda for t in steps)
+    assert float(ours.state[a[0]]["step"]) == 3.0 and ours.state[a[0]]["step"] is ours.state[a[1]]["step"]
     ours2 = FusedAdamW(a, lr=1e-3, weight_decay=1e-2)
     ours2.load_state_dict(sd_ref)
     ref2 = torch.optim.AdamW(b, lr=1e-3, weight_decay=1e-2, foreach=False, fused=False)
