@@ -549,6 +549,7 @@ def _gemm_preferred(B, D, H, W, K, N, k, stride, pad, bias):
     return bool(L.fcd_conv_gemm_tc_tma_ok(B, D, H, W)) and L.fcd_conv_gemm_tc_ksplit_vol(B, D, H, W, K, N) > 0
 
 
+USE_SMALLC = os.environ.get("FCD_SMALLC", "1") != "0"     # dedicated weight-gradient kernel of the first (2-channel) conv
 USE_ROWGEMM = os.environ.get("FCD_ROWGEMM", "1") != "0"   # persistent TMA + tcgen05 kernel for 1x1x1 convs / k2s2 deconvs
 
 
@@ -735,8 +736,17 @@ class ConvFn(Function):
                 nsg = 0
                 if std3 and USE_GEMM_TC and Kp >= 64 and Np >= 64:
                     nsg = _lib.lib().fcd_wgrad_gemm_tc_nsplit(B * D * H * W, Kp, Np)
-                ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (std3 and nsg == 0) else 0
-                if nsg > 0:
+                nsc = 0
+                if USE_SMALLC and stride == 1 and pad == (k - 1) // 2 and seg == Ci and Kp == 16:
+                    nsc = _lib.lib().fcd_wgrad_smallc_nsplit(B, D, H, W, Ci, Np, k)
+                ns = _lib.lib().fcd_wgrad3_tc_nsplit(B, D, H, W) if (std3 and nsg == 0 and nsc == 0) else 0
+                if nsc > 0:
+                    # the network's first conv (2 real input channels): (tap, ci) pairs as one mma.sync N dimension
+                    ns = nsc
+                    part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)
+                    call("fcd_wgrad_smallc", X=x, ldx=ld(x), dY=dy, ldy=ld(dy), part=part, Bn=B, D=D, H=H, W=W, Ci=Ci,
+                         Kp=Kp, k=k, nsplit=ns)
+                elif nsg > 0:
                     # deep levels (>= 64 channels both sides): tcgen05 GEMM with the voxels as the K dimension
                     ns = nsg
                     part = torch.empty((ns, T, Np, Kp), dtype=torch.float32, device=x.device)

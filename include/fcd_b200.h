@@ -92,6 +92,13 @@ FCD_API int fcd_wgrad_gemm_tc_nsplit(long long M, int Kp, int Np);
 FCD_API int fcd_wgrad_gemm_tc(const void* X, long long ldx, const void* dY, long long ldy, float* part, int Bn, int D,
                               int H, int W, int Kp, int Np, cudaStream_t stream);
 FCD_API int fcd_wgrad_gemm_tc_error(void);
+/* weight gradient of the first conv of every network (k = 3 pad 1, or k = 1; stride 1; <= 2 real input channels in a
+ * 16-channel row, 16 output channels, large volume): the (tap, ci) pairs as the N dimension of one mma.sync contraction
+ * over the voxels (csrc/wgrad_smallc.cu).  _nsplit() = number of partials (0 = shape not taken);
+ * part[nsplit][k^3][16][Kp] is finished by fcd_wgrad_reduce. */
+FCD_API int fcd_wgrad_smallc_nsplit(int Bn, int D, int H, int W, int Ci, int Np, int k);
+FCD_API int fcd_wgrad_smallc(const void* X, long long ldx, const void* dY, long long ldy, float* part, int Bn, int D, int H,
+                             int W, int Ci, int Kp, int k, int nsplit, cudaStream_t stream);
 FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
                       int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
                       int nsplit, cudaStream_t stream);

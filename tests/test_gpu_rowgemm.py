@@ -118,3 +118,35 @@ def test_deconv_k2s2_rowgemm(ops, B, Ci, Co, D, H, W, bias):
     close(wt2.grad, gwt, rel=8e-3, what="deconv wgrad")
     if bias:
         close(bt2.grad, gb[0], rel=6e-3, what="deconv bias grad")
+
+
+@pytest.mark.parametrize("B,Ci,Co,D,H,W,k", [
+    (2, 2, 16, 32, 64, 64, 3),      # encoder1.conv1: 54 (tap, ci) columns = 7 n-tiles
+    (2, 2, 16, 32, 64, 64, 1),      # encoder1.conv3 (1x1x1 residual): one n-tile, no halo
+    (1, 1, 16, 36, 60, 128, 3),     # one input channel (27 columns = 4 n-tiles), H not a multiple of the 8-row tile
+    (1, 2, 12, 9, 250, 128, 3),     # 12 real output channels in the 16-channel rows, short depth (segments of >= 4 planes)
+])
+def test_first_layer_weight_gradient(ops, B, Ci, Co, D, H, W, k):
+    """fcd_wgrad_smallc (the first conv of every network: <= 2 real input channels) against torch autograd, and against
+    the generic kernels on the same inputs."""
+    from fcd_b200 import _lib
+    assert _lib.lib().fcd_wgrad_smallc_nsplit(B, D, H, W, Ci, 16, k) > 0
+    x = rnd(B, Ci, D, H, W)
+    w = rnd(Co, Ci, k, k, k, scale=(2.0 / (Ci * k ** 3)) ** 0.5, seed=1).requires_grad_(True)
+    ref = F.conv3d(x, w, None, padding=(k - 1) // 2)
+    dy = rnd(*ref.shape, seed=3)
+    (gw,) = torch.autograd.grad(ref, [w], dy)
+    grads = {}
+    for on in (True, False):
+        ops.USE_SMALLC = on
+        try:
+            w2 = w.detach().clone().requires_grad_(True)
+            y = ops.conv3d(ops.to_channels_last(x), w2, None, k=k, stride=1, pad=(k - 1) // 2)
+            y.backward(ops.to_channels_last(dy, 16))
+            torch.cuda.synchronize()
+            grads[on] = w2.grad.clone()
+        finally:
+            ops.USE_SMALLC = True
+    assert _err() == 0
+    close(grads[True], gw, rel=6e-3, what="first-layer wgrad")
+    close(grads[True], grads[False], rel=6e-3, what="first-layer wgrad vs the generic kernel")
