@@ -21,8 +21,16 @@
 // work items); at the end each CTA writes ONE partial dW, and fcd_wgrad_reduce sums the <= 148 partials in a fixed
 // order (deterministic, no atomics).
 //
-// Warps: 0-1 S producers (cp.async 16 B pieces, as conv_tc.cu), 2 U producer, 3-5 MMA issuers (warp kh owns taps
-// (kh, 0..2) and their accumulators), then warps 0-3 dump TMEM.
+// The three kw taps are FOLDED INTO N (round 2): the U tile is staged three times, copy kw shifted by kw-1 voxels along W
+// (B_kw[v] = U[v - (kw-1)], zeros outside the volume), the copies' channel octets consecutive at the N-group stride -- so
+// one instruction with N = 3 CU and A = the centre column S[v + (kd-1, kh-1, 0)] accumulates sum_v U[v-(kw-1)] S[v+..] =
+// sum_v' U[v'] S[v' + (kd-1, kh-1, kw-1)] for kw = 0..2 at once (every (v', tap) pair is still counted exactly once over
+// the volume: by the tile that holds v = v' + kw - 1).  24 instead of 72 tcgen05.mma per plane; an M64 x N48 instruction
+// costs 28 cycles against 3 x 23 for three N16 ones (section 3.1's instruction table).  The TMEM columns of warp kh are
+// [kw][n] as before, so the dump is unchanged.
+//
+// Warps: 0-1 S producers (cp.async 16 B pieces, as conv_tc.cu), 2-4 U producers (one per kw copy), 5-7 MMA issuers (warp kh
+// owns taps (kh, 0..2) and their accumulators), then warps 0-2 dump TMEM.
 #include "tc_common.cuh"
 
 namespace {
@@ -30,10 +38,10 @@ namespace {
 using namespace tc;
 
 constexpr int TH = 16, TW = 8, HH = TH + 2, HW = TW + 2, HV = HH * HW;
-constexpr int NPS = 2;                    // S producer warps
+constexpr int NPS = 2;                    // S producer warps (4 measured no faster)
 constexpr int NMMA = 3;
-constexpr int NTHREADS = 32 * (NPS + 1 + NMMA);
-constexpr int NU = 4;                     // U ring slots
+constexpr int NPU = 3;                    // U producer warps: one per kw copy
+constexpr int NTHREADS = 32 * (NPS + NPU + NMMA);
 constexpr int DEPTH = 3;                  // cp.async groups in flight per producer lane
 
 struct WgradTcParams {
@@ -50,13 +58,20 @@ template <int CS, int CU, int DL>
 struct Cfg {
     static constexpr int NS = DL + 2;                       // S ring slots = planes of one item
     static constexpr int PS_BYTES = HV * CS * 2;            // [CS/8][180][8]
-    static constexpr int PU_BYTES = TH * TW * CU * 2;       // [CU/8][128][8]
+    static constexpr int PU_COPY = TH * TW * CU * 2;        // one kw copy: [CU/8][128][8]
+    static constexpr int PU_BYTES = 3 * PU_COPY;            // [kw][CU/8][128][8]
     static constexpr int M = CS == 16 ? 64 : 128;           // 3 kd taps x CS rows (+ one ignored plane's worth)
     static constexpr int SBO_A = HV * 16, LBO_A = HW * 16;  // M-group (channel octet / next plane), K-group (next h row)
     static constexpr int SBO_B = TH * TW * 16, LBO_B = TW * 16;
     static constexpr int TCOLS = 9 * CU;
     static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
     // the ignored 4th plane of the last window reads past the S ring: the U ring sits right behind it
+    // U ring: with kw folded into N a plane is 24 instructions (~0.35 us): the ring and the producer's cp.async depth must
+    // cover ~2 us of load latency.  As many slots as fit beside the S ring in one CTA's shared memory (<= 12), DU planes
+    // of cp.async in flight.
+    // (measured, 16->16 @128^3: 12 slots / 6 planes in flight with ONE CTA per SM 0.367 ms, 4 slots with two CTAs 0.260 ms)
+    static constexpr int NU = 4;
+    static constexpr int DU = 2;
     static constexpr int SMEM = NS * PS_BYTES + NU * PU_BYTES + 1024;
     static constexpr int CTAS_PER_SM = (2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;   // issue-bound: interleave two CTAs
     static_assert(PS_BYTES % 128 == 0 && PU_BYTES % 128 == 0, "alignment");
@@ -75,7 +90,7 @@ __device__ __forceinline__ Item decode(const WgradTcParams& p, int item, int DL)
 template <int CS, int CU, int DL>
 __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3_tc_kernel(const WgradTcParams p) {
     using K = Cfg<CS, CU, DL>;
-    constexpr int NS = K::NS;
+    constexpr int NS = K::NS, NU = K::NU;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sring = smem;
     unsigned char* uring = smem + NS * K::PS_BYTES;
@@ -96,7 +111,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
     if (tid == 0) {
         wait_ctx_init(ctx, p.status, 4);
         for (int s = 0; s < NS; ++s) { mbar_init(FULL_S(s), 32 * NPS); mbar_init(EMPTY_S(s), NMMA); }
-        for (int s = 0; s < NU; ++s) { mbar_init(FULL_U(s), 32); mbar_init(EMPTY_U(s), NMMA); }
+        for (int s = 0; s < NU; ++s) { mbar_init(FULL_U(s), 32 * NPU); mbar_init(EMPTY_U(s), NMMA); }
         mbar_init(DONE, NMMA);
         fence_barrier_init();
     }
@@ -159,8 +174,10 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
         cp_async_wait<0>();
         fence_proxy_async();
         flush_to(seq);
-    } else if (warp == NPS) {
-        // ===================================================================== U producer: planes d0 .. d0+DL-1 (no halo)
+    } else if (warp < NPS + NPU) {
+        // ===================================================================== U producers: planes d0 .. d0+DL-1; warp kw
+        // stages copy kw of every plane (the U tile shifted by kw - 1 voxels along W)
+        const int kw = warp - NPS;
         constexpr int C8 = CU / 8, VS = 32 / C8, NJ = (TH * TW) / VS;
         const int c8 = lane % C8, v0 = lane / C8;
         const uint32_t ring_u = smem_u32(uring);
@@ -180,14 +197,16 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
 #pragma unroll
                 for (int q = 0; q < NJ; ++q) {
                     const int v = v0 + q * VS;               // tile voxel: hh = v / 8, ww = v % 8
-                    const bool ok = it.h0 + (v >> 3) < p.H && it.w0 + (v & 7) < p.W;      // ragged edge tile: zero rows
-                    cp_async16(dst0 + q * VS * 16, ok ? plane + ((long long)(v >> 3) * p.W + (v & 7)) * p.ldu : Up, ok);
+                    const int ws = (v & 7) - (kw - 1);       // copy kw holds U shifted by kw - 1 voxels along W
+                    const bool ok = it.h0 + (v >> 3) < p.H && it.w0 + ws >= 0 && it.w0 + ws < p.W;       // zero outside
+                    cp_async16(dst0 + kw * K::PU_COPY + q * VS * 16,
+                               ok ? plane + ((long long)(v >> 3) * p.W + ws) * p.ldu : Up, ok);
                 }
                 cp_async_commit();
-                if (seq + 1 >= 2) {                         // NU = 4: hand over with a lag of one plane
-                    cp_async_wait<1>();
+                if (seq + 1 >= K::DU) {                     // DU planes of copies in flight
+                    cp_async_wait<K::DU - 1>();
                     fence_proxy_async();
-                    flush_to(seq);
+                    flush_to(seq + 2 - K::DU);
                 }
             }
         }
@@ -196,8 +215,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
         flush_to(seq);
     } else {
         // ===================================================================== MMA issuers: warp kh owns taps (kh, kw=0..2)
-        const int kh = warp - NPS - 1;
-        constexpr uint32_t idesc = umma_idesc(K::M, CU, 1, 1);           // both operands MN-major
+        const int kh = warp - NPS - NPU;
+        constexpr uint32_t idesc = umma_idesc(K::M, 3 * CU, 1, 1);       // both operands MN-major; N = (kw, n)
         constexpr uint32_t A_HI = ((K::SBO_A >> 4) & 0x3fffu) | (1u << 14);
         constexpr uint32_t B_HI = ((K::SBO_B >> 4) & 0x3fffu) | (1u << 14);
         const uint32_t a_lo0 = ((smem_u32(sring) >> 4) & 0x3fffu) | ((uint32_t)(K::LBO_A >> 4) << 16);
@@ -214,16 +233,13 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CS, CU, DL>::CTAS_PER_SM) wgrad3
                 if (lane == 0) {
                     const uint32_t a_pl = a_lo0 + j * (K::PS_BYTES >> 4) + ((kh * HW * 16) >> 4);
                     const uint32_t b_pl = b_lo0 + us * (K::PU_BYTES >> 4);
+                    const uint32_t d_tmem = tmem_base + kh * 3 * CU;
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const uint32_t d_tmem = tmem_base + (kh * 3 + kw) * CU;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {     // 16 voxels = tile rows 2ks, 2ks+1
-                            const uint32_t a_lo = a_pl + (((2 * ks * HW + kw) * 16) >> 4);
-                            const uint32_t b_lo = b_pl + ((2 * ks * TW * 16) >> 4);
-                            umma_f16(d_tmem, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, idesc,
-                                     ks ? 1u : first);
-                        }
+                    for (int ks = 0; ks < 8; ++ks) {         // 16 voxels = tile rows 2ks, 2ks+1; centre column of the halo
+                        const uint32_t a_lo = a_pl + (((2 * ks * HW + 1) * 16) >> 4);
+                        const uint32_t b_lo = b_pl + ((2 * ks * TW * 16) >> 4);
+                        umma_f16(d_tmem, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, idesc,
+                                 ks ? 1u : first);
                     }
                     umma_commit(EMPTY_S(j));                 // window slides: plane j is done (for this warp)
                     if (j == DL - 1) { umma_commit(EMPTY_S(DL)); umma_commit(EMPTY_S(DL + 1)); }
