@@ -25,9 +25,12 @@ constexpr int WBM = 128;   // voxels per stage (8 warps x 16)
 
 __device__ __forceinline__ int wswz(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
 
-template <int TP>
+// G: 16-voxel groups per warp per stage.  The pointwise launches on big volumes (G = 4) were bound by their two
+// __syncthreads per 128-voxel stage (two ldmatrix + two mma per warp between barriers), not by the loads.
+template <int TP, int G>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WGradParams p) {
-    constexpr int Q_BYTES = WBM * 32;
+    constexpr int WT = WBM * G;               // voxels per stage
+    constexpr int Q_BYTES = WT * 32;
     constexpr int STAGE_BYTES = Q_BYTES * (1 + TP);
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -45,34 +48,38 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WGradParams p) {
     const int ntap = min(TP, T - t0);
     const int split = blockIdx.x;
     const int tile0 = split * p.tiles_per_split;
-    const int ntiles_total = (p.M + WBM - 1) / WBM;
+    const int ntiles_total = (p.M + WT - 1) / WT;
     const int tile1 = min(tile0 + p.tiles_per_split, ntiles_total);
 
     // each thread loads one 16B chunk of Q and of every tap's P tile: row = tid/2, chunk = tid&1
     const int lrow = tid >> 1, lch = tid & 1;
 
     auto load_stage = [&](int tile, int slot) {
-        const int m = tile * WBM + lrow;
-        const bool ok = m < p.M;
         const uint32_t sq = sbase + slot * STAGE_BYTES;
-        const bf16* qsrc = p.Q;
-        if (ok) qsrc += (long long)m * p.ldq + nblk * 16 + lch * 8;
-        cp_async16(sq + wswz(lrow, lch), qsrc, ok);
-        int mm = ok ? m : 0;
-        const int x = mm % p.Wm; mm /= p.Wm;
-        const int y = mm % p.Hm; mm /= p.Hm;
-        const int z = mm % p.Dm; mm /= p.Dm;
-        const long long base = (long long)mm * p.Ds * p.Hs * p.Ws;
 #pragma unroll
-        for (int j = 0; j < TP; ++j) {
-            if (j < ntap) {
-                const int t = t0 + j;
-                const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
-                const int sz = z * p.stride + tz - p.pad, sy = y * p.stride + ty - p.pad, sx = x * p.stride + tx - p.pad;
-                const bool v = ok && sz >= 0 && sz < p.Ds && sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
-                const bf16* src = p.P;
-                if (v) src += (base + ((long long)sz * p.Hs + sy) * p.Ws + sx) * p.ldp + kblk * 16 + lch * 8;
-                cp_async16(sq + Q_BYTES * (1 + j) + wswz(lrow, lch), src, v);
+        for (int gq = 0; gq < G; ++gq) {
+            const int row = gq * WBM + lrow;
+            const int m = tile * WT + row;
+            const bool ok = m < p.M;
+            const bf16* qsrc = p.Q;
+            if (ok) qsrc += (long long)m * p.ldq + nblk * 16 + lch * 8;
+            cp_async16(sq + wswz(row, lch), qsrc, ok);
+            int mm = ok ? m : 0;
+            const int x = mm % p.Wm; mm /= p.Wm;
+            const int y = mm % p.Hm; mm /= p.Hm;
+            const int z = mm % p.Dm; mm /= p.Dm;
+            const long long base = (long long)mm * p.Ds * p.Hs * p.Ws;
+#pragma unroll
+            for (int j = 0; j < TP; ++j) {
+                if (j < ntap) {
+                    const int t = t0 + j;
+                    const int tx = t % p.kw, ty = (t / p.kw) % p.kh, tz = t / (p.kw * p.kh);
+                    const int sz = z * p.stride + tz - p.pad, sy = y * p.stride + ty - p.pad, sx = x * p.stride + tx - p.pad;
+                    const bool v = ok && sz >= 0 && sz < p.Ds && sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
+                    const bf16* src = p.P;
+                    if (v) src += (base + ((long long)sz * p.Hs + sy) * p.Ws + sx) * p.ldp + kblk * 16 + lch * 8;
+                    cp_async16(sq + Q_BYTES * (1 + j) + wswz(row, lch), src, v);
+                }
             }
         }
     };
@@ -94,22 +101,25 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WGradParams p) {
         cp_async_wait<1>();
         __syncthreads();
         const uint32_t sq = sbase + slot * STAGE_BYTES;
-        // A fragment: Q^T block (16 n x 16 voxels of this warp)
-        uint32_t a[4];
-        {
-            int v = warp * 16 + (lane & 7) + ((lane >> 4) << 3);
-            int ch = (lane >> 3) & 1;
-            ldmatrix_x4_trans(a[0], a[1], a[2], a[3], sq + wswz(v, ch));
-        }
 #pragma unroll
-        for (int j = 0; j < TP; ++j) {
-            if (j < ntap) {
-                uint32_t b0, b1, b2, b3;
-                int v = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-                int ch = lane >> 4;
-                ldmatrix_x4_trans(b0, b1, b2, b3, sq + Q_BYTES * (1 + j) + wswz(v, ch));
-                mma_bf16_16816(acc[j][0], a, b0, b1);
-                mma_bf16_16816(acc[j][1], a, b2, b3);
+        for (int gq = 0; gq < G; ++gq) {
+            // A fragment: Q^T block (16 n x 16 voxels of this warp)
+            uint32_t a[4];
+            {
+                int v = gq * WBM + warp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                int ch = (lane >> 3) & 1;
+                ldmatrix_x4_trans(a[0], a[1], a[2], a[3], sq + wswz(v, ch));
+            }
+#pragma unroll
+            for (int j = 0; j < TP; ++j) {
+                if (j < ntap) {
+                    uint32_t b0, b1, b2, b3;
+                    int v = gq * WBM + warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    int ch = lane >> 4;
+                    ldmatrix_x4_trans(b0, b1, b2, b3, sq + Q_BYTES * (1 + j) + wswz(v, ch));
+                    mma_bf16_16816(acc[j][0], a, b0, b1);
+                    mma_bf16_16816(acc[j][1], a, b2, b3);
+                }
             }
         }
         __syncthreads();
@@ -144,20 +154,20 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WGradParams p) {
     }
 }
 
-template <int TP>
+template <int TP, int G>
 int launch_wgrad(const WGradParams& p, cudaStream_t stream) {
-    constexpr int pipe = 2 * WBM * 32 * (1 + TP);
+    constexpr int pipe = 2 * WBM * G * 32 * (1 + TP);
     constexpr int red = 8 * 256 * 4;
     constexpr int smem = pipe > red ? pipe : red;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(wgrad_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(wgrad_kernel<TP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     const int T = p.kd * p.kh * p.kw;
     const int npass = (T + TP - 1) / TP;
     dim3 grid(p.nsplit, (p.Np / 16) * (p.Kp / 16) * npass);
-    wgrad_kernel<TP><<<grid, 256, smem, stream>>>(p);
+    wgrad_kernel<TP, G><<<grid, 256, smem, stream>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -396,15 +406,20 @@ FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp
     long long M = (long long)Bn * Dm * Hm * Wm;
     if (M <= 0 || M > 0x7fffffffLL) return -1;
     p.M = (int)M;
-    int ntiles = (p.M + WBM - 1) / WBM;
+    const int T = kd * kh * kw;
+    const int G = fcd_wgrad_group(M, T);
+    int ntiles = (p.M + WBM * G - 1) / (WBM * G);
     if (nsplit > ntiles) return -1;
     p.nsplit = nsplit;
     p.tiles_per_split = (ntiles + nsplit - 1) / nsplit;
-    const int T = kd * kh * kw;
-    if (T == 1) return launch_wgrad<1>(p, stream);
-    if (T == 8) return launch_wgrad<8>(p, stream);
-    return launch_wgrad<9>(p, stream);
+    if (T == 1) return G == 4 ? launch_wgrad<1, 4>(p, stream) : launch_wgrad<1, 1>(p, stream);
+    if (T == 8) return launch_wgrad<8, 1>(p, stream);
+    return launch_wgrad<9, 1>(p, stream);
 }
+
+// 16-voxel groups per warp per pipeline stage of fcd_wgrad: 4 for one-tap (1x1x1 conv / linear) gradients on at least 2^18
+// voxels, else 1.  A stage holds 128 * group voxels: callers size nsplit <= ceil(M / (128 * group)).
+FCD_API int fcd_wgrad_group(long long M, int T) { return (T == 1 && M >= (1LL << 18)) ? 4 : 1; }
 
 FCD_API int fcd_wgrad_reduce(const float* part, float* out, int nsplit, int T, int N, int K, int Np, int Kp,
                              long long sn, long long sk, long long st, int kseg, int ksegpad, int accumulate,

@@ -292,10 +292,12 @@ def pack_weight(w, T, N, K, Np, Kp, sn, sk, st, kseg=None, ksegpad=None, nseg=No
 
 
 def _nsplit(M, Np, Kp, T):
-    ntiles = (M + 127) // 128
+    grp = _lib.lib().fcd_wgrad_group(M, T)
+    tile = 128 * grp                                     # voxels per pipeline stage of fcd_wgrad
+    ntiles = (M + tile - 1) // tile
     tp = 1 if T == 1 else (8 if T == 8 else 9)
     gy = (Np // 16) * (Kp // 16) * ((T + tp - 1) // tp)
-    n = max(1, min(ntiles, 592 // max(gy, 1)))
+    n = max(1, min(ntiles, (444 if grp == 4 else 592) // max(gy, 1)))     # resident CTAs: one wave (64 KB stages: 3 per SM)
     cap = max(1, (64 << 20) // (T * Np * Kp * 4))
     return max(1, min(n, cap))
 

@@ -99,6 +99,7 @@ FCD_API int fcd_wgrad_gemm_tc_error(void);
 FCD_API int fcd_wgrad_smallc_nsplit(int Bn, int D, int H, int W, int Ci, int Np, int k);
 FCD_API int fcd_wgrad_smallc(const void* X, long long ldx, const void* dY, long long ldy, float* part, int Bn, int D, int H,
                              int W, int Ci, int Kp, int k, int nsplit, cudaStream_t stream);
+FCD_API int fcd_wgrad_group(long long M, int T);
 FCD_API int fcd_wgrad(const void* Q, long long ldq, const void* P, long long ldp, float* part, int Bn, int Ds, int Hs,
                       int Ws, int Dm, int Hm, int Wm, int Np, int Kp, int kd, int kh, int kw, int stride, int pad,
                       int nsplit, cudaStream_t stream);
