@@ -5,5 +5,6 @@ from .get_loss import CombinedLoss, get_loss_function_from_params  # noqa: F401
 from .get_model import get_model  # noqa: F401
 from .inferers import post_process, post_process_segment, sliding_window_inference  # noqa: F401
 from ._lib import PipelineError, check_errors  # noqa: F401
+from .metrics import calculate_voxel_level_metrics, evaluate_fp  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .sampling import GpuPatchSampler  # noqa: F401

@@ -1,23 +1,33 @@
 // On-device patch sampling and augmentation: the part of the reference's MONAI training pipeline that
-// runs per patch -- RandCropByPosNegLabeld(pos=1, neg=1, num_samples), RandFlipd x 3 (p = 0.5 each), RandShiftIntensityd
-// (offsets 0.1, p = 0.5) and RandGaussianNoised (std 0.1, p = 0.5) (get_transforms.py:63-84) -- on a whole pre-processed
-// volume that is already resident in HBM, with no host round trip and no host random numbers: every decision is a
-// counter-based hash of (seed, sample, purpose), also written to a small `meta` record so that a test (or a debugger)
-// can reproduce the crop exactly.  RandRotated (get_transforms.py:75) needs MONAI's affine-grid conventions, which the
-// oracle cannot pin without a MONAI install: not built.
+// runs per patch -- RandCropByPosNegLabeld(pos=1, neg=1, num_samples), RandFlipd x 3 (p = 0.5 each), RandRotated(range_y =
+// pi/2, bilinear / nearest, p = 0.5), RandShiftIntensityd (offsets 0.1, p = 0.5), RandGaussianNoised (std 0.1, p = 0.5),
+// RandCoarseDropoutd(holes=5, spatial_size=16^3, fill 0) and GridMaskd (utils/gridmask.py:8-72) (get_transforms.py:45-89)
+// -- on a whole pre-processed volume that is already resident in HBM, with no host round trip and no host random numbers:
+// every decision is a counter-based hash of (seed, sample, purpose), also written to a small `meta` record so that a test
+// (or a debugger) can reproduce the patch exactly.
 //
 //   fcd_fg_block_counts : foreground (label > 0) voxels per block of 4096 voxels
 //   fcd_pick_centers    : per sample: foreground or background (p = pos / (pos + neg); the other class when one is empty),
 //                         the r-th voxel of that class in flat order (r uniform), centre clamped so the patch fits
-//                         (MONAI correct_crop_centers: start = centre - roi/2 in [0, dim - roi]); flips, shift, noise std
-//   fcd_crop_augment    : out[s][c][z][y][x] = img[c][z0 + flip(z)]... + shift_s + std_s * N(0,1), label likewise (no
-//                         intensity change); fp32 NCDHW outputs = what the reference's DataLoader hands to train.py:371
+//                         (MONAI correct_crop_centers: start = centre - roi/2 in [0, dim - roi]); flips, rotation angle,
+//                         shift, noise std, hole corners, grid period / phases
+//   fcd_crop_augment    : one gather pass per patch: crop -> flips -> rotation about spatial axis 1 around the patch centre
+//                         (src = c + R (p - c); image bilinear, label nearest, border padding: MONAI Rotate with
+//                         keep_size [RECALLED]) -> + std_s * N(0,1) + shift_s -> holes = 0 -> * grid mask; the label gets
+//                         the spatial transforms only; fp32 NCDHW outputs = what the reference's DataLoader hands to
+//                         train.py:371.  The interpolation is written with explicit round-to-nearest multiplies and adds
+//                         (no FMA contraction) so that the numpy oracle reproduces it bit for bit.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kBlockVox = 4096;
-constexpr int kMeta = 12;      // per sample: z0, y0, x0, flip bits, shift, noise std, picked class (1 fg / 0 bg), rank, cz, cy, cx, 0
+constexpr int kMaxHoles = 8;
+// per sample: 0-2 z0, y0, x0; 3 flip bits; 4 shift; 5 noise std; 6 picked class (1 fg / 0 bg); 7 rank; 8-10 cz, cy, cx;
+// 11 rotated (0/1); 12 cos; 13 sin; 14 angle; 15 holes applied; 16.. hole corners (z, y, x) x kMaxHoles; 40 grid mask on;
+// 41 period d; 42 stripe width l; 43-45 phases (axis 0, 1, 2); 46 inverted; 47 reserved
+constexpr int kMeta = 48;
+constexpr int kHole0 = 16, kGrid0 = 40;
 
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {     // "lowbias32" integer hash
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -58,7 +68,10 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
                                                            int nb, int D, int H, int W, int rd, int rh, int rw, int S,
                                                            unsigned long long seed, float pos_ratio, float flip_p,
                                                            float shift_max, float shift_p, float noise_std,
-                                                           float noise_p, float* __restrict__ meta) {
+                                                           float noise_p, float rot_p, float rot_range, float cd_p,
+                                                           int holes, int hz, int hy, int hx, float grid_p, int d1,
+                                                           int d2, double grid_ratio, int grid_invert,
+                                                           float* __restrict__ meta) {
     const long long V = (long long)D * H * W;
     __shared__ long long s_fg;
     if (threadIdx.x == 0) {
@@ -109,36 +122,133 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
         m[5] = (u01(seed, s, 5, 0) < noise_p) ? u01(seed, s, 5, 1) * noise_std : 0.f;
         m[6] = fg ? 1.f : 0.f;
         m[7] = (float)r;
-        m[8] = (float)cz; m[9] = (float)cy; m[10] = (float)cx; m[11] = 0.f;
+        m[8] = (float)cz; m[9] = (float)cy; m[10] = (float)cx;
+        for (int i = 11; i < kMeta; ++i) m[i] = 0.f;
+        // RandRotated(range_y): angle ~ U(-range, range) about spatial axis 1
+        if (u01(seed, s, 6, 0) < rot_p) {
+            const float ang = (2.f * u01(seed, s, 6, 1) - 1.f) * rot_range;
+            m[11] = 1.f; m[12] = cosf(ang); m[13] = sinf(ang); m[14] = ang;
+        }
+        // RandCoarseDropout: `holes` boxes of (hz, hy, hx), corner uniform in [0, dim - size]
+        if (u01(seed, s, 7, 0) < cd_p) {
+            m[15] = (float)holes;
+            const int dims[3] = {rd, rh, rw}, hs[3] = {hz, hy, hx};
+            for (int h = 0; h < holes; ++h)
+                for (int a = 0; a < 3; ++a) {
+                    const int span = dims[a] - hs[a] + 1;
+                    int c0 = (int)(u01(seed, s, 7, 1 + 3 * h + a) * (float)span);
+                    m[kHole0 + 3 * h + a] = (float)(c0 > span - 1 ? span - 1 : c0);
+                }
+        }
+        // GridMask (utils/gridmask.py:20-45): period d in [d1, d2), stripe width ceil(d * ratio), one phase per axis
+        if (u01(seed, s, 9, 0) < grid_p) {
+            int d = d1 + (int)(u01(seed, s, 9, 1) * (float)(d2 - d1));
+            if (d > d2 - 1) d = d2 - 1;
+            m[kGrid0] = 1.f; m[kGrid0 + 1] = (float)d; m[kGrid0 + 2] = (float)(int)ceil((double)d * grid_ratio);
+            for (int a = 0; a < 3; ++a) {
+                int st = (int)(u01(seed, s, 9, 2 + a) * (float)d);
+                m[kGrid0 + 3 + a] = (float)(st > d - 1 ? d - 1 : st);
+            }
+            m[kGrid0 + 6] = grid_invert ? 1.f : 0.f;
+        }
     }
+}
+
+// value of the cropped + flipped patch at patch coordinates (q0, q1, q2)
+__device__ __forceinline__ float patch_at(const float* __restrict__ src, int H, int W, int z0, int y0, int x0, int flips,
+                                          int rd, int rh, int rw, int q0, int q1, int q2) {
+    const int sz = z0 + ((flips & 1) ? rd - 1 - q0 : q0);
+    const int sy = y0 + ((flips & 2) ? rh - 1 - q1 : q1);
+    const int sx = x0 + ((flips & 4) ? rw - 1 - q2 : q2);
+    return __ldg(src + ((long long)sz * H + sy) * W + sx);
 }
 
 // grid: (x-chunks, rd * rh rows, S); each thread 4 consecutive x of one output row, all channels
 __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restrict__ img, const float* __restrict__ label,
                                                            int C, int D, int H, int W, int rd, int rh, int rw,
                                                            const float* __restrict__ meta, unsigned long long seed,
+                                                           int hz, int hy, int hx, int hh,
                                                            float* __restrict__ out_img, float* __restrict__ out_lab) {
     const int s = blockIdx.z;
     const float* m = meta + (long long)s * kMeta;
     const int z0 = (int)m[0], y0 = (int)m[1], x0 = (int)m[2], flips = (int)m[3];
     const float shift = m[4], nstd = m[5];
+    const bool rot = m[11] != 0.f;
+    const float cs = m[12], sn = m[13];
+    const int nholes = (int)m[15];
+    const bool grid = m[kGrid0] != 0.f;
     const int row = blockIdx.y, z = row / rh, y = row % rh;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= rw) return;
-    // RandFlipd(spatial_axis=a) reverses axis a of the CROPPED patch
-    const int sz = z0 + ((flips & 1) ? rd - 1 - z : z);
-    const int sy = y0 + ((flips & 2) ? rh - 1 - y : y);
     const long long V = (long long)D * H * W, P = (long long)rd * rh * rw;
-    const long long src_row = ((long long)sz * H + sy) * W;
     const long long dst = ((long long)z * rh + y) * rw + x4;
+
+    // rotation about spatial axis 1: source coordinates on axes 0 and 2 (border padding), shared by all channels
+    int i0[4], i0b[4], i2[4], i2b[4], n0[4], n2[4];
+    float w0[4], w2[4];
+    if (rot) {
+        const float c0 = (float)(rd - 1) * 0.5f, c2 = (float)(rw - 1) * 0.5f;
+        const float e0 = (float)z - c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float e2 = (float)(x4 + i) - c2;
+            float s0 = __fadd_rn(c0, __fadd_rn(__fmul_rn(cs, e0), __fmul_rn(sn, e2)));
+            float s2 = __fadd_rn(c2, __fsub_rn(__fmul_rn(cs, e2), __fmul_rn(sn, e0)));
+            s0 = fminf(fmaxf(s0, 0.f), (float)(rd - 1));
+            s2 = fminf(fmaxf(s2, 0.f), (float)(rw - 1));
+            const float f0 = floorf(s0), f2 = floorf(s2);
+            w0[i] = __fsub_rn(s0, f0); w2[i] = __fsub_rn(s2, f2);
+            i0[i] = (int)f0; i2[i] = (int)f2;
+            i0b[i] = min(i0[i] + 1, rd - 1); i2b[i] = min(i2[i] + 1, rw - 1);
+            n0[i] = (int)rintf(s0); n2[i] = (int)rintf(s2);           // nearest: round half to even (grid_sample)
+        }
+    }
+    // coarse-dropout holes and grid mask of the 4 voxels (image channels only)
+    float keep[4] = {1.f, 1.f, 1.f, 1.f};
+    bool hole[4] = {false, false, false, false};
+    for (int h = 0; h < nholes; ++h) {
+        const int bz = (int)m[kHole0 + 3 * h], by = (int)m[kHole0 + 3 * h + 1], bx = (int)m[kHole0 + 3 * h + 2];
+        if (z >= bz && z < bz + hz && y >= by && y < by + hy) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hole[i] |= (x4 + i >= bx && x4 + i < bx + hx);
+        }
+    }
+    if (grid) {
+        // utils/gridmask.py:34-66: a cube of edge hh, stripes [d i + st, d i + st + l) zeroed on each axis, centre-cropped
+        const int d = (int)m[kGrid0 + 1], l = (int)m[kGrid0 + 2];
+        const int st0 = (int)m[kGrid0 + 3], st1 = (int)m[kGrid0 + 4], st2 = (int)m[kGrid0 + 5];
+        const bool inv = m[kGrid0 + 6] != 0.f;
+        auto striped = [d, l](int p, int st) { int r = (p - st) % d; if (r < 0) r += d; return r < l; };
+        const bool zy = striped(z + (hh - rd) / 2, st0) || striped(y + (hh - rh) / 2, st1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool masked = zy || striped(x4 + i + (hh - rw) / 2, st2);
+            keep[i] = (masked != inv) ? 0.f : 1.f;
+        }
+    }
+
     for (int c = 0; c <= C; ++c) {                       // c == C: the label
-        const float* src = (c < C ? img + (long long)c * V : label) + src_row;
+        const float* src = (c < C ? img + (long long)c * V : label);
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int x = x4 + i;
-            const int sx = x0 + ((flips & 4) ? rw - 1 - x : x);
-            v[i] = x < rw ? src[sx] : 0.f;
+            if (x >= rw) { v[i] = 0.f; continue; }
+            if (!rot) {
+                // RandFlipd(spatial_axis=a) reverses axis a of the CROPPED patch
+                v[i] = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, z, y, x);
+            } else if (c == C) {
+                v[i] = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, n0[i], y, n2[i]);
+            } else {
+                const float v00 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0[i], y, i2[i]);
+                const float v01 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0[i], y, i2b[i]);
+                const float v10 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b[i], y, i2[i]);
+                const float v11 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b[i], y, i2b[i]);
+                const float u2 = __fsub_rn(1.f, w2[i]), u0 = __fsub_rn(1.f, w0[i]);
+                const float a = __fadd_rn(__fmul_rn(v00, u2), __fmul_rn(v01, w2[i]));
+                const float b = __fadd_rn(__fmul_rn(v10, u2), __fmul_rn(v11, w2[i]));
+                v[i] = __fadd_rn(__fmul_rn(a, u0), __fmul_rn(b, w0[i]));
+            }
         }
         if (c < C) {
             if (nstd > 0.f) {
@@ -154,7 +264,11 @@ __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restri
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += shift;
+            for (int i = 0; i < 4; ++i) {
+                v[i] += shift;
+                if (hole[i]) v[i] = 0.f;                 // RandCoarseDropout(fill_value=0)
+                if (grid) v[i] = __fmul_rn(v[i], keep[i]);   // img * mask
+            }
         }
         float* o = (c < C ? out_img + ((long long)s * C + c) * P : out_lab + (long long)s * P) + dst;
         if (x4 + 3 < rw && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -178,24 +292,33 @@ FCD_API int fcd_fg_block_counts(const float* label, long long V, int* counts, cu
     return (int)cudaGetLastError();
 }
 
-// meta[S][12] from (label, counts): crop starts, flip bits (bit a = spatial axis a), intensity shift, noise std, class
+// meta[S][fcd_sampling_meta_floats()] from (label, counts): crop starts, flip bits (bit a = spatial axis a), rotation,
+// intensity shift, noise std, class, hole corners, grid mask (layout at the top of this file)
 FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H, int W, int rd, int rh, int rw, int S,
                              unsigned long long seed, float pos_ratio, float flip_p, float shift_max, float shift_p,
-                             float noise_std, float noise_p, float* meta, cudaStream_t st) {
+                             float noise_std, float noise_p, float rot_p, float rot_range, float cd_p, int holes, int hz,
+                             int hy, int hx, float grid_p, int d1, int d2, double grid_ratio, int grid_invert,
+                             float* meta, cudaStream_t st) {
     if (rd > D || rh > H || rw > W || S < 1 || rd < 1 || rh < 1 || rw < 1) return -1;
+    if (holes < 0 || holes > kMaxHoles || hz < 1 || hy < 1 || hx < 1 || hz > rd || hy > rh || hx > rw) return -1;
+    if (d1 < 1 || d2 <= d1 || grid_ratio < 0.0) return -1;
     const long long V = (long long)D * H * W;
     const int nb = (int)((V + kBlockVox - 1) / kBlockVox);
     pick_centers_kernel<<<1, 256, 0, st>>>(label, counts, nb, D, H, W, rd, rh, rw, S, seed, pos_ratio, flip_p, shift_max,
-                                           shift_p, noise_std, noise_p, meta);
+                                           shift_p, noise_std, noise_p, rot_p, rot_range, cd_p, holes, hz, hy, hx,
+                                           grid_p, d1, d2, grid_ratio, grid_invert, meta);
     return (int)cudaGetLastError();
 }
 
-// img [C][D][H][W] fp32, label [D][H][W] fp32 -> out_img [S][C][rd][rh][rw], out_lab [S][1][rd][rh][rw] (fp32, NCDHW)
+// img [C][D][H][W] fp32, label [D][H][W] fp32 -> out_img [S][C][rd][rh][rw], out_lab [S][1][rd][rh][rw] (fp32, NCDHW);
+// (hz, hy, hx) = the hole size fcd_pick_centers was given, hh = ceil(sqrt(rd^2 + rh^2 + rw^2)) (utils/gridmask.py:31)
 FCD_API int fcd_crop_augment(const float* img, const float* label, int C, int D, int H, int W, int rd, int rh, int rw,
-                             int S, const float* meta, unsigned long long seed, float* out_img, float* out_lab,
-                             cudaStream_t st) {
+                             int S, const float* meta, unsigned long long seed, int hz, int hy, int hx, int hh,
+                             float* out_img, float* out_lab, cudaStream_t st) {
     if (rd > D || rh > H || rw > W || S < 1 || C < 1 || (long long)rd * rh > 65535) return -1;
+    if (hh < rd || hh < rh || hh < rw) return -1;
     dim3 grid((rw + 511) / 512, rd * rh, S);
-    crop_augment_kernel<<<grid, 128, 0, st>>>(img, label, C, D, H, W, rd, rh, rw, meta, seed, out_img, out_lab);
+    crop_augment_kernel<<<grid, 128, 0, st>>>(img, label, C, D, H, W, rd, rh, rw, meta, seed, hz, hy, hx, hh, out_img,
+                                              out_lab);
     return (int)cudaGetLastError();
 }

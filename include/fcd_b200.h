@@ -210,18 +210,26 @@ FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, i
                          int tv_exclude, const unsigned char* keep, const float* pbuf, const float* res, const float* gout,
                          float* dpred, cudaStream_t stream);
 
-/* ---- on-device patch sampling + augmentation (get_transforms.py:63-84: RandCropByPosNegLabeld, RandFlipd x 3,
- * RandShiftIntensityd, RandGaussianNoised) on a volume resident in HBM; decisions = counter hash of (seed, sample),
- * recorded in meta[S][fcd_sampling_meta_floats()] = z0, y0, x0, flip bits, shift, noise std, class, rank, cz, cy, cx, 0 ---- */
+/* ---- on-device patch sampling + augmentation (get_transforms.py:45-89: RandCropByPosNegLabeld, RandFlipd x 3,
+ * RandRotated(range_y), RandShiftIntensityd, RandGaussianNoised, RandCoarseDropoutd, GridMaskd = utils/gridmask.py:8-72)
+ * on a volume resident in HBM; decisions = counter hash of (seed, sample), recorded in
+ * meta[S][fcd_sampling_meta_floats()]: 0-2 z0, y0, x0; 3 flip bits; 4 shift; 5 noise std; 6 class; 7 rank; 8-10 cz, cy, cx;
+ * 11 rotated; 12 cos; 13 sin; 14 angle; 15 holes applied; 16-39 hole corners (z, y, x) x 8; 40 grid mask on; 41 period d;
+ * 42 stripe width; 43-45 phases; 46 inverted; 47 reserved.
+ * pick_centers: rot_p / rot_range = probability and half-range (radians) of the rotation about spatial axis 1; cd_p,
+ * holes (<= 8), (hz, hy, hx) = coarse dropout; grid_p, [d1, d2), grid_ratio, grid_invert = GridMask.
+ * crop_augment: (hz, hy, hx) as above, hh = ceil(sqrt(rd^2 + rh^2 + rw^2)) (the mask cube of utils/gridmask.py:31). ---- */
 FCD_API int fcd_sampling_block_voxels(void);
 FCD_API int fcd_sampling_meta_floats(void);
 FCD_API int fcd_fg_block_counts(const float* label, long long V, int* counts, cudaStream_t stream);
 FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H, int W, int rd, int rh, int rw, int S,
                              unsigned long long seed, float pos_ratio, float flip_p, float shift_max, float shift_p,
-                             float noise_std, float noise_p, float* meta, cudaStream_t stream);
+                             float noise_std, float noise_p, float rot_p, float rot_range, float cd_p, int holes, int hz,
+                             int hy, int hx, float grid_p, int d1, int d2, double grid_ratio, int grid_invert,
+                             float* meta, cudaStream_t stream);
 FCD_API int fcd_crop_augment(const float* img, const float* label, int C, int D, int H, int W, int rd, int rh, int rw,
-                             int S, const float* meta, unsigned long long seed, float* out_img, float* out_lab,
-                             cudaStream_t stream);
+                             int S, const float* meta, unsigned long long seed, int hz, int hy, int hx, int hh,
+                             float* out_img, float* out_lab, cudaStream_t stream);
 
 /* ---- TransformerBlock token path: pos_embed add + LayerNorm (conv_blocks.py:72-77) ---- */
 FCD_API int fcd_ln_fwd(const void* x, long long ldx, const float* pos, const float* w, const float* b, void* t,
@@ -307,6 +315,21 @@ FCD_API int fcd_sw_finalize(const float* acc, const int* cz, const int* cy, cons
 FCD_API long long fcd_post_process_ws_bytes(int D, int H, int W);
 FCD_API int fcd_post_process(const float* pred_f, const void* pred_u8, float threshold, int l_min, float* out_mask,
                              float* out_lab, int D, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream);
+
+/* ---- voxel-level evaluation counts (metrics.py:74-126 `_compute_metrics`, called from train.py:220; seg_fcd_test.py:
+ *      160-178 Dice / IoU; utils/utils_common.py:37-60 `evaluate_fp`), integer and bit-exact.
+ *      fcd_confusion_counts: `items` volumes of n voxels each (one per (subject, channel)), prediction fp32 (pred_f) or
+ *      uint8 (pred_u8), exactly one non-NULL; counts[items][4] = tp, fp, tn, fn of (pred > thr_pred) vs (label >
+ *      thr_label) (MONAI get_confusion_matrix's column order); the call zeroes `counts` itself.
+ *      fcd_component_overlap: cc = component ids (fp32 whole numbers in [0, max_id], 0 = background, e.g. out_lab of
+ *      fcd_post_process), label = ground truth; out[0] = distinct ids present, out[1] = ids with a voxel where label != 0,
+ *      out[2] = voxels with an id outside [0, max_id] (must be 0); evaluate_fp(cc, label) = out[0] - out[1].
+ *      ws: fcd_component_overlap_ws_bytes(max_id) bytes of device scratch. ---- */
+FCD_API int fcd_confusion_counts(const float* pred_f, const void* pred_u8, const float* label, float thr_pred,
+                                 float thr_label, long long n, int items, long long* counts, cudaStream_t stream);
+FCD_API long long fcd_component_overlap_ws_bytes(long long max_id);
+FCD_API int fcd_component_overlap(const float* cc, const float* label, long long V, long long max_id, void* ws,
+                                  long long ws_bytes, long long* out, cudaStream_t stream);
 
 /* ---- optimizer step: torch.optim.AdamW as built by train_utils.py:63-71 and stepped at train.py:382, for ALL parameter
  *      tensors in one launch.  jobs: device array of njobs records {float* p; const float* g; float* m; float* v;

@@ -875,6 +875,14 @@ def _mod(name, **attrs):
     return m
 
 
+class MapTransform:
+    """monai.transforms.MapTransform as far as utils/gridmask.py uses it: stores the keys as a tuple [RECALLED]."""
+
+    def __init__(self, keys, allow_missing_keys: bool = False):
+        self.keys = (keys,) if isinstance(keys, str) else tuple(keys)
+        self.allow_missing_keys = allow_missing_keys
+
+
 def install():
     """Register the stand-in `monai`, `thop`, `timm`, `pyparsing` modules (idempotent)."""
     if "monai" in sys.modules and getattr(sys.modules["monai"], "__fcd_shim__", False):
@@ -900,6 +908,8 @@ def install():
     _mod("monai.losses", DiceLoss=DiceLoss, DiceCELoss=DiceCELoss, DiceFocalLoss=DiceFocalLoss, FocalLoss=FocalLoss,
          GeneralizedDiceLoss=GeneralizedDiceLoss, GeneralizedDiceFocalLoss=GeneralizedDiceFocalLoss)
     _mod("monai.inferers", sliding_window_inference=sliding_window_inference)
+    # utils/gridmask.py:5 subclasses MapTransform for its dictionary wrapper; only `keys` is used (gridmask.py:126, 144)
+    _mod("monai.transforms", MapTransform=MapTransform)
     if "thop" not in sys.modules:
         _mod("thop", profile=lambda *a, **k: (0, 0), clever_format=lambda x, *a, **k: x)
     if "pyparsing" not in sys.modules:

@@ -45,6 +45,12 @@ def load():
     return gm, gl, uc
 
 
+def load_gridmask():
+    """utils/gridmask.py of the reference (numpy + torch; its MONAI base class comes from the shim)."""
+    load()
+    return _load_by_path("fcd_ref_gridmask", os.path.join(REFERENCE_ROOT, "utils", "gridmask.py"))
+
+
 def default_params():
     load()
     return importlib.import_module("config").get_default_params()

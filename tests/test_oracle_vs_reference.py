@@ -136,3 +136,46 @@ def test_combined_loss_matches_reference():
         ref = gl.CombinedLoss(p, torch.device("cpu"))(pred, tgt)
         ora = olosses.combined_loss(p, pred, tgt)
         assert abs(float(ref) - float(ora)) <= 1e-6 * max(1.0, abs(float(ref))), over
+
+
+def test_gridmask_oracle_matches_reference_class():
+    """oracle/sampling.gridmask against utils/gridmask.py:8-72 (Grid.__call__) with its np.random draws substituted:
+    bit-exact masks, both modes, cubic and ragged patches, every phase corner case (stripe cut by the cube border)."""
+    import numpy as np
+    from oracle import sampling as osamp
+    gm = ref_loader.load_gridmask()
+    rng = np.random.default_rng(3)
+    for shape in ((16, 16, 16), (12, 20, 9), (32, 24, 40)):
+        for mode in (0, 1):
+            for ratio in (0.5, 0.3):
+                for _ in range(6):
+                    d = int(rng.integers(3, 12))
+                    st = [int(rng.integers(0, d)) for _ in range(3)]
+                    img = torch.from_numpy(rng.random((2,) + shape, dtype=np.float32)) + 0.5
+                    draws = iter([d] + st + [0])
+                    grid = gm.Grid(3, 12, rotate=1, ratio=ratio, mode=mode, prob=1.0)
+                    with mock.patch.object(np.random, "rand", lambda: 0.0), \
+                            mock.patch.object(np.random, "randint", lambda *a, **k: next(draws)):
+                        ref = grid(img)
+                    mine = img.numpy() * osamp.gridmask(shape, d, st, ratio=ratio, invert=bool(mode))[None]
+                    assert np.array_equal(ref.numpy(), mine), (shape, mode, ratio, d, st)
+    # the dictionary wrapper the training pipeline uses (get_transforms.py:49) routes to the same Grid
+    wrap = gm.GridMaskd(keys=["image"], apply_prob=0.0)
+    x = torch.ones(1, 4, 4, 4)
+    assert wrap({"image": x})["image"] is x
+
+
+def test_evaluate_fp_oracle_matches_reference():
+    """oracle/metrics.evaluate_fp against utils/utils_common.py:37-60 on scipy-labelled random masks."""
+    import numpy as np
+    from scipy import ndimage as nd
+    from oracle import metrics as om
+    _, _, uc = ref_loader.load()
+    rng = np.random.default_rng(5)
+    for k in range(6):
+        pred = nd.binary_dilation(rng.random((24, 28, 20)) < 0.004, iterations=1 + k % 3)
+        lab = nd.binary_dilation(rng.random((24, 28, 20)) < 0.002, iterations=2).astype(np.float32)
+        cc, n = nd.label(pred)
+        assert n > 3
+        assert om.evaluate_fp(cc, lab) == int(uc.evaluate_fp(cc, lab))
+    assert om.evaluate_fp(np.zeros((4, 4, 4)), np.ones((4, 4, 4))) == int(uc.evaluate_fp(np.zeros((4, 4, 4)), np.ones((4, 4, 4)))) == 0
