@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) fg_block_counts_kernel(const float* __res
     }
 }
 
-// one block; thread s < S decides sample s
+// one WARP per sample (8 per block): the lanes scan the per-block counts and then the voxels of the chosen block 32 at a
+// time (ballot + popcount), which finds the same r-th voxel of the class in flat order as a serial walk; lane 0 writes
 __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restrict__ label, const int* __restrict__ counts,
                                                            int nb, int D, int H, int W, int rd, int rh, int rw, int S,
                                                            unsigned long long seed, float pos_ratio, float flip_p,
@@ -72,16 +73,25 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
                                                            int holes, int hz, int hy, int hx, float grid_p, int d1,
                                                            int d2, double grid_ratio, int grid_invert,
                                                            float* __restrict__ meta) {
+    constexpr unsigned kFull = 0xffffffffu;
     const long long V = (long long)D * H * W;
-    __shared__ long long s_fg;
-    if (threadIdx.x == 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ long long s_part[8];
+    {
         long long t = 0;
-        for (int b = 0; b < nb; ++b) t += counts[b];
-        s_fg = t;
+        for (int b = threadIdx.x; b < nb; b += 256) t += counts[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+        if (lane == 0) s_part[warp] = t;
     }
     __syncthreads();
-    const long long F = s_fg, G = V - F;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    long long F = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) F += s_part[w];
+    const long long G = V - F;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= S) return;
+    {
         bool fg = u01(seed, s, 0, 0) < pos_ratio;
         if (F == 0) fg = false;
         if (G == 0) fg = true;
@@ -90,23 +100,48 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
         const double u = ((double)u01(seed, s, 1, 0) + (double)u01(seed, s, 2, 0) * (1.0 / 16777216.0));
         long long r = (long long)(u * (double)n);
         if (r >= n) r = n - 1;
-        // block holding the r-th voxel of the class, then the voxel inside it
+        // block holding the r-th voxel of the class: first block with (voxels of the class before it) + (its own) > r
         long long acc = 0;
-        int b = 0;
-        for (; b < nb; ++b) {
-            const long long inb = min((long long)kBlockVox, V - (long long)b * kBlockVox);
-            const long long c = fg ? counts[b] : inb - counts[b];
-            if (acc + c > r) break;
-            acc += c;
-        }
-        long long v = (long long)b * kBlockVox, left = r - acc;
-        for (;; ++v) {
-            const bool is = label[v] > 0.f;
-            if (is == fg) {
-                if (left == 0) break;
-                --left;
+        int b = -1;
+        for (int b0 = 0; b0 < nb && b < 0; b0 += 32) {
+            const int bi = b0 + lane;
+            long long c = 0;
+            if (bi < nb) {
+                const long long inb = min((long long)kBlockVox, V - (long long)bi * kBlockVox);
+                c = fg ? counts[bi] : inb - counts[bi];
+            }
+            long long incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const long long total = __shfl_sync(kFull, incl, 31);
+            if (acc + total > r) {
+                const int l = __ffs(__ballot_sync(kFull, acc + incl > r)) - 1;
+                b = b0 + l;
+                acc += __shfl_sync(kFull, incl - c, l);
+            } else {
+                acc += total;
             }
         }
+        // ... then the voxel inside it
+        const long long base = (long long)b * kBlockVox;
+        int left = (int)(r - acc);
+        long long v = base;
+        for (int i0 = 0; i0 < kBlockVox; i0 += 32) {
+            const long long vi = base + i0 + lane;
+            const bool match = vi < V && ((label[vi] > 0.f) == fg);
+            unsigned mm = __ballot_sync(kFull, match);
+            const int cnt = __popc(mm);
+            if (left < cnt) {
+                for (int k = 0; k < left; ++k) mm &= mm - 1;         // drop the `left` lowest matches
+                v = base + i0 + (__ffs(mm) - 1);
+                break;
+            }
+            left -= cnt;
+        }
+        if (lane != 0) return;
         int cx = (int)(v % W), cy = (int)((v / W) % H), cz = (int)(v / ((long long)W * H));
         auto start = [](int c, int roi, int dim) {
             int s0 = c - roi / 2;
@@ -163,11 +198,12 @@ __device__ __forceinline__ float patch_at(const float* __restrict__ src, int H, 
     return __ldg(src + ((long long)sz * H + sy) * W + sx);
 }
 
-// grid: (x-chunks, rd * rh rows, S); each thread 4 consecutive x of one output row, all channels
+// grid: (x-chunks, row groups, S); block = rpb rows x tpr threads (tpr = threads a row needs, a multiple of 32), each thread
+// 4 consecutive x of one output row, all channels
 __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restrict__ img, const float* __restrict__ label,
                                                            int C, int D, int H, int W, int rd, int rh, int rw,
                                                            const float* __restrict__ meta, unsigned long long seed,
-                                                           int hz, int hy, int hx, int hh,
+                                                           int hz, int hy, int hx, int hh, int tpr,
                                                            float* __restrict__ out_img, float* __restrict__ out_lab) {
     const int s = blockIdx.z;
     const float* m = meta + (long long)s * kMeta;
@@ -177,9 +213,9 @@ __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restri
     const float cs = m[12], sn = m[13];
     const int nholes = (int)m[15];
     const bool grid = m[kGrid0] != 0.f;
-    const int row = blockIdx.y, z = row / rh, y = row % rh;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (x4 >= rw) return;
+    const int row = blockIdx.y * (128 / tpr) + threadIdx.x / tpr, z = row / rh, y = row % rh;
+    const int x4 = (blockIdx.x * tpr + threadIdx.x % tpr) * 4;
+    if (x4 >= rw || row >= rd * rh) return;
     const long long V = (long long)D * H * W, P = (long long)rd * rh * rw;
     const long long dst = ((long long)z * rh + y) * rw + x4;
 
@@ -304,7 +340,7 @@ FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H
     if (d1 < 1 || d2 <= d1 || grid_ratio < 0.0) return -1;
     const long long V = (long long)D * H * W;
     const int nb = (int)((V + kBlockVox - 1) / kBlockVox);
-    pick_centers_kernel<<<1, 256, 0, st>>>(label, counts, nb, D, H, W, rd, rh, rw, S, seed, pos_ratio, flip_p, shift_max,
+    pick_centers_kernel<<<(S + 7) / 8, 256, 0, st>>>(label, counts, nb, D, H, W, rd, rh, rw, S, seed, pos_ratio, flip_p, shift_max,
                                            shift_p, noise_std, noise_p, rot_p, rot_range, cd_p, holes, hz, hy, hx,
                                            grid_p, d1, d2, grid_ratio, grid_invert, meta);
     return (int)cudaGetLastError();
@@ -315,10 +351,17 @@ FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H
 FCD_API int fcd_crop_augment(const float* img, const float* label, int C, int D, int H, int W, int rd, int rh, int rw,
                              int S, const float* meta, unsigned long long seed, int hz, int hy, int hx, int hh,
                              float* out_img, float* out_lab, cudaStream_t st) {
-    if (rd > D || rh > H || rw > W || S < 1 || C < 1 || (long long)rd * rh > 65535) return -1;
+    if (rd > D || rh > H || rw > W || S < 1 || S > 65535 || C < 1) return -1;
     if (hh < rd || hh < rh || hh < rw) return -1;
-    dim3 grid((rw + 511) / 512, rd * rh, S);
-    crop_augment_kernel<<<grid, 128, 0, st>>>(img, label, C, D, H, W, rd, rh, rw, meta, seed, hz, hy, hx, hh, out_img,
-                                              out_lab);
+    // threads per row: what rw needs (4 voxels each), rounded up to whole warps, at most the block
+    int tpr = (((rw + 3) / 4 + 31) / 32) * 32;
+    if (tpr > 128) tpr = 128;
+    if (tpr == 96) tpr = 128;                            // rows per block must divide the block
+    const int rpb = 128 / tpr;
+    const long long gy = ((long long)rd * rh + rpb - 1) / rpb;
+    if (gy > 65535) return -1;
+    dim3 grid((rw + 4 * tpr - 1) / (4 * tpr), (unsigned)gy, S);
+    crop_augment_kernel<<<grid, 128, 0, st>>>(img, label, C, D, H, W, rd, rh, rw, meta, seed, hz, hy, hx, hh, tpr,
+                                              out_img, out_lab);
     return (int)cudaGetLastError();
 }

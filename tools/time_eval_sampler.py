@@ -61,5 +61,13 @@ for tag, kw in (("crop_flip_shift_noise", dict(rotate_prob=0.0)), ("all_augmenta
         sampler.coarse_dropout_prob = sampler.gridmask_prob = 0.0
     ms = timed(lambda: sampler(img, lab, 11))
     alg = 4 * 3 * 128 ** 3 * 4 * 2
-    out["sampler_" + tag] = dict(ms=round(ms, 4), patches_per_s=round(4 / ms * 1e3, 1), gbps=round(alg / ms / 1e6, 1))
+    prof = _lib.Profiler()
+    _lib.set_profiler(prof)
+    for _ in range(5):
+        flush.zero_()
+        sampler(img, lab, 11)
+    _lib.set_profiler(None)
+    per = {k: round(v["ms"] / v["calls"], 4) for k, v in prof.summary().items()}
+    out["sampler_" + tag] = dict(ms=round(ms, 4), patches_per_s=round(4 / ms * 1e3, 1), gbps=round(alg / ms / 1e6, 1),
+                                 crop_gbps=round(alg / per["fcd_crop_augment"] / 1e6, 1), per_call_ms=per)
 print(json.dumps(out))
