@@ -54,14 +54,9 @@ def _ratio(a, b):
     return torch.where(b != 0, a / b, torch.full_like(a, float("nan")))
 
 
-def compute_metrics(y_pred: torch.Tensor, y_true: torch.Tensor, compute_roc_auc: bool = False,
-                    compute_hd95: bool = False, as_tensors: bool = False) -> dict:
-    """metrics.py:74-126 `_compute_metrics`: {'Prec', 'Sens', 'F1', 'DC'} of [B, C, ...] tensors binarised at 0.5.
-    Python floats as the reference returns (ONE device->host copy of 4 doubles), or 0-d device tensors with
-    as_tensors=True (no synchronisation)."""
-    if compute_roc_auc or compute_hd95:
-        raise NotImplementedError("ROC-AUC / HD95 (metrics.py:108-121) are not built: evaluation extras outside SURVEY 8")
-    c = _drop_background(confusion_counts(y_pred, y_true)).double()
+def metrics_from_counts(counts: torch.Tensor, as_tensors: bool = False) -> dict:
+    """The dictionary of `_compute_metrics` (metrics.py:97-104) from a [B, C, 4] confusion table."""
+    c = _drop_background(counts).double()
     tp, fp, fn = c[..., 0], c[..., 1], c[..., 3]
     dice = torch.where(tp + fn > 0, 2 * tp / (2 * tp + fp + fn).clamp(min=1), torch.full_like(tp, float("nan")))
     m = c.mean(1).mean(0)
@@ -71,6 +66,35 @@ def compute_metrics(y_pred: torch.Tensor, y_true: torch.Tensor, compute_roc_auc:
     if as_tensors:
         return dict(zip(keys, vals.unbind(0)))
     return dict(zip(keys, vals.tolist()))
+
+
+def compute_metrics(y_pred: torch.Tensor, y_true: torch.Tensor, compute_roc_auc: bool = False,
+                    compute_hd95: bool = False, as_tensors: bool = False) -> dict:
+    """metrics.py:74-126 `_compute_metrics`: {'Prec', 'Sens', 'F1', 'DC'} of [B, C, ...] tensors binarised at 0.5.
+    Python floats as the reference returns (ONE device->host copy of 4 doubles), or 0-d device tensors with
+    as_tensors=True (no synchronisation)."""
+    if compute_roc_auc or compute_hd95:
+        raise NotImplementedError("ROC-AUC / HD95 (metrics.py:108-121) are not built: evaluation extras outside SURVEY 8")
+    return metrics_from_counts(confusion_counts(y_pred, y_true), as_tensors)
+
+
+class VoxelMetricAccumulator:
+    """The global branch of calculate_voxel_level_metrics (metrics.py:156-160) without keeping the volumes: the reference
+    concatenates every subject's prediction and label and counts per (subject, channel); the per-subject count tables
+    are all that computation reads, so `update` keeps 4 integers per subject and channel (subjects may differ in size,
+    which torch.cat in the reference cannot take)."""
+
+    def __init__(self):
+        self.tables = []
+
+    def update(self, pred: torch.Tensor, label: torch.Tensor) -> None:
+        lift = lambda t: t[None, None] if t.dim() == 3 else t
+        self.tables.append(confusion_counts(lift(pred), lift(label)))
+
+    def aggregate(self, as_tensors: bool = False) -> dict:
+        if not self.tables:
+            raise RuntimeError("VoxelMetricAccumulator.aggregate: no subject was added")
+        return metrics_from_counts(torch.cat(self.tables), as_tensors)
 
 
 def calculate_voxel_level_metrics(predictions, labels, compute_roc_auc: bool = False, compute_hd95: bool = False,

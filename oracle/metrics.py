@@ -41,19 +41,24 @@ def _nanmean_channels_then_batch(f):
     return float(per_b.sum() / nb) if nb > 0 else 0.0
 
 
-def compute_metrics(y_pred, y_true):
-    """metrics.py:74-126 `_compute_metrics` without the optional ROC-AUC / HD95 branches: {'Prec','Sens','F1','DC'}
-    (+ 'Spec', which the reference computes and then leaves out of its dict)."""
-    c = _drop_background(confusion_counts(y_pred, y_true)).astype(np.float64)
+def metrics_from_counts(counts):
+    """The dictionary of metrics.py:74-104 from the [B, C, 4] count table ('Spec' is computed by the reference and then
+    left out of its dict)."""
+    c = _drop_background(np.asarray(counts)).astype(np.float64)
     tp, fp, tn, fn = (c[..., i] for i in range(4))
     denom = 2 * tp + fp + fn                                   # |p| + |t|
     with np.errstate(divide="ignore", invalid="ignore"):
         dice = np.where(tp + fn > 0, 2 * tp / denom, np.nan)
-        m = c.mean(1).mean(0)                                  # no NaN in a count table: plain means
-        mtp, mfp, mtn, mfn = m
-        ratio = lambda a, b: float(a / b) if b != 0 else float("nan")
-        return {"Prec": ratio(mtp, mtp + mfp), "Sens": ratio(mtp, mtp + mfn), "Spec": ratio(mtn, mtn + mfp),
-                "F1": ratio(2 * mtp, 2 * mtp + mfn + mfp), "DC": _nanmean_channels_then_batch(dice)}
+    mtp, mfp, mtn, mfn = c.mean(1).mean(0)                     # no NaN in a count table: plain means
+    ratio = lambda a, b: float(a / b) if b != 0 else float("nan")
+    return {"Prec": ratio(mtp, mtp + mfp), "Sens": ratio(mtp, mtp + mfn), "Spec": ratio(mtn, mtn + mfp),
+            "F1": ratio(2 * mtp, 2 * mtp + mfn + mfp), "DC": _nanmean_channels_then_batch(dice)}
+
+
+def compute_metrics(y_pred, y_true):
+    """metrics.py:74-126 `_compute_metrics` without the optional ROC-AUC / HD95 branches: {'Prec','Sens','F1','DC'}
+    (+ 'Spec')."""
+    return metrics_from_counts(confusion_counts(y_pred, y_true))
 
 
 def calculate_voxel_level_metrics(predictions, labels, average_across_subjects=False):

@@ -105,3 +105,54 @@ def test_evaluate_fp_counts_components_without_overlap():
     assert got == om.evaluate_fp(ids, lab)
     assert int(metrics.evaluate_fp(torch.zeros((D, H, W), device=DEV), torch.from_numpy(lab).to(DEV))) == 0
     assert int(metrics.evaluate_fp(torch.from_numpy(ids).to(DEV), torch.from_numpy(lab).to(DEV), max_id=10)) == -1
+
+
+def test_evaluate_loop_matches_the_oracle_pipeline():
+    """fcd_b200.evaluate (ModelTrainer.evaluate, train.py:184-234) on three synthetic subjects of different sizes with an
+    exact-arithmetic predictor: the oracle pipeline is oracle sliding window (roi = patch_size, sw_batch_size 2, overlap
+    0.25) -> softmax >= 0.5 -> scipy post_process_segment(min_region_size) -> numpy confusion counts / metrics; the
+    post-processed masks and count tables must be identical, the metrics agree to 1e-12, the loss to fp32 accuracy."""
+    import fcd_b200
+    from fcd_b200 import evaluation, metrics
+    from oracle import inferer as oinf
+    from oracle import losses as olosses
+    from oracle import metrics as om
+    from oracle import synth
+    from tests.test_gpu_inference import _ExactNet, _dyadic
+
+    params = fcd_b200.get_default_params()
+    params.update(patch_size=(32, 32, 32), min_region_size=20, loss="DiceCELoss")
+    w = _dyadic((2, 2, 3, 3, 3), 5, 0.125, 0.5)
+    net = _ExactNet(w)
+    net.train()
+    sizes = [(48, 40, 56), (32, 64, 40), (40, 40, 40)]
+    data, ref_tables, ref_losses, ref_masks = [], [], [], []
+    for i, size in enumerate(sizes):
+        x = _dyadic((1, 2) + size, 10 + i, 0.25, 2.0)
+        y = synth.label(1, size, seed=30 + i, n_blobs=3)
+        data.append({"image": x, "label": y})
+        logits = oinf.sliding_window_inference(x, params["patch_size"], 2, net.forward, 0.25)
+        ref_losses.append(float(olosses.combined_loss(params, logits, y)))
+        lab = oinf.label_map(logits, "threshold")
+        mask, _ = oinf.post_process_segment((lab[0, 1] > 0.5).float().numpy(), params["min_region_size"])
+        ref_masks.append(mask)
+        ref_tables.append(om.confusion_counts(mask[None, None], y.numpy()))
+    loss_fn = fcd_b200.CombinedLoss(params, DEV)
+    # per subject: masks and count tables
+    acc = metrics.VoxelMetricAccumulator()
+    for d, mask, tab in zip(data, ref_masks, ref_tables):
+        loss, pred, truth = evaluation.evaluate_subject(net, d["image"].to(DEV), d["label"].to(DEV), params, loss_fn)
+        assert np.array_equal(pred.cpu().numpy(), mask)
+        acc.update(pred, truth)
+        assert np.array_equal(acc.tables[-1].cpu().numpy(), tab)
+    # the whole loop (subjects of different sizes: the reference's torch.cat could not even take them)
+    val_loss, got = fcd_b200.evaluate(net, data, params, loss_fn, device=DEV)
+    assert net.training                                           # the mode is restored
+    ref = om.metrics_from_counts(np.concatenate(ref_tables))
+    for k in ("Prec", "Sens", "F1", "DC"):
+        assert _close(got[k], ref[k]), (k, got[k], ref[k])
+    assert abs(val_loss - sum(ref_losses) / 3) <= 2e-5 * max(1.0, abs(sum(ref_losses) / 3))
+    # without post-processing the thresholded FCD channel itself is scored
+    _, pred, _ = evaluation.evaluate_subject(net, data[0]["image"].to(DEV), data[0]["label"].to(DEV), params, None, False)
+    logits = oinf.sliding_window_inference(data[0]["image"], params["patch_size"], 2, net.forward, 0.25)
+    assert np.array_equal(pred.cpu().numpy(), oinf.label_map(logits, "threshold")[0, 1].numpy())
