@@ -87,16 +87,31 @@ __global__ void __launch_bounds__(kThreads) component_mark_kernel(const float* _
                                                                   const float* __restrict__ label, long long V,
                                                                   long long max_id, unsigned char* __restrict__ flags,
                                                                   unsigned long long* __restrict__ out) {
-    const long long stride = (long long)gridDim.x * kThreads;
     int bad = 0;
-    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += stride) {
-        const float c = cc[v];
-        if (c == 0.f) continue;
+    auto mark = [&](float c, float l) {
+        if (c == 0.f) return;
         const long long id = (long long)c;
-        if (id < 1 || id > max_id || (float)id != c) { ++bad; continue; }
+        if (id < 1 || id > max_id || (float)id != c) { ++bad; return; }
         // same-value byte stores from many threads: benign
         if (flags[id] == 0) flags[id] = 1;
-        if (label[v] != 0.f && flags[max_id + 1 + id] == 0) flags[max_id + 1 + id] = 1;
+        if (l != 0.f && flags[max_id + 1 + id] == 0) flags[max_id + 1 + id] = 1;
+    };
+    if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(cc) | reinterpret_cast<uintptr_t>(label)) & 15) == 0) {
+        const long long V4 = V >> 2, stride = (long long)gridDim.x * kThreads;
+        const float4* c4 = reinterpret_cast<const float4*>(cc);
+        const float4* l4 = reinterpret_cast<const float4*>(label);
+        for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V4; v += 2 * stride) {
+            // two independent 16-byte loads per stream in flight
+            const bool two = v + stride < V4;
+            const float4 ca = __ldg(c4 + v), la = __ldg(l4 + v);
+            const float4 cb = two ? __ldg(c4 + v + stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 lb = two ? __ldg(l4 + v + stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mark(ca.x, la.x); mark(ca.y, la.y); mark(ca.z, la.z); mark(ca.w, la.w);
+            mark(cb.x, lb.x); mark(cb.y, lb.y); mark(cb.z, lb.z); mark(cb.w, lb.w);
+        }
+    } else {
+        const long long stride = (long long)gridDim.x * kThreads;
+        for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < V; v += stride) mark(cc[v], label[v]);
     }
     if (bad) atomicAdd(out + 2, (unsigned long long)bad);
 }

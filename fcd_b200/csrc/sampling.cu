@@ -47,9 +47,19 @@ __global__ void __launch_bounds__(256) fg_block_counts_kernel(const float* __res
                                                               int* __restrict__ counts) {
     const long long base = (long long)blockIdx.x * kBlockVox;
     int n = 0;
-    for (int i = threadIdx.x; i < kBlockVox; i += 256) {
-        const long long v = base + i;
-        if (v < V && label[v] > 0.f) ++n;
+    if (base + kBlockVox <= V && (reinterpret_cast<uintptr_t>(label) & 15) == 0) {
+        // whole block inside the volume: four independent 16-byte loads per thread
+        const float4* p = reinterpret_cast<const float4*>(label + base);
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(p + k * 256 + threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n += (q[k].x > 0.f) + (q[k].y > 0.f) + (q[k].z > 0.f) + (q[k].w > 0.f);
+    } else {
+        for (int i = threadIdx.x; i < kBlockVox; i += 256) {
+            const long long v = base + i;
+            if (v < V && label[v] > 0.f) ++n;
+        }
     }
     __shared__ int sh[8];
 #pragma unroll
@@ -100,22 +110,34 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
         const double u = ((double)u01(seed, s, 1, 0) + (double)u01(seed, s, 2, 0) * (1.0 / 16777216.0));
         long long r = (long long)(u * (double)n);
         if (r >= n) r = n - 1;
-        // block holding the r-th voxel of the class: first block with (voxels of the class before it) + (its own) > r
-        long long acc = 0;
-        int b = -1;
-        for (int b0 = 0; b0 < nb && b < 0; b0 += 32) {
-            const int bi = b0 + lane;
-            long long c = 0;
-            if (bi < nb) {
-                const long long inb = min((long long)kBlockVox, V - (long long)bi * kBlockVox);
-                c = fg ? counts[bi] : inb - counts[bi];
-            }
+        // block holding the r-th voxel of the class: first block with (voxels of the class before it) + (its own) > r.
+        // Two levels: every lane sums a contiguous chunk of the blocks (independent loads), one warp scan picks the
+        // chunk, the warp scans that chunk 32 blocks at a time.
+        auto class_count = [&](int bi) -> long long {
+            if (bi >= nb) return 0;
+            const long long inb = min((long long)kBlockVox, V - (long long)bi * kBlockVox);
+            return fg ? (long long)counts[bi] : inb - counts[bi];
+        };
+        auto warp_scan = [&](long long c) {            // inclusive prefix over the lanes
             long long incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long up = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += up;
             }
+            return incl;
+        };
+        const int chunk = (nb + 31) / 32;              // blocks per lane
+        long long mine = 0;
+        for (int j = 0; j < chunk; ++j) mine += class_count(lane * chunk + j);
+        long long incl = warp_scan(mine);
+        const int lsel = __ffs(__ballot_sync(kFull, incl > r)) - 1;        // r < n: some lane passes
+        long long acc = __shfl_sync(kFull, incl - mine, lsel);             // voxels of the class before the chunk
+        int b = -1;
+        for (int b0 = lsel * chunk; b < 0; b0 += 32) {
+            const int bi = b0 + lane;
+            const long long c = bi < (lsel + 1) * chunk ? class_count(bi) : 0;
+            incl = warp_scan(c);
             const long long total = __shfl_sync(kFull, incl, 31);
             if (acc + total > r) {
                 const int l = __ffs(__ballot_sync(kFull, acc + incl > r)) - 1;
@@ -125,11 +147,35 @@ __global__ void __launch_bounds__(256) pick_centers_kernel(const float* __restri
                 acc += total;
             }
         }
-        // ... then the voxel inside it
+        // ... then the voxel inside it, the same way: 128 consecutive voxels per lane, then 32 at a time
         const long long base = (long long)b * kBlockVox;
         int left = (int)(r - acc);
+        constexpr int kPerLane = kBlockVox / 32;
+        int cnt_lane = 0;
+        {
+            const long long v0 = base + (long long)lane * kPerLane;
+            if (v0 + kPerLane <= V && (reinterpret_cast<uintptr_t>(label) & 15) == 0) {
+                const float4* p = reinterpret_cast<const float4*>(label + v0);
+#pragma unroll 8
+                for (int j = 0; j < kPerLane / 4; ++j) {
+                    const float4 q = __ldg(p + j);
+                    cnt_lane += ((q.x > 0.f) == fg) + ((q.y > 0.f) == fg) + ((q.z > 0.f) == fg) + ((q.w > 0.f) == fg);
+                }
+            } else {
+                for (int j = 0; j < kPerLane; ++j)
+                    cnt_lane += (v0 + j < V) && ((label[v0 + j] > 0.f) == fg);
+            }
+        }
+        int incl_v = cnt_lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl_v, o);
+            if (lane >= o) incl_v += up;
+        }
+        const int vsel = __ffs(__ballot_sync(kFull, incl_v > left)) - 1;
+        left -= __shfl_sync(kFull, incl_v - cnt_lane, vsel);
         long long v = base;
-        for (int i0 = 0; i0 < kBlockVox; i0 += 32) {
+        for (int i0 = vsel * kPerLane; i0 < (vsel + 1) * kPerLane; i0 += 32) {
             const long long vi = base + i0 + lane;
             const bool match = vi < V && ((label[vi] > 0.f) == fg);
             unsigned mm = __ballot_sync(kFull, match);
@@ -195,12 +241,12 @@ __device__ __forceinline__ float patch_at(const float* __restrict__ src, int H, 
     const int sz = z0 + ((flips & 1) ? rd - 1 - q0 : q0);
     const int sy = y0 + ((flips & 2) ? rh - 1 - q1 : q1);
     const int sx = x0 + ((flips & 4) ? rw - 1 - q2 : q2);
-    return __ldg(src + ((long long)sz * H + sy) * W + sx);
+    return __ldg(src + ((sz * H + sy) * W + sx));          // D * H * W < 2^31 (checked by the entry point)
 }
 
 // grid: (x-chunks, row groups, S); block = rpb rows x tpr threads (tpr = threads a row needs, a multiple of 32), each thread
 // 4 consecutive x of one output row, all channels
-__global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restrict__ img, const float* __restrict__ label,
+__global__ void __launch_bounds__(128, 6) crop_augment_kernel(const float* __restrict__ img, const float* __restrict__ label,
                                                            int C, int D, int H, int W, int rd, int rh, int rw,
                                                            const float* __restrict__ meta, unsigned long long seed,
                                                            int hz, int hy, int hx, int hh, int tpr,
@@ -219,26 +265,10 @@ __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restri
     const long long V = (long long)D * H * W, P = (long long)rd * rh * rw;
     const long long dst = ((long long)z * rh + y) * rw + x4;
 
-    // rotation about spatial axis 1: source coordinates on axes 0 and 2 (border padding), shared by all channels
-    int i0[4], i0b[4], i2[4], i2b[4], n0[4], n2[4];
-    float w0[4], w2[4];
-    if (rot) {
-        const float c0 = (float)(rd - 1) * 0.5f, c2 = (float)(rw - 1) * 0.5f;
-        const float e0 = (float)z - c0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float e2 = (float)(x4 + i) - c2;
-            float s0 = __fadd_rn(c0, __fadd_rn(__fmul_rn(cs, e0), __fmul_rn(sn, e2)));
-            float s2 = __fadd_rn(c2, __fsub_rn(__fmul_rn(cs, e2), __fmul_rn(sn, e0)));
-            s0 = fminf(fmaxf(s0, 0.f), (float)(rd - 1));
-            s2 = fminf(fmaxf(s2, 0.f), (float)(rw - 1));
-            const float f0 = floorf(s0), f2 = floorf(s2);
-            w0[i] = __fsub_rn(s0, f0); w2[i] = __fsub_rn(s2, f2);
-            i0[i] = (int)f0; i2[i] = (int)f2;
-            i0b[i] = min(i0[i] + 1, rd - 1); i2b[i] = min(i2[i] + 1, rw - 1);
-            n0[i] = (int)rintf(s0); n2[i] = (int)rintf(s2);           // nearest: round half to even (grid_sample)
-        }
-    }
+    // rotation about spatial axis 1: source coordinates on axes 0 and 2 (border padding).  They are recomputed per channel
+    // (a dozen flops) instead of being kept in registers across the channel loop: occupancy matters more here.
+    const float c0 = (float)(rd - 1) * 0.5f, c2 = (float)(rw - 1) * 0.5f;
+    const float e0 = (float)z - c0;
     // coarse-dropout holes and grid mask of the 4 voxels (image channels only)
     float keep[4] = {1.f, 1.f, 1.f, 1.f};
     bool hole[4] = {false, false, false, false};
@@ -273,18 +303,29 @@ __global__ void __launch_bounds__(128) crop_augment_kernel(const float* __restri
             if (!rot) {
                 // RandFlipd(spatial_axis=a) reverses axis a of the CROPPED patch
                 v[i] = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, z, y, x);
-            } else if (c == C) {
-                v[i] = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, n0[i], y, n2[i]);
-            } else {
-                const float v00 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0[i], y, i2[i]);
-                const float v01 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0[i], y, i2b[i]);
-                const float v10 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b[i], y, i2[i]);
-                const float v11 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b[i], y, i2b[i]);
-                const float u2 = __fsub_rn(1.f, w2[i]), u0 = __fsub_rn(1.f, w0[i]);
-                const float a = __fadd_rn(__fmul_rn(v00, u2), __fmul_rn(v01, w2[i]));
-                const float b = __fadd_rn(__fmul_rn(v10, u2), __fmul_rn(v11, w2[i]));
-                v[i] = __fadd_rn(__fmul_rn(a, u0), __fmul_rn(b, w0[i]));
+                continue;
             }
+            const float e2 = (float)x - c2;
+            float s0 = __fadd_rn(c0, __fadd_rn(__fmul_rn(cs, e0), __fmul_rn(sn, e2)));
+            float s2 = __fadd_rn(c2, __fsub_rn(__fmul_rn(cs, e2), __fmul_rn(sn, e0)));
+            s0 = fminf(fmaxf(s0, 0.f), (float)(rd - 1));
+            s2 = fminf(fmaxf(s2, 0.f), (float)(rw - 1));
+            if (c == C) {                                 // label: nearest, round half to even (grid_sample)
+                v[i] = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, (int)rintf(s0), y, (int)rintf(s2));
+                continue;
+            }
+            const float f0 = floorf(s0), f2 = floorf(s2);
+            const float w0 = __fsub_rn(s0, f0), w2 = __fsub_rn(s2, f2);
+            const int i0 = (int)f0, i2 = (int)f2;
+            const int i0b = min(i0 + 1, rd - 1), i2b = min(i2 + 1, rw - 1);
+            const float v00 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0, y, i2);
+            const float v01 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0, y, i2b);
+            const float v10 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b, y, i2);
+            const float v11 = patch_at(src, H, W, z0, y0, x0, flips, rd, rh, rw, i0b, y, i2b);
+            const float u2 = __fsub_rn(1.f, w2), u0 = __fsub_rn(1.f, w0);
+            const float a = __fadd_rn(__fmul_rn(v00, u2), __fmul_rn(v01, w2));
+            const float b = __fadd_rn(__fmul_rn(v10, u2), __fmul_rn(v11, w2));
+            v[i] = __fadd_rn(__fmul_rn(a, u0), __fmul_rn(b, w0));
         }
         if (c < C) {
             if (nstd > 0.f) {
@@ -351,7 +392,7 @@ FCD_API int fcd_pick_centers(const float* label, const int* counts, int D, int H
 FCD_API int fcd_crop_augment(const float* img, const float* label, int C, int D, int H, int W, int rd, int rh, int rw,
                              int S, const float* meta, unsigned long long seed, int hz, int hy, int hx, int hh,
                              float* out_img, float* out_lab, cudaStream_t st) {
-    if (rd > D || rh > H || rw > W || S < 1 || S > 65535 || C < 1) return -1;
+    if (rd > D || rh > H || rw > W || S < 1 || S > 65535 || C < 1 || (long long)D * H * W > 0x7fffffffLL) return -1;
     if (hh < rd || hh < rh || hh < rw) return -1;
     // threads per row: what rw needs (4 voxels each), rounded up to whole warps, at most the block
     int tpr = (((rw + 3) / 4 + 31) / 32) * 32;
