@@ -149,14 +149,26 @@ __global__ void uf_init(const unsigned char* __restrict__ m, const int* __restri
     L[i] = (int)(i - (lane - s0));
 }
 
+// Unions of every active voxel with its FORWARD neighbours (reach R = 1; R = 2 for background voxels next to the
+// foreground), deduplicated by runs: uf_init already joined the voxels of an x-run inside a 32-voxel segment, so
+//   * if my predecessor x-1 is in my run and reaches the neighbour row too (reach Rp >= row distance), it has connected
+//     the run to the row's voxels up to x-1+Rp: I only look at the ones beyond that;
+//   * a row voxel whose own predecessor is active, in the same 32-voxel segment (joined by uf_init) and already known to
+//     be connected to me needs no union of its own.
+// A dense mask makes ~3 unions per run and row pair instead of 13 (62) per voxel; the resulting partition is the same
+// (checked exhaustively against the full walk by a CPU model of these rules, and against scipy by the tests).
 template <bool BG>
 __global__ void uf_merge(const unsigned char* __restrict__ m, const int* __restrict__ misc, int* __restrict__ L, Dims d) {
     const long long i = blockIdx.x * (long long)TB + threadIdx.x;
-    if (i >= d.N) return;
-    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
-    if (!uf_active<BG>(m, misc, i, z, y, x)) return;
-    int R = 1;
-    if (BG) {
+    const int lane = threadIdx.x & 31;
+    int x = 0, y = 0, z = 0;
+    bool act = false;
+    if (i < d.N) {
+        x = (int)(i % d.W); y = (int)((i / d.W) % d.H); z = (int)(i / ((long long)d.W * d.H));
+        act = uf_active<BG>(m, misc, i, z, y, x);
+    }
+    int R = act ? 1 : 0;
+    if (BG && act) {
         // walk the 5x5x5 forward half only when a foreground voxel sits in my 3x3x3 neighbourhood
         bool near = false;
         for (int dz = -1; dz <= 1 && !near; ++dz)
@@ -168,16 +180,37 @@ __global__ void uf_merge(const unsigned char* __restrict__ m, const int* __restr
                 }
         R = near ? 2 : 1;
     }
+    // reach of the previous voxel if it belongs to my run (same warp: uf_init runs never cross a 32-voxel segment)
+    const int Rl = __shfl_up_sync(0xffffffffu, R, 1);
+    if (!act) return;
+    const int Rp = (lane != 0 && x > 0) ? Rl : 0;
+    // my own row: x+1 only across a segment boundary (inside a segment uf_init joined the run), x+2 for reach 2
+    for (int dx = 1; dx <= R; ++dx) {
+        if (x + dx >= d.W) break;
+        if (dx == 1 && lane != 31) continue;
+        if (uf_active<BG>(m, misc, i + dx, z, y, x + dx)) uf_union(L, (int)i, (int)(i + dx));
+    }
     for (int dz = 0; dz <= R; ++dz)
-        for (int dy = (dz == 0 ? 0 : -R); dy <= R; ++dy)
-            for (int dx = ((dz == 0 && dy == 0) ? 1 : -R); dx <= R; ++dx) {
-                const int zz = z + dz, yy = y + dy, xx = x + dx;
-                if (zz >= d.D || yy < 0 || yy >= d.H || xx < 0 || xx >= d.W) continue;
-                const long long j = ((long long)zz * d.H + yy) * d.W + xx;
-                if (!uf_active<BG>(m, misc, j, zz, yy, xx)) continue;
-                if (dz == 0 && dy == 0 && dx == 1 && (i & 31) != 31) continue;   // same run segment: joined by uf_init
-                uf_union(L, (int)i, (int)j);
+        for (int dy = -R; dy <= R; ++dy) {
+            if (dz == 0 && dy <= 0) continue;
+            const int zz = z + dz, yy = y + dy;
+            if (zz >= d.D || yy < 0 || yy >= d.H) continue;
+            const long long jrow = ((long long)zz * d.H + yy) * d.W;
+            const int rowdist = dz > (dy < 0 ? -dy : dy) ? dz : (dy < 0 ? -dy : dy);
+            const bool covered = Rp >= rowdist;
+            const int lo = covered ? x + Rp : x - R;
+            // is the row voxel before `lo` active (then, if covered, my run is already connected to it)
+            bool prev_act = false;
+            if (covered && lo - 1 < d.W) prev_act = uf_active<BG>(m, misc, jrow + lo - 1, zz, yy, lo - 1);
+            for (int xx = lo; xx <= x + R; ++xx) {
+                if (xx < 0) continue;
+                if (xx >= d.W) break;
+                const long long j = jrow + xx;
+                const bool a = uf_active<BG>(m, misc, j, zz, yy, xx);
+                if (a && !(prev_act && (j & 31) != 0)) uf_union(L, (int)i, (int)j);
+                prev_act = a;
             }
+        }
 }
 
 __global__ void uf_flatten(int* __restrict__ L, Dims d) {
