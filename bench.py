@@ -664,20 +664,52 @@ def main():
                 # the label map this (untrained) model predicts -- usually one huge component, the worst case for
                 # connected components -- and on a realistic one (three lesions, ~1 % foreground)
                 def time_pp(m):
+                    """median over 7 calls, each bracketed by its own events (a host stall between two of the ~21
+                    launches of a call -- allocator, GC -- would otherwise be charged to the device)"""
                     for _ in range(4):
                         post_process_segment(m, 50)
                     torch.cuda.synchronize()
-                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    p0.record()
-                    for _ in range(5):
+                    ts = []
+                    for _ in range(7):
+                        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        p0.record()
                         out_m, _ = post_process_segment(m, 50)
-                    p1.record()
-                    torch.cuda.synchronize()
-                    return p0.elapsed_time(p1) / 5, out_m
+                        p1.record()
+                        torch.cuda.synchronize()
+                        ts.append(p0.elapsed_time(p1))
+                    return sorted(ts)[len(ts) // 2], out_m
                 pp_ms, pp_mask = time_pp(lab[0, 0])
                 _, lesions = synthetic.make_batch(1, 2, tuple(vshape[2:]), seed=5)
                 lesions = lesions[0, 0].to(dev)
                 pp_ms_real, pp_mask_real = time_pp(lesions)
+                # the reference's validation loop for one subject through the reference-facing API, with ITS settings
+                # (train.py:148-234: sw_batch_size 2, overlap 0.25 -> 9 forwards of 2 windows; loss; softmax >= 0.5;
+                # post-processing; confusion counts), everything on the device; one read of the metrics at the end
+                val = None
+                if world == 1:
+                    try:
+                        from fcd_b200 import evaluation, metrics as fmetrics
+                        lab_vol = synthetic.make_batch(1, 2, tuple(vshape[2:]), seed=5)[1].to(dev)
+                        for _ in range(2):
+                            evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn)
+                        torch.cuda.synchronize()
+                        acc = fmetrics.VoxelMetricAccumulator()
+                        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        n_val = 4
+                        v0.record()
+                        for _ in range(n_val):
+                            vl, vp, vt = evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn)
+                            acc.update(vp, vt)
+                        vm = acc.aggregate()
+                        v1.record()
+                        torch.cuda.synchronize()
+                        val = {"what": "fcd_b200.evaluate_subject per 256x256x192 subject: sliding window (sw_batch_size 2, "
+                                       "overlap 0.25) + loss + label map + device post-processing + confusion counts; "
+                                       "metrics read once at the end",
+                               "ms_per_subject": v0.elapsed_time(v1) / n_val, "subjects_per_s": 1e3 * n_val / v0.elapsed_time(v1),
+                               "val_loss": float(vl), "metrics": {k: (None if v != v else v) for k, v in vm.items()}}
+                    except Exception as e:      # an extra: never lose the volume numbers over it
+                        val = {"error": f"{type(e).__name__}: {e}"[:200]}
             errs = _kernel_errors()
             bad = torch.tensor([float(errs["word"] != 0)], device=dev)
             if world > 1:                      # a time-out on ANY rank voids the volume every rank contributed to
@@ -702,7 +734,8 @@ def main():
                                     "ms_synthetic_lesions": pp_ms_real, "fg_fraction_synthetic": float(lesions.mean()),
                                     "kept_voxels_synthetic": int(pp_mask_real.sum().item()),
                                     "ms_model_label_map": pp_ms, "fg_fraction_model": float(lab_h.float().mean()),
-                                    "kept_voxels_model": int(pp_mask.sum().item())}}
+                                    "kept_voxels_model": int(pp_mask.sum().item())},
+                   "validation_loop": val}
         except Exception as e:
             aux = {"error": f"{type(e).__name__}: {e}"[:300]}
 
