@@ -690,24 +690,35 @@ def main():
                     try:
                         from fcd_b200 import evaluation, metrics as fmetrics
                         lab_vol = synthetic.make_batch(1, 2, tuple(vshape[2:]), seed=5)[1].to(dev)
-                        for _ in range(2):
-                            evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn)
-                        torch.cuda.synchronize()
-                        acc = fmetrics.VoxelMetricAccumulator()
-                        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        n_val = 4
-                        v0.record()
-                        for _ in range(n_val):
-                            vl, vp, vt = evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn)
-                            acc.update(vp, vt)
-                        vm = acc.aggregate()
-                        v1.record()
-                        torch.cuda.synchronize()
-                        val = {"what": "fcd_b200.evaluate_subject per 256x256x192 subject: sliding window (sw_batch_size 2, "
-                                       "overlap 0.25) + loss + label map + device post-processing + confusion counts; "
-                                       "metrics read once at the end",
-                               "ms_per_subject": v0.elapsed_time(v1) / n_val, "subjects_per_s": 1e3 * n_val / v0.elapsed_time(v1),
-                               "val_loss": float(vl), "metrics": {k: (None if v != v else v) for k, v in vm.items()}}
+                        def time_val(bs):
+                            for _ in range(2):
+                                evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn, sw_batch_size=bs)
+                            torch.cuda.synchronize()
+                            acc = fmetrics.VoxelMetricAccumulator()
+                            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            n_val = 4
+                            v0.record()
+                            for _ in range(n_val):
+                                vl, vp, vt = evaluation.evaluate_subject(model, vol_d, lab_vol, params, loss_fn,
+                                                                         sw_batch_size=bs)
+                                acc.update(vp, vt)
+                            vm = acc.aggregate()
+                            v1.record()
+                            torch.cuda.synchronize()
+                            return v0.elapsed_time(v1) / n_val, float(vl), vm
+                        ms_ref, vl, vm = time_val(2)
+                        ms_full, vl2, vm2 = time_val(18)
+                        val = {"what": "fcd_b200.evaluate_subject per 256x256x192 subject: sliding window (overlap 0.25) + loss "
+                                       "+ label map + device post-processing + confusion counts; metrics read once at the "
+                                       "end.  sw_batch_size 2 = the reference's hard-coded value (9 forwards of 2 windows), "
+                                       "18 = all windows in one forward (same arithmetic; the deep levels pick their split-K "
+                                       "order from the row count, so logits agree to bf16 rounding and labels differ on "
+                                       "near-ties only -- an untrained model has many)",
+                               "ms_per_subject": ms_ref, "subjects_per_s": 1e3 / ms_ref,
+                               "ms_per_subject_sw_batch_18": ms_full, "subjects_per_s_sw_batch_18": 1e3 / ms_full,
+                               "val_loss": vl, "metrics": {k: (None if v != v else v) for k, v in vm.items()},
+                               "val_loss_sw_batch_18": vl2,
+                               "metrics_sw_batch_18": {k: (None if v != v else v) for k, v in vm2.items()}}
                     except Exception as e:      # an extra: never lose the volume numbers over it
                         val = {"error": f"{type(e).__name__}: {e}"[:200]}
             errs = _kernel_errors()
