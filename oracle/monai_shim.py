@@ -875,6 +875,26 @@ def _mod(name, **attrs):
     return m
 
 
+class _InertTransform:
+    """Stand-in for a monai.transforms class that is constructed but never applied in the tests."""
+
+    def __init__(self, *args, **kwargs):
+        self.args = args
+        self.__dict__.update(kwargs)
+
+    def __call__(self, data):
+        raise NotImplementedError(f"{type(self).__name__}: the MONAI shim only records this transform's arguments")
+
+
+class _Compose(_InertTransform):
+    def __init__(self, transforms=(), *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.transforms = list(transforms)
+
+    def append(self, t):
+        self.transforms.append(t)
+
+
 class MapTransform:
     """monai.transforms.MapTransform as far as utils/gridmask.py uses it: stores the keys as a tuple [RECALLED]."""
 
@@ -909,7 +929,12 @@ def install():
          GeneralizedDiceLoss=GeneralizedDiceLoss, GeneralizedDiceFocalLoss=GeneralizedDiceFocalLoss)
     _mod("monai.inferers", sliding_window_inference=sliding_window_inference)
     # utils/gridmask.py:5 subclasses MapTransform for its dictionary wrapper; only `keys` is used (gridmask.py:126, 144)
-    _mod("monai.transforms", MapTransform=MapTransform)
+    tr = _mod("monai.transforms", MapTransform=MapTransform, Compose=_Compose)
+    # get_transforms.py:2-9 imports two dozen dictionary transforms by name only to build its pipelines; none of them is
+    # on the path under test (the per-case file transforms are out of scope, the per-patch ones are restated by
+    # oracle/sampling.py).  Any other name resolves to an inert record of its constructor arguments, which is all
+    # FCDTrainTransform.set_prob touches (`self.coarse_dropout.prob`, get_transforms.py:116-120).
+    tr.__getattr__ = lambda name: type(name, (_InertTransform,), {})
     if "thop" not in sys.modules:
         _mod("thop", profile=lambda *a, **k: (0, 0), clever_format=lambda x, *a, **k: x)
     if "pyparsing" not in sys.modules:

@@ -51,6 +51,13 @@ def load_gridmask():
     return _load_by_path("fcd_ref_gridmask", os.path.join(REFERENCE_ROOT, "utils", "gridmask.py"))
 
 
+def load_transforms():
+    """get_transforms.py of the reference (FCDTrainTransform: the probability ramp of coarse dropout / GridMask); its
+    MONAI transform classes are inert records from the shim, its GridMaskd is the reference's own utils/gridmask.py."""
+    load()
+    return importlib.import_module("get_transforms")
+
+
 def default_params():
     load()
     return importlib.import_module("config").get_default_params()

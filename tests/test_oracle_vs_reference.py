@@ -179,3 +179,39 @@ def test_evaluate_fp_oracle_matches_reference():
         assert n > 3
         assert om.evaluate_fp(cc, lab) == int(uc.evaluate_fp(cc, lab))
     assert om.evaluate_fp(np.zeros((4, 4, 4)), np.ones((4, 4, 4))) == int(uc.evaluate_fp(np.zeros((4, 4, 4)), np.ones((4, 4, 4)))) == 0
+
+
+def test_sampler_probability_ramp_matches_reference():
+    """GpuPatchSampler.set_prob / has_gradual_prob against FCDTrainTransform (get_transforms.py:39-50, 113-126) run live:
+    the coarse-dropout probability lands in RandCoarseDropoutd.prob, the GridMask one in utils/gridmask.py's Grid.prob."""
+    import fcd_b200
+    gt = ref_loader.load_transforms()
+    base = ref_loader.default_params()
+    cases = [dict(), dict(coarse_dropout_max_prob=0.3), dict(gridmask_max_prob=0.4),
+             dict(coarse_dropout_max_prob=0.25, coarse_dropout_start_epoch=10, gridmask_max_prob=0.5, gridmask_start_epoch=20)]
+    for over in cases:
+        p = dict(base)
+        p.update(patch_size=(32, 32, 32), samples_per_case=2, **over)
+        ref = gt.FCDTrainTransform(p)
+        mine = fcd_b200.GpuPatchSampler(p)
+        assert mine.has_gradual_prob() == ref.has_gradual_prob()
+        assert mine.coarse_dropout_prob == ref.coarse_dropout.prob and mine.gridmask_prob == ref.gridmask.grid.prob
+        for epoch in (0, 1, 9, 10, 11, 20, 35, 60, 99, 100):
+            ref.set_prob(epoch, 100)
+            mine.set_prob(epoch, 100)
+            assert mine.coarse_dropout_prob == ref.coarse_dropout.prob, (over, epoch)
+            assert mine.gridmask_prob == ref.gridmask.grid.prob, (over, epoch)
+    # the constructor arguments the sampler's defaults restate (get_transforms.py:45, 49, 70-81)
+    ref = gt.FCDTrainTransform(dict(base, patch_size=(32, 32, 32), samples_per_case=2))
+    cd = ref.coarse_dropout
+    assert (cd.holes, tuple(cd.spatial_size), cd.fill_value) == (5, (16, 16, 16), 0)
+    g = ref.gridmask.grid
+    assert (g.d1, g.d2, g.ratio, g.mode) == (16, 32, 0.5, 0)
+    names = [type(t).__name__ for t in ref.train_transforms.transforms]
+    assert names[-9:] == ["RandCropByPosNegLabeld", "RandFlipd", "RandFlipd", "RandFlipd", "RandRotated",
+                          "RandShiftIntensityd", "RandGaussianNoised", "RandCoarseDropoutd", "GridMaskd"]
+    rot, shift, noise = ref.train_transforms.transforms[-5:-2]
+    assert abs(rot.range_y - torch.pi / 2) < 1e-12 and rot.prob == 0.5 and list(rot.mode) == ["bilinear", "nearest"]
+    assert (shift.offsets, shift.prob, noise.std, noise.prob) == (0.1, 0.5, 0.1, 0.5)
+    crop = ref.train_transforms.transforms[-9]
+    assert (crop.pos, crop.neg, crop.num_samples) == (1, 1, 2)
