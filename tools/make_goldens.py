@@ -159,10 +159,54 @@ def run_sliding_and_postproc():
     print("sliding/postproc", cases, pp)
 
 
+GRIDMASK_CASES = [
+    # shape, d, (st_d, st_h, st_w), ratio, mode
+    ((16, 16, 16), 5, (0, 3, 4), 0.5, 0), ((12, 20, 9), 4, (3, 0, 1), 0.3, 1), ((32, 24, 40), 11, (10, 2, 7), 0.5, 0),
+    ((24, 24, 24), 16, (15, 8, 0), 0.5, 0), ((20, 33, 17), 3, (2, 2, 2), 0.9, 1),
+]
+
+
+def run_augment_and_metrics():
+    """utils/gridmask.py:8-72 (Grid.__call__ with its np.random draws substituted) and utils/utils_common.py:37-60
+    (evaluate_fp) of the reference on small seeded inputs: what oracle/sampling.gridmask and oracle/metrics.evaluate_fp
+    are checked against where /root/reference is absent."""
+    from scipy import ndimage as nd
+    gm = ref_loader.load_gridmask()
+    _, _, uc = ref_loader.load()
+    masks = {}
+    for k, (shape, d, st, ratio, mode) in enumerate(GRIDMASK_CASES):
+        draws = iter([d] + list(st) + [0])
+        grid = gm.Grid(2, 64, rotate=1, ratio=ratio, mode=mode, prob=1.0)
+        with mock.patch.object(np.random, "rand", lambda: 0.0), \
+                mock.patch.object(np.random, "randint", lambda *a, **kw: next(draws)):
+            out = grid(torch.ones((1,) + tuple(shape)))
+        masks[f"mask_{k}"] = np.packbits(out[0].numpy().astype(bool))
+    np.savez_compressed(os.path.join(OUT, "gridmask_cases.npz"),
+                        meta=json.dumps([dict(shape=list(c[0]), d=c[1], st=list(c[2]), ratio=c[3], mode=c[4])
+                                         for c in GRIDMASK_CASES]), **masks)
+    fp = []
+    for k in range(5):
+        pred = nd.binary_dilation(synth.tensor((24, 28, 20), "fp_pred", 40 + k, 1.0, dist="normal").numpy() > 2.6,
+                                  iterations=1 + k % 3)
+        lab = nd.binary_dilation(synth.tensor((24, 28, 20), "fp_lab", 50 + k, 1.0, dist="normal").numpy() > 2.0,
+                                 iterations=2).astype(np.float32)
+        cc, n = nd.label(pred)
+        fp.append(dict(seed=k, components=int(n), fp=int(uc.evaluate_fp(cc, lab))))
+    with open(os.path.join(OUT, "evaluate_fp_cases.json"), "w") as f:
+        json.dump(fp, f, indent=1)
+    print("gridmask", [int(np.unpackbits(v).sum()) for v in masks.values()], "evaluate_fp", fp)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    for c in MODEL_CASES:
-        run_model_case(*c)
-    run_loss_cases()
-    run_sliding_and_postproc()
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only in (None, "models"):
+        for c in MODEL_CASES:
+            run_model_case(*c)
+    if only in (None, "loss"):
+        run_loss_cases()
+    if only in (None, "sliding"):
+        run_sliding_and_postproc()
+    if only in (None, "augment"):
+        run_augment_and_metrics()
