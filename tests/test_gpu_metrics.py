@@ -156,3 +156,22 @@ def test_evaluate_loop_matches_the_oracle_pipeline():
     _, pred, _ = evaluation.evaluate_subject(net, data[0]["image"].to(DEV), data[0]["label"].to(DEV), params, None, False)
     logits = oinf.sliding_window_inference(data[0]["image"], params["patch_size"], 2, net.forward, 0.25)
     assert np.array_equal(pred.cpu().numpy(), oinf.label_map(logits, "threshold")[0, 1].numpy())
+
+
+def test_evaluate_fp_matches_the_reference_goldens():
+    """tests/golden/evaluate_fp_cases.json holds utils/utils_common.py:37-60's own counts (tools/make_goldens.py)."""
+    import json
+    import os
+    from scipy import ndimage as nd
+    from fcd_b200 import metrics
+    from oracle import synth
+    from tests import helpers as H
+    for c in json.load(open(os.path.join(H.GOLDEN, "evaluate_fp_cases.json"))):
+        k = c["seed"]
+        pred = nd.binary_dilation(synth.tensor((24, 28, 20), "fp_pred", 40 + k, 1.0, dist="normal").numpy() > 2.6,
+                                  iterations=1 + k % 3)
+        lab = nd.binary_dilation(synth.tensor((24, 28, 20), "fp_lab", 50 + k, 1.0, dist="normal").numpy() > 2.0,
+                                 iterations=2).astype(np.float32)
+        cc, n = nd.label(pred)
+        got = int(metrics.evaluate_fp(torch.from_numpy(cc.astype(np.float32)).to(DEV), torch.from_numpy(lab).to(DEV)))
+        assert n == c["components"] and got == c["fp"], c
