@@ -218,7 +218,8 @@ FCD_API int fcd_loss_bwd(const float* pred, const float* target, int B, int D, i
  * 42 stripe width; 43-45 phases; 46 inverted; 47 reserved.
  * pick_centers: rot_p / rot_range = probability and half-range (radians) of the rotation about spatial axis 1; cd_p,
  * holes (<= 8), (hz, hy, hx) = coarse dropout; grid_p, [d1, d2), grid_ratio, grid_invert = GridMask.
- * crop_augment: (hz, hy, hx) as above, hh = ceil(sqrt(rd^2 + rh^2 + rw^2)) (the mask cube of utils/gridmask.py:31). ---- */
+ * crop_augment: (hz, hy, hx) as above, hh = ceil(sqrt(rd^2 + rh^2 + rw^2)) (the mask cube of utils/gridmask.py:31);
+ * D*H*W < 2^31, S <= 65535, ceil(rd*rh / rows per block) <= 65535 (else -1). ---- */
 FCD_API int fcd_sampling_block_voxels(void);
 FCD_API int fcd_sampling_meta_floats(void);
 FCD_API int fcd_fg_block_counts(const float* label, long long V, int* counts, cudaStream_t stream);
