@@ -216,3 +216,59 @@ def test_slab_bounds_and_label_assembly():
         full = torch.stack([vol[:, :, r * slab:(r + 1) * slab].permute(0, 2, 1, 3, 4) for r in range(world)])
         out = assemble_label_slabs(full, pz, D)
         assert torch.equal(out, vol[:, :, pz:pz + D])
+
+
+def test_metric_reductions_from_count_tables():
+    """Host side of fcd_b200.metrics (the ratios and MONAI's mean reductions on a [B, C, 4] confusion table; plain torch,
+    so it runs without a GPU) against oracle/metrics.py: random tables, background dropped for C > 1, subjects without a
+    lesion (Dice NaN, left out of the mean), all-empty tables (0 / 0 -> NaN precision and sensitivity, Dice 0)."""
+    import math
+    import numpy as np
+    from fcd_b200 import metrics
+    from oracle import metrics as om
+    rng = np.random.default_rng(0)
+    tables = [rng.integers(0, 1000, (B, C, 4)) for B, C in ((1, 1), (3, 1), (2, 2), (4, 3))]
+    t = rng.integers(1, 50, (3, 1, 4))
+    t[1, 0, [0, 3]] = 0                       # subject 1: no ground-truth voxel
+    tables.append(t)
+    tables.append(np.zeros((2, 1, 4), np.int64) + np.array([0, 0, 512, 0]))      # nothing predicted, nothing to find
+    tables.append(np.array([[[0, 7, 100, 0]], [[0, 0, 107, 0]]]))                # false positives only
+    for tab in tables:
+        ref = om.metrics_from_counts(tab)
+        got = metrics.metrics_from_counts(torch.from_numpy(np.asarray(tab, np.int64)))
+        assert list(got) == ["Prec", "Sens", "F1", "DC"]
+        for k in got:
+            assert (math.isnan(got[k]) and math.isnan(ref[k])) or abs(got[k] - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])), (k, tab)
+        dev = metrics.metrics_from_counts(torch.from_numpy(np.asarray(tab, np.int64)), as_tensors=True)
+        assert all(v.dim() == 0 and v.dtype == torch.float64 for v in dev.values())
+    with pytest.raises(RuntimeError):
+        metrics.confusion_counts(torch.zeros(1, 1, 2, 2, 2), torch.zeros(1, 1, 2, 2, 2))      # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        metrics.VoxelMetricAccumulator().aggregate()
+
+
+def test_patch_sampler_host_logic():
+    """GpuPatchSampler without a GPU: argument checks, MONAI's hole-size clipping, the mask cube edge of
+    utils/gridmask.py:31, the probability ramp (get_transforms.py:116-126) and the no-CPU-fallback rule."""
+    import math
+    import fcd_b200
+    s = fcd_b200.GpuPatchSampler(dict(patch_size=(20, 31, 27), samples_per_case=3), hole_size=(5, 40, 3))
+    assert s.roi == (20, 31, 27) and s.hole_size == (5, 31, 3) and s.num_samples == 3
+    assert s.hh == math.ceil(math.sqrt(20 * 20 + 31 * 31 + 27 * 27))
+    assert not s.has_gradual_prob() and s.coarse_dropout_prob == 0.0 and s.gridmask_prob == 0.0
+    s.set_prob(5, 10)
+    assert s.coarse_dropout_prob == 0.0 and s.gridmask_prob == 0.0
+    r = fcd_b200.GpuPatchSampler(dict(patch_size=16, coarse_dropout_max_prob=0.4, coarse_dropout_start_epoch=10,
+                                      gridmask_max_prob=0.6, gridmask_start_epoch=0))
+    assert r.has_gradual_prob() and r.gridmask_prob == 0.6 and r.coarse_dropout_prob == 0.0
+    r.set_prob(5, 110)
+    assert r.coarse_dropout_prob == 0.0 and r.gridmask_prob == pytest.approx(0.6 * 5 / 110)
+    r.set_prob(60, 110)
+    assert r.coarse_dropout_prob == pytest.approx(0.4 * 0.5) and r.gridmask_prob == pytest.approx(0.6 * 60 / 110)
+    r.set_prob(500, 110)
+    assert r.coarse_dropout_prob == pytest.approx(0.4) and r.gridmask_prob == pytest.approx(0.6)
+    for bad in (dict(pos=0, neg=0), dict(holes=9), dict(grid_spacing_range=(8, 8))):
+        with pytest.raises(ValueError):
+            fcd_b200.GpuPatchSampler(dict(patch_size=16), **bad)
+    with pytest.raises(RuntimeError):
+        s(torch.zeros(2, 24, 32, 28), torch.zeros(1, 24, 32, 28), seed=1)
