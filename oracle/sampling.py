@@ -6,7 +6,9 @@ the reference's per-patch transforms (get_transforms.py:45-89):
   RandFlip per axis; RandShiftIntensity (img + offset); RandGaussianNoise (img + N(0, std'), std' ~ U(0, std));
   RandRotate(range_y, keep_size, bilinear / nearest, padding 'border') [RECALLED: MONAI Rotate resamples the patch on the
     grid src = c + R (p - c), c = (size - 1) / 2, R = create_rotate about spatial axis 1; the SIGN convention of the angle
-    is not pinned -- the angle is drawn symmetrically, so the distribution of patches does not depend on it];
+    is not pinned -- the angle is drawn symmetrically, so the distribution of patches does not depend on it].  The
+    resampling itself IS pinned: tests/test_oracle_goldens.py checks `_rotate_axis1` against torch's affine_grid +
+    grid_sample (the resampler MONAI calls; bilinear / nearest, padding 'border', both align_corners conventions);
   RandCoarseDropout(holes, spatial_size, fill_value=0) [RECALLED: `holes` boxes, corner uniform in [0, dim - size]];
   GridMask: utils/gridmask.py:20-72 of the reference itself -- `gridmask()` below is checked BIT-EXACT against that class
     imported live with its np.random draws substituted (tests/test_oracle_vs_reference.py).
